@@ -1,0 +1,207 @@
+/*
+ * turbomesh_gpu.h -- C ABI of the B200 (sm_100a) back-end for turbomesh's hot path:
+ * 2D boundary-blended linear TFI + multi-block elliptic (Winslow) smoothing.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only, no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * turbomesh repository).  The Zig-side binding is in zig/cuda.zig, the integration
+ * recipe in INTEGRATION.md.
+ *
+ * Conventions
+ *  - all coordinates are fp64, interleaved x0,y0,x1,y1,... exactly like
+ *    `Mat2d.data` / `Vec2d` (src/core/types.zig:16-27, 78-101): node (i,j) of a block of
+ *    size (ni,nj) lives at doubles [2*(i*nj+j), 2*(i*nj+j)+1]  (j is the fastest index).
+ *  - every function returns 0 (TM_OK) on success or a negative tm_status; the message of
+ *    the last failure on the calling thread is available from tm_last_error().
+ *  - the library never frees or keeps host pointers handed to it; results are written in
+ *    place into the caller's block arrays (as smooth.zig:139-153 does).
+ *  - there is NO CPU fallback: without a usable CUDA device every compute entry point
+ *    returns TM_ERR_NO_DEVICE.
+ */
+#ifndef TURBOMESH_GPU_H
+#define TURBOMESH_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TM_ABI_VERSION 1
+
+typedef enum tm_status {
+    TM_OK = 0,
+    TM_ERR_INVALID_ARGUMENT = -1,
+    TM_ERR_NO_DEVICE = -2,        /* no CUDA device / driver: there is no CPU fallback        */
+    TM_ERR_CUDA = -3,             /* a CUDA runtime call failed                                */
+    TM_ERR_TOPOLOGY = -4,         /* inconsistent mesh topology (what smooth.zig:220-275,
+                                     627-651 asserts or panics on)                             */
+    TM_ERR_UNSUPPORTED = -5,      /* topology the reference cannot express either
+                                     (e.g. > 4 overlapping junction copies, smooth.zig:1221)   */
+    TM_ERR_NOT_CONVERGED = -6,    /* only returned when opts.fail_on_no_convergence != 0       */
+    TM_ERR_OUT_OF_MEMORY = -7
+} tm_status;
+
+/* boundary.zig:8-13 (enum order is part of the ABI) */
+typedef enum tm_side { TM_SIDE_I_MIN = 0, TM_SIDE_I_MAX = 1, TM_SIDE_J_MIN = 2, TM_SIDE_J_MAX = 3 } tm_side;
+
+/* boundary.zig:172-176 */
+typedef enum tm_condition_kind { TM_BC_WALL = 0, TM_BC_INLET = 1, TM_BC_OUTLET = 2 } tm_condition_kind;
+
+/* view of discrete.Block2d.points (discrete.zig:138-140, types.zig:78-81) */
+typedef struct tm_block {
+    uint64_t ni, nj; /* Mat2d.size                                                     */
+    double *xy;      /* Mat2d.data.ptr viewed as [*]f64, 2*ni*nj doubles, host memory  */
+} tm_block;
+
+/* boundary.Range (boundary.zig:15-19); start > end means reversed traversal */
+typedef struct tm_range {
+    uint64_t block;
+    uint32_t side; /* tm_side */
+    uint32_t _pad;
+    uint64_t start, end;
+} tm_range;
+
+/* boundary.Connection (boundary.zig:119-123); periodicity maps ranges[0] onto ranges[1]: x0 + p == x1 */
+typedef struct tm_connection {
+    tm_range ranges[2];
+    int32_t has_periodicity;
+    int32_t _pad;
+    double periodicity[2];
+} tm_connection;
+
+/* boundary.Condition (boundary.zig:178-181) */
+typedef struct tm_condition {
+    tm_range range;
+    uint32_t kind; /* tm_condition_kind */
+    uint32_t _pad;
+} tm_condition;
+
+/* wall_control_function.Algorithm (wall_control_function.zig:10-20, 56-61) */
+typedef enum tm_control_function { TM_CF_LAPLACE = 0, TM_CF_WHITE = 1 } tm_control_function;
+
+/* How one outer iteration is advanced.
+ *  TM_SOLVER_PICARD_BICGSTAB  reference semantics (smooth.zig:104-154): coefficients lagged at the
+ *      previous outer iterate, the linear system solved for x and y by a matrix-free right-preconditioned
+ *      BiCGStab (BiCGStab.zig:279-370, preconditioner `diagonal`, solver.zig:22-24).
+ *  TM_SOLVER_RELAX  throughput path: `sweeps_per_iteration` damped-Jacobi sweeps of the same 9-point
+ *      operator with the coefficients recomputed from the current iterate (32 B/node-update); converges
+ *      to the same fixed point as the Picard iteration.
+ *  TM_SOLVER_PICARD_JACOBI  lagged coefficients, inner damped-Jacobi sweeps until the inner tolerance.
+ */
+typedef enum tm_solver { TM_SOLVER_PICARD_BICGSTAB = 0, TM_SOLVER_RELAX = 1, TM_SOLVER_PICARD_JACOBI = 2 } tm_solver;
+
+typedef struct tm_smooth_options {
+    uint32_t struct_size;          /* sizeof(tm_smooth_options), for ABI evolution               */
+    uint32_t solver;               /* tm_solver                                                  */
+    uint64_t iterations;           /* outer iterations (`iterations` of smooth.mesh)             */
+    uint32_t control_function;     /* tm_control_function                                        */
+    uint32_t fail_on_no_convergence;
+    double white_ds_target;        /* White.ds_target                                            */
+    double white_theta_target;     /* White.theta_target (default pi/2)                          */
+    /* inner linear solve (Picard modes); defaults of the reference: rtol 1e-6, atol 1e-8, 1000 */
+    double rtol, atol;
+    uint64_t max_inner_iterations;
+    /* relaxation */
+    double omega;                  /* Jacobi damping, 0 < omega <= 1                             */
+    uint64_t sweeps_per_iteration; /* TM_SOLVER_RELAX: sweeps per outer iteration                */
+    double stop_max_update;        /* > 0: stop the outer loop early once max|x_new-x_old| <= this */
+    int32_t device;                /* CUDA device ordinal, -1 = current                          */
+    int32_t _pad;
+} tm_smooth_options;
+
+typedef struct tm_smooth_stats {
+    uint64_t outer_iterations;     /* outer iterations actually run                              */
+    uint64_t inner_iterations;     /* total Krylov iterations / Jacobi sweeps                    */
+    uint64_t operator_applications;/* applications of the 9-point operator to the whole mesh     */
+    uint64_t nodes;                /* total node count                                           */
+    double last_sumsq_x, last_sumsq_y; /* sums of smooth.zig:112-134 for the last outer iteration */
+    double last_residual;          /* (sumsq_x+sumsq_y)^2, the number smooth.zig:136-137 logs    */
+    double last_max_update;        /* max-norm of the last outer update                          */
+    double last_inner_residual;    /* max over x,y of the final inner residual norm              */
+    double gpu_seconds;            /* device time of the smoothing loop (CUDA events)            */
+    int32_t converged;             /* all inner solves reached their tolerance                   */
+    int32_t _pad;
+} tm_smooth_stats;
+
+/* -------------------------------------------------------------------------------------------------
+ * One-shot entry points with HOST buffers (what the Zig call sites bind)
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Replaces tfi.linear2dBoundaryBlendedControlFunction (src/core/tfi.zig:112-208) as called from
+ * discrete.Block2d.init (src/core/discrete.zig:142-159).  Edges are interleaved x,y host arrays:
+ * x_i_min,x_i_max,s1,s2 have ni entries; x_j_min,x_j_max,t1,t2 have nj entries.  out_xy receives
+ * 2*ni*nj doubles.  Bit-exact with the reference's operation order (no FMA contraction). */
+int tm_tfi_block(uint64_t ni, uint64_t nj,
+                 const double *x_i_min, const double *x_i_max,
+                 const double *x_j_min, const double *x_j_max,
+                 const double *s1, const double *s2, const double *t1, const double *t2,
+                 double *out_xy);
+
+/* Replaces smoothing.smooth.mesh (src/core/smoothing/smooth.zig:74-166): smooths all blocks in place. */
+int tm_smooth_mesh(tm_block *blocks, size_t n_blocks,
+                   const tm_connection *connections, size_t n_connections,
+                   const tm_condition *conditions, size_t n_conditions,
+                   const tm_smooth_options *opts, tm_smooth_stats *stats);
+
+/* Fills *opts with the defaults (reference tolerances, Laplace control function, Picard/BiCGStab). */
+void tm_smooth_options_default(tm_smooth_options *opts);
+
+/* -------------------------------------------------------------------------------------------------
+ * Device-resident mesh handle (benchmarks, batches, multi-GPU): H2D/D2H only when asked
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tm_mesh tm_mesh; /* opaque */
+
+/* Builds the device mesh: topology analysis (node kinds, junctions, interface tables; smooth.zig:1234-1529),
+ * device allocation.  `stream` is a cudaStream_t (NULL = a stream owned by the handle). Block coordinate
+ * pointers may be NULL at creation (fill them with tm_mesh_tfi_block or tm_mesh_upload_block). */
+int tm_mesh_create(const tm_block *blocks, size_t n_blocks,
+                   const tm_connection *connections, size_t n_connections,
+                   const tm_condition *conditions, size_t n_conditions,
+                   int device, void *stream, tm_mesh **out);
+void tm_mesh_destroy(tm_mesh *mesh);
+
+int tm_mesh_upload_block(tm_mesh *mesh, size_t block, const double *xy);     /* host -> device  */
+int tm_mesh_download_block(tm_mesh *mesh, size_t block, double *xy);         /* device -> host  */
+/* TFI of one block directly into the device mesh; edge arrays are HOST pointers (O(ni+nj) data). */
+int tm_mesh_tfi_block(tm_mesh *mesh, size_t block,
+                      const double *x_i_min, const double *x_i_max,
+                      const double *x_j_min, const double *x_j_max,
+                      const double *s1, const double *s2, const double *t1, const double *t2);
+/* Freezes the current coordinates as the initial mesh: checks interface coincidence
+ * (connectionDataCheck, smooth.zig:220-275), captures fixed/sliding boundary values
+ * (smooth.zig:790-796, 853-858) and initialises the control function (wall_control_function.zig:27-42). */
+int tm_mesh_begin_smoothing(tm_mesh *mesh, const tm_smooth_options *opts);
+/* Runs opts->iterations outer iterations on the device-resident mesh (may be called repeatedly). */
+int tm_mesh_smooth(tm_mesh *mesh, const tm_smooth_options *opts, tm_smooth_stats *stats);
+/* Blocks until all work queued on the mesh's stream has finished. */
+int tm_mesh_synchronize(tm_mesh *mesh);
+
+/* Accessors (mirror the WASM surface, src/wasm/lib.zig:97-124) */
+uint64_t tm_mesh_block_count(const tm_mesh *mesh);
+uint64_t tm_mesh_node_count(const tm_mesh *mesh);
+int tm_mesh_block_size(const tm_mesh *mesh, size_t block, uint64_t *ni, uint64_t *nj);
+/* device pointer to the current coordinates of a block (interleaved x,y) */
+double *tm_mesh_block_device_ptr(tm_mesh *mesh, size_t block);
+/* device pointer / host copy of the control function (P,Q per node, wall_control_function.zig:24) */
+int tm_mesh_download_control_function(tm_mesh *mesh, size_t block, double *pq);
+/* node kind per block-boundary node in the reference's flat boundary numbering (boundary.zig:248-285);
+ * values: 0 fixed, 1 smoothed, 2 connected, 3 laplacian_smoothed, 4 sliding_circ (smooth.zig:1168-1174).
+ * `kinds` receives 2*(ni+nj-2) bytes. */
+int tm_mesh_download_boundary_kinds(tm_mesh *mesh, size_t block, uint8_t *kinds);
+
+/* -------------------------------------------------------------------------------------------------
+ * Misc
+ * ------------------------------------------------------------------------------------------------- */
+const char *tm_last_error(void);
+int tm_abi_version(void);
+/* number of CUDA kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t tm_kernel_launch_count(void);
+/* name, SM count, memory of the device in use; returns TM_ERR_NO_DEVICE when there is none */
+int tm_device_info(int device, char *name, size_t name_len, int *sm_count, uint64_t *global_mem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURBOMESH_GPU_H */

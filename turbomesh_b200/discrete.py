@@ -1,0 +1,149 @@
+"""Discrete mesh model -- host-side mirror of ``src/core/discrete.zig``.
+
+``Block2d.init`` is one of the two call sites of the accelerated path: it allocates the block and runs
+the boundary-blended TFI (``discrete.zig:142-159`` -> ``tfi.zig:112-208``) -- here through the C ABI
+(``tm_tfi_block``) on the GPU.  There is no CPU fallback; a ``tfi=`` callable can be injected (the test
+suite injects the CPU oracle as the checker).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import clustering as cluster
+from .boundary import Condition, Connection
+from .geometry import Line
+from .spline import FittingSpline
+
+
+class Edge:
+    """``discrete.zig:12-91``: points (n,2) + clustering (n,) of one block edge."""
+
+    def __init__(self, points: np.ndarray, clustering: np.ndarray):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.clustering = np.ascontiguousarray(clustering, dtype=np.float64)
+        assert self.points.shape == (len(self.clustering), 2)
+
+    @staticmethod
+    def init(n: int, curve, clustering) -> "Edge":
+        """``Edge.init``, ``discrete.zig:17-31``."""
+        u = cluster.create(clustering, n)
+        if isinstance(curve, (Line, FittingSpline)):
+            data = curve.interpolate(u)
+        else:
+            raise TypeError("curve must be a Line or a FittingSpline")
+        return Edge(data, u)
+
+    def copy(self) -> "Edge":
+        return Edge(self.points.copy(), self.clustering.copy())
+
+    @staticmethod
+    def combine(edges: Sequence["EdgeView"]) -> "Edge":
+        """``Edge.combine``, ``discrete.zig:38-91``: concatenates views, dropping the duplicated joints."""
+        assert len(edges) > 1
+        tol = 1e-10
+        for k in range(len(edges) - 1):
+            a = edges[k].edge.points[edges[k].end]
+            b = edges[k + 1].edge.points[edges[k + 1].start]
+            if not (abs(a[0] - b[0]) <= tol and abs(a[1] - b[1]) <= tol):
+                raise ValueError(f"edges {k + 1} and {k + 2} cannot be combined as end points do not match: {a} and {b}")
+        n = sum(e.len() for e in edges) - (len(edges) - 1)
+        u = np.empty(n, dtype=np.float64)
+        points = np.empty((n, 2), dtype=np.float64)
+        start = 0
+        for e in edges:
+            start += e.clone_points(points[start:]) - 1
+        start = 0
+        last_value = 0.0
+        for e in edges:
+            start += e.clone_clustering(u[start:], last_value) - 1
+            last_value = float(u[start])
+        for k in range(n):
+            u[k] = u[k] / last_value
+        return Edge(points, u)
+
+
+@dataclass
+class EdgeView:
+    """``discrete.zig:94-136``."""
+
+    edge: Edge
+    start: int
+    end: int
+
+    def len(self) -> int:
+        return abs(self.start - self.end) + 1
+
+    def clone_points(self, buffer: np.ndarray) -> int:
+        n = self.len()
+        if self.start > self.end:
+            buffer[:n] = self.edge.points[self.end : self.start + 1][::-1]
+        else:
+            buffer[:n] = self.edge.points[self.start : self.end + 1]
+        return n
+
+    def clone_clustering(self, buffer: np.ndarray, initial_value: float) -> int:
+        # NOTE (reference behaviour): for reversed views the deltas are still accumulated from
+        # min(start, end) upwards, i.e. the clustering is not reversed (discrete.zig:119-135).
+        buffer[0] = initial_value
+        first, last = min(self.start, self.end), max(self.start, self.end)
+        last_value = float(self.edge.clustering[first])
+        i_buf = 1
+        for i in range(first + 1, last + 1):
+            delta = float(self.edge.clustering[i]) - last_value
+            buffer[i_buf] = initial_value + delta
+            i_buf += 1
+        return i_buf
+
+
+TfiFn = Callable[..., np.ndarray]
+
+
+def _default_tfi(*args) -> np.ndarray:
+    from .smoothing import tfi_block  # GPU back-end (C ABI); raises if the CUDA library is unusable
+
+    return tfi_block(*args)
+
+
+class Block2d:
+    """``discrete.zig:138-164``; ``points`` is the ``Mat2d`` view: array (ni, nj, 2), j fastest."""
+
+    def __init__(self, points: np.ndarray):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        assert self.points.ndim == 3 and self.points.shape[2] == 2
+
+    @property
+    def size(self):
+        return self.points.shape[0], self.points.shape[1]
+
+    @staticmethod
+    def init(i_min: Edge, i_max: Edge, j_min: Edge, j_max: Edge, tfi: Optional[TfiFn] = None) -> "Block2d":
+        assert len(i_min.points) == len(i_max.points)
+        assert len(j_min.points) == len(j_max.points)
+        fn = tfi or _default_tfi
+        pts = fn(i_min.points, i_max.points, j_min.points, j_max.points,
+                 i_min.clustering, i_max.clustering, j_min.clustering, j_max.clustering)
+        return Block2d(pts)
+
+
+@dataclass
+class Mesh:
+    """``discrete.zig:166-195``."""
+
+    blocks: List[Block2d] = field(default_factory=list)
+    names: List[str] = field(default_factory=list)
+    connections: List[Connection] = field(default_factory=list)
+    boundary_conditions: List[Condition] = field(default_factory=list)
+
+    def add_block(self, name: str, block: Block2d) -> int:
+        self.blocks.append(block)
+        self.names.append(name)
+        return len(self.blocks) - 1
+
+    def num_nodes(self) -> int:
+        return sum(b.size[0] * b.size[1] for b in self.blocks)
+
+    def copy(self) -> "Mesh":
+        return Mesh([Block2d(b.points.copy()) for b in self.blocks], list(self.names), list(self.connections), list(self.boundary_conditions))
