@@ -88,9 +88,8 @@ typedef enum tm_control_function { TM_CF_LAPLACE = 0, TM_CF_WHITE = 1 } tm_contr
  *  TM_SOLVER_RELAX  throughput path: `sweeps_per_iteration` damped-Jacobi sweeps of the same 9-point
  *      operator with the coefficients recomputed from the current iterate (32 B/node-update); converges
  *      to the same fixed point as the Picard iteration.
- *  TM_SOLVER_PICARD_JACOBI  lagged coefficients, inner damped-Jacobi sweeps until the inner tolerance.
  */
-typedef enum tm_solver { TM_SOLVER_PICARD_BICGSTAB = 0, TM_SOLVER_RELAX = 1, TM_SOLVER_PICARD_JACOBI = 2 } tm_solver;
+typedef enum tm_solver { TM_SOLVER_PICARD_BICGSTAB = 0, TM_SOLVER_RELAX = 1 } tm_solver;
 
 typedef struct tm_smooth_options {
     uint32_t struct_size;          /* sizeof(tm_smooth_options), for ABI evolution               */
@@ -164,11 +163,13 @@ void tm_mesh_destroy(tm_mesh *mesh);
 
 int tm_mesh_upload_block(tm_mesh *mesh, size_t block, const double *xy);     /* host -> device  */
 int tm_mesh_download_block(tm_mesh *mesh, size_t block, double *xy);         /* device -> host  */
-/* TFI of one block directly into the device mesh; edge arrays are HOST pointers (O(ni+nj) data). */
+/* TFI of one block directly into the device mesh; edge arrays are HOST pointers (O(ni+nj) data) and stay
+ * cached on the device, so tm_mesh_tfi_block_resident can re-run the TFI without any host traffic. */
 int tm_mesh_tfi_block(tm_mesh *mesh, size_t block,
                       const double *x_i_min, const double *x_i_max,
                       const double *x_j_min, const double *x_j_max,
                       const double *s1, const double *s2, const double *t1, const double *t2);
+int tm_mesh_tfi_block_resident(tm_mesh *mesh, size_t block);
 /* Freezes the current coordinates as the initial mesh: checks interface coincidence
  * (connectionDataCheck, smooth.zig:220-275), captures fixed/sliding boundary values
  * (smooth.zig:790-796, 853-858) and initialises the control function (wall_control_function.zig:27-42). */

@@ -1,0 +1,75 @@
+"""First GPU parity tests: CUDA path through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from turbomesh_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _max_diff(a, b):
+    return max(float(np.abs(x.points - y.points).max()) for x, y in zip(a.blocks, b.blocks))
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (5, 7), (129, 33), (64, 257), (300, 131)])
+def test_tfi_bit_exact_single_block(orc, gpu_lib, shape):
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.single_block(*shape)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    assert np.array_equal(gpu.blocks[0].points, cpu.blocks[0].points)
+
+
+def test_tfi_bit_exact_different_clusterings(orc, gpu_lib):
+    from turbomesh_b200 import smoothing
+    from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform
+
+    ni, nj = 77, 53
+    s1, s2 = Roberts(0.5, 1.03).compute(ni), Uniform().compute(ni)
+    t1, t2 = SingleHyperbolicClustering(0.01).compute(nj), Roberts(0.0, 1.2).compute(nj)
+    xi_min = np.stack([s1, 0.1 * np.sin(3 * s1)], axis=1)
+    xi_max = np.stack([s2 * 1.1 - 0.05, 1 + 0.1 * np.cos(2 * s2)], axis=1)
+    xj_min = np.stack([xi_min[0, 0] + (xi_max[0, 0] - xi_min[0, 0]) * t1, xi_min[0, 1] + (xi_max[0, 1] - xi_min[0, 1]) * t1 + 0.05 * np.sin(np.pi * t1)], axis=1)
+    xj_max = np.stack([xi_min[-1, 0] + (xi_max[-1, 0] - xi_min[-1, 0]) * t2, xi_min[-1, 1] + (xi_max[-1, 1] - xi_min[-1, 1]) * t2], axis=1)
+    xj_min[0], xj_min[-1], xj_max[0], xj_max[-1] = xi_min[0], xi_max[0], xi_min[-1], xi_max[-1]
+    a = smoothing.tfi_block(xi_min, xi_max, xj_min, xj_max, s1, s2, t1, t2)
+    b = orc.tfi(xi_min, xi_max, xj_min, xj_max, s1, s2, t1, t2)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("args", [(2, 2, 12, 9), (4, 2, 33, 17), (4, 1, 20, 30), (8, 8, 16, 12)])
+def test_picard_bicgstab_matches_oracle_cascade(orc, gpu_lib, args):
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.cascade(*args)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    assert _max_diff(gpu, cpu) == 0.0
+    st = smoothing.smooth_mesh(gpu, 4, smoothing.CudaSolver.tight())
+    orc.smooth_mesh(cpu, 4, orc.tight_options())
+    chord = 1.0
+    assert _max_diff(gpu, cpu) <= 1e-9 * chord, st
+
+
+def test_picard_bicgstab_matches_oracle_single_block(orc, gpu_lib):
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.single_block(65, 49)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    smoothing.smooth_mesh(gpu, 5, smoothing.CudaSolver.tight())
+    orc.smooth_mesh(cpu, 5, orc.tight_options())
+    assert _max_diff(gpu, cpu) <= 1e-9
+
+
+def test_relax_converges_to_picard_fixed_point(orc, gpu_lib):
+    """Nonlinear Jacobi sweeps and the Picard iteration share their fixed point."""
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.cascade(2, 2, 12, 9)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    st = smoothing.smooth_mesh(gpu, 400, smoothing.CudaSolver(method="relax", sweeps_per_iteration=50, omega=0.9, stop_max_update=1e-14))
+    orc.smooth_mesh(cpu, 30, orc.tight_options())
+    assert _max_diff(gpu, cpu) <= 1e-9, st

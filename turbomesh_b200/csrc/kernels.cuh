@@ -1,0 +1,690 @@
+// kernels.cuh -- sm_100a device code for turbomesh's hot path (fp64, HBM-bound, no tensor cores).
+//
+//   tfi_kernel              tfi.linear2dBoundaryBlendedControlFunction          src/core/tfi.zig:112-208
+//   winslow_interior_kernel StencilData.init + fillBlockInternalPointData       src/core/smoothing/smooth.zig:192-215, 923-992
+//                           fused with the solver's use of the row (relaxation sweep / operator apply / residual),
+//                           so the 9 coefficients live only in registers (matrix-free)
+//   winslow_boundary_kernel fillBlockConnectionData (interface rows), junction rows, sliding rows, connected copies
+//                                                                               smooth.zig:994-1105, 813-859, 1115-1165
+//   white_*                 White.initControlFunction / White.update            wall_control_function.zig:70-473
+//   vector kernels          BiCGStab.zig:279-370 with x and y advanced in lock-step (double2 per node)
+//
+// Data layout: all blocks concatenated in the reference's global row order, AoS double2 (x,y) per node,
+// j fastest inside a block (types.zig:78-101).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "topology.hpp"
+
+namespace tmesh {
+
+struct DevBlock {
+    int64_t off;
+    int32_t ni, nj;
+};
+struct Tile {
+    int32_t block, i0, j0, _pad;
+};
+
+constexpr int TILE_J = 128;  // threads per CTA = nodes along j per tile
+constexpr int TILE_I = 64;   // rows marched per CTA
+
+enum Mode : int { MODE_RELAX = 0, MODE_APPLY = 1, MODE_RESID = 2, MODE_DINV = 3 };
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double2* p) { return *p; }
+__device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-level reduction of K sums + 1 max; thread 0 writes them to out[0..K] (K sums then the max).
+template <int K, int NT>
+__device__ __forceinline__ void block_reduce_store(double (&sums)[K], double mx, double* out) {
+    __shared__ double sh[(K + 1) * (NT / 32)];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) sums[k] = warp_sum(sums[k]);
+    mx = warp_max(mx);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sh[k * (NT / 32) + w] = sums[k];
+        sh[K * (NT / 32) + w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int q = 0; q < NT / 32; ++q) s += sh[k * (NT / 32) + q];
+            out[k] = s;
+        }
+        double m = 0.0;
+        for (int q = 0; q < NT / 32; ++q) m = fmax(m, sh[K * (NT / 32) + q]);
+        out[K] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TFI.  Bit-exact with the reference: explicit round-to-nearest intrinsics are never contracted into
+// FMAs, and the association follows tfi.zig:185-197 (scale, add, addAll left-to-right from (0,0)).
+// One thread owns one j column and marches ROWS rows; edge data of the column stays in registers,
+// edge data of the row is a warp-uniform (broadcast) read-only load.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tfi_component(double u, double v, double omu, double omv, double uv, double u_omv, double omu_v, double omu_omv,
+                                                double x0j, double xnj, double xi0, double xim, double x00, double xn0, double x0m, double xnm) {
+    const double u_ij = __dadd_rn(__dmul_rn(omu, x0j), __dmul_rn(u, xnj));
+    const double v_ij = __dadd_rn(__dmul_rn(omv, xi0), __dmul_rn(v, xim));
+    double acc = __dadd_rn(0.0, __dmul_rn(uv, xnm));
+    acc = __dadd_rn(acc, __dmul_rn(u_omv, xn0));
+    acc = __dadd_rn(acc, __dmul_rn(omu_v, x0m));
+    acc = __dadd_rn(acc, __dmul_rn(omu_omv, x00));
+    return __dsub_rn(__dadd_rn(u_ij, v_ij), acc);
+}
+
+constexpr int TFI_ROWS = 16;
+__global__ void __launch_bounds__(TILE_J) tfi_kernel(int ni, int nj, const double2* __restrict__ x_i_min, const double2* __restrict__ x_i_max,
+                                                     const double2* __restrict__ x_j_min, const double2* __restrict__ x_j_max,
+                                                     const double* __restrict__ s1, const double* __restrict__ s2, const double* __restrict__ t1,
+                                                     const double* __restrict__ t2, double2* __restrict__ out) {
+    const int j = blockIdx.x * TILE_J + threadIdx.x;
+    const int i_begin = blockIdx.y * TFI_ROWS;
+    if (j >= nj) return;
+    const double t1_j = __ldg(t1 + j), t2_j = __ldg(t2 + j);
+    const double2 x0j = ldg2(x_j_min + j), xnj = ldg2(x_j_max + j);
+    const double2 x00 = ldg2(x_i_min), xn0 = ldg2(x_i_min + (ni - 1)), x0m = ldg2(x_j_min + (nj - 1)), xnm = ldg2(x_i_max + (ni - 1));
+    const double omt1 = __dsub_rn(1.0, t1_j), dt = __dsub_rn(t2_j, t1_j);
+    const int i_end = min(i_begin + TFI_ROWS, ni);
+    for (int i = i_begin; i < i_end; ++i) {
+        const double s1_i = __ldg(s1 + i), s2_i = __ldg(s2 + i);
+        const double2 xi0 = ldg2(x_i_min + i), xim = ldg2(x_i_max + i);
+        const double ds = __dsub_rn(s2_i, s1_i);
+        // tfi.zig:185-186 (the two denominators are the same product with the factors swapped; IEEE multiplication commutes)
+        const double u = __ddiv_rn(__dadd_rn(__dmul_rn(omt1, s1_i), __dmul_rn(t1_j, s2_i)), __dsub_rn(1.0, __dmul_rn(ds, dt)));
+        const double v = __ddiv_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, s1_i), t1_j), __dmul_rn(s1_i, t2_j)), __dsub_rn(1.0, __dmul_rn(dt, ds)));
+        const double omu = __dsub_rn(1.0, u), omv = __dsub_rn(1.0, v);
+        const double uv = __dmul_rn(u, v), u_omv = __dmul_rn(u, omv), omu_v = __dmul_rn(omu, v), omu_omv = __dmul_rn(omu, omv);
+        double2 r;
+        r.x = tfi_component(u, v, omu, omv, uv, u_omv, omu_v, omu_omv, x0j.x, xnj.x, xi0.x, xim.x, x00.x, xn0.x, x0m.x, xnm.x);
+        r.y = tfi_component(u, v, omu, omv, uv, u_omv, omu_v, omu_omv, x0j.y, xnj.y, xi0.y, xim.y, x00.y, xn0.y, x0m.y, xnm.y);
+        out[(size_t)i * nj + j] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The Winslow row (StencilData.init, smooth.zig:192-215) in "difference form".
+//   W,E = nodes (i-1,j),(i+1,j); metric terms use central differences of the LAGGED coordinates:
+//     x_xi = (E-W)/2, x_eta = (N-S)/2; g11 = |x_xi|^2, g22 = |x_eta|^2, g12 = x_xi.x_eta
+//   row:  g22[(1+P/2)E + (1-P/2)W] + g11[(1+Q/2)N + (1-Q/2)S] - (g12/2)[(NE-SE)-(NW-SW)] - 2(g11+g22) C
+//   With D_r = u[r][j+1]-u[r][j-1] and S_r = u[r][j+1]+u[r][j-1] the off-diagonal part is
+//     off = g22[(E+W) + P/2 (E-W)] + g11[S_i + Q/2 D_i] - (g12/2)(D_{i+1} - D_{i-1})
+// ---------------------------------------------------------------------------------------------------
+struct Metric {
+    double g11, g22, g12;
+};
+__device__ __forceinline__ Metric metric_terms(double2 W, double2 E, double2 Deta /* N - S */) {
+    const double x_xi = 0.5 * (E.x - W.x), y_xi = 0.5 * (E.y - W.y);
+    const double x_eta = 0.5 * Deta.x, y_eta = 0.5 * Deta.y;
+    Metric m;
+    m.g22 = x_eta * x_eta + y_eta * y_eta;
+    m.g12 = x_xi * x_eta + y_xi * y_eta;
+    m.g11 = x_xi * x_xi + y_xi * y_xi;
+    return m;
+}
+__device__ __forceinline__ double2 offdiag_sum(const Metric& m, double P, double Q, double2 W, double2 E, double2 Ssum, double2 Deta, double2 Dp, double2 Dm) {
+    double2 r;
+    r.x = m.g22 * ((E.x + W.x) + 0.5 * P * (E.x - W.x)) + m.g11 * (Ssum.x + 0.5 * Q * Deta.x) - 0.5 * m.g12 * (Dp.x - Dm.x);
+    r.y = m.g22 * ((E.y + W.y) + 0.5 * P * (E.y - W.y)) + m.g11 * (Ssum.y + 0.5 * Q * Deta.y) - 0.5 * m.g12 * (Dp.y - Dm.y);
+    return r;
+}
+
+// What a row produces, shared by interior and interface rows.
+//   RELAX: (1-w) C + w * off / (2(g11+g22))          (damped Jacobi update of the row)
+//   APPLY: off - 2(g11+g22) C                         (A v, homogeneous)
+//   RESID: -(off - 2(g11+g22) C)                      (b - A x; the rhs of these rows is 0 once periodic shifts are folded in)
+//   DINV : 1 / (-2(g11+g22))                          (Jacobi preconditioner, GMRES.zig:176-196)
+template <int MODE>
+__device__ __forceinline__ double2 row_result(const Metric& m, double2 off, double2 C, double omega) {
+    const double diag = 2.0 * (m.g11 + m.g22);
+    if (MODE == MODE_RELAX) {
+        const double inv = 1.0 / diag;
+        return make_double2(C.x + omega * (off.x * inv - C.x), C.y + omega * (off.y * inv - C.y));
+    } else if (MODE == MODE_APPLY) {
+        return make_double2(off.x - diag * C.x, off.y - diag * C.y);
+    } else if (MODE == MODE_RESID) {
+        return make_double2(diag * C.x - off.x, diag * C.y - off.y);
+    } else {
+        const double d = diag == 0.0 ? 1.0 : -1.0 / diag;
+        return make_double2(d, d);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Interior rows of all blocks.  One CTA = one tile (TILE_J columns x TILE_I rows) of one block; a thread owns
+// one j column and marches along i with a 3-row register window, so every node is loaded once per sweep
+// from HBM/L2 (its j-1/j+1 neighbours are L1 hits of the same 128-byte lines).  Stores are coalesced 16 B.
+//   u      field the row is applied to            xc   lagged coordinates (LAGGED; otherwise xc == u)
+//   pq     control function P,Q (HAS_PQ)          out  result field
+//   stats  per-CTA partials: sum dx^2, sum dy^2, (dot slots), max|d|   (only when STATS)
+// STATS for RELAX: d = out - u.  For APPLY: partial dots with `dotv` (rhat.v, or t.s and t.t) -- see K.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
+__global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __restrict__ tiles, const DevBlock* __restrict__ blocks,
+                                                                   const double2* __restrict__ u, const double2* __restrict__ xc,
+                                                                   const double2* __restrict__ pq, double2* __restrict__ out, double omega,
+                                                                   const double2* __restrict__ dot_a, double* __restrict__ partials) {
+    const Tile t = tiles[blockIdx.x];
+    const DevBlock b = blocks[t.block];
+    const int nj = b.nj;
+    const int j = t.j0 + threadIdx.x;
+    const bool active = j <= nj - 2;
+    const int jc = active ? j : nj - 2;  // clamp: inactive lanes recompute the last column, never store
+    const int i_begin = t.i0, i_end = min(t.i0 + TILE_I, b.ni - 1);
+    const double2* ub = u + b.off;
+    const double2* cb = LAGGED ? xc + b.off : ub;
+    double2* ob = out + b.off;
+
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
+
+    // register window: rows i-1 (m), i (0), i+1 (p)
+    size_t idx = (size_t)(i_begin - 1) * nj + jc;
+    double2 Cm = ld2(ub + idx), Dm = ld2(ub + idx + 1) - ld2(ub + idx - 1);
+    idx += nj;
+    double2 l = ld2(ub + idx - 1), r = ld2(ub + idx + 1);
+    double2 C0 = ld2(ub + idx), D0 = r - l, S0 = r + l;
+    double2 cCm, cC0, cD0;
+    if (LAGGED) {
+        cCm = ld2(cb + idx - nj);
+        cC0 = ld2(cb + idx);
+        cD0 = ld2(cb + idx + 1) - ld2(cb + idx - 1);
+    }
+#pragma unroll 4
+    for (int i = i_begin; i < i_end; ++i) {
+        const size_t ip = idx + nj;  // row i+1
+        const double2 lp = ld2(ub + ip - 1), rp = ld2(ub + ip + 1);
+        const double2 Cp = ld2(ub + ip), Dp = rp - lp, Sp = rp + lp;
+        double2 cCp, cDp;
+        Metric m;
+        if (LAGGED) {
+            cCp = ld2(cb + ip);
+            cDp = ld2(cb + ip + 1) - ld2(cb + ip - 1);
+            m = metric_terms(cCm, cCp, cD0);
+        } else {
+            m = metric_terms(Cm, Cp, D0);
+        }
+        double P = 0.0, Q = 0.0;
+        if (HAS_PQ) {
+            const double2 f = ldg2(pq + b.off + idx);
+            P = f.x; Q = f.y;
+        }
+        const double2 off = offdiag_sum(m, P, Q, Cm, Cp, S0, D0, Dp, Dm);
+        const double2 res = row_result<MODE>(m, off, C0, omega);
+        if (active) {
+            ob[idx] = res;
+            if (STATS == 1) {  // update norms (smooth.zig:112-134) of a relaxation sweep
+                const double dx = res.x - C0.x, dy = res.y - C0.y;
+                s0 += dx * dx; s1 += dy * dy;
+                mx = fmax(mx, fmax(fabs(dx), fabs(dy)));
+            } else if (STATS == 2) {  // dot(a, res) per component
+                const double2 a = ld2(dot_a + b.off + idx);
+                s0 += a.x * res.x; s1 += a.y * res.y;
+            } else if (STATS == 3) {  // dot(res, a) and dot(res, res) per component  (t.s, t.t)
+                const double2 a = ld2(dot_a + b.off + idx);
+                s0 += a.x * res.x; s1 += a.y * res.y;
+                s2 += res.x * res.x; s3 += res.y * res.y;
+            } else if (STATS == 4) {  // sum of squares of res (||r||^2)
+                s0 += res.x * res.x; s1 += res.y * res.y;
+            }
+        }
+        Cm = C0; Dm = D0;
+        C0 = Cp; D0 = Dp; S0 = Sp;
+        if (LAGGED) { cCm = cC0; cC0 = cCp; cD0 = cDp; }
+        idx = ip;
+    }
+    if (STATS != 0) {
+        double sums[4] = {s0, s1, s2, s3};
+        block_reduce_store<4, TILE_J>(sums, mx, partials + (size_t)blockIdx.x * 5);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Boundary rows: one thread per free boundary row (smoothed interface rows, then junction rows, then sliding
+// rows).  RELAX additionally writes the row's `connected` copies (x_slave = x_root + shift).
+// ---------------------------------------------------------------------------------------------------
+constexpr int BND_THREADS = 128;
+
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
+__global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows,
+                                                                       int n_j, const SlidingRow* __restrict__ lrows, int n_l,
+                                                                       const SlaveRow* __restrict__ slaves, const double2* __restrict__ u,
+                                                                       const double2* __restrict__ xc, const double2* __restrict__ pq,
+                                                                       double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
+                                                                       double* __restrict__ partials) {
+    const int r = blockIdx.x * BND_THREADS + threadIdx.x;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
+    double2 res = make_double2(0.0, 0.0), old = make_double2(0.0, 0.0);
+    int64_t self = -1;
+    int sb = 0, se = 0;
+    if (r < n_s) {
+        const SmoothedRow row = srows[r];
+        self = row.g0;
+        sb = row.slave_begin; se = row.slave_end;
+        const double2 per = make_double2(row.px, row.py);
+        // values the row is applied to; block-1 columns are shifted by -periodicity in the affine modes
+        // (equivalent to the reference's rhs = p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)), smooth.zig:1060-1061)
+        const bool affine = (MODE == MODE_RELAX || MODE == MODE_RESID);
+        const double2 sh = affine ? per : make_double2(0.0, 0.0);
+        const double2 C = ld2(u + row.g0);
+        const double2 W = ld2(u + row.g0 - row.d0), E = ld2(u + row.g0 + row.d0);
+        const double2 S = ld2(u + row.g0 + row.n0), SW = ld2(u + row.g0 - row.d0 + row.n0), SE = ld2(u + row.g0 + row.d0 + row.n0);
+        const double2 N = ld2(u + row.g1 + row.n1) - sh, NW = ld2(u + row.g1 - row.d1 + row.n1) - sh, NE = ld2(u + row.g1 + row.d1 + row.n1) - sh;
+        Metric m;
+        if (LAGGED) {
+            const double2 cW = ld2(xc + row.g0 - row.d0), cE = ld2(xc + row.g0 + row.d0), cS = ld2(xc + row.g0 + row.n0);
+            const double2 cN = ld2(xc + row.g1 + row.n1) - per;  // smooth.zig:1032
+            m = metric_terms(cW, cE, cN - cS);
+        } else {
+            m = metric_terms(W, E, (ld2(u + row.g1 + row.n1) - per) - S);
+        }
+        double P = 0.0, Q = 0.0;
+        if (HAS_PQ) {
+            const double2 f = ldg2(pq + row.g0);
+            if (row.periodic) { P = f.x; Q = f.y; } else { P = f.y; Q = f.x; }  // smooth.zig:1040-1041 vs 1082-1083
+        }
+        const double2 off = offdiag_sum(m, P, Q, W, E, N + S, N - S, NE - SE, NW - SW);
+        res = row_result<MODE>(m, off, C, omega);
+        old = C;
+        if (STATS == 4 && row.periodic) {  // rhs of the reference's row: p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)) = p * g11 (1 + Q/2)
+            const double a = m.g11 * (1.0 + 0.5 * Q);
+            s2 = (row.px * a) * (row.px * a); s3 = (row.py * a) * (row.py * a);
+        }
+    } else if (r < n_s + n_j) {
+        const JunctionRow row = jrows[r - n_s];
+        self = row.self;
+        sb = row.slave_begin; se = row.slave_end;
+        const double2 C = ld2(u + row.self);
+        double2 sum = make_double2(0.0, 0.0);
+        for (int k = 0; k < row.n; ++k) sum = sum + ld2(u + row.nbr[k]);
+        const double n = (double)row.n;
+        if (MODE == MODE_RELAX) {
+            res = make_double2(C.x + omega * ((sum.x - row.rhs_x) / n - C.x), C.y + omega * ((sum.y - row.rhs_y) / n - C.y));
+        } else if (MODE == MODE_APPLY) {
+            res = make_double2(sum.x - n * C.x, sum.y - n * C.y);
+        } else if (MODE == MODE_RESID) {
+            res = make_double2(row.rhs_x - (sum.x - n * C.x), row.rhs_y - (sum.y - n * C.y));
+        } else {
+            res = make_double2(-1.0 / n, -1.0 / n);
+        }
+        old = C;
+    } else if (r < n_s + n_j + n_l) {
+        const SlidingRow row = lrows[r - n_s - n_j];
+        self = row.self;
+        sb = row.slave_begin; se = row.slave_end;
+        const double2 C = ld2(u + row.self), I = ld2(u + row.inner);
+        const double ys = (double)row.ysign;
+        if (MODE == MODE_RELAX) {
+            res = make_double2(row.rhs_x, I.y + ys * row.rhs_y);
+        } else if (MODE == MODE_APPLY) {
+            res = make_double2(C.x, ys * (C.y - I.y));
+        } else if (MODE == MODE_RESID) {
+            res = make_double2(row.rhs_x - C.x, row.rhs_y - ys * (C.y - I.y));
+        } else {
+            res = make_double2(1.0, ys);
+        }
+        old = C;
+    }
+    if (self >= 0) {
+        out[self] = res;
+        if (MODE == MODE_RELAX) {
+            for (int k = sb; k < se; ++k) {
+                const SlaveRow sl = slaves[k];
+                out[sl.self] = make_double2(res.x + sl.sx, res.y + sl.sy);
+            }
+        }
+        if (STATS == 1) {
+            // the reference sums over ALL nodes (smooth.zig:117-133): count the row and its copies
+            const double dx = res.x - old.x, dy = res.y - old.y;
+            const double w = 1.0 + (double)(se - sb);
+            s0 = w * dx * dx; s1 = w * dy * dy;
+            mx = fmax(fabs(dx), fabs(dy));
+        } else if (STATS == 2) {
+            const double2 a = ld2(dot_a + self);
+            s0 = a.x * res.x; s1 = a.y * res.y;
+        } else if (STATS == 3) {
+            const double2 a = ld2(dot_a + self);
+            s0 = a.x * res.x; s1 = a.y * res.y; s2 = res.x * res.x; s3 = res.y * res.y;
+        } else if (STATS == 4) {
+            s0 = res.x * res.x; s1 = res.y * res.y;  // s2, s3 may already hold the periodic rhs term
+        }
+    }
+    if (STATS != 0) {
+        double sums[4] = {s0, s1, s2, s3};
+        block_reduce_store<4, BND_THREADS>(sums, mx, partials + (size_t)blockIdx.x * 5);
+    }
+}
+
+// v[slave] = v[root] (+ shift when affine): keeps `connected` copies consistent (smooth.zig:804-812)
+__global__ void sync_slaves_kernel(const SlaveRow* __restrict__ slaves, int n, double2* __restrict__ v, int affine) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const SlaveRow s = slaves[k];
+    const double2 r = v[s.root];
+    v[s.self] = affine ? make_double2(r.x + s.sx, r.y + s.sy) : r;
+}
+
+// begin_smoothing: capture rhs_x of sliding rows from the initial mesh (smooth.zig:853-857), apply the
+// (normally empty) fixed overrides.
+__global__ void capture_boundary_kernel(SlidingRow* __restrict__ lrows, int n_l, const FixedOverride* __restrict__ fo, int n_fo, double2* __restrict__ x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_l) {
+        if (lrows[k].rhs_x_from_initial) lrows[k].rhs_x = x[lrows[k].self].x;
+    } else if (k < n_l + n_fo) {
+        const FixedOverride f = fo[k - n_l];
+        x[f.self] = make_double2(f.x, f.y);
+    }
+}
+
+// connectionDataCheck (smooth.zig:220-275): max over all interface node pairs of |x0 + p - x1|_inf; also the
+// index of the worst pair so the error message can name it.
+__global__ void pair_check_kernel(const PairCheck* __restrict__ pairs, int n, const double2* __restrict__ x, double tol, unsigned long long* __restrict__ worst) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const PairCheck p = pairs[k];
+    const double2 a = x[p.g0], b = x[p.g1];
+    const double ex = fabs((a.x + p.px) - b.x), ey = fabs((a.y + p.py) - b.y);
+    const double e = fmax(ex, ey);
+    if (!(e <= tol)) {
+        // pack (error as ordered bits of a non-negative double, pair index) -> atomicMax keeps the worst
+        const unsigned long long bits = isnan(e) ? 0x7ff8000000000000ull : (unsigned long long)__double_as_longlong(e);
+        atomicMax(worst, (bits & 0xffffffff00000000ull) | (unsigned long long)(unsigned)k);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// White wall control function (blocks 0 and 1, wall = line j = 0).  wall_control_function.zig:70-473
+// wall_pq holds the accumulated (P,Q) of every wall node: [block 0: ni0 entries][block 1: ni1 entries].
+// ---------------------------------------------------------------------------------------------------
+struct WhiteParams {
+    int64_t off0, off1;        // global offsets of blocks 0, 1
+    int32_t ni0, nj0, ni1, nj1;
+    int32_t c_in0, c_in1, c_al0;  // connection 0: inward shifts on both sides, along shift on side 0
+    int32_t _pad;
+    double ds_target, theta_target;
+};
+
+__device__ __forceinline__ void white_eq610(double x_xi, double y_xi, double x_xi2, double y_xi2, double x_eta, double y_eta, double x_eta2, double y_eta2,
+                                            double& p, double& q) {
+    const double g11 = x_xi * x_xi + y_xi * y_xi;
+    const double g22 = x_eta * x_eta + y_eta * y_eta;
+    p = -(x_xi * x_xi2 + y_xi * y_xi2) / g11 - (x_xi * x_eta2 + y_xi * y_eta2) / g22;
+    q = -(x_eta * x_eta2 + y_eta * y_eta2) / g22 - (x_eta * x_xi2 + y_eta * y_xi2) / g11;
+}
+__device__ __forceinline__ void white_delta(const WhiteParams& w, double x_xi, double y_xi, double x_eta, double y_eta, double& p, double& q) {
+    // White.computeUpdate, wall_control_function.zig:293-309
+    const double g11 = x_xi * x_xi + y_xi * y_xi;
+    const double g12 = x_xi * x_eta + y_xi * y_eta;
+    const double g22 = x_eta * x_eta + y_eta * y_eta;
+    const double ds = sqrt(g22);
+    const double theta = acos(g12 / sqrt(g11 * g22));
+    const double delta_p = -atan2(w.theta_target - theta, w.theta_target);
+    const double delta_q = atan2(w.ds_target - ds, w.ds_target);
+    p += 0.1 * delta_p;
+    q += 0.1 * delta_q;
+}
+
+// one thread per wall node; `update` = 0: initControlFunction, 1: update
+__global__ void white_wall_kernel(WhiteParams w, const double2* __restrict__ x, double2* __restrict__ wall_pq, int update) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= w.ni0 + w.ni1) return;
+    const int blk = t < w.ni0 ? 0 : 1;
+    const int i = blk ? t - w.ni0 : t;
+    const int ni = blk ? w.ni1 : w.ni0, nj = blk ? w.nj1 : w.nj0;
+    const double2* d = x + (blk ? w.off1 : w.off0);
+    const size_t l = (size_t)i * nj;
+    const double2 c = d[l], e1 = d[l + 1];
+    double x_xi, y_xi, x_xi2 = 0, y_xi2 = 0;
+    if (i == 0) {  // forward
+        const double2 a = d[l + nj];
+        x_xi = -c.x + a.x; y_xi = -c.y + a.y;
+        if (!update) { const double2 a2 = d[l + 2 * (size_t)nj]; x_xi2 = c.x - 2 * a.x + a2.x; y_xi2 = c.y - 2 * a.y + a2.y; }
+    } else if (i == ni - 1) {  // backward
+        const double2 a = d[l - nj];
+        x_xi = c.x - a.x; y_xi = c.y - a.y;
+        if (!update) { const double2 a2 = d[l - 2 * (size_t)nj]; x_xi2 = c.x - 2 * a.x + a2.x; y_xi2 = c.y - 2 * a.y + a2.y; }
+    } else {  // central
+        const double2 a = d[l + nj], b = d[l - nj];
+        x_xi = 0.5 * (a.x - b.x); y_xi = 0.5 * (a.y - b.y);
+        x_xi2 = a.x - 2 * c.x + b.x; y_xi2 = a.y - 2 * c.y + b.y;
+    }
+    const double x_eta = -c.x + e1.x, y_eta = -c.y + e1.y;
+    double p, q;
+    if (!update) {
+        const double2 e2 = d[l + 2];
+        white_eq610(x_xi, y_xi, x_xi2, y_xi2, x_eta, y_eta, c.x - 2 * e1.x + e2.x, c.y - 2 * e1.y + e2.y, p, q);
+    } else {
+        const double2 acc = wall_pq[t];
+        p = acc.x; q = acc.y;
+        white_delta(w, x_xi, y_xi, x_eta, y_eta, p, q);
+    }
+    if (t == 0) {
+        // connection 0 (block0:j_min <-> block1:j_min) shares the wall node 0; xi runs across the two blocks,
+        // eta along the connection (wall_control_function.zig:203-279, 394-472)
+        const double2* d1 = x + w.off1;
+        const double2 ip1 = d[w.c_in0], im1 = d1[w.c_in1], jp1 = d[w.c_al0];
+        if (!update) {
+            const double2 jp2 = d[2 * w.c_al0];
+            white_eq610(0.5 * (ip1.x - im1.x), 0.5 * (ip1.y - im1.y), ip1.x - 2 * c.x + im1.x, ip1.y - 2 * c.y + im1.y, -c.x + jp1.x, -c.y + jp1.y,
+                        c.x - 2 * jp1.x + jp2.x, c.y - 2 * jp1.y + jp2.y, p, q);  // overwrites the corner value
+        } else {
+            // applied on top of the corner update above; note the sign flip of the xi derivative (:429-431)
+            white_delta(w, -0.5 * (ip1.x - im1.x), -0.5 * (ip1.y - im1.y), -c.x + jp1.x, -c.y + jp1.y, p, q);
+        }
+    }
+    wall_pq[t] = make_double2(p, q);
+}
+
+// blends the wall values linearly along j: factor = 1 - j/(nj-1)   (wall_control_function.zig:104-111)
+__global__ void white_blend_kernel(WhiteParams w, const double2* __restrict__ wall_pq, double2* __restrict__ pq) {
+    const int64_t n0 = (int64_t)w.ni0 * w.nj0, n1 = (int64_t)w.ni1 * w.nj1;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n0 + n1) return;
+    const int blk = t < n0 ? 0 : 1;
+    const int64_t l = blk ? t - n0 : t;
+    const int nj = blk ? w.nj1 : w.nj0;
+    const int i = (int)(l / nj), j = (int)(l - (int64_t)i * nj);
+    const double2 a = wall_pq[blk ? w.ni0 + i : i];
+    double2 r = a;
+    if (j > 0) {
+        const double factor = 1 - (double)j / ((double)nj - 1);
+        r = make_double2(factor * a.x, factor * a.y);
+    }
+    pq[(blk ? w.off1 : w.off0) + l] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Reductions and the BiCGStab control block.  All scalars stay on the device; the host only polls `done`.
+// ---------------------------------------------------------------------------------------------------
+struct SolveCtl {
+    double rho_old[2], rho_new[2], alpha[2], omega[2], beta[2];
+    double tol[2], norm_b[2], norm_r[2];
+    double sumsq[2], max_update;   // outer-iteration statistics (smooth.zig:112-137)
+    int32_t done[2];               // 1 converged, 2 breakdown / iteration cap
+    int32_t iters[2];
+    int32_t stage_dummy, _pad;
+};
+
+enum ReduceOp : int {
+    RED_UPDATE_STATS = 0,  // sums[0,1] -> sumsq, max -> max_update
+    RED_INIT = 1,          // sums[0,1] = ||r||^2 ; sums[2,3] = ||b||^2 -> tol, rho_new = ||r||^2 (rhat = r), done if ||r|| <= tol
+    RED_ALPHA = 2,         // sums[0,1] = rhat.v -> alpha = rho_new / that
+    RED_NORM_S = 3,        // sums[0,1] = ||s||^2 -> done if <= tol
+    RED_OMEGA = 4,         // sums[0,1] = t.s ; sums[2,3] = t.t -> omega
+    RED_NORM_R = 5,        // sums[0,1] = ||r||^2 ; sums[2,3] = rhat.r -> done?, rho_old = rho_new, rho_new = rhat.r, beta
+};
+
+// Sums `n_part` per-CTA partial records (5 doubles each: 4 sums + 1 max) in a fixed order -> deterministic.
+template <int NT>
+__global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ partials, int n_part, int op, SolveCtl* __restrict__ ctl, double rtol, double atol,
+                                                    int max_iters, const double* __restrict__ extra /* optional second partial array (boundary kernel) */,
+                                                    int n_extra, const double* __restrict__ bconst /* RED_INIT: constant part of ||b||^2 */) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    double mx = 0.0;
+    for (int k = threadIdx.x; k < n_part + n_extra; k += NT) {
+        const double* p = k < n_part ? partials + (size_t)k * 5 : extra + (size_t)(k - n_part) * 5;
+        s[0] += p[0]; s[1] += p[1]; s[2] += p[2]; s[3] += p[3];
+        mx = fmax(mx, p[4]);
+    }
+    __shared__ double out[5];
+    block_reduce_store<4, NT>(s, mx, out);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double eps = 1e-30;  // breakdown_eps, BiCGStab.zig:280
+    if (op == RED_UPDATE_STATS) {
+        ctl->sumsq[0] = out[0]; ctl->sumsq[1] = out[1]; ctl->max_update = out[4];
+        return;
+    }
+    for (int c = 0; c < 2; ++c) {
+        if (op == RED_INIT) {
+            const double nr = sqrt(out[c]), nb = sqrt(out[2 + c] + bconst[c]);
+            ctl->norm_b[c] = nb; ctl->norm_r[c] = nr;
+            ctl->tol[c] = fmax(atol, rtol * nb);                 // BiCGStab.zig:291
+            ctl->rho_old[c] = 1.0; ctl->alpha[c] = 1.0; ctl->omega[c] = 1.0;
+            ctl->rho_new[c] = out[c];                             // rhat = r
+            ctl->iters[c] = 0;
+            ctl->done[c] = nr <= ctl->tol[c] ? 1 : 0;
+            if (!ctl->done[c] && fabs(ctl->rho_new[c]) < eps) ctl->done[c] = 2;
+            ctl->beta[c] = (ctl->rho_new[c] / ctl->rho_old[c]) * (ctl->alpha[c] / ctl->omega[c]);
+            continue;
+        }
+        if (ctl->done[c]) continue;
+        if (op == RED_ALPHA) {
+            if (fabs(out[c]) < eps) { ctl->done[c] = 2; ctl->alpha[c] = 0.0; }
+            else ctl->alpha[c] = ctl->rho_new[c] / out[c];
+        } else if (op == RED_NORM_S) {
+            ctl->iters[c] += 1;
+            ctl->norm_r[c] = sqrt(out[c]);
+            if (ctl->norm_r[c] <= ctl->tol[c]) ctl->done[c] = 1;
+        } else if (op == RED_OMEGA) {
+            if (fabs(out[2 + c]) < eps) { ctl->done[c] = 2; ctl->omega[c] = 0.0; }
+            else {
+                ctl->omega[c] = out[c] / out[2 + c];
+                if (fabs(ctl->omega[c]) < eps) { ctl->done[c] = 2; ctl->omega[c] = 0.0; }
+            }
+        } else if (op == RED_NORM_R) {
+            ctl->norm_r[c] = sqrt(out[c]);
+            if (ctl->norm_r[c] <= ctl->tol[c]) { ctl->done[c] = 1; continue; }
+            ctl->rho_old[c] = ctl->rho_new[c];
+            ctl->rho_new[c] = out[2 + c];
+            if (fabs(ctl->rho_new[c]) < eps || ctl->iters[c] >= max_iters) { ctl->done[c] = 2; continue; }
+            ctl->beta[c] = (ctl->rho_new[c] / ctl->rho_old[c]) * (ctl->alpha[c] / ctl->omega[c]);
+        }
+    }
+}
+
+constexpr int VEC_THREADS = 256;
+
+// p = r + beta (p - omega v); phat = dinv * p                      (BiCGStab.zig:310-314)
+__global__ void __launch_bounds__(VEC_THREADS) bicg_p_kernel(int64_t n, const SolveCtl* __restrict__ ctl, const double2* __restrict__ r, double2* __restrict__ p,
+                                                             const double2* __restrict__ v, const double2* __restrict__ dinv, double2* __restrict__ phat) {
+    const double bx = ctl->beta[0], by = ctl->beta[1], ox = ctl->omega[0], oy = ctl->omega[1];
+    const bool dx = ctl->done[0] != 0, dy = ctl->done[1] != 0;
+    for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
+        const double2 rr = r[k], vv = v[k], di = dinv[k];
+        double2 pp = p[k];
+        if (!dx) pp.x = rr.x + bx * (pp.x - ox * vv.x);
+        if (!dy) pp.y = rr.y + by * (pp.y - oy * vv.y);
+        p[k] = pp;
+        phat[k] = make_double2(dx ? 0.0 : di.x * pp.x, dy ? 0.0 : di.y * pp.y);
+    }
+}
+
+// s = r - alpha v; x += alpha phat; shat = dinv * s (into phat); partial ||s||^2     (BiCGStab.zig:324-340)
+__global__ void __launch_bounds__(VEC_THREADS) bicg_s_kernel(int64_t n, const SolveCtl* __restrict__ ctl, const double2* __restrict__ r, const double2* __restrict__ v,
+                                                             double2* __restrict__ s, double2* __restrict__ x, const double2* __restrict__ dinv,
+                                                             double2* __restrict__ phat, double* __restrict__ partials) {
+    const double ax = ctl->alpha[0], ay = ctl->alpha[1];
+    const bool dx = ctl->done[0] != 0, dy = ctl->done[1] != 0;
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
+        const double2 rr = r[k], vv = v[k], ph = phat[k], di = dinv[k];
+        double2 ss = s[k], xx = x[k];
+        if (!dx) { ss.x = rr.x - ax * vv.x; xx.x += ax * ph.x; }
+        if (!dy) { ss.y = rr.y - ay * vv.y; xx.y += ay * ph.y; }
+        s[k] = ss; x[k] = xx;
+        phat[k] = make_double2(dx ? 0.0 : di.x * ss.x, dy ? 0.0 : di.y * ss.y);
+        // fixed / connected nodes carry zeros in every Krylov vector, so the plain sum is the norm over free rows
+        if (!dx) s0 += ss.x * ss.x;
+        if (!dy) s1 += ss.y * ss.y;
+    }
+    double sums[4] = {s0, s1, 0.0, 0.0};
+    block_reduce_store<4, VEC_THREADS>(sums, 0.0, partials + (size_t)blockIdx.x * 5);
+}
+
+// x += omega shat; r = s - omega t; partials ||r||^2 and rhat.r                         (BiCGStab.zig:352-366)
+__global__ void __launch_bounds__(VEC_THREADS) bicg_r_kernel(int64_t n, const SolveCtl* __restrict__ ctl, const double2* __restrict__ s, const double2* __restrict__ t,
+                                                             double2* __restrict__ r, double2* __restrict__ x, const double2* __restrict__ shat,
+                                                             const double2* __restrict__ rhat, double* __restrict__ partials) {
+    const double ox = ctl->omega[0], oy = ctl->omega[1];
+    const bool dx = ctl->done[0] != 0, dy = ctl->done[1] != 0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
+        const double2 ss = s[k], tt = t[k], sh = shat[k], rh = rhat[k];
+        double2 rr = r[k], xx = x[k];
+        if (!dx) { xx.x += ox * sh.x; rr.x = ss.x - ox * tt.x; s0 += rr.x * rr.x; s2 += rh.x * rr.x; }
+        if (!dy) { xx.y += oy * sh.y; rr.y = ss.y - oy * tt.y; s1 += rr.y * rr.y; s3 += rh.y * rr.y; }
+        r[k] = rr; x[k] = xx;
+    }
+    double sums[4] = {s0, s1, s2, s3};
+    block_reduce_store<4, VEC_THREADS>(sums, 0.0, partials + (size_t)blockIdx.x * 5);
+}
+
+// Constant part of ||b||^2 of the reference's full right-hand side (BiCGStab.zig:289-291): fixed rows carry their
+// coordinate, connected rows their (periodic) rhs, sliding rows (rhs_x, rhs_y), junction rows their periodic rhs.
+// Interior rows are 0 and periodic interface rows are added per solve (they depend on the lagged coordinates).
+struct RhsTerm {
+    int64_t g;          // node whose coordinate is the rhs (from_x / from_y), else unused
+    double cx, cy;      // constant rhs
+    int32_t from_x, from_y;
+};
+__global__ void __launch_bounds__(VEC_THREADS) rhs_const_kernel(const RhsTerm* __restrict__ terms, int n, const double2* __restrict__ x, double* __restrict__ out2) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = threadIdx.x; k < n; k += VEC_THREADS) {
+        const RhsTerm t = terms[k];
+        double bx = t.cx, by = t.cy;
+        if (t.from_x | t.from_y) { const double2 v = x[t.g]; if (t.from_x) bx = v.x; if (t.from_y) by = v.y; }
+        s0 += bx * bx; s1 += by * by;
+    }
+    __shared__ double red[5];
+    double sums[4] = {s0, s1, 0.0, 0.0};
+    block_reduce_store<4, VEC_THREADS>(sums, 0.0, red);
+    __syncthreads();
+    if (threadIdx.x == 0) { out2[0] = red[0]; out2[1] = red[1]; }
+}
+
+// update statistics between two full coordinate fields (Picard modes): sum dx^2, sum dy^2, max |d|
+__global__ void __launch_bounds__(VEC_THREADS) diff_stats_kernel(int64_t n, const double2* __restrict__ a, const double2* __restrict__ b, double* __restrict__ partials) {
+    double s0 = 0.0, s1 = 0.0, mx = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
+        const double2 p = a[k], q = b[k];
+        const double dx = p.x - q.x, dy = p.y - q.y;
+        s0 += dx * dx; s1 += dy * dy;
+        mx = fmax(mx, fmax(fabs(dx), fabs(dy)));
+    }
+    double sums[4] = {s0, s1, 0.0, 0.0};
+    block_reduce_store<4, VEC_THREADS>(sums, mx, partials + (size_t)blockIdx.x * 5);
+}
+
+}  // namespace tmesh

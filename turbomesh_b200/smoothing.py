@@ -1,0 +1,255 @@
+"""Smoothing front-end -- host-side mirror of ``src/core/smoothing/`` routed through the C ABI.
+
+* ``tfi_block``      -> ``tm_tfi_block``    (``tfi.linear2dBoundaryBlendedControlFunction``, tfi.zig:112-208)
+* ``mesh`` / ``smooth_mesh`` -> ``tm_smooth_mesh`` (``smoothing.smooth.mesh``, smooth.zig:74-166)
+* ``DeviceMesh``     -> the ``tm_mesh_*`` handle API (device-resident meshes for benchmarks and batches)
+
+Everything here needs the CUDA library and a GPU; nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import TmBlock, TmCondition, TmConnection, TmSmoothOptions, TmSmoothStats, check
+
+
+# ---- solver.Option / wall_control_function.Algorithm mirrors -------------------------------------
+@dataclass
+class White:
+    """``wall_control_function.White`` (wall_control_function.zig:56-61)."""
+
+    ds_target: float
+    theta_target: float = 0.5 * math.pi
+
+
+@dataclass
+class Laplace:
+    pass
+
+
+@dataclass
+class CudaSolver:
+    """The ``"cuda"`` variant added to ``solver.Option`` (solver.zig:18-27); see INTEGRATION.md.
+
+    ``method``: ``"picard_bicgstab"`` reproduces the reference's outer/inner structure (lagged coefficients, linear
+    solve per outer iteration, tolerances with the reference's defaults); ``"relax"`` runs ``sweeps_per_iteration``
+    damped-Jacobi sweeps of the nonlinear system per outer iteration.
+    """
+
+    method: str = "picard_bicgstab"
+    rtol: float = 1e-6
+    atol: float = 1e-8
+    max_inner_iterations: int = 1000
+    omega: float = 1.0
+    sweeps_per_iteration: int = 1
+    stop_max_update: float = 0.0
+    fail_on_no_convergence: bool = False
+    device: int = -1
+
+    @staticmethod
+    def tight(**kw) -> "CudaSolver":
+        """'Exact Picard step' settings used for parity against the tight-tolerance oracle."""
+        kw.setdefault("rtol", 1e-15)
+        kw.setdefault("atol", 1e-15)
+        kw.setdefault("max_inner_iterations", 200000)
+        return CudaSolver(**kw)
+
+
+def make_options(iterations: int, solver: Optional[CudaSolver] = None, control_function=None) -> TmSmoothOptions:
+    solver = solver or CudaSolver()
+    control_function = control_function or Laplace()
+    o = TmSmoothOptions()
+    _lib.load().tm_smooth_options_default(C.byref(o))
+    o.solver = {"picard_bicgstab": _lib.TM_SOLVER_PICARD_BICGSTAB, "relax": _lib.TM_SOLVER_RELAX}[solver.method]
+    o.iterations = int(iterations)
+    o.rtol, o.atol, o.max_inner_iterations = solver.rtol, solver.atol, int(solver.max_inner_iterations)
+    o.omega, o.sweeps_per_iteration, o.stop_max_update = solver.omega, int(solver.sweeps_per_iteration), solver.stop_max_update
+    o.fail_on_no_convergence = 1 if solver.fail_on_no_convergence else 0
+    o.device = solver.device
+    if isinstance(control_function, White):
+        o.control_function = _lib.TM_CF_WHITE
+        o.white_ds_target, o.white_theta_target = control_function.ds_target, control_function.theta_target
+    else:
+        o.control_function = _lib.TM_CF_LAPLACE
+    return o
+
+
+def control_function_from_json(obj: dict):
+    (tag, val), = obj.items()
+    if tag == "laplace":
+        return Laplace()
+    if tag == "white":
+        return White(float(val["ds_target"]), float(val.get("theta_target", 0.5 * math.pi)))
+    raise ValueError(f"unknown wall control function {tag!r}")
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _edge_args(x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2)]
+    ni, nj = len(arrs[4]), len(arrs[6])
+    if arrs[0].shape != (ni, 2) or arrs[1].shape != (ni, 2) or arrs[2].shape != (nj, 2) or arrs[3].shape != (nj, 2) or len(arrs[5]) != ni or len(arrs[7]) != nj:
+        raise ValueError("inconsistent edge sizes")
+    return arrs, ni, nj
+
+
+def tfi_block(x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """GPU TFI of one block with host buffers (``tm_tfi_block``); returns the ``Mat2d`` view (ni, nj, 2)."""
+    arrs, ni, nj = _edge_args(x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2)
+    if out is None:
+        out = np.empty((ni, nj, 2), dtype=np.float64)
+    assert out.shape == (ni, nj, 2) and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+    check(_lib.load().tm_tfi_block(ni, nj, *[_dp(a) for a in arrs], _dp(out)))
+    return out
+
+
+class _CMesh:
+    """Flattens a ``discrete.Mesh`` into the C-ABI arrays (keeps the numpy buffers alive)."""
+
+    def __init__(self, mesh, with_coords: bool = True):
+        self.nb, self.nc, self.nbc = len(mesh.blocks), len(mesh.connections), len(mesh.boundary_conditions)
+        self.arrays = []
+        self.blocks = (TmBlock * max(self.nb, 1))()
+        for k, b in enumerate(mesh.blocks):
+            a = b.points
+            if not (a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.ndim == 3 and a.shape[2] == 2):
+                raise ValueError("block points must be C-contiguous float64 arrays of shape (ni, nj, 2)")
+            self.arrays.append(a)
+            self.blocks[k].ni, self.blocks[k].nj = a.shape[0], a.shape[1]
+            self.blocks[k].xy = _dp(a) if with_coords else None
+        self.conns = (TmConnection * max(self.nc, 1))()
+        for k, c in enumerate(mesh.connections):
+            for s in range(2):
+                r = c.ranges[s]
+                cr = self.conns[k].ranges[s]
+                cr.block, cr.side, cr.start, cr.end = r.block, int(r.side), r.start, r.end
+            if c.periodicity is not None:
+                self.conns[k].has_periodicity = 1
+                self.conns[k].periodicity[0], self.conns[k].periodicity[1] = c.periodicity
+        self.bcs = (TmCondition * max(self.nbc, 1))()
+        for k, bc in enumerate(mesh.boundary_conditions):
+            r = bc.range
+            cr = self.bcs[k].range
+            cr.block, cr.side, cr.start, cr.end = r.block, int(r.side), r.start, r.end
+            self.bcs[k].kind = int(bc.kind)
+
+
+def smooth_mesh(mesh, iterations: int, solver: Optional[CudaSolver] = None, control_function=None) -> dict:
+    """``smoothing.smooth.mesh`` (smooth.zig:74-166) on the GPU with host buffers: smooths ``mesh`` in place."""
+    opts = make_options(iterations, solver, control_function)
+    cm = _CMesh(mesh)
+    st = TmSmoothStats()
+    check(_lib.load().tm_smooth_mesh(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, C.byref(opts), C.byref(st)))
+    return st.as_dict()
+
+
+mesh = smooth_mesh  # the reference's name: smoothing.smooth.mesh
+
+
+class DeviceMesh:
+    """Device-resident mesh (``tm_mesh_*``): upload / TFI once, smooth repeatedly, download when needed."""
+
+    def __init__(self, mesh, device: int = -1, stream: int = 0, upload: bool = True):
+        self._L = _lib.load()
+        self._cm = _CMesh(mesh, with_coords=upload)
+        self.mesh = mesh
+        h = C.c_void_p()
+        cm = self._cm
+        check(self._L.tm_mesh_create(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self._opts = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tm_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def node_count(self) -> int:
+        return int(self._L.tm_mesh_node_count(self._h))
+
+    def tfi_block(self, block: int, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2):
+        arrs, ni, nj = _edge_args(x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2)
+        check(self._L.tm_mesh_tfi_block(self._h, block, *[_dp(a) for a in arrs]))
+
+    def tfi_block_resident(self, block: int):
+        check(self._L.tm_mesh_tfi_block_resident(self._h, block))
+
+    def upload_block(self, block: int, xy: np.ndarray):
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        check(self._L.tm_mesh_upload_block(self._h, block, _dp(xy)))
+
+    def download_block(self, block: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        ni, nj = C.c_uint64(), C.c_uint64()
+        check(self._L.tm_mesh_block_size(self._h, block, C.byref(ni), C.byref(nj)))
+        if out is None:
+            out = np.empty((ni.value, nj.value, 2), dtype=np.float64)
+        check(self._L.tm_mesh_download_block(self._h, block, _dp(out)))
+        return out
+
+    def download(self):
+        """Copies all blocks back into ``self.mesh`` (in place, like smooth.zig:139-153)."""
+        for k, b in enumerate(self.mesh.blocks):
+            self.download_block(k, b.points)
+        return self.mesh
+
+    def begin_smoothing(self, solver: Optional[CudaSolver] = None, control_function=None):
+        self._opts = make_options(0, solver, control_function)
+        check(self._L.tm_mesh_begin_smoothing(self._h, C.byref(self._opts)))
+
+    def smooth(self, iterations: int, solver: Optional[CudaSolver] = None, control_function=None) -> dict:
+        opts = make_options(iterations, solver, control_function)
+        st = TmSmoothStats()
+        check(self._L.tm_mesh_smooth(self._h, C.byref(opts), C.byref(st)))
+        return st.as_dict()
+
+    def synchronize(self):
+        check(self._L.tm_mesh_synchronize(self._h))
+
+    def control_function(self, block: int) -> np.ndarray:
+        ni, nj = C.c_uint64(), C.c_uint64()
+        check(self._L.tm_mesh_block_size(self._h, block, C.byref(ni), C.byref(nj)))
+        out = np.empty((ni.value, nj.value, 2), dtype=np.float64)
+        check(self._L.tm_mesh_download_control_function(self._h, block, _dp(out)))
+        return out
+
+    def boundary_kinds(self, block: int) -> np.ndarray:
+        ni, nj = C.c_uint64(), C.c_uint64()
+        check(self._L.tm_mesh_block_size(self._h, block, C.byref(ni), C.byref(nj)))
+        out = np.empty(2 * (ni.value + nj.value - 2), dtype=np.uint8)
+        check(self._L.tm_mesh_download_boundary_kinds(self._h, block, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def block_device_ptr(self, block: int) -> int:
+        return int(self._L.tm_mesh_block_device_ptr(self._h, block) or 0)
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().tm_kernel_launch_count())
+
+
+def device_info(device: int = -1) -> dict:
+    name = C.create_string_buffer(256)
+    sms, mem = C.c_int(), C.c_uint64()
+    check(_lib.load().tm_device_info(device, name, 256, C.byref(sms), C.byref(mem)))
+    return {"name": name.value.decode(), "sm_count": sms.value, "global_mem_bytes": mem.value}
