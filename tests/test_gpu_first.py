@@ -27,7 +27,9 @@ def test_tfi_bit_exact_different_clusterings(orc, gpu_lib):
 
     ni, nj = 77, 53
     s1, s2 = Roberts(0.5, 1.03).compute(ni), Uniform().compute(ni)
-    t1, t2 = SingleHyperbolicClustering(0.01).compute(nj), Roberts(0.0, 1.2).compute(nj)
+    t1, t2 = SingleHyperbolicClustering(0.01).compute(nj), Roberts(0.5, 1.2).compute(nj)
+    for c in (s1, s2, t1, t2):
+        c[0], c[-1] = 0.0, 1.0
     xi_min = np.stack([s1, 0.1 * np.sin(3 * s1)], axis=1)
     xi_max = np.stack([s2 * 1.1 - 0.05, 1 + 0.1 * np.cos(2 * s2)], axis=1)
     xj_min = np.stack([xi_min[0, 0] + (xi_max[0, 0] - xi_min[0, 0]) * t1, xi_min[0, 1] + (xi_max[0, 1] - xi_min[0, 1]) * t1 + 0.05 * np.sin(np.pi * t1)], axis=1)

@@ -30,7 +30,7 @@ struct Tile {
 constexpr int TILE_J = 128;  // threads per CTA = nodes along j per tile
 constexpr int TILE_I = 64;   // rows marched per CTA
 
-enum Mode : int { MODE_RELAX = 0, MODE_APPLY = 1, MODE_RESID = 2, MODE_DINV = 3 };
+enum Mode : int { MODE_RELAX = 0, MODE_APPLY = 1, MODE_RESID = 2 };
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
@@ -151,24 +151,23 @@ __device__ __forceinline__ double2 offdiag_sum(const Metric& m, double P, double
     return r;
 }
 
-// What a row produces, shared by interior and interface rows.
+// What a row produces, shared by interior and interface rows.  The Krylov modes work on the row-scaled system
+// D^-1 A x = D^-1 b (D = diagonal, the reference's `diagonal` preconditioner, GMRES.zig:176-196, applied from the
+// left as GMRES.zig:300-423 does): residuals are then "Jacobi updates", i.e. lengths, and the stopping test is
+// meaningful at any geometric scale.
 //   RELAX: (1-w) C + w * off / (2(g11+g22))          (damped Jacobi update of the row)
-//   APPLY: off - 2(g11+g22) C                         (A v, homogeneous)
-//   RESID: -(off - 2(g11+g22) C)                      (b - A x; the rhs of these rows is 0 once periodic shifts are folded in)
-//   DINV : 1 / (-2(g11+g22))                          (Jacobi preconditioner, GMRES.zig:176-196)
+//   APPLY: (A v)_i / a_ii     =  C - off / (2(g11+g22))             (homogeneous)
+//   RESID: (b - A x)_i / a_ii =  off / (2(g11+g22)) - C             (rhs of these rows is 0 once periodic shifts are folded in)
 template <int MODE>
 __device__ __forceinline__ double2 row_result(const Metric& m, double2 off, double2 C, double omega) {
     const double diag = 2.0 * (m.g11 + m.g22);
+    const double inv = diag == 0.0 ? 1.0 : 1.0 / diag;  // zero diagonal -> 1.0 as in GMRES.zig:190-194
     if (MODE == MODE_RELAX) {
-        const double inv = 1.0 / diag;
         return make_double2(C.x + omega * (off.x * inv - C.x), C.y + omega * (off.y * inv - C.y));
     } else if (MODE == MODE_APPLY) {
-        return make_double2(off.x - diag * C.x, off.y - diag * C.y);
-    } else if (MODE == MODE_RESID) {
-        return make_double2(diag * C.x - off.x, diag * C.y - off.y);
+        return make_double2(C.x - off.x * inv, C.y - off.y * inv);
     } else {
-        const double d = diag == 0.0 ? 1.0 : -1.0 / diag;
-        return make_double2(d, d);
+        return make_double2(off.x * inv - C.x, off.y * inv - C.y);
     }
 }
 
@@ -321,12 +320,10 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
         const double n = (double)row.n;
         if (MODE == MODE_RELAX) {
             res = make_double2(C.x + omega * ((sum.x - row.rhs_x) / n - C.x), C.y + omega * ((sum.y - row.rhs_y) / n - C.y));
-        } else if (MODE == MODE_APPLY) {
-            res = make_double2(sum.x - n * C.x, sum.y - n * C.y);
-        } else if (MODE == MODE_RESID) {
-            res = make_double2(row.rhs_x - (sum.x - n * C.x), row.rhs_y - (sum.y - n * C.y));
+        } else if (MODE == MODE_APPLY) {  // row / a_ii with a_ii = -n
+            res = make_double2(C.x - sum.x / n, C.y - sum.y / n);
         } else {
-            res = make_double2(-1.0 / n, -1.0 / n);
+            res = make_double2((sum.x - row.rhs_x) / n - C.x, (sum.y - row.rhs_y) / n - C.y);
         }
         old = C;
     } else if (r < n_s + n_j + n_l) {
@@ -337,12 +334,10 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
         const double ys = (double)row.ysign;
         if (MODE == MODE_RELAX) {
             res = make_double2(row.rhs_x, I.y + ys * row.rhs_y);
-        } else if (MODE == MODE_APPLY) {
-            res = make_double2(C.x, ys * (C.y - I.y));
-        } else if (MODE == MODE_RESID) {
-            res = make_double2(row.rhs_x - C.x, row.rhs_y - ys * (C.y - I.y));
+        } else if (MODE == MODE_APPLY) {  // a_ii = 1 (x) and ysign (y)
+            res = make_double2(C.x, C.y - I.y);
         } else {
-            res = make_double2(1.0, ys);
+            res = make_double2(row.rhs_x - C.x, ys * row.rhs_y - (C.y - I.y));
         }
         old = C;
     }
@@ -376,13 +371,15 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
     }
 }
 
-// v[slave] = v[root] (+ shift when affine): keeps `connected` copies consistent (smooth.zig:804-812)
-__global__ void sync_slaves_kernel(const SlaveRow* __restrict__ slaves, int n, double2* __restrict__ v, int affine) {
+// mode 0: v[slave] = v[root]; mode 1: v[slave] = v[root] + shift (keeps `connected` copies consistent,
+// smooth.zig:804-812); mode 2: v[slave] = 0 (Krylov vectors carry zeros in eliminated rows)
+__global__ void sync_slaves_kernel(const SlaveRow* __restrict__ slaves, int n, double2* __restrict__ v, int mode) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const SlaveRow s = slaves[k];
+    if (mode == 2) { v[s.self] = make_double2(0.0, 0.0); return; }
     const double2 r = v[s.root];
-    v[s.self] = affine ? make_double2(r.x + s.sx, r.y + s.sy) : r;
+    v[s.self] = mode == 1 ? make_double2(r.x + s.sx, r.y + s.sy) : r;
 }
 
 // begin_smoothing: capture rhs_x of sliding rows from the initial mesh (smooth.zig:853-857), apply the
@@ -521,7 +518,7 @@ struct SolveCtl {
     double rho_old[2], rho_new[2], alpha[2], omega[2], beta[2];
     double tol[2], norm_b[2], norm_r[2];
     double sumsq[2], max_update;   // outer-iteration statistics (smooth.zig:112-137)
-    int32_t done[2];               // 1 converged, 2 breakdown / iteration cap
+    int32_t done[2];               // 1 converged, 2 breakdown, 3 iteration cap
     int32_t iters[2];
     int32_t stage_dummy, _pad;
 };
@@ -533,6 +530,7 @@ enum ReduceOp : int {
     RED_NORM_S = 3,        // sums[0,1] = ||s||^2 -> done if <= tol
     RED_OMEGA = 4,         // sums[0,1] = t.s ; sums[2,3] = t.t -> omega
     RED_NORM_R = 5,        // sums[0,1] = ||r||^2 ; sums[2,3] = rhat.r -> done?, rho_old = rho_new, rho_new = rhat.r, beta
+    RED_RESTART = 6,       // like RED_INIT from the true residual, but keeps tol / iteration counts (restart after breakdown)
 };
 
 // Sums `n_part` per-CTA partial records (5 doubles each: 4 sums + 1 max) in a fixed order -> deterministic.
@@ -557,14 +555,18 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ p
         return;
     }
     for (int c = 0; c < 2; ++c) {
-        if (op == RED_INIT) {
-            const double nr = sqrt(out[c]), nb = sqrt(out[2 + c] + bconst[c]);
-            ctl->norm_b[c] = nb; ctl->norm_r[c] = nr;
-            ctl->tol[c] = fmax(atol, rtol * nb);                 // BiCGStab.zig:291
+        if (op == RED_INIT || op == RED_RESTART) {
+            const double nr = sqrt(out[c]);
+            ctl->norm_r[c] = nr;
+            if (op == RED_INIT) {
+                const double nb = sqrt(out[2 + c] + bconst[c]);
+                ctl->norm_b[c] = nb;
+                ctl->tol[c] = fmax(atol, rtol * nb);             // GMRES.zig:305-306 / BiCGStab.zig:291
+                ctl->iters[c] = 0;
+            }
             ctl->rho_old[c] = 1.0; ctl->alpha[c] = 1.0; ctl->omega[c] = 1.0;
             ctl->rho_new[c] = out[c];                             // rhat = r
-            ctl->iters[c] = 0;
-            ctl->done[c] = nr <= ctl->tol[c] ? 1 : 0;
+            ctl->done[c] = nr <= ctl->tol[c] ? 1 : (ctl->iters[c] >= max_iters ? 3 : 0);
             if (!ctl->done[c] && fabs(ctl->rho_new[c]) < eps) ctl->done[c] = 2;
             ctl->beta[c] = (ctl->rho_new[c] / ctl->rho_old[c]) * (ctl->alpha[c] / ctl->omega[c]);
             continue;
@@ -588,7 +590,8 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ p
             if (ctl->norm_r[c] <= ctl->tol[c]) { ctl->done[c] = 1; continue; }
             ctl->rho_old[c] = ctl->rho_new[c];
             ctl->rho_new[c] = out[2 + c];
-            if (fabs(ctl->rho_new[c]) < eps || ctl->iters[c] >= max_iters) { ctl->done[c] = 2; continue; }
+            if (ctl->iters[c] >= max_iters) { ctl->done[c] = 3; continue; }
+            if (fabs(ctl->rho_new[c]) < eps) { ctl->done[c] = 2; continue; }
             ctl->beta[c] = (ctl->rho_new[c] / ctl->rho_old[c]) * (ctl->alpha[c] / ctl->omega[c]);
         }
     }
@@ -596,55 +599,52 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ p
 
 constexpr int VEC_THREADS = 256;
 
-// p = r + beta (p - omega v); phat = dinv * p                      (BiCGStab.zig:310-314)
+// p = r + beta (p - omega v)                                        (BiCGStab.zig:310-312)
 __global__ void __launch_bounds__(VEC_THREADS) bicg_p_kernel(int64_t n, const SolveCtl* __restrict__ ctl, const double2* __restrict__ r, double2* __restrict__ p,
-                                                             const double2* __restrict__ v, const double2* __restrict__ dinv, double2* __restrict__ phat) {
+                                                             const double2* __restrict__ v) {
     const double bx = ctl->beta[0], by = ctl->beta[1], ox = ctl->omega[0], oy = ctl->omega[1];
     const bool dx = ctl->done[0] != 0, dy = ctl->done[1] != 0;
     for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
-        const double2 rr = r[k], vv = v[k], di = dinv[k];
+        const double2 rr = r[k], vv = v[k];
         double2 pp = p[k];
-        if (!dx) pp.x = rr.x + bx * (pp.x - ox * vv.x);
-        if (!dy) pp.y = rr.y + by * (pp.y - oy * vv.y);
+        pp.x = dx ? 0.0 : rr.x + bx * (pp.x - ox * vv.x);
+        pp.y = dy ? 0.0 : rr.y + by * (pp.y - oy * vv.y);
         p[k] = pp;
-        phat[k] = make_double2(dx ? 0.0 : di.x * pp.x, dy ? 0.0 : di.y * pp.y);
     }
 }
 
-// s = r - alpha v; x += alpha phat; shat = dinv * s (into phat); partial ||s||^2     (BiCGStab.zig:324-340)
+// s = r - alpha v; x += alpha p; partial ||s||^2                    (BiCGStab.zig:324-334)
+// x is advanced on free rows only (p is read before its connected copies are meaningful for x); the copies of x are
+// restored by one affine sync after the solve.
 __global__ void __launch_bounds__(VEC_THREADS) bicg_s_kernel(int64_t n, const SolveCtl* __restrict__ ctl, const double2* __restrict__ r, const double2* __restrict__ v,
-                                                             double2* __restrict__ s, double2* __restrict__ x, const double2* __restrict__ dinv,
-                                                             double2* __restrict__ phat, double* __restrict__ partials) {
+                                                             double2* __restrict__ s, double2* __restrict__ x, const double2* __restrict__ p,
+                                                             double* __restrict__ partials) {
     const double ax = ctl->alpha[0], ay = ctl->alpha[1];
     const bool dx = ctl->done[0] != 0, dy = ctl->done[1] != 0;
     double s0 = 0.0, s1 = 0.0;
     for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
-        const double2 rr = r[k], vv = v[k], ph = phat[k], di = dinv[k];
-        double2 ss = s[k], xx = x[k];
-        if (!dx) { ss.x = rr.x - ax * vv.x; xx.x += ax * ph.x; }
-        if (!dy) { ss.y = rr.y - ay * vv.y; xx.y += ay * ph.y; }
+        const double2 rr = r[k], vv = v[k], pp = p[k];
+        double2 ss = make_double2(0.0, 0.0), xx = x[k];
+        if (!dx) { ss.x = rr.x - ax * vv.x; xx.x += ax * pp.x; s0 += ss.x * ss.x; }
+        if (!dy) { ss.y = rr.y - ay * vv.y; xx.y += ay * pp.y; s1 += ss.y * ss.y; }
         s[k] = ss; x[k] = xx;
-        phat[k] = make_double2(dx ? 0.0 : di.x * ss.x, dy ? 0.0 : di.y * ss.y);
-        // fixed / connected nodes carry zeros in every Krylov vector, so the plain sum is the norm over free rows
-        if (!dx) s0 += ss.x * ss.x;
-        if (!dy) s1 += ss.y * ss.y;
     }
     double sums[4] = {s0, s1, 0.0, 0.0};
     block_reduce_store<4, VEC_THREADS>(sums, 0.0, partials + (size_t)blockIdx.x * 5);
 }
 
-// x += omega shat; r = s - omega t; partials ||r||^2 and rhat.r                         (BiCGStab.zig:352-366)
+// x += omega s; r = s - omega t; partials ||r||^2 and rhat.r       (BiCGStab.zig:352-366)
 __global__ void __launch_bounds__(VEC_THREADS) bicg_r_kernel(int64_t n, const SolveCtl* __restrict__ ctl, const double2* __restrict__ s, const double2* __restrict__ t,
-                                                             double2* __restrict__ r, double2* __restrict__ x, const double2* __restrict__ shat,
-                                                             const double2* __restrict__ rhat, double* __restrict__ partials) {
+                                                             double2* __restrict__ r, double2* __restrict__ x, const double2* __restrict__ rhat,
+                                                             double* __restrict__ partials) {
     const double ox = ctl->omega[0], oy = ctl->omega[1];
     const bool dx = ctl->done[0] != 0, dy = ctl->done[1] != 0;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
-        const double2 ss = s[k], tt = t[k], sh = shat[k], rh = rhat[k];
+        const double2 ss = s[k], tt = t[k], rh = rhat[k];
         double2 rr = r[k], xx = x[k];
-        if (!dx) { xx.x += ox * sh.x; rr.x = ss.x - ox * tt.x; s0 += rr.x * rr.x; s2 += rh.x * rr.x; }
-        if (!dy) { xx.y += oy * sh.y; rr.y = ss.y - oy * tt.y; s1 += rr.y * rr.y; s3 += rh.y * rr.y; }
+        if (!dx) { xx.x += ox * ss.x; rr.x = ss.x - ox * tt.x; s0 += rr.x * rr.x; s2 += rh.x * rr.x; }
+        if (!dy) { xx.y += oy * ss.y; rr.y = ss.y - oy * tt.y; s1 += rr.y * rr.y; s3 += rh.y * rr.y; }
         r[k] = rr; x[k] = xx;
     }
     double sums[4] = {s0, s1, s2, s3};

@@ -114,7 +114,7 @@ struct tm_mesh {
     DevBuf<unsigned long long> d_worst;
     DevBuf<SolveCtl> d_ctl;
     SolveCtl* h_ctl = nullptr;  // pinned
-    DevBuf<double2> kr, krhat, kp, kv, ks, kt, kphat, kdinv;
+    DevBuf<double2> kr, krhat, kp, kv, ks, kt;
     bool krylov_ready = false;
     std::vector<EdgeCache> edges;
     std::vector<uint8_t> have_coords;
@@ -174,7 +174,7 @@ void build_rhs_terms(tm_mesh* m, std::vector<RhsTerm>& terms) {
 
 void ensure_krylov(tm_mesh* m) {
     if (m->krylov_ready) return;
-    for (DevBuf<double2>* v : {&m->kr, &m->krhat, &m->kp, &m->kv, &m->ks, &m->kt, &m->kphat, &m->kdinv}) {
+    for (DevBuf<double2>* v : {&m->kr, &m->krhat, &m->kp, &m->kv, &m->ks, &m->kt}) {
         v->alloc(size_t(m->N));
         v->zero(m->stream);
     }
@@ -212,9 +212,9 @@ void launch_reduce(tm_mesh* m, int op, const tm_smooth_options* o, bool from_row
         LAUNCH((reduce_kernel<256>), 1, 256, m->stream, m->part_vec.p, m->vec_grid, op, m->d_ctl.p, o->rtol, o->atol, max_it, (const double*)nullptr, 0, m->bconst.p);
 }
 
-void sync_slaves(tm_mesh* m, double2* v, bool affine) {
+void sync_slaves(tm_mesh* m, double2* v, int mode) {
     const int n = int(m->topo.slaves.size());
-    if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, m->stream, m->d_slaves.p, n, v, affine ? 1 : 0);
+    if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, m->stream, m->d_slaves.p, n, v, mode);
 }
 
 void fetch_ctl(tm_mesh* m) {
@@ -263,44 +263,63 @@ void run_relax(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     }
 }
 
+// BiCGStab iterations (BiCGStab.zig:303-366) on the row-scaled system until both components report done.
+void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st, double2* x, const double2* xc) {
+    cudaStream_t s = m->stream;
+    const int64_t N = m->N;
+    const int check_every = 8;
+    for (uint64_t k = 0;; ++k) {
+        if (k % check_every == 0) {
+            fetch_ctl(m);
+            if (m->h_ctl->done[0] && m->h_ctl->done[1]) break;
+        }
+        LAUNCH(bicg_p_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->kr.p, m->kp.p, m->kv.p);
+        sync_slaves(m, m->kp.p, 0);
+        launch_rows<MODE_APPLY, 2>(m, true, m->kp.p, xc, m->kv.p, 1.0, m->krhat.p);   // v = A p, partial rhat.v
+        launch_reduce(m, RED_ALPHA, o, true);
+        LAUNCH(bicg_s_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->kr.p, m->kv.p, m->ks.p, x, m->kp.p, m->part_vec.p);
+        launch_reduce(m, RED_NORM_S, o, false);
+        sync_slaves(m, m->ks.p, 0);
+        launch_rows<MODE_APPLY, 3>(m, true, m->ks.p, xc, m->kt.p, 1.0, m->ks.p);      // t = A s, partials t.s and t.t
+        sync_slaves(m, m->ks.p, 2);
+        launch_reduce(m, RED_OMEGA, o, true);
+        LAUNCH(bicg_r_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->ks.p, m->kt.p, m->kr.p, x, m->krhat.p, m->part_vec.p);
+        launch_reduce(m, RED_NORM_R, o, false);
+        st->operator_applications += 2;
+    }
+}
+
+// One outer (Picard) iteration = the reference's fill + solve(x) + solve(y) (smooth.zig:104-154), with the two
+// solves advanced in lock-step by a matrix-free BiCGStab on the row-scaled system.  One extension over BiCGStab.zig
+// that only matters when the tolerance is tighter than the reference's: whenever the solver reports convergence or
+// breaks down, the recursive residual is replaced by the true one and, if that is still above the tolerance, the
+// iteration restarts from there (at most `max_restarts` times).
 void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     ensure_krylov(m);
     cudaStream_t s = m->stream;
     const int64_t N = m->N;
     const size_t bytes = size_t(N) * sizeof(double2);
-    const int check_every = 8;
+    const int max_restarts = 40;
     st->converged = 1;
     for (uint64_t it = 0; it < o->iterations; ++it) {
         if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true);
         const double2* xc = m->X[m->cur].p;      // lagged coordinates: the mesh before this iteration
         double2* x = m->X[1 - m->cur].p;         // x_new / y_new, warm-started from the mesh (GMRES.zig:157-174)
         CUDA_TRY(cudaMemcpyAsync(x, xc, bytes, cudaMemcpyDeviceToDevice, s));
-        launch_rows<MODE_DINV, 0>(m, true, xc, xc, m->kdinv.p, 1.0, nullptr);
-        launch_rows<MODE_RESID, 4>(m, true, x, xc, m->kr.p, 1.0, nullptr);
-        st->operator_applications += 1;
-        launch_reduce(m, RED_INIT, o, true);
-        CUDA_TRY(cudaMemcpyAsync(m->krhat.p, m->kr.p, bytes, cudaMemcpyDeviceToDevice, s));
-        m->kp.zero(s);
-        m->kv.zero(s);
-        uint64_t k = 0;
-        for (;; ++k) {
-            if (k % check_every == 0) {
-                fetch_ctl(m);
-                if (m->h_ctl->done[0] && m->h_ctl->done[1]) break;
-            }
-            LAUNCH(bicg_p_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->kr.p, m->kp.p, m->kv.p, m->kdinv.p, m->kphat.p);
-            sync_slaves(m, m->kphat.p, false);
-            launch_rows<MODE_APPLY, 2>(m, true, m->kphat.p, xc, m->kv.p, 1.0, m->krhat.p);
-            launch_reduce(m, RED_ALPHA, o, true);
-            LAUNCH(bicg_s_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->kr.p, m->kv.p, m->ks.p, x, m->kdinv.p, m->kphat.p, m->part_vec.p);
-            launch_reduce(m, RED_NORM_S, o, false);
-            sync_slaves(m, m->kphat.p, false);
-            launch_rows<MODE_APPLY, 3>(m, true, m->kphat.p, xc, m->kt.p, 1.0, m->ks.p);
-            launch_reduce(m, RED_OMEGA, o, true);
-            LAUNCH(bicg_r_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->ks.p, m->kt.p, m->kr.p, x, m->kphat.p, m->krhat.p, m->part_vec.p);
-            launch_reduce(m, RED_NORM_R, o, false);
-            st->operator_applications += 2;
+        for (int cycle = 0;; ++cycle) {
+            if (cycle > 0) sync_slaves(m, x, 1);
+            launch_rows<MODE_RESID, 4>(m, true, x, xc, m->kr.p, 1.0, nullptr);        // r = D^-1 (b - A x)
+            st->operator_applications += 1;
+            launch_reduce(m, cycle == 0 ? RED_INIT : RED_RESTART, o, true);
+            fetch_ctl(m);
+            const int d0 = m->h_ctl->done[0], d1 = m->h_ctl->done[1];
+            if ((d0 == 1 && d1 == 1) || d0 == 3 || d1 == 3 || cycle > max_restarts) break;
+            CUDA_TRY(cudaMemcpyAsync(m->krhat.p, m->kr.p, bytes, cudaMemcpyDeviceToDevice, s));
+            m->kp.zero(s);
+            m->kv.zero(s);
+            bicgstab_cycle(m, o, st, x, xc);
         }
+        sync_slaves(m, x, 1);
         st->inner_iterations += uint64_t(m->h_ctl->iters[0]) + uint64_t(m->h_ctl->iters[1]);
         st->last_inner_residual = std::fmax(m->h_ctl->norm_r[0], m->h_ctl->norm_r[1]);
         if (m->h_ctl->done[0] != 1 || m->h_ctl->done[1] != 1) st->converged = 0;  // log.warn "did not converge", BiCGStab.zig:368-369
