@@ -1,0 +1,191 @@
+"""CPU tests that earn the oracle its trust (PARITY UNPINNED against the Zig binary, see oracle/turbomesh_oracle.c):
+analytic identities, an independent scipy sparse-LU solve of the assembled system, the reference's adjacent
+known-answer vectors and its runtime invariants."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from util import load_fixture, max_diff  # noqa: E402
+
+from turbomesh_b200 import synthetic  # noqa: E402
+from turbomesh_b200.boundary import Condition, ConditionTag, Connection, Range, Side  # noqa: E402
+from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform  # noqa: E402
+from turbomesh_b200.discrete import Block2d, Mesh  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------- TFI
+def _line(a, b, u):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return a[None, :] + u[:, None] * (b - a)[None, :]
+
+
+def test_tfi_reproduces_bilinear_patch(orc):
+    """Straight edges + identical clusterings on opposite sides => TFI is the bilinear map (tfi.zig:185-197)."""
+    ni, nj = 17, 11
+    s, t = Roberts(0.5, 1.1).compute(ni), SingleHyperbolicClustering(0.02).compute(nj)
+    s[0], s[-1], t[0], t[-1] = 0, 1, 0, 1
+    c00, cn0, c0m, cnm = (0.1, -0.2), (2.0, 0.3), (-0.4, 1.5), (2.5, 2.2)
+    out = orc.tfi(_line(c00, cn0, s), _line(c0m, cnm, s), _line(c00, c0m, t), _line(cn0, cnm, t), s, s, t, t)
+    S, T = np.meshgrid(s, t, indexing="ij")
+    exact = ((1 - S) * (1 - T))[..., None] * np.array(c00) + (S * (1 - T))[..., None] * np.array(cn0) \
+        + ((1 - S) * T)[..., None] * np.array(c0m) + (S * T)[..., None] * np.array(cnm)
+    assert np.abs(out - exact).max() < 1e-14
+
+
+def test_tfi_boundary_nodes_equal_edges_up_to_rounding(orc):
+    spec = synthetic.single_block(33, 21)
+    b = spec.blocks[0]
+    out = orc.tfi(*b.edge_args())
+    assert np.abs(out[:, 0] - b.i_min.points).max() < 1e-15
+    assert np.abs(out[:, -1] - b.i_max.points).max() < 1e-15
+    assert np.abs(out[0, :] - b.j_min.points).max() < 1e-15
+    assert np.abs(out[-1, :] - b.j_max.points).max() < 1e-15
+    assert not np.isnan(out).any()
+
+
+def test_tfi_rejects_bad_clustering_and_corners(orc):
+    spec = synthetic.single_block(9, 7)
+    args = [a.copy() for a in spec.blocks[0].edge_args()]
+    bad = [a.copy() for a in args]
+    bad[4][0] = 0.1  # s1[0] != 0 (tfi.zig:135)
+    with pytest.raises(orc.OracleError):
+        orc.tfi(*bad)
+    bad = [a.copy() for a in args]
+    bad[2][0, 0] += 1e-3  # x_j_min[0] != x_i_min[0] (tfi.zig:150-153)
+    with pytest.raises(orc.OracleError):
+        orc.tfi(*bad)
+
+
+# ------------------------------------------------------------------------------------ Krylov solvers
+def _umfpack_known_answer():
+    """The 5x5 system of the reference's own UMFPACK test (umfpack.zig:71-97), given there in CSC form."""
+    Ap = [0, 2, 5, 9, 10, 12]
+    Ai = [0, 1, 0, 2, 4, 1, 2, 3, 4, 2, 1, 4]
+    Ax = [2.0, 3.0, 3.0, -1.0, 4.0, 4.0, -3.0, 1.0, 2.0, 2.0, 6.0, 1.0]
+    b = np.array([8.0, 45.0, -3.0, 3.0, 19.0])
+    A = sp.csc_matrix((Ax, Ai, Ap), shape=(5, 5)).tocsr()
+    A.sort_indices()
+    return A, b
+
+
+@pytest.mark.parametrize("solver,precond", [("gmres", "ilu0"), ("gmres", "diagonal"), ("bicgstab", "ilu0"), ("bicgstab", "diagonal")])
+def test_krylov_known_answer_umfpack_5x5(orc, solver, precond):
+    A, b = _umfpack_known_answer()
+    x, st = orc.csr_solve(A.indptr, A.indices, A.data, b, opts=orc.options(solver=solver, preconditioner=precond, rtol=1e-14, atol=1e-14))
+    assert np.abs(x - np.arange(1.0, 6.0)).max() < 1e-9, (x, st)
+
+
+def test_krylov_matches_scipy_on_random_sparse(orc):
+    rng = np.random.default_rng(7)
+    n = 200
+    A = sp.random(n, n, density=0.03, random_state=rng, format="csr") + sp.diags(np.full(n, 4.0))
+    A = A.tocsr()
+    A.sort_indices()
+    b = rng.standard_normal(n)
+    ref = spla.splu(A.tocsc()).solve(b)
+    for solver in ("gmres", "bicgstab"):
+        x, st = orc.csr_solve(A.indptr, A.indices, A.data, b, opts=orc.options(solver=solver, preconditioner="ilu0", rtol=1e-13, atol=1e-13))
+        assert np.abs(x - ref).max() < 1e-9, (solver, st)
+
+
+# ------------------------------------------------------------------------- assembled system vs scipy
+def _csr(system):
+    p, i, v, rx, ry = system.csr()
+    return sp.csr_matrix((v, i, p), shape=(system.dof, system.dof)), rx, ry
+
+
+@pytest.mark.parametrize("name,args", [("cascade", (4, 2, 13, 9)), ("cascade", (2, 2, 12, 9)), ("cascade", (4, 1, 10, 14)), ("single", (21, 17))])
+def test_one_picard_step_equals_direct_solve(orc, name, args):
+    """The oracle's tight Krylov solve of the assembled system equals an independent sparse-LU solve (what the
+    reference's `umfpack` option computes, umfpack.zig:42-53)."""
+    spec = synthetic.cascade(*args) if name == "cascade" else synthetic.single_block(*args)
+    mesh = synthetic.materialize(spec, orc.tfi)
+    ref = mesh.copy()
+    S = orc.System(ref, orc.tight_options())
+    S.fill(0)
+    p, i, v, _, _ = S.csr()
+    # reference invariants: ascending columns in every row (smooth.zig:679-687), square system, one row per node
+    for r in range(S.dof):
+        assert np.all(np.diff(i[p[r]:p[r + 1]]) > 0)
+    sol = []
+    for y_mode in (False, True):
+        S.fill_specific(y_mode)
+        A, rx, ry = _csr(S)
+        sol.append(spla.splu(A.tocsc()).solve(ry if y_mode else rx))
+    direct = np.stack(sol, axis=1)
+    orc.smooth_mesh(mesh, 1, orc.tight_options())
+    got = np.concatenate([b.points.reshape(-1, 2) for b in mesh.blocks])
+    assert np.abs(got - direct).max() < 1e-11
+
+
+def test_uniform_cartesian_grid_is_a_fixed_point(orc):
+    ni, nj = 12, 9
+    x, y = np.meshgrid(np.linspace(0, 1.1, ni), np.linspace(0, 0.8, nj), indexing="ij")
+    mesh = Mesh([Block2d(np.stack([x, y], axis=-1))], ["b"], [], [])
+    ref = mesh.copy()
+    st = orc.smooth_mesh(mesh, 2, orc.tight_options())
+    assert max_diff(mesh, ref) < 1e-14 and st["last_max_update"] < 1e-14
+
+
+def test_affine_grid_is_a_fixed_point_and_smoothing_is_translation_equivariant(orc):
+    spec = synthetic.cascade(2, 2, 10, 8)
+    a = synthetic.materialize(spec, orc.tfi)
+    b = a.copy()
+    shift = np.array([0.25, -0.125])  # exactly representable, keeps the 1e-15 coincidence check valid
+    for blk in b.blocks:
+        blk.points += shift
+    orc.smooth_mesh(a, 3, orc.tight_options())
+    orc.smooth_mesh(b, 3, orc.tight_options())
+    for x, y in zip(a.blocks, b.blocks):
+        assert np.abs((x.points + shift) - y.points).max() < 1e-11
+
+
+# -------------------------------------------------------------------------------- topology / kinds
+def test_t106_classification_counts(orc):
+    spec, z, meta = load_fixture("t106_white")
+    mesh = synthetic.materialize(spec, orc.tfi)
+    assert [b.size for b in mesh.blocks] == [(221, 41), (121, 41), (11, 41), (11, 51), (121, 41), (161, 11), (21, 91), (11, 131)]
+    assert mesh.num_nodes() == 25118
+    for k, b in enumerate(mesh.blocks):  # golden TFI
+        assert np.array_equal(b.points, z[f"tfi_b{k}"])
+    S = orc.System(mesh)
+    kinds = np.bincount(S.kinds(), minlength=5)
+    assert kinds.sum() == sum(2 * (b.size[0] + b.size[1] - 2) for b in mesh.blocks)
+    assert kinds[3] == len(S.junctions()) == 12
+    assert kinds[1] == sum(c.len() - 2 for c in mesh.connections)  # one smoothed node per interior interface node
+    assert kinds[4] == 220  # inlet 91 + outlet 131 minus the two corners taken by periodic connections
+    for j in S.junctions():
+        assert len(j["ids"]) <= 4 and len(j["stencil"]) <= 6 and j["ids"] == sorted(j["ids"])
+
+
+def test_connection_mismatch_is_reported(orc):
+    spec = synthetic.cascade(2, 2, 10, 8)
+    mesh = synthetic.materialize(spec, orc.tfi)
+    mesh.blocks[2].points[0, 3, 0] += 1e-12  # block (1,0), j_min side: > 1e-15 (smooth.zig:221)
+    with pytest.raises(orc.OracleError, match="non matching"):
+        orc.smooth_mesh(mesh, 1)
+
+
+def test_single_block_without_connections_smooths(orc):
+    """Deviation D1: the reference underflows on a mesh with zero connections (smooth.zig:1364)."""
+    mesh = synthetic.materialize(synthetic.single_block(25, 19), orc.tfi)
+    ref = mesh.copy()
+    st = orc.smooth_mesh(mesh, 3, orc.tight_options())
+    assert st["not_converged"] == 0 and 1e-6 < max_diff(mesh, ref) < 0.1
+    for a, b in zip(mesh.blocks, ref.blocks):  # all block-boundary nodes are fixed
+        for sl in (np.s_[0, :], np.s_[-1, :], np.s_[:, 0], np.s_[:, -1]):
+            assert np.array_equal(a.points[sl], b.points[sl])
+
+
+def test_golden_t106_white_is_reproduced(orc):
+    """The committed golden mesh is what the oracle computes from the committed inputs (10 outer iterations, White)."""
+    spec, z, meta = load_fixture("t106_laplace")
+    mesh = synthetic.materialize(spec, orc.tfi)
+    orc.smooth_mesh(mesh, meta["iterations"], orc.tight_options(max_iters=100000))
+    err = max(float(np.abs(b.points - z[f"smooth_b{k}"]).max()) for k, b in enumerate(mesh.blocks))
+    assert err < 1e-12

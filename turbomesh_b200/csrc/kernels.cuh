@@ -129,8 +129,10 @@ __global__ void __launch_bounds__(TILE_J) tfi_kernel(int ni, int nj, const doubl
 //   W,E = nodes (i-1,j),(i+1,j); metric terms use central differences of the LAGGED coordinates:
 //     x_xi = (E-W)/2, x_eta = (N-S)/2; g11 = |x_xi|^2, g22 = |x_eta|^2, g12 = x_xi.x_eta
 //   row:  g22[(1+P/2)E + (1-P/2)W] + g11[(1+Q/2)N + (1-Q/2)S] - (g12/2)[(NE-SE)-(NW-SW)] - 2(g11+g22) C
-//   With D_r = u[r][j+1]-u[r][j-1] and S_r = u[r][j+1]+u[r][j-1] the off-diagonal part is
-//     off = g22[(E+W) + P/2 (E-W)] + g11[S_i + Q/2 D_i] - (g12/2)(D_{i+1} - D_{i-1})
+//   The off-diagonal coefficients sum to the diagonal 2(g11+g22), so the row only sees differences to C:
+//     rel = g22[(E-C)+(W-C) + P/2 (E-W)] + g11[R_i + Q/2 D_i] - (g12/2)(D_{i+1} - D_{i-1})
+//   with D_r = u[r][j+1]-u[r][j-1] and R_r = (u[r][j+1]-u[r][j]) + (u[r][j-1]-u[r][j]).  Evaluating the row this
+//   way is translation invariant: its rounding error scales with the cell size, not with |x|.
 // ---------------------------------------------------------------------------------------------------
 struct Metric {
     double g11, g22, g12;
@@ -144,30 +146,31 @@ __device__ __forceinline__ Metric metric_terms(double2 W, double2 E, double2 Det
     m.g11 = x_xi * x_xi + y_xi * y_xi;
     return m;
 }
-__device__ __forceinline__ double2 offdiag_sum(const Metric& m, double P, double Q, double2 W, double2 E, double2 Ssum, double2 Deta, double2 Dp, double2 Dm) {
+// rel = (row applied to u) + 2(g11+g22) C - ... i.e. sum_k a_k (u_k - C) over the 8 neighbours
+__device__ __forceinline__ double2 row_rel(const Metric& m, double P, double Q, double2 C, double2 W, double2 E, double2 Rj, double2 Deta, double2 Dp, double2 Dm) {
     double2 r;
-    r.x = m.g22 * ((E.x + W.x) + 0.5 * P * (E.x - W.x)) + m.g11 * (Ssum.x + 0.5 * Q * Deta.x) - 0.5 * m.g12 * (Dp.x - Dm.x);
-    r.y = m.g22 * ((E.y + W.y) + 0.5 * P * (E.y - W.y)) + m.g11 * (Ssum.y + 0.5 * Q * Deta.y) - 0.5 * m.g12 * (Dp.y - Dm.y);
+    r.x = m.g22 * (((E.x - C.x) + (W.x - C.x)) + 0.5 * P * (E.x - W.x)) + m.g11 * (Rj.x + 0.5 * Q * Deta.x) - 0.5 * m.g12 * (Dp.x - Dm.x);
+    r.y = m.g22 * (((E.y - C.y) + (W.y - C.y)) + 0.5 * P * (E.y - W.y)) + m.g11 * (Rj.y + 0.5 * Q * Deta.y) - 0.5 * m.g12 * (Dp.y - Dm.y);
     return r;
 }
 
 // What a row produces, shared by interior and interface rows.  The Krylov modes work on the row-scaled system
 // D^-1 A x = D^-1 b (D = diagonal, the reference's `diagonal` preconditioner, GMRES.zig:176-196, applied from the
 // left as GMRES.zig:300-423 does): residuals are then "Jacobi updates", i.e. lengths, and the stopping test is
-// meaningful at any geometric scale.
-//   RELAX: (1-w) C + w * off / (2(g11+g22))          (damped Jacobi update of the row)
-//   APPLY: (A v)_i / a_ii     =  C - off / (2(g11+g22))             (homogeneous)
-//   RESID: (b - A x)_i / a_ii =  off / (2(g11+g22)) - C             (rhs of these rows is 0 once periodic shifts are folded in)
+// meaningful at any geometric scale.  With a_ii = -2(g11+g22):
+//   RELAX: C + w * rel / (2(g11+g22))                 (damped Jacobi update of the row)
+//   APPLY: (A v)_i / a_ii     = -rel / (2(g11+g22))   (homogeneous)
+//   RESID: (b - A x)_i / a_ii = +rel / (2(g11+g22))   (rhs of these rows is 0 once periodic shifts are folded in)
 template <int MODE>
-__device__ __forceinline__ double2 row_result(const Metric& m, double2 off, double2 C, double omega) {
+__device__ __forceinline__ double2 row_result(const Metric& m, double2 rel, double2 C, double omega) {
     const double diag = 2.0 * (m.g11 + m.g22);
     const double inv = diag == 0.0 ? 1.0 : 1.0 / diag;  // zero diagonal -> 1.0 as in GMRES.zig:190-194
     if (MODE == MODE_RELAX) {
-        return make_double2(C.x + omega * (off.x * inv - C.x), C.y + omega * (off.y * inv - C.y));
+        return make_double2(C.x + omega * (rel.x * inv), C.y + omega * (rel.y * inv));
     } else if (MODE == MODE_APPLY) {
-        return make_double2(C.x - off.x * inv, C.y - off.y * inv);
+        return make_double2(-(rel.x * inv), -(rel.y * inv));
     } else {
-        return make_double2(off.x * inv - C.x, off.y * inv - C.y);
+        return make_double2(rel.x * inv, rel.y * inv);
     }
 }
 
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
     double2 Cm = ld2(ub + idx), Dm = ld2(ub + idx + 1) - ld2(ub + idx - 1);
     idx += nj;
     double2 l = ld2(ub + idx - 1), r = ld2(ub + idx + 1);
-    double2 C0 = ld2(ub + idx), D0 = r - l, S0 = r + l;
+    double2 C0 = ld2(ub + idx), D0 = r - l, R0 = (r - C0) + (l - C0);
     double2 cCm, cC0, cD0;
     if (LAGGED) {
         cCm = ld2(cb + idx - nj);
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
     for (int i = i_begin; i < i_end; ++i) {
         const size_t ip = idx + nj;  // row i+1
         const double2 lp = ld2(ub + ip - 1), rp = ld2(ub + ip + 1);
-        const double2 Cp = ld2(ub + ip), Dp = rp - lp, Sp = rp + lp;
+        const double2 Cp = ld2(ub + ip), Dp = rp - lp, Rp = (rp - Cp) + (lp - Cp);
         double2 cCp, cDp;
         Metric m;
         if (LAGGED) {
@@ -229,8 +232,8 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
             const double2 f = ldg2(pq + b.off + idx);
             P = f.x; Q = f.y;
         }
-        const double2 off = offdiag_sum(m, P, Q, Cm, Cp, S0, D0, Dp, Dm);
-        const double2 res = row_result<MODE>(m, off, C0, omega);
+        const double2 rel = row_rel(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
+        const double2 res = row_result<MODE>(m, rel, C0, omega);
         if (active) {
             ob[idx] = res;
             if (STATS == 1) {  // update norms (smooth.zig:112-134) of a relaxation sweep
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
             }
         }
         Cm = C0; Dm = D0;
-        C0 = Cp; D0 = Dp; S0 = Sp;
+        C0 = Cp; D0 = Dp; R0 = Rp;
         if (LAGGED) { cCm = cC0; cC0 = cCp; cD0 = cDp; }
         idx = ip;
     }
@@ -303,8 +306,8 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
             const double2 f = ldg2(pq + row.g0);
             if (row.periodic) { P = f.x; Q = f.y; } else { P = f.y; Q = f.x; }  // smooth.zig:1040-1041 vs 1082-1083
         }
-        const double2 off = offdiag_sum(m, P, Q, W, E, N + S, N - S, NE - SE, NW - SW);
-        res = row_result<MODE>(m, off, C, omega);
+        const double2 rel = row_rel(m, P, Q, C, W, E, (N - C) + (S - C), N - S, NE - SE, NW - SW);
+        res = row_result<MODE>(m, rel, C, omega);
         old = C;
         if (STATS == 4 && row.periodic) {  // rhs of the reference's row: p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)) = p * g11 (1 + Q/2)
             const double a = m.g11 * (1.0 + 0.5 * Q);
@@ -315,15 +318,15 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
         self = row.self;
         sb = row.slave_begin; se = row.slave_end;
         const double2 C = ld2(u + row.self);
-        double2 sum = make_double2(0.0, 0.0);
-        for (int k = 0; k < row.n; ++k) sum = sum + ld2(u + row.nbr[k]);
+        double2 sum = make_double2(0.0, 0.0);  // sum_k (x_k - C): translation invariant like the Winslow rows
+        for (int k = 0; k < row.n; ++k) sum = sum + (ld2(u + row.nbr[k]) - C);
         const double n = (double)row.n;
         if (MODE == MODE_RELAX) {
-            res = make_double2(C.x + omega * ((sum.x - row.rhs_x) / n - C.x), C.y + omega * ((sum.y - row.rhs_y) / n - C.y));
+            res = make_double2(C.x + omega * ((sum.x - row.rhs_x) / n), C.y + omega * ((sum.y - row.rhs_y) / n));
         } else if (MODE == MODE_APPLY) {  // row / a_ii with a_ii = -n
-            res = make_double2(C.x - sum.x / n, C.y - sum.y / n);
+            res = make_double2(-(sum.x / n), -(sum.y / n));
         } else {
-            res = make_double2((sum.x - row.rhs_x) / n - C.x, (sum.y - row.rhs_y) / n - C.y);
+            res = make_double2((sum.x - row.rhs_x) / n, (sum.y - row.rhs_y) / n);
         }
         old = C;
     } else if (r < n_s + n_j + n_l) {
