@@ -24,11 +24,11 @@ struct DevBlock {
     int32_t ni, nj;
 };
 struct Tile {
-    int32_t block, i0, j0, _pad;
+    int32_t block, i0, j0, rows;  // rows marched by the CTA starting at interior row i0
 };
 
 constexpr int TILE_J = 128;  // threads per CTA = nodes along j per tile
-constexpr int TILE_I = 64;   // rows marched per CTA
+constexpr int TILE_I = 32;   // default rows marched per CTA (the host balances waves, see build_tiles)
 
 enum Mode : int { MODE_RELAX = 0, MODE_APPLY = 1, MODE_RESID = 2 };
 
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
     const int j = t.j0 + threadIdx.x;
     const bool active = j <= nj - 2;
     const int jc = active ? j : nj - 2;  // clamp: inactive lanes recompute the last column, never store
-    const int i_begin = t.i0, i_end = min(t.i0 + TILE_I, b.ni - 1);
+    const int i_begin = t.i0, i_end = min(t.i0 + t.rows, b.ni - 1);
     const double2* ub = u + b.off;
     const double2* cb = LAGGED ? xc + b.off : ub;
     double2* ob = out + b.off;
@@ -255,6 +255,130 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
         C0 = Cp; D0 = Dp; R0 = Rp;
         if (LAGGED) { cCm = cC0; cC0 = cCp; cD0 = cDp; }
         idx = ip;
+    }
+    if (STATS != 0) {
+        double sums[4] = {s0, s1, s2, s3};
+        block_reduce_store<4, TILE_J>(sums, mx, partials + (size_t)blockIdx.x * 5);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Same rows, fed by the async copy engine (the throughput path: coefficients from the field itself).
+// Thread 0 streams row segments of TILE_J+2 nodes into a shared-memory ring with 1-D bulk async copies
+// (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier; the ring keeps BULK_NS*BULK_R rows in flight per CTA
+// without holding registers, which is what a latency-bound fp64 stencil needs to approach the HBM roofline.
+// Consumers read a node and its j-1/j+1 neighbours from shared memory (3 x LDS.128), keep the 3-row window in
+// registers and store results straight from registers (coalesced 16 B per thread).
+// ---------------------------------------------------------------------------------------------------
+constexpr int BULK_R = 4;    // rows per pipeline stage
+constexpr int BULK_NS = 3;   // stages
+constexpr int BULK_ROW = TILE_J + 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int MODE, bool HAS_PQ, int STATS>
+__global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Tile* __restrict__ tiles, const DevBlock* __restrict__ blocks,
+                                                                        const double2* __restrict__ u, const double2* __restrict__ pq,
+                                                                        double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
+                                                                        double* __restrict__ partials) {
+    __shared__ __align__(128) double2 ring[BULK_NS][BULK_R][BULK_ROW];
+    __shared__ __align__(8) uint64_t full[BULK_NS];
+    const Tile t = tiles[blockIdx.x];
+    const DevBlock b = blocks[t.block];
+    const int nj = b.nj;
+    const int tid = threadIdx.x;
+    const int j = t.j0 + tid;
+    const bool active = j <= nj - 2;
+    const int i_begin = t.i0, i_end = min(t.i0 + t.rows, b.ni - 1);
+    const int width = min(TILE_J, nj - 1 - t.j0) + 2;          // nodes per row segment incl. the two halo columns
+    const uint32_t row_bytes = (uint32_t)width * (uint32_t)sizeof(double2);
+    const int n_rows = (i_end - i_begin) + 2;                   // rows i_begin-1 .. i_end
+    const int n_chunks = (n_rows + BULK_R - 1) / BULK_R;
+    const double2* ub = u + b.off;
+    double2* ob = out + b.off;
+    const double2* src0 = ub + (size_t)(i_begin - 1) * nj + (t.j0 - 1);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < BULK_NS; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue_chunk = [&](int c) {  // thread 0 only
+        const int s = c % BULK_NS;
+        const int r0 = c * BULK_R, r1 = min(r0 + BULK_R, n_rows);
+        mbar_expect_tx(&full[s], (uint32_t)(r1 - r0) * row_bytes);
+        for (int r = r0; r < r1; ++r) bulk_load(&ring[s][r - r0][0], src0 + (size_t)r * nj, row_bytes, &full[s]);
+    };
+    if (tid == 0) {
+        for (int c = 0; c < BULK_NS && c < n_chunks; ++c) issue_chunk(c);
+    }
+
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
+    double2 Cm = make_double2(0, 0), Dm = Cm, C0 = Cm, D0 = Cm, R0 = Cm;
+    const int tl = active ? tid : 0;  // inactive lanes read a valid column, never store
+    long long idx = (long long)(i_begin - 2) * nj + (active ? j : t.j0);  // block-local index of the row being finished (k-2)
+    for (int k = 0; k < n_rows; ++k) {
+        const int c = k / BULK_R, slot = k - c * BULK_R, s = c % BULK_NS;
+        if (slot == 0) mbar_wait(&full[s], (uint32_t)((c / BULK_NS) & 1));
+        const double2 lp = ring[s][slot][tl], Cp = ring[s][slot][tl + 1], rp = ring[s][slot][tl + 2];
+        const double2 Dp = rp - lp, Rp = (rp - Cp) + (lp - Cp);
+        if (k >= 2) {
+            const Metric m = metric_terms(Cm, Cp, D0);
+            double P = 0.0, Q = 0.0;
+            if (HAS_PQ) {
+                const double2 f = ldg2(pq + b.off + idx);
+                P = f.x; Q = f.y;
+            }
+            const double2 rel = row_rel(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
+            const double2 res = row_result<MODE>(m, rel, C0, omega);
+            if (active) {
+                ob[idx] = res;
+                if (STATS == 1) {
+                    const double dx = res.x - C0.x, dy = res.y - C0.y;
+                    s0 += dx * dx; s1 += dy * dy;
+                    mx = fmax(mx, fmax(fabs(dx), fabs(dy)));
+                } else if (STATS == 2) {
+                    const double2 a = ld2(dot_a + b.off + idx);
+                    s0 += a.x * res.x; s1 += a.y * res.y;
+                } else if (STATS == 3) {
+                    const double2 a = ld2(dot_a + b.off + idx);
+                    s0 += a.x * res.x; s1 += a.y * res.y;
+                    s2 += res.x * res.x; s3 += res.y * res.y;
+                } else if (STATS == 4) {
+                    s0 += res.x * res.x; s1 += res.y * res.y;
+                }
+            }
+        }
+        Cm = C0; Dm = D0;
+        C0 = Cp; D0 = Dp; R0 = Rp;
+        idx += nj;
+        if (slot == BULK_R - 1 || k == n_rows - 1) {
+            __syncthreads();  // every thread has copied this stage into registers: the stage may be refilled
+            if (tid == 0 && c + BULK_NS < n_chunks) issue_chunk(c + BULK_NS);
+        }
     }
     if (STATS != 0) {
         double sums[4] = {s0, s1, s2, s3};

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -120,6 +121,8 @@ struct tm_mesh {
     std::vector<uint8_t> have_coords;
 
     int n_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
+    int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
+    bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
     bool begun = false;
     int cf = TM_CF_LAPLACE;
     WhiteParams wp{};
@@ -142,8 +145,12 @@ void build_tiles(tm_mesh* m) {
     for (size_t b = 0; b < m->topo.blocks.size(); ++b) {
         const auto& B = m->topo.blocks[b];
         blocks.push_back(DevBlock{B.off, int32_t(B.ni), int32_t(B.nj)});
-        for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += TILE_I)
-            for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += TILE_J) tiles.push_back(Tile{int32_t(b), int32_t(i0), int32_t(j0), 0});
+        // rows per CTA: about TILE_I, evened out over the block so no CTA gets a short remainder
+        const int64_t interior_i = B.ni - 2;
+        const int64_t n_i = std::max<int64_t>(1, (interior_i + m->tile_rows - 1) / m->tile_rows);
+        const int64_t rows = (interior_i + n_i - 1) / n_i;
+        for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += rows)
+            for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += TILE_J) tiles.push_back(Tile{int32_t(b), int32_t(i0), int32_t(j0), int32_t(rows)});
     }
     m->n_tiles = int(tiles.size());
     m->d_tiles.upload(tiles, m->stream);
@@ -199,9 +206,21 @@ void launch_rows(tm_mesh* m, bool lagged, const double2* u, const double2* xc, d
                    m->d_jrows.p, int(m->topo.junction_rows.size()), m->d_lrows.p, int(m->topo.sliding.size()), m->d_slaves.p, u, xc, pq, out, omega,  \
                    dot_a, m->part_bnd.p);                                                                                                             \
     } while (0)
+#define TM_ROWS_BULK(PQ)                                                                                                                          \
+    do {                                                                                                                                          \
+        if (m->n_tiles > 0)                                                                                                                       \
+            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), m->n_tiles, TILE_J, s, m->d_tiles.p, m->d_blocks.p, u, pq, out, omega, dot_a, \
+                   m->part_int.p);                                                                                                                \
+        if (m->n_bnd_rows > 0)                                                                                                                    \
+            LAUNCH((winslow_boundary_kernel<MODE, false, PQ, STATS>), m->n_bnd_ctas, BND_THREADS, s, m->d_srows.p, int(m->topo.smoothed.size()),  \
+                   m->d_jrows.p, int(m->topo.junction_rows.size()), m->d_lrows.p, int(m->topo.sliding.size()), m->d_slaves.p, u, xc, pq, out,     \
+                   omega, dot_a, m->part_bnd.p);                                                                                                  \
+    } while (0)
     if (lagged) { if (has_pq) TM_ROWS(true, true); else TM_ROWS(true, false); }
+    else if (m->use_bulk) { if (has_pq) TM_ROWS_BULK(true); else TM_ROWS_BULK(false); }
     else        { if (has_pq) TM_ROWS(false, true); else TM_ROWS(false, false); }
 #undef TM_ROWS
+#undef TM_ROWS_BULK
 }
 
 void launch_reduce(tm_mesh* m, int op, const tm_smooth_options* o, bool from_rows) {
@@ -409,6 +428,8 @@ int tm_mesh_create(const tm_block* blocks, size_t n_blocks, const tm_connection*
         m = new tm_mesh();
         if (device < 0) CUDA_TRY(cudaGetDevice(&m->device)); else m->device = device;
         m->topo.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
+        if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
+        if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
         if (stream) m->stream = (cudaStream_t)stream;
         else { CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
         CUDA_TRY(cudaEventCreate(&m->ev0));
@@ -424,6 +445,12 @@ int tm_mesh_create(const tm_block* blocks, size_t n_blocks, const tm_connection*
         m->d_cslaves.upload(m->topo.const_slaves, m->stream);
         m->d_fo.upload(m->topo.fixed_overrides, m->stream);
         m->d_pairs.upload(m->topo.pairs, m->stream);
+        {
+            std::vector<RhsTerm> terms;
+            build_rhs_terms(m, terms);
+            for (const auto& c : m->topo.connected_rhs) terms.push_back(RhsTerm{c.self, c.x, c.y, 0, 0});  // smooth.zig:904-915
+            m->d_rhs_terms.upload(terms, m->stream);
+        }
         m->n_bnd_rows = int(m->topo.smoothed.size() + m->topo.junction_rows.size() + m->topo.sliding.size());
         m->n_bnd_ctas = bnd_ctas(m->n_bnd_rows);
         int sms = 148;
@@ -576,12 +603,8 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
         const int n_cs = int(m->topo.const_slaves.size());
         if (n_cs > 0) LAUNCH(sync_slaves_kernel, (n_cs + 127) / 128, 128, s, m->d_cslaves.p, n_cs, x, 1);
         CUDA_TRY(cudaMemcpyAsync(m->X[1 - m->cur].p, x, size_t(m->N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-        // constant part of ||b||^2
-        std::vector<RhsTerm> terms;
-        build_rhs_terms(m, terms);
-        for (const auto& c : m->topo.connected_rhs) terms.push_back(RhsTerm{c.self, c.x, c.y, 0, 0});  // smooth.zig:904-915
-        m->d_rhs_terms.upload(terms, s);
-        if (!terms.empty()) LAUNCH(rhs_const_kernel, 1, VEC_THREADS, s, m->d_rhs_terms.p, int(terms.size()), (const double2*)x, m->bconst.p);
+        // constant part of ||b||^2 (the term table was uploaded by tm_mesh_create)
+        if (m->d_rhs_terms.n > 0) LAUNCH(rhs_const_kernel, 1, VEC_THREADS, s, m->d_rhs_terms.p, int(m->d_rhs_terms.n), (const double2*)x, m->bconst.p);
         else m->bconst.zero(s);
         // control function (ControlFunction.init, wall_control_function.zig:27-42)
         m->cf = int(o->control_function);
