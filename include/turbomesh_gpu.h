@@ -193,6 +193,43 @@ int tm_mesh_download_control_function(tm_mesh *mesh, size_t block, double *pq);
 int tm_mesh_download_boundary_kinds(tm_mesh *mesh, size_t block, uint8_t *kinds);
 
 /* -------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, whole blocks assigned to ranks (DESIGN.md "Multi-GPU")
+ * ------------------------------------------------------------------------------------------------- */
+#define TM_UNIQUE_ID_BYTES 128
+
+/* Rank 0 obtains an id (ncclGetUniqueId) and hands the bytes to the other ranks with its own plumbing
+ * (MPI, torch.distributed, a file ...) before every rank calls tm_mesh_create_distributed. */
+int tm_dist_get_unique_id(uint8_t *id /* TM_UNIQUE_ID_BYTES */);
+
+/* Like tm_mesh_create, for rank `rank` of `n_ranks`: every rank passes the SAME global block / connection / condition
+ * arrays (coordinates are only read for the blocks it owns and may be NULL elsewhere) and block_owner[n_blocks].
+ * Rows are computed by the owner of their node; per sweep / operator application the ranks exchange the few nodes
+ * their neighbours read (NCCL send/recv) and all-reduce the residual / Krylov scalars.  All other tm_mesh_* calls
+ * keep global block indices and are valid for owned blocks; tm_mesh_begin_smoothing and tm_mesh_smooth are collective.
+ * rank = -1 builds ALL ranks inside this process on one GPU (no NCCL): an emulation for testing the multi-rank
+ * logic, every block is then addressable through the one handle. */
+int tm_mesh_create_distributed(const tm_block *blocks, size_t n_blocks,
+                               const tm_connection *connections, size_t n_connections,
+                               const tm_condition *conditions, size_t n_conditions,
+                               const int32_t *block_owner, int rank, int n_ranks,
+                               const uint8_t *unique_id /* TM_UNIQUE_ID_BYTES; may be NULL when n_ranks == 1 or rank == -1 */,
+                               int device, void *stream, tm_mesh **out);
+uint64_t tm_mesh_local_node_count(const tm_mesh *mesh); /* nodes of the blocks held by this process */
+
+/* Host-only view of the partition (needs no GPU): sizes of rank `rank`'s local field and its exchange lists.
+ * ghost_ids / send_ids (may be NULL) receive the global node ids grouped by peer rank in ascending rank order;
+ * counts (may be NULL) receives 2*n_ranks entries: [ghosts from peer p, sends to peer p]. */
+typedef struct tm_dist_plan_info {
+    uint64_t n_own, n_ghost, n_synth, n_send;
+    uint64_t n_smoothed, n_junction, n_sliding, n_slaves;
+} tm_dist_plan_info;
+int tm_dist_plan(const tm_block *blocks, size_t n_blocks,
+                 const tm_connection *connections, size_t n_connections,
+                 const tm_condition *conditions, size_t n_conditions,
+                 const int32_t *block_owner, int rank, int n_ranks,
+                 tm_dist_plan_info *info, int64_t *ghost_ids, int64_t *send_ids, int64_t *counts);
+
+/* -------------------------------------------------------------------------------------------------
  * Misc
  * ------------------------------------------------------------------------------------------------- */
 const char *tm_last_error(void);

@@ -1,0 +1,74 @@
+"""Multi-rank logic on ONE GPU: all ranks are emulated inside one process (tm_mesh_create_distributed with rank = -1),
+the halo exchange becomes device copies and the all-reduce a tiny kernel; everything else (ownership, ghosts,
+synthesised copies, partial reductions) is the code path the NCCL ranks run."""
+import numpy as np
+import pytest
+
+from turbomesh_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(spec_mesh, owner, n_ranks, solver, iterations, cf=None):
+    from turbomesh_b200 import smoothing
+
+    mesh = spec_mesh.copy()
+    kw = {} if owner is None else dict(owner=owner, rank=None, n_ranks=n_ranks)
+    with smoothing.DeviceMesh(mesh, **kw) as dm:
+        dm.begin_smoothing(solver, cf)
+        st = dm.smooth(iterations, solver, cf)
+        dm.download()
+    return mesh, st
+
+
+def _md(a, b):
+    return max(float(np.abs(x.points - y.points).max()) for x, y in zip(a.blocks, b.blocks))
+
+
+@pytest.mark.parametrize("args,n_ranks", [((4, 2, 21, 13), 2), ((4, 2, 21, 13), 4), ((8, 8, 12, 10), 8), ((4, 1, 20, 30), 2)])
+def test_emulated_ranks_match_single_rank_relax(gpu_lib, orc, args, n_ranks):
+    from turbomesh_b200 import smoothing
+
+    n_bi, n_bj = args[0], args[1]
+    mesh0 = synthetic.materialize(synthetic.cascade(*args), orc.tfi)
+    owner = [bi * n_ranks // n_bi for bi in range(n_bi) for _ in range(n_bj)]  # block columns -> ranks
+    sol = smoothing.CudaSolver(method="relax", sweeps_per_iteration=40, omega=0.9)
+    one, st1 = _run(mesh0, None, 1, sol, 3)
+    many, stn = _run(mesh0, owner, n_ranks, sol, 3)
+    assert _md(one, many) <= 1e-14
+    assert abs(st1["last_max_update"] - stn["last_max_update"]) <= 1e-15
+    assert abs(st1["last_sumsq_x"] - stn["last_sumsq_x"]) <= 1e-12 * max(st1["last_sumsq_x"], 1e-30)
+
+
+@pytest.mark.parametrize("owner_kind", ["columns", "interleaved"])
+def test_emulated_ranks_match_single_rank_picard(gpu_lib, orc, owner_kind):
+    from turbomesh_b200 import smoothing
+
+    args, n_ranks = (4, 2, 21, 13), 2
+    mesh0 = synthetic.materialize(synthetic.cascade(*args), orc.tfi)
+    nb = args[0] * args[1]
+    owner = [b * n_ranks // nb for b in range(nb)] if owner_kind == "columns" else [b % n_ranks for b in range(nb)]
+    sol = smoothing.CudaSolver.tight()
+    one, st1 = _run(mesh0, None, 1, sol, 3)
+    many, stn = _run(mesh0, owner, n_ranks, sol, 3)
+    assert st1["converged"] == 1 and stn["converged"] == 1
+    assert _md(one, many) <= 1e-10
+    ref = mesh0.copy()
+    orc.smooth_mesh(ref, 3, orc.tight_options())
+    assert _md(ref, many) <= 1e-9
+
+
+def test_emulated_ranks_t106_white(gpu_lib):
+    """T106 with the White control function split over 2 ranks (blocks 0 and 1 stay together)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import chord_of, load_fixture
+    from turbomesh_b200 import smoothing
+
+    spec, z, meta = load_fixture("t106_white")
+    mesh0 = synthetic.materialize(spec, smoothing.tfi_block)
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    many, st = _run(mesh0, [0, 0, 0, 1, 1, 1, 0, 1], 2, smoothing.CudaSolver.tight(), meta["iterations"], cf)
+    err = max(float(np.abs(b.points - z[f"smooth_b{k}"]).max()) for k, b in enumerate(many.blocks))
+    assert st["converged"] == 1
+    assert err <= max(1e-9 * chord_of(many), 2.0 * meta["oracle_spread"])

@@ -50,6 +50,17 @@ class TmSmoothStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
 
 
+class TmDistPlanInfo(C.Structure):
+    _fields_ = [("n_own", C.c_uint64), ("n_ghost", C.c_uint64), ("n_synth", C.c_uint64), ("n_send", C.c_uint64),
+                ("n_smoothed", C.c_uint64), ("n_junction", C.c_uint64), ("n_sliding", C.c_uint64), ("n_slaves", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+TM_UNIQUE_ID_BYTES = 128
+
+
 class TurbomeshGpuError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"turbomesh_gpu error {code}: {message}")
@@ -82,6 +93,14 @@ def load():
                                  C.POINTER(TmSmoothOptions), C.POINTER(TmSmoothStats)]
     L.tm_mesh_create.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t,
                                  C.c_int, vp, C.POINTER(vp)]
+    L.tm_dist_get_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.tm_mesh_create_distributed.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t,
+                                             C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, vp, C.POINTER(vp)]
+    L.tm_mesh_local_node_count.argtypes = [vp]
+    L.tm_mesh_local_node_count.restype = C.c_uint64
+    L.tm_dist_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t,
+                               C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(TmDistPlanInfo), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                               C.POINTER(C.c_int64)]
     L.tm_mesh_destroy.argtypes = [vp]
     L.tm_mesh_destroy.restype = None
     L.tm_mesh_upload_block.argtypes = [vp, C.c_size_t, dp]

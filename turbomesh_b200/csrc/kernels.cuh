@@ -403,11 +403,11 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
     double2 res = make_double2(0.0, 0.0), old = make_double2(0.0, 0.0);
     int64_t self = -1;
-    int sb = 0, se = 0;
+    int sb = 0, se = 0, n_copies = 0;
     if (r < n_s) {
         const SmoothedRow row = srows[r];
         self = row.g0;
-        sb = row.slave_begin; se = row.slave_end;
+        sb = row.slave_begin; se = row.slave_end; n_copies = row.n_copies;
         const double2 per = make_double2(row.px, row.py);
         // values the row is applied to; block-1 columns are shifted by -periodicity in the affine modes
         // (equivalent to the reference's rhs = p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)), smooth.zig:1060-1061)
@@ -416,14 +416,14 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
         const double2 C = ld2(u + row.g0);
         const double2 W = ld2(u + row.g0 - row.d0), E = ld2(u + row.g0 + row.d0);
         const double2 S = ld2(u + row.g0 + row.n0), SW = ld2(u + row.g0 - row.d0 + row.n0), SE = ld2(u + row.g0 + row.d0 + row.n0);
-        const double2 N = ld2(u + row.g1 + row.n1) - sh, NW = ld2(u + row.g1 - row.d1 + row.n1) - sh, NE = ld2(u + row.g1 + row.d1 + row.n1) - sh;
+        const double2 N = ld2(u + row.iN) - sh, NW = ld2(u + row.iNW) - sh, NE = ld2(u + row.iNE) - sh;
         Metric m;
         if (LAGGED) {
             const double2 cW = ld2(xc + row.g0 - row.d0), cE = ld2(xc + row.g0 + row.d0), cS = ld2(xc + row.g0 + row.n0);
-            const double2 cN = ld2(xc + row.g1 + row.n1) - per;  // smooth.zig:1032
+            const double2 cN = ld2(xc + row.iN) - per;  // smooth.zig:1032
             m = metric_terms(cW, cE, cN - cS);
         } else {
-            m = metric_terms(W, E, (ld2(u + row.g1 + row.n1) - per) - S);
+            m = metric_terms(W, E, (ld2(u + row.iN) - per) - S);
         }
         double P = 0.0, Q = 0.0;
         if (HAS_PQ) {
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
     } else if (r < n_s + n_j) {
         const JunctionRow row = jrows[r - n_s];
         self = row.self;
-        sb = row.slave_begin; se = row.slave_end;
+        sb = row.slave_begin; se = row.slave_end; n_copies = row.n_copies;
         const double2 C = ld2(u + row.self);
         double2 sum = make_double2(0.0, 0.0);  // sum_k (x_k - C): translation invariant like the Winslow rows
         for (int k = 0; k < row.n; ++k) sum = sum + (ld2(u + row.nbr[k]) - C);
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
     } else if (r < n_s + n_j + n_l) {
         const SlidingRow row = lrows[r - n_s - n_j];
         self = row.self;
-        sb = row.slave_begin; se = row.slave_end;
+        sb = row.slave_begin; se = row.slave_end; n_copies = row.n_copies;
         const double2 C = ld2(u + row.self), I = ld2(u + row.inner);
         const double ys = (double)row.ysign;
         if (MODE == MODE_RELAX) {
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
         if (STATS == 1) {
             // the reference sums over ALL nodes (smooth.zig:117-133): count the row and its copies
             const double dx = res.x - old.x, dy = res.y - old.y;
-            const double w = 1.0 + (double)(se - sb);
+            const double w = 1.0 + (double)n_copies;
             s0 = w * dx * dx; s1 = w * dy * dy;
             mx = fmax(fabs(dx), fabs(dy));
         } else if (STATS == 2) {
@@ -507,6 +507,12 @@ __global__ void sync_slaves_kernel(const SlaveRow* __restrict__ slaves, int n, d
     if (mode == 2) { v[s.self] = make_double2(0.0, 0.0); return; }
     const double2 r = v[s.root];
     v[s.self] = mode == 1 ? make_double2(r.x + s.sx, r.y + s.sy) : r;
+}
+
+// halo exchange, send side: gathers the owned nodes that peers ghost into one contiguous buffer (per-peer segments)
+__global__ void pack_kernel(const int64_t* __restrict__ idx, int64_t n, const double2* __restrict__ v, double2* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = v[idx[k]];
 }
 
 // begin_smoothing: capture rhs_x of sliding rows from the initial mesh (smooth.zig:853-857), apply the
@@ -660,22 +666,8 @@ enum ReduceOp : int {
     RED_RESTART = 6,       // like RED_INIT from the true residual, but keeps tol / iteration counts (restart after breakdown)
 };
 
-// Sums `n_part` per-CTA partial records (5 doubles each: 4 sums + 1 max) in a fixed order -> deterministic.
-template <int NT>
-__global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ partials, int n_part, int op, SolveCtl* __restrict__ ctl, double rtol, double atol,
-                                                    int max_iters, const double* __restrict__ extra /* optional second partial array (boundary kernel) */,
-                                                    int n_extra, const double* __restrict__ bconst /* RED_INIT: constant part of ||b||^2 */) {
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    double mx = 0.0;
-    for (int k = threadIdx.x; k < n_part + n_extra; k += NT) {
-        const double* p = k < n_part ? partials + (size_t)k * 5 : extra + (size_t)(k - n_part) * 5;
-        s[0] += p[0]; s[1] += p[1]; s[2] += p[2]; s[3] += p[3];
-        mx = fmax(mx, p[4]);
-    }
-    __shared__ double out[5];
-    block_reduce_store<4, NT>(s, mx, out);
-    __syncthreads();
-    if (threadIdx.x != 0) return;
+// Turns the reduced sums (red[0..3]) and max (red[4]) into solver scalars; thread 0 of one CTA.
+__device__ __forceinline__ void finalize_reduction(const double* out, int op, SolveCtl* __restrict__ ctl, double rtol, double atol, int max_iters) {
     const double eps = 1e-30;  // breakdown_eps, BiCGStab.zig:280
     if (op == RED_UPDATE_STATS) {
         ctl->sumsq[0] = out[0]; ctl->sumsq[1] = out[1]; ctl->max_update = out[4];
@@ -686,7 +678,7 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ p
             const double nr = sqrt(out[c]);
             ctl->norm_r[c] = nr;
             if (op == RED_INIT) {
-                const double nb = sqrt(out[2 + c] + bconst[c]);
+                const double nb = sqrt(out[2 + c]);
                 ctl->norm_b[c] = nb;
                 ctl->tol[c] = fmax(atol, rtol * nb);             // GMRES.zig:305-306 / BiCGStab.zig:291
                 ctl->iters[c] = 0;
@@ -722,6 +714,44 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ p
             ctl->beta[c] = (ctl->rho_new[c] / ctl->rho_old[c]) * (ctl->alpha[c] / ctl->omega[c]);
         }
     }
+}
+
+// Sums `n_part` (+ `n_extra`) per-CTA partial records (5 doubles each: 4 sums + 1 max) in a fixed order ->
+// deterministic.  The rank-local result goes to red[0..4]; with one rank the solver scalars are finalised in the same
+// launch, with several ranks red is all-reduced first (sum / max) and finalize_kernel follows.
+template <int NT>
+__global__ void __launch_bounds__(NT) reduce_kernel(const double* __restrict__ partials, int n_part, const double* __restrict__ extra, int n_extra,
+                                                    double* __restrict__ red, const double* __restrict__ bconst /* RED_INIT: this rank's constant part of ||b||^2 */,
+                                                    int finalize, int op, SolveCtl* __restrict__ ctl, double rtol, double atol, int max_iters) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    double mx = 0.0;
+    for (int k = threadIdx.x; k < n_part + n_extra; k += NT) {
+        const double* p = k < n_part ? partials + (size_t)k * 5 : extra + (size_t)(k - n_part) * 5;
+        s[0] += p[0]; s[1] += p[1]; s[2] += p[2]; s[3] += p[3];
+        mx = fmax(mx, p[4]);
+    }
+    __shared__ double out[5];
+    block_reduce_store<4, NT>(s, mx, out);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (op == RED_INIT) { out[2] += bconst[0]; out[3] += bconst[1]; }
+    for (int k = 0; k < 5; ++k) red[k] = out[k];
+    if (finalize) finalize_reduction(out, op, ctl, rtol, atol, max_iters);
+}
+__global__ void finalize_kernel(const double* __restrict__ red, int op, SolveCtl* __restrict__ ctl, double rtol, double atol, int max_iters) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) finalize_reduction(red, op, ctl, rtol, atol, max_iters);
+}
+// In-process emulation of several ranks on one GPU (tests): the "all-reduce" of their red[] records.
+struct RedPtrs { double* p[16]; };
+__global__ void combine_red_kernel(RedPtrs reds, int n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double out[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < n; ++r) {
+        for (int k = 0; k < 4; ++k) out[k] += reds.p[r][k];
+        out[4] = fmax(out[4], reds.p[r][4]);
+    }
+    for (int r = 0; r < n; ++r)
+        for (int k = 0; k < 5; ++k) reds.p[r][k] = out[k];
 }
 
 constexpr int VEC_THREADS = 256;
@@ -781,11 +811,6 @@ __global__ void __launch_bounds__(VEC_THREADS) bicg_r_kernel(int64_t n, const So
 // Constant part of ||b||^2 of the reference's full right-hand side (BiCGStab.zig:289-291): fixed rows carry their
 // coordinate, connected rows their (periodic) rhs, sliding rows (rhs_x, rhs_y), junction rows their periodic rhs.
 // Interior rows are 0 and periodic interface rows are added per solve (they depend on the lagged coordinates).
-struct RhsTerm {
-    int64_t g;          // node whose coordinate is the rhs (from_x / from_y), else unused
-    double cx, cy;      // constant rhs
-    int32_t from_x, from_y;
-};
 __global__ void __launch_bounds__(VEC_THREADS) rhs_const_kernel(const RhsTerm* __restrict__ terms, int n, const double2* __restrict__ x, double* __restrict__ out2) {
     double s0 = 0.0, s1 = 0.0;
     for (int k = threadIdx.x; k < n; k += VEC_THREADS) {

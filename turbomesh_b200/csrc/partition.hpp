@@ -1,0 +1,225 @@
+// partition.hpp -- host-side localisation of the global topology for one rank (one process per GPU).
+//
+// The reference has no distributed runtime; this is the B200-native sharding of its one global
+// system: whole blocks are assigned to ranks, every rank keeps its own blocks plus *ghost* copies of the few remote
+// nodes its rows read -- per cross-rank connection the partner's first interior line (for the 9-point interface row,
+// smooth.zig:994-1105) and the interface line itself (for the `connected` copies, smooth.zig:804-812), plus the
+// diagonal neighbours of junction rows (smooth.zig:1457-1511).  Once per sweep / operator application each rank packs
+// the owned nodes its peers ghost and receives its ghosts straight into the tail of the field (no unpack).
+//
+// A remote node that is itself a `connected` copy is never received: the rank keeps a *synthesised* slot for it and
+// derives it from the copy's root (received or owned) exactly like its own copies, so every copy of a node is updated
+// at the same point of the algorithm as on a single GPU.
+//
+// Every rank builds the same global Topology and derives the lists of ALL ranks from it, so the send list of rank a
+// towards b is by construction the ghost list of b from a (both sorted by global id) -- no handshake is needed.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "topology.hpp"
+
+namespace tmesh {
+
+struct LocalTables {
+    int rank = 0, n_ranks = 1;
+    std::vector<int32_t> own_blocks;             // global block ids owned by this rank, ascending
+    std::vector<int64_t> loff;                   // per global block: offset of its node (0,0) in the local field, -1 if remote
+    int64_t n_own = 0, n_ghost = 0, n_synth = 0, n_local = 0; // local field = [own nodes][ghosts from rank 0][from rank 1]...[synthesised copies]
+    std::vector<int64_t> synth_ids;              // sorted global ids of remote `connected` copies kept as synthesised slots
+    std::vector<std::vector<int64_t>> ghost_ids; // per peer: sorted global ids read here, owned there
+    std::vector<std::vector<int64_t>> send_ids;  // per peer: sorted global ids owned here, read there
+    std::vector<int64_t> ghost_base, send_base;  // per peer (n_ranks+1 entries): offsets in the ghost region / send buffer
+    std::vector<int64_t> send_lidx;              // local indices to pack, concatenated over peers
+    // rows owned by this rank, all node references are local indices
+    std::vector<SmoothedRow> smoothed;
+    std::vector<JunctionRow> junction_rows;
+    std::vector<SlidingRow> sliding;
+    std::vector<SlaveRow> slaves;                // [0, n_slaves_local_root): root row owned here (written by the root's
+    int64_t n_slaves_local_root = 0;             //  thread in sweeps); the rest have ghost roots (synced after exchange)
+    std::vector<SlaveRow> const_slaves;
+    std::vector<FixedOverride> fixed_overrides;
+    std::vector<PairCheck> pairs;                // owned by the rank of the side-1 node
+    std::vector<RhsTerm> rhs_terms;
+    bool owns_white = false;                     // blocks 0 and 1 (the O-grid halves White works on) live here
+};
+
+inline int owner_of_node(const Topology& T, const std::vector<int32_t>& owner, int64_t g) { return owner[T.block_of(g)]; }
+
+struct ReadSets {
+    std::vector<std::vector<int64_t>> recv;  // per owning rank: remote nodes received every exchange (sorted, unique)
+    std::vector<int64_t> synth;              // remote `connected` copies derived locally from their root (sorted, unique)
+};
+
+// remote nodes read by the rows of rank r
+inline ReadSets read_sets(const Topology& T, const std::vector<int32_t>& owner, int r, int n_ranks, const std::map<int64_t, int64_t>& root_of) {
+    ReadSets out;
+    out.recv.assign(size_t(n_ranks), {});
+    auto recv = [&](int64_t g) {
+        const int o = owner_of_node(T, owner, g);
+        if (o != r) out.recv[size_t(o)].push_back(g);
+    };
+    auto need = [&](int64_t g) {
+        if (owner_of_node(T, owner, g) == r) return;
+        const auto it = root_of.find(g);
+        if (it != root_of.end()) { out.synth.push_back(g); recv(it->second); }  // a copy: keep a slot, fetch its root instead
+        else recv(g);
+    };
+    for (const auto& row : T.smoothed)
+        if (owner_of_node(T, owner, row.g0) == r) { need(row.iN); need(row.iNW); need(row.iNE); }
+    for (const auto& row : T.junction_rows)
+        if (owner_of_node(T, owner, row.self) == r)
+            for (int k = 0; k < row.n; ++k) need(row.nbr[k]);
+    for (const auto* list : {&T.slaves, &T.const_slaves})
+        for (const auto& s : *list)
+            if (owner_of_node(T, owner, s.self) == r) need(s.root);
+    for (const auto& p : T.pairs)
+        if (owner_of_node(T, owner, p.g1) == r) need(p.g0);
+    for (auto& v : out.recv) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+    std::sort(out.synth.begin(), out.synth.end());
+    out.synth.erase(std::unique(out.synth.begin(), out.synth.end()), out.synth.end());
+    return out;
+}
+
+inline void validate_owner(const Topology& T, const std::vector<int32_t>& owner, int n_ranks) {
+    if (owner.size() != T.blocks.size()) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block_owner must have one entry per block");
+    for (size_t b = 0; b < owner.size(); ++b)
+        if (owner[b] < 0 || owner[b] >= n_ranks) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %zu: owner %d out of range (%d ranks)", b, owner[b], n_ranks);
+}
+
+inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner, int rank, int n_ranks) {
+    validate_owner(T, owner, n_ranks);
+    if (rank < 0 || rank >= n_ranks) TM_THROW(TM_ERR_INVALID_ARGUMENT, "rank %d out of range (%d ranks)", rank, n_ranks);
+    LocalTables L;
+    L.rank = rank; L.n_ranks = n_ranks;
+    L.loff.assign(T.blocks.size(), -1);
+    for (size_t b = 0; b < T.blocks.size(); ++b) {
+        if (owner[b] != rank) continue;
+        L.own_blocks.push_back(int32_t(b));
+        L.loff[b] = L.n_own;
+        L.n_own += T.blocks[b].ni * T.blocks[b].nj;
+    }
+    std::map<int64_t, int64_t> root_of;  // copy -> root, for copies whose root is a free row
+    for (const auto& s : T.slaves) root_of[s.self] = s.root;
+    {
+        ReadSets mine_sets = read_sets(T, owner, rank, n_ranks, root_of);
+        L.ghost_ids = std::move(mine_sets.recv);
+        L.synth_ids = std::move(mine_sets.synth);
+    }
+    L.send_ids.assign(size_t(n_ranks), {});
+    for (int p = 0; p < n_ranks; ++p) {
+        if (p == rank) continue;
+        L.send_ids[size_t(p)] = read_sets(T, owner, p, n_ranks, root_of).recv[size_t(rank)];
+    }
+    L.ghost_base.assign(size_t(n_ranks) + 1, 0);
+    L.send_base.assign(size_t(n_ranks) + 1, 0);
+    for (int p = 0; p < n_ranks; ++p) {
+        L.ghost_base[size_t(p) + 1] = L.ghost_base[size_t(p)] + int64_t(L.ghost_ids[size_t(p)].size());
+        L.send_base[size_t(p) + 1] = L.send_base[size_t(p)] + int64_t(L.send_ids[size_t(p)].size());
+    }
+    L.n_ghost = L.ghost_base[size_t(n_ranks)];
+    L.n_synth = int64_t(L.synth_ids.size());
+    L.n_local = L.n_own + L.n_ghost + L.n_synth;
+
+    auto lidx = [&](int64_t g) -> int64_t {
+        const size_t b = T.block_of(g);
+        if (owner[b] == rank) return L.loff[b] + (g - T.blocks[b].off);
+        {
+            const auto it = std::lower_bound(L.synth_ids.begin(), L.synth_ids.end(), g);
+            if (it != L.synth_ids.end() && *it == g) return L.n_own + L.n_ghost + int64_t(it - L.synth_ids.begin());
+        }
+        const auto& v = L.ghost_ids[size_t(owner[b])];
+        const auto it = std::lower_bound(v.begin(), v.end(), g);
+        if (it == v.end() || *it != g) TM_THROW(TM_ERR_TOPOLOGY, "internal: node %lld is not in the ghost set of rank %d", (long long)g, rank);
+        return L.n_own + L.ghost_base[size_t(owner[b])] + int64_t(it - v.begin());
+    };
+    auto mine = [&](int64_t g) { return owner_of_node(T, owner, g) == rank; };
+
+    for (int p = 0; p < n_ranks; ++p)
+        for (int64_t g : L.send_ids[size_t(p)]) L.send_lidx.push_back(lidx(g));
+
+    // slaves owned here: those whose root row is also here are written by the root's thread
+    std::map<int64_t, std::vector<SlaveRow>> by_root;  // keyed by the root's global id
+    std::vector<SlaveRow> remote_root;
+    for (const auto& s : T.slaves) {
+        const bool synth = std::binary_search(L.synth_ids.begin(), L.synth_ids.end(), s.self);
+        if (!mine(s.self) && !synth) continue;
+        SlaveRow l{lidx(s.self), lidx(s.root), s.sx, s.sy};
+        if (mine(s.root)) by_root[s.root].push_back(l);
+        else remote_root.push_back(l);
+    }
+    auto attach = [&](int64_t root_g, int32_t& bgn, int32_t& end) {
+        bgn = end = int32_t(L.slaves.size());
+        const auto it = by_root.find(root_g);
+        if (it == by_root.end()) return;
+        for (const auto& s : it->second) L.slaves.push_back(s);
+        end = int32_t(L.slaves.size());
+        by_root.erase(it);
+    };
+    for (const auto& row : T.smoothed) {
+        if (!mine(row.g0)) continue;
+        SmoothedRow l = row;
+        const int64_t g0 = row.g0;
+        l.g0 = lidx(g0); l.iN = lidx(row.iN); l.iNW = lidx(row.iNW); l.iNE = lidx(row.iNE);
+        attach(g0, l.slave_begin, l.slave_end);
+        L.smoothed.push_back(l);
+    }
+    for (const auto& row : T.junction_rows) {
+        if (!mine(row.self)) continue;
+        JunctionRow l = row;
+        l.self = lidx(row.self);
+        for (int k = 0; k < row.n; ++k) l.nbr[k] = lidx(row.nbr[k]);
+        attach(row.self, l.slave_begin, l.slave_end);
+        L.junction_rows.push_back(l);
+    }
+    for (const auto& row : T.sliding) {
+        if (!mine(row.self)) continue;
+        SlidingRow l = row;
+        l.self = lidx(row.self); l.inner = lidx(row.inner);
+        attach(row.self, l.slave_begin, l.slave_end);
+        L.sliding.push_back(l);
+    }
+    if (!by_root.empty()) TM_THROW(TM_ERR_TOPOLOGY, "internal: %zu slave groups without a root row", by_root.size());
+    L.n_slaves_local_root = int64_t(L.slaves.size());
+    for (const auto& s : remote_root) L.slaves.push_back(s);
+
+    for (const auto& s : T.const_slaves)
+        if (mine(s.self)) L.const_slaves.push_back({lidx(s.self), lidx(s.root), s.sx, s.sy});
+    for (const auto& f : T.fixed_overrides)
+        if (mine(f.self)) L.fixed_overrides.push_back({lidx(f.self), f.x, f.y});
+    for (const auto& p : T.pairs)
+        if (mine(p.g1)) L.pairs.push_back({lidx(p.g0), lidx(p.g1), p.px, p.py, p.conn, p.point});
+
+    // rows of the reference system with a non-zero rhs (smooth.zig:780-921), restricted to this rank
+    std::vector<uint8_t> over(size_t(T.n_boundary), 0);
+    for (const auto& f : T.fixed_overrides) {
+        over[size_t(T.bid_of_global(f.self))] = 1;
+        if (mine(f.self)) L.rhs_terms.push_back(RhsTerm{0, f.x, f.y, 0, 0});
+    }
+    for (int32_t b : L.own_blocks) {
+        const auto& B = T.blocks[size_t(b)];
+        auto visit = [&](int64_t i, int64_t j) {
+            const int64_t local = i * B.nj + j;
+            const size_t id = size_t(T.bid(size_t(b), local));
+            if (T.kind[id] == K_FIXED && !over[id]) L.rhs_terms.push_back(RhsTerm{L.loff[size_t(b)] + local, 0.0, 0.0, 1, 1});
+        };
+        for (int64_t j = 0; j < B.nj; ++j) { visit(0, j); visit(B.ni - 1, j); }
+        for (int64_t i = 1; i + 1 < B.ni; ++i) { visit(i, 0); visit(i, B.nj - 1); }
+    }
+    for (const auto& s : T.sliding)
+        if (mine(s.self)) L.rhs_terms.push_back(RhsTerm{lidx(s.self), s.rhs_x, s.rhs_y, s.rhs_x_from_initial, 0});
+    for (const auto& j : T.junction_rows)
+        if (mine(j.self)) L.rhs_terms.push_back(RhsTerm{0, j.rhs_x, j.rhs_y, 0, 0});
+    for (const auto& c : T.connected_rhs)
+        if (mine(c.self)) L.rhs_terms.push_back(RhsTerm{0, c.x, c.y, 0, 0});  // smooth.zig:904-915
+
+    L.owns_white = T.blocks.size() >= 2 && owner[0] == rank && owner[1] == rank;
+    return L;
+}
+
+}  // namespace tmesh

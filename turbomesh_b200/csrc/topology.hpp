@@ -43,12 +43,13 @@ struct BlockInfo {
 
 // ---- device-visible PODs (copied verbatim to the GPU) -------------------------------------------
 struct SmoothedRow {       // interior interface node, side-0 copy g0 with partner g1
-    int64_t g0, g1;
-    int32_t d0, n0, d1, n1; // along (in_connection_direction_shift) / inward (first_internal_point_shift)
+    int64_t g0;             // the row's own node; its block-0 neighbours are g0 -/+ d0 (along) and + n0 (inward)
+    int64_t iN, iNW, iNE;   // block-1 nodes g1+n1, g1-d1+n1, g1+d1+n1 (explicit: they may be ghosts of another rank)
+    int32_t d0, n0;         // along (in_connection_direction_shift) / inward (first_internal_point_shift) of side 0
     double px, py;          // periodicity mapping side 0 onto side 1 (0 when not periodic)
     int32_t periodic;       // periodic rows use (P,Q), the others (Q,P): smooth.zig:1040-1041 vs 1082-1083
-    int32_t slave_begin, slave_end;
-    int32_t _pad;
+    int32_t slave_begin, slave_end;  // this rank's copies written by the row's thread
+    int32_t n_copies;       // all `connected` copies of the node in the whole mesh (weight of the row in sum dx^2)
 };
 struct JunctionRow {        // sum_k x_k - n x_self = rhs
     int64_t self;
@@ -56,7 +57,7 @@ struct JunctionRow {        // sum_k x_k - n x_self = rhs
     double rhs_x, rhs_y;
     int32_t n;
     int32_t slave_begin, slave_end;
-    int32_t _pad;
+    int32_t n_copies;
 };
 struct SlidingRow {         // x-solve: x_self = rhs_x ; y-solve: ysign*(y_self - y_inner) = rhs_y
     int64_t self, inner;
@@ -64,6 +65,7 @@ struct SlidingRow {         // x-solve: x_self = rhs_x ; y-solve: ysign*(y_self 
     int32_t rhs_x_from_initial; // 1: rhs_x is captured from the initial mesh (smooth.zig:853-857)
     int32_t ysign;
     int32_t slave_begin, slave_end;
+    int32_t n_copies, _pad;
 };
 struct SlaveRow {           // x_self = x_root + shift
     int64_t self, root;
@@ -72,6 +74,11 @@ struct SlaveRow {           // x_self = x_root + shift
 struct FixedOverride {      // a fixed node whose rhs was overwritten by the periodic loop (smooth.zig:904-915)
     int64_t self;
     double x, y;
+};
+struct RhsTerm {            // a row of the reference system with a non-zero right-hand side (for ||b||, BiCGStab.zig:289-291)
+    int64_t g;              // node whose coordinate is the rhs (from_x / from_y), else unused
+    double cx, cy;          // constant rhs
+    int32_t from_x, from_y;
 };
 struct PairCheck {          // connectionDataCheck, smooth.zig:220-275
     int64_t g0, g1;
@@ -94,7 +101,7 @@ struct Topology {
     std::vector<SmoothedRow> smoothed;
     std::vector<JunctionRow> junction_rows;
     std::vector<SlidingRow> sliding;
-    std::vector<SlaveRow> slaves;         // sorted by owning free row, then by id
+    std::vector<SlaveRow> slaves;         // every connected node whose root is a free row (any order)
     std::vector<SlaveRow> const_slaves;   // slaves of fixed nodes: constants, applied once
     std::vector<FixedOverride> fixed_overrides;
     std::vector<FixedOverride> connected_rhs; // non-zero rhs of `connected` rows (periodic copies), for ||b||
@@ -294,12 +301,11 @@ struct Topology {
         std::vector<int64_t> master(nbn, -1);         // per flat boundary id of a connected node: global id of its master
         std::vector<double> rhs(2 * nbn, 0.0);        // rhs of constant rows (connected / sliding-y / fixed overrides)
         std::vector<uint8_t> rhs_over(nbn, 0);        // rhs overwritten by the periodic loop
-        std::vector<int32_t> smoothed_of(nbn, -1), sliding_of(nbn, -1), junction_of(nbn, -1);
+        std::vector<int32_t> smoothed_of(nbn, -1), sliding_of(nbn, -1);
 
         // junction copies are tied to the primary (smooth.zig:738-747)
         for (size_t l = 0; l < junctions.size(); ++l) {
             const auto& jn = junctions[l];
-            junction_of[size_t(bid_of_global(jn.copies[0].g))] = int32_t(l);
             for (size_t k = 1; k < jn.copies.size(); ++k) {
                 const int64_t id = bid_of_global(jn.copies[k].g);
                 if (kind[size_t(id)] != K_CONNECTED) TM_THROW(TM_ERR_TOPOLOGY, "junction copy %lld was re-classified (inconsistent topology)", (long long)jn.copies[k].g);
@@ -337,8 +343,9 @@ struct Topology {
                         TM_THROW(TM_ERR_TOPOLOGY, "connection %zu overlaps another connection", c);
                     master[size_t(i1)] = g0;
                     SmoothedRow row{};
-                    row.g0 = g0; row.g1 = g1;
-                    row.d0 = int32_t(a0); row.n0 = int32_t(n0); row.d1 = int32_t(a1); row.n1 = int32_t(n1);
+                    row.g0 = g0;
+                    row.iN = g1 + n1; row.iNW = g1 - a1 + n1; row.iNE = g1 + a1 + n1;
+                    row.d0 = int32_t(a0); row.n0 = int32_t(n0);
                     row.px = px; row.py = py; row.periodic = cn.has_periodicity ? 1 : 0;
                     if (smoothed_of[size_t(i0)] >= 0) smoothed[size_t(smoothed_of[size_t(i0)])] = row; // later connection overwrites
                     else { smoothed_of[size_t(i0)] = int32_t(smoothed.size()); smoothed.push_back(row); }
@@ -401,8 +408,6 @@ struct Topology {
             }
         }
         // eliminate connected rows: x_self = x_master - rhs_self, chains followed to the root
-        struct Tmp { SlaveRow row; int owner_type; int32_t owner; };
-        std::vector<Tmp> tmp;
         for (size_t b = 0; b < blocks.size(); ++b) {
             const int64_t nbb = 2 * (blocks[b].ni + blocks[b].nj - 2);
             for (int64_t q = 0; q < nbb; ++q) {
@@ -419,38 +424,25 @@ struct Topology {
                     root = master[cur];
                     const int64_t rid = bid_of_global(root);
                     if (rid < 0) TM_THROW(TM_ERR_TOPOLOGY, "master of node %lld is not a boundary node", (long long)self);
-                    if (kind[size_t(rid)] != K_CONNECTED) { cur = size_t(rid); break; }
                     cur = size_t(rid);
+                    if (kind[cur] != K_CONNECTED) break;
                 }
-                Tmp t{{self, root, sx, sy}, 0, -1};
-                switch (kind[cur]) {
-                    case K_FIXED: t.owner_type = -1; break;
-                    case K_SMOOTHED: t.owner_type = 0; t.owner = smoothed_of[cur]; break;
-                    case K_LAPLACIAN: t.owner_type = 1; t.owner = junction_of[cur]; break;
-                    default: t.owner_type = 2; t.owner = sliding_of[cur]; break;
-                }
-                if (t.owner_type >= 0 && t.owner < 0) TM_THROW(TM_ERR_TOPOLOGY, "internal: root of node %lld has no row", (long long)self);
-                tmp.push_back(t);
+                if (kind[cur] == K_FIXED) const_slaves.push_back({self, root, sx, sy});
+                else slaves.push_back({self, root, sx, sy});
             }
         }
-        std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp& x, const Tmp& y) {
-            if (x.owner_type != y.owner_type) return x.owner_type < y.owner_type;
-            return x.owner < y.owner;
-        });
-        for (auto& r : smoothed) r.slave_begin = r.slave_end = 0;
-        for (auto& r : junction_rows) r.slave_begin = r.slave_end = 0;
-        for (auto& r : sliding) r.slave_begin = r.slave_end = 0;
-        for (const auto& t : tmp) {
-            if (t.owner_type < 0) { const_slaves.push_back(t.row); continue; }
-            const int32_t pos = int32_t(slaves.size());
-            slaves.push_back(t.row);
-            int32_t *bgn, *end;
-            if (t.owner_type == 0) { bgn = &smoothed[size_t(t.owner)].slave_begin; end = &smoothed[size_t(t.owner)].slave_end; }
-            else if (t.owner_type == 1) { bgn = &junction_rows[size_t(t.owner)].slave_begin; end = &junction_rows[size_t(t.owner)].slave_end; }
-            else { bgn = &sliding[size_t(t.owner)].slave_begin; end = &sliding[size_t(t.owner)].slave_end; }
-            if (*end == *bgn) *bgn = pos;
-            *end = pos + 1;
-        }
+        // per root: how many copies hang off it anywhere in the mesh
+        std::vector<std::pair<int64_t, int32_t>> cnt;
+        for (const auto& sl : slaves) cnt.push_back({sl.root, 1});
+        std::sort(cnt.begin(), cnt.end());
+        auto copies_of = [&](int64_t g) {
+            const auto lo = std::lower_bound(cnt.begin(), cnt.end(), std::make_pair(g, int32_t(0)));
+            const auto hi = std::upper_bound(cnt.begin(), cnt.end(), std::make_pair(g, int32_t(2)));
+            return int32_t(hi - lo);
+        };
+        for (auto& r : smoothed) { r.slave_begin = r.slave_end = 0; r.n_copies = copies_of(r.g0); }
+        for (auto& r : junction_rows) { r.slave_begin = r.slave_end = 0; r.n_copies = copies_of(r.self); }
+        for (auto& r : sliding) { r.slave_begin = r.slave_end = 0; r.n_copies = copies_of(r.self); r._pad = 0; }
     }
 
     int64_t local_of_bid(size_t block, int64_t q) const { // inverse of bid() within a block

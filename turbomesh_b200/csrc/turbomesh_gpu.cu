@@ -2,19 +2,25 @@
 //
 // Host orchestration of the sm_100a kernels in kernels.cuh: device mesh handle, topology upload, the outer
 // (Picard) loop of smoothing.smooth.mesh (src/core/smoothing/smooth.zig:74-166), the matrix-free BiCGStab
-// (src/core/smoothing/BiCGStab.zig:279-370) and the relaxation sweeps.  No CPU compute path exists here:
-// without a CUDA device every entry point fails with TM_ERR_NO_DEVICE.
+// (src/core/smoothing/BiCGStab.zig:279-370), the relaxation sweeps and the multi-GPU halo exchange (one process per
+// GPU, NCCL send/recv over NVLink once per sweep / operator application).  No CPU compute path exists here: without a
+// CUDA device every entry point fails with TM_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <nccl.h>  // types only: NCCL is resolved at run time with dlopen, single-GPU use needs no libnccl
+
 #include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/turbomesh_gpu.h"
 #include "kernels.cuh"
+#include "partition.hpp"
 
 using namespace tmesh;
 
@@ -82,23 +88,68 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
     ~DevBuf() { release(); }
 };
+
+// ---- NCCL, resolved lazily so that single-GPU users need no libnccl ------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    void load() {
+        if (lib) return;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) TM_THROW(TM_ERR_UNSUPPORTED, "multi-GPU needs NCCL but libnccl.so.2 could not be loaded: %s", dlerror());
+#define TM_SYM(field, sym)                                                                         \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, sym));                                    \
+    if (!field) TM_THROW(TM_ERR_UNSUPPORTED, "libnccl lacks symbol %s", sym)
+        TM_SYM(GetUniqueId, "ncclGetUniqueId");
+        TM_SYM(CommInitRank, "ncclCommInitRank");
+        TM_SYM(CommDestroy, "ncclCommDestroy");
+        TM_SYM(Send, "ncclSend");
+        TM_SYM(Recv, "ncclRecv");
+        TM_SYM(AllReduce, "ncclAllReduce");
+        TM_SYM(GroupStart, "ncclGroupStart");
+        TM_SYM(GroupEnd, "ncclGroupEnd");
+        TM_SYM(GetErrorString, "ncclGetErrorString");
+#undef TM_SYM
+    }
+};
+NcclApi g_nccl;
+#define NCCL_TRY(expr)                                                                                              \
+    do {                                                                                                            \
+        ncclResult_t _r = (expr);                                                                                   \
+        if (_r != ncclSuccess) TM_THROW(TM_ERR_CUDA, "%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+    } while (0)
 
 struct EdgeCache {  // device copies of the four edges + clusterings of one block (TFI inputs)
     DevBuf<double> buf;
     bool valid = false;
 };
 
-}  // namespace
-
-struct tm_mesh {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    Topology topo;
-    int64_t N = 0;
-
+// Everything one rank keeps on its GPU.  A distributed mesh holds exactly one; the in-process emulation of several
+// ranks on one GPU (tests of the multi-rank logic) holds all of them.
+struct RankMesh {
+    LocalTables L;
+    int64_t N = 0;  // local field length: own + ghosts + synthesised copies
     DevBuf<double2> X[2];
     int cur = 0;
     DevBuf<double2> pq, wall_pq;
@@ -111,25 +162,43 @@ struct tm_mesh {
     DevBuf<FixedOverride> d_fo;
     DevBuf<PairCheck> d_pairs;
     DevBuf<RhsTerm> d_rhs_terms;
-    DevBuf<double> part_int, part_bnd, part_vec, bconst;
+    DevBuf<int64_t> d_send_idx;
+    DevBuf<double2> sendbuf;
+    DevBuf<double> part_int, part_bnd, part_vec, bconst, red;
     DevBuf<unsigned long long> d_worst;
     DevBuf<SolveCtl> d_ctl;
-    SolveCtl* h_ctl = nullptr;  // pinned
     DevBuf<double2> kr, krhat, kp, kv, ks, kt;
     bool krylov_ready = false;
-    std::vector<EdgeCache> edges;
+    std::vector<EdgeCache> edges;        // indexed by position in L.own_blocks
     std::vector<uint8_t> have_coords;
-
     int n_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
-    int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
-    bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
+    bool has_pq = false;
+    WhiteParams wp{};
+};
+
+}  // namespace
+
+struct tm_mesh {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Topology topo;
+    std::vector<int32_t> owner;
+    int n_ranks = 1;
+    bool emulated = false;                       // all ranks live in this process on one GPU (tests)
+    std::vector<std::unique_ptr<RankMesh>> ranks;  // the ranks held by this process
+    ncclComm_t comm = nullptr;
+    SolveCtl* h_ctl = nullptr;                   // pinned
     bool begun = false;
     int cf = TM_CF_LAPLACE;
-    WhiteParams wp{};
     uint64_t outer_done = 0;  // outer iterations since begin_smoothing (the `n` of system.fill(n), smooth.zig:1107-1110)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
+    bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
 
     ~tm_mesh() {
+        ranks.clear();
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -139,113 +208,187 @@ struct tm_mesh {
 
 namespace {
 
-void build_tiles(tm_mesh* m) {
+int bnd_ctas(int rows) { return (rows + BND_THREADS - 1) / BND_THREADS; }
+
+void build_rank(tm_mesh* m, RankMesh& r, int rank) {
+    cudaStream_t s = m->stream;
+    r.L = localize(m->topo, m->owner, rank, m->n_ranks);
+    r.N = r.L.n_local;
+    r.X[0].alloc(size_t(std::max<int64_t>(r.N, 1)));
+    r.X[1].alloc(size_t(std::max<int64_t>(r.N, 1)));
+    r.X[0].zero(s);
+    r.X[1].zero(s);
     std::vector<Tile> tiles;
-    std::vector<DevBlock> blocks;
-    for (size_t b = 0; b < m->topo.blocks.size(); ++b) {
+    std::vector<DevBlock> blocks(m->topo.blocks.size(), DevBlock{0, 0, 0});
+    for (size_t k = 0; k < r.L.own_blocks.size(); ++k) {
+        const size_t b = size_t(r.L.own_blocks[k]);
         const auto& B = m->topo.blocks[b];
-        blocks.push_back(DevBlock{B.off, int32_t(B.ni), int32_t(B.nj)});
-        // rows per CTA: about TILE_I, evened out over the block so no CTA gets a short remainder
+        blocks[b] = DevBlock{r.L.loff[b], int32_t(B.ni), int32_t(B.nj)};
+        // rows per CTA: about tile_rows, evened out over the block so that no CTA gets a short remainder
         const int64_t interior_i = B.ni - 2;
         const int64_t n_i = std::max<int64_t>(1, (interior_i + m->tile_rows - 1) / m->tile_rows);
         const int64_t rows = (interior_i + n_i - 1) / n_i;
         for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += rows)
             for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += TILE_J) tiles.push_back(Tile{int32_t(b), int32_t(i0), int32_t(j0), int32_t(rows)});
     }
-    m->n_tiles = int(tiles.size());
-    m->d_tiles.upload(tiles, m->stream);
-    m->d_blocks.upload(blocks, m->stream);
-}
-
-void build_rhs_terms(tm_mesh* m, std::vector<RhsTerm>& terms) {
-    // the rows of the reference system whose rhs is not zero by construction (smooth.zig:780-921)
-    const Topology& T = m->topo;
-    std::vector<uint8_t> over(size_t(T.n_boundary), 0);
-    for (const auto& f : T.fixed_overrides) {
-        terms.push_back(RhsTerm{f.self, f.x, f.y, 0, 0});
-        over[size_t(T.bid_of_global(f.self))] = 1;
-    }
-    for (size_t b = 0; b < T.blocks.size(); ++b) {
-        const auto& B = T.blocks[b];
-        auto visit = [&](int64_t i, int64_t j) {
-            const int64_t local = i * B.nj + j;
-            const size_t id = size_t(T.bid(b, local));
-            if (T.kind[id] == K_FIXED && !over[id]) terms.push_back(RhsTerm{B.off + local, 0.0, 0.0, 1, 1});
-        };
-        for (int64_t j = 0; j < B.nj; ++j) { visit(0, j); visit(B.ni - 1, j); }
-        for (int64_t i = 1; i + 1 < B.ni; ++i) { visit(i, 0); visit(i, B.nj - 1); }
-    }
-    for (const auto& s : T.sliding) terms.push_back(RhsTerm{s.self, s.rhs_x, s.rhs_y, s.rhs_x_from_initial, 0});
-    for (const auto& j : T.junction_rows) terms.push_back(RhsTerm{j.self, j.rhs_x, j.rhs_y, 0, 0});
+    r.n_tiles = int(tiles.size());
+    r.d_tiles.upload(tiles, s);
+    r.d_blocks.upload(blocks, s);
+    r.d_srows.upload(r.L.smoothed, s);
+    r.d_jrows.upload(r.L.junction_rows, s);
+    r.d_lrows.upload(r.L.sliding, s);
+    r.d_slaves.upload(r.L.slaves, s);
+    r.d_cslaves.upload(r.L.const_slaves, s);
+    r.d_fo.upload(r.L.fixed_overrides, s);
+    r.d_pairs.upload(r.L.pairs, s);
+    r.d_rhs_terms.upload(r.L.rhs_terms, s);
+    r.d_send_idx.upload(r.L.send_lidx, s);
+    r.sendbuf.alloc(r.L.send_lidx.size());
+    r.n_bnd_rows = int(r.L.smoothed.size() + r.L.junction_rows.size() + r.L.sliding.size());
+    r.n_bnd_ctas = bnd_ctas(r.n_bnd_rows);
+    int sms = 148;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+    const int64_t want = (r.N + VEC_THREADS - 1) / VEC_THREADS;
+    r.vec_grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sms) * 8)));
+    r.part_int.alloc(size_t(std::max(r.n_tiles, 1)) * 5);
+    r.part_bnd.alloc(size_t(std::max(r.n_bnd_ctas, 1)) * 5);
+    r.part_vec.alloc(size_t(r.vec_grid) * 5);
+    r.part_int.zero(s); r.part_bnd.zero(s); r.part_vec.zero(s);
+    r.bconst.alloc(2); r.bconst.zero(s);
+    r.red.alloc(5); r.red.zero(s);
+    r.d_worst.alloc(1);
+    r.d_ctl.alloc(1); r.d_ctl.zero(s);
+    r.edges.resize(r.L.own_blocks.size());
+    r.have_coords.assign(r.L.own_blocks.size(), 0);
 }
 
 void ensure_krylov(tm_mesh* m) {
-    if (m->krylov_ready) return;
-    for (DevBuf<double2>* v : {&m->kr, &m->krhat, &m->kp, &m->kv, &m->ks, &m->kt}) {
-        v->alloc(size_t(m->N));
-        v->zero(m->stream);
+    for (auto& rp : m->ranks) {
+        RankMesh& r = *rp;
+        if (r.krylov_ready) continue;
+        for (DevBuf<double2>* v : {&r.kr, &r.krhat, &r.kp, &r.kv, &r.ks, &r.kt}) {
+            v->alloc(size_t(std::max<int64_t>(r.N, 1)));
+            v->zero(m->stream);
+        }
+        r.krylov_ready = true;
     }
-    m->krylov_ready = true;
 }
 
-int bnd_ctas(int rows) { return (rows + BND_THREADS - 1) / BND_THREADS; }
+// ---- halo exchange: every rank's ghost slots of `field` are refreshed from their owners ------------------------
+template <class Get>
+void exchange(tm_mesh* m, Get get) {
+    if (m->n_ranks == 1) return;
+    cudaStream_t s = m->stream;
+    for (auto& rp : m->ranks) {
+        RankMesh& r = *rp;
+        const int64_t n = int64_t(r.L.send_lidx.size());
+        if (n > 0) LAUNCH(pack_kernel, unsigned((n + 255) / 256), 256, s, (const int64_t*)r.d_send_idx.p, n, (const double2*)get(r), r.sendbuf.p);
+    }
+    if (m->emulated) {
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            for (int p = 0; p < m->n_ranks; ++p) {
+                const int64_t cnt = r.L.send_base[size_t(p) + 1] - r.L.send_base[size_t(p)];
+                if (cnt == 0) continue;
+                RankMesh& d = *m->ranks[size_t(p)];
+                CUDA_TRY(cudaMemcpyAsync(get(d) + d.L.n_own + d.L.ghost_base[size_t(r.L.rank)], r.sendbuf.p + r.L.send_base[size_t(p)],
+                                         size_t(cnt) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+            }
+        }
+    } else {
+        RankMesh& r = *m->ranks[0];
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int p = 0; p < m->n_ranks; ++p) {
+            const int64_t ns = r.L.send_base[size_t(p) + 1] - r.L.send_base[size_t(p)];
+            const int64_t ng = r.L.ghost_base[size_t(p) + 1] - r.L.ghost_base[size_t(p)];
+            if (ns > 0) NCCL_TRY(g_nccl.Send(r.sendbuf.p + r.L.send_base[size_t(p)], size_t(ns) * 2, ncclDouble, p, m->comm, s));
+            if (ng > 0) NCCL_TRY(g_nccl.Recv(get(r) + r.L.n_own + r.L.ghost_base[size_t(p)], size_t(ng) * 2, ncclDouble, p, m->comm, s));
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+    }
+}
+
+// copies of nodes: mode 0 homogeneous / 1 affine / 2 zero; `only_remote_root` restricts to copies whose root is a ghost
+void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root = false) {
+    const int64_t first = only_remote_root ? r.L.n_slaves_local_root : 0;
+    const int n = int(int64_t(r.L.slaves.size()) - first);
+    if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, m->stream, (const SlaveRow*)(r.d_slaves.p + first), n, v, mode);
+}
 
 // ---- kernel dispatch over the (LAGGED, HAS_PQ) template space -------------------------------------
 template <int MODE, int STATS>
-void launch_rows(tm_mesh* m, bool lagged, const double2* u, const double2* xc, double2* out, double omega, const double2* dot_a) {
-    const bool has_pq = m->cf == TM_CF_WHITE;
-    const double2* pq = m->pq.p;
+void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const double2* xc, double2* out, double omega, const double2* dot_a) {
+    const bool has_pq = r.has_pq;
+    const double2* pq = r.pq.p;
     cudaStream_t s = m->stream;
-#define TM_ROWS(LAG, PQ)                                                                                                                              \
-    do {                                                                                                                                              \
-        if (m->n_tiles > 0)                                                                                                                           \
-            LAUNCH((winslow_interior_kernel<MODE, LAG, PQ, STATS>), m->n_tiles, TILE_J, s, m->d_tiles.p, m->d_blocks.p, u, xc, pq, out, omega, dot_a, \
-                   m->part_int.p);                                                                                                                    \
-        if (m->n_bnd_rows > 0)                                                                                                                        \
-            LAUNCH((winslow_boundary_kernel<MODE, LAG, PQ, STATS>), m->n_bnd_ctas, BND_THREADS, s, m->d_srows.p, int(m->topo.smoothed.size()),        \
-                   m->d_jrows.p, int(m->topo.junction_rows.size()), m->d_lrows.p, int(m->topo.sliding.size()), m->d_slaves.p, u, xc, pq, out, omega,  \
-                   dot_a, m->part_bnd.p);                                                                                                             \
+#define TM_BND(LAG, PQ)                                                                                                                           \
+    if (r.n_bnd_rows > 0)                                                                                                                         \
+        LAUNCH((winslow_boundary_kernel<MODE, LAG, PQ, STATS>), r.n_bnd_ctas, BND_THREADS, s, (const SmoothedRow*)r.d_srows.p,                   \
+               int(r.L.smoothed.size()), (const JunctionRow*)r.d_jrows.p, int(r.L.junction_rows.size()), (const SlidingRow*)r.d_lrows.p,         \
+               int(r.L.sliding.size()), (const SlaveRow*)r.d_slaves.p, u, xc, pq, out, omega, dot_a, r.part_bnd.p)
+#define TM_ROWS(LAG, PQ)                                                                                                                          \
+    do {                                                                                                                                          \
+        if (r.n_tiles > 0)                                                                                                                        \
+            LAUNCH((winslow_interior_kernel<MODE, LAG, PQ, STATS>), r.n_tiles, TILE_J, s, (const Tile*)r.d_tiles.p, (const DevBlock*)r.d_blocks.p, \
+                   u, xc, pq, out, omega, dot_a, r.part_int.p);                                                                                   \
+        TM_BND(LAG, PQ);                                                                                                                          \
     } while (0)
 #define TM_ROWS_BULK(PQ)                                                                                                                          \
     do {                                                                                                                                          \
-        if (m->n_tiles > 0)                                                                                                                       \
-            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), m->n_tiles, TILE_J, s, m->d_tiles.p, m->d_blocks.p, u, pq, out, omega, dot_a, \
-                   m->part_int.p);                                                                                                                \
-        if (m->n_bnd_rows > 0)                                                                                                                    \
-            LAUNCH((winslow_boundary_kernel<MODE, false, PQ, STATS>), m->n_bnd_ctas, BND_THREADS, s, m->d_srows.p, int(m->topo.smoothed.size()),  \
-                   m->d_jrows.p, int(m->topo.junction_rows.size()), m->d_lrows.p, int(m->topo.sliding.size()), m->d_slaves.p, u, xc, pq, out,     \
-                   omega, dot_a, m->part_bnd.p);                                                                                                  \
+        if (r.n_tiles > 0)                                                                                                                        \
+            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), r.n_tiles, TILE_J, s, (const Tile*)r.d_tiles.p, (const DevBlock*)r.d_blocks.p, \
+                   u, pq, out, omega, dot_a, r.part_int.p);                                                                                       \
+        TM_BND(false, PQ);                                                                                                                        \
     } while (0)
     if (lagged) { if (has_pq) TM_ROWS(true, true); else TM_ROWS(true, false); }
     else if (m->use_bulk) { if (has_pq) TM_ROWS_BULK(true); else TM_ROWS_BULK(false); }
-    else        { if (has_pq) TM_ROWS(false, true); else TM_ROWS(false, false); }
+    else { if (has_pq) TM_ROWS(false, true); else TM_ROWS(false, false); }
 #undef TM_ROWS
 #undef TM_ROWS_BULK
+#undef TM_BND
 }
 
+// rank-local reduction of the per-CTA partials, all-reduce over ranks, solver scalars
 void launch_reduce(tm_mesh* m, int op, const tm_smooth_options* o, bool from_rows) {
     const int max_it = o->max_inner_iterations > 0x7fffffffull ? 0x7fffffff : int(o->max_inner_iterations);
-    if (from_rows)
-        LAUNCH((reduce_kernel<256>), 1, 256, m->stream, m->part_int.p, m->n_tiles, op, m->d_ctl.p, o->rtol, o->atol, max_it, m->part_bnd.p, m->n_bnd_ctas, m->bconst.p);
-    else
-        LAUNCH((reduce_kernel<256>), 1, 256, m->stream, m->part_vec.p, m->vec_grid, op, m->d_ctl.p, o->rtol, o->atol, max_it, (const double*)nullptr, 0, m->bconst.p);
+    const int single = m->n_ranks == 1 ? 1 : 0;
+    cudaStream_t s = m->stream;
+    for (auto& rp : m->ranks) {
+        RankMesh& r = *rp;
+        if (from_rows)
+            LAUNCH((reduce_kernel<256>), 1, 256, s, (const double*)r.part_int.p, r.n_tiles, (const double*)r.part_bnd.p, r.n_bnd_ctas, r.red.p,
+                   (const double*)r.bconst.p, single, op, r.d_ctl.p, o->rtol, o->atol, max_it);
+        else
+            LAUNCH((reduce_kernel<256>), 1, 256, s, (const double*)r.part_vec.p, r.vec_grid, (const double*)nullptr, 0, r.red.p, (const double*)r.bconst.p,
+                   single, op, r.d_ctl.p, o->rtol, o->atol, max_it);
+    }
+    if (single) return;
+    if (m->emulated) {
+        RedPtrs ptrs{};
+        for (size_t k = 0; k < m->ranks.size(); ++k) ptrs.p[k] = m->ranks[k]->red.p;
+        LAUNCH(combine_red_kernel, 1, 32, s, ptrs, int(m->ranks.size()));
+    } else {
+        RankMesh& r = *m->ranks[0];
+        NCCL_TRY(g_nccl.AllReduce(r.red.p, r.red.p, 4, ncclDouble, ncclSum, m->comm, s));
+        NCCL_TRY(g_nccl.AllReduce(r.red.p + 4, r.red.p + 4, 1, ncclDouble, ncclMax, m->comm, s));
+    }
+    for (auto& rp : m->ranks) LAUNCH(finalize_kernel, 1, 32, s, (const double*)rp->red.p, op, rp->d_ctl.p, o->rtol, o->atol, max_it);
 }
 
-void sync_slaves(tm_mesh* m, double2* v, int mode) {
-    const int n = int(m->topo.slaves.size());
-    if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, m->stream, m->d_slaves.p, n, v, mode);
-}
-
-void fetch_ctl(tm_mesh* m) {
-    CUDA_TRY(cudaMemcpyAsync(m->h_ctl, m->d_ctl.p, sizeof(SolveCtl), cudaMemcpyDeviceToHost, m->stream));
+void fetch_ctl(tm_mesh* m) {  // the solver scalars are identical on all ranks after the all-reduce
+    CUDA_TRY(cudaMemcpyAsync(m->h_ctl, m->ranks[0]->d_ctl.p, sizeof(SolveCtl), cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
 }
 
 void white_step(tm_mesh* m, bool update) {
-    const int nw = m->wp.ni0 + m->wp.ni1;
-    LAUNCH(white_wall_kernel, (nw + 127) / 128, 128, m->stream, m->wp, m->X[m->cur].p, m->wall_pq.p, update ? 1 : 0);
-    const int64_t nn = int64_t(m->wp.ni0) * m->wp.nj0 + int64_t(m->wp.ni1) * m->wp.nj1;
-    LAUNCH(white_blend_kernel, unsigned((nn + 255) / 256), 256, m->stream, m->wp, m->wall_pq.p, m->pq.p);
+    for (auto& rp : m->ranks) {
+        RankMesh& r = *rp;
+        if (!r.has_pq) continue;
+        const int nw = r.wp.ni0 + r.wp.ni1;
+        LAUNCH(white_wall_kernel, (nw + 127) / 128, 128, m->stream, r.wp, (const double2*)r.X[r.cur].p, r.wall_pq.p, update ? 1 : 0);
+        const int64_t nn = int64_t(r.wp.ni0) * r.wp.nj0 + int64_t(r.wp.ni1) * r.wp.nj1;
+        LAUNCH(white_blend_kernel, unsigned((nn + 255) / 256), 256, m->stream, r.wp, (const double2*)r.wall_pq.p, r.pq.p);
+    }
 }
 
 void validate_options(const tm_smooth_options* o) {
@@ -264,11 +407,17 @@ void run_relax(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
         if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true);
         for (uint64_t sw = 0; sw < o->sweeps_per_iteration; ++sw) {
             const bool last = sw + 1 == o->sweeps_per_iteration;
-            const double2* u = m->X[m->cur].p;
-            double2* out = m->X[1 - m->cur].p;
-            if (last) launch_rows<MODE_RELAX, 1>(m, false, u, u, out, o->omega, nullptr);
-            else launch_rows<MODE_RELAX, 0>(m, false, u, u, out, o->omega, nullptr);
-            m->cur = 1 - m->cur;
+            for (auto& rp : m->ranks) {
+                RankMesh& r = *rp;
+                const double2* u = r.X[r.cur].p;
+                double2* out = r.X[1 - r.cur].p;
+                if (last) launch_rows<MODE_RELAX, 1>(m, r, false, u, u, out, o->omega, nullptr);
+                else launch_rows<MODE_RELAX, 0>(m, r, false, u, u, out, o->omega, nullptr);
+                r.cur = 1 - r.cur;
+            }
+            exchange(m, [](RankMesh& r) { return r.X[r.cur].p; });
+            if (m->n_ranks > 1)
+                for (auto& rp : m->ranks) sync_slaves(m, *rp, rp->X[rp->cur].p, 1, true);
             st->inner_iterations += 1;
             st->operator_applications += 1;
         }
@@ -282,27 +431,46 @@ void run_relax(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     }
 }
 
+// v = D^-1 A p on every rank: refresh ghosts of p, make its copies consistent, apply the rows
+template <int STATS, class GetIn, class GetOut, class GetDot>
+void apply_operator(tm_mesh* m, GetIn in, GetOut out, GetDot dot) {
+    exchange(m, in);
+    for (auto& rp : m->ranks) {
+        RankMesh& r = *rp;
+        sync_slaves(m, r, in(r), 0);
+        launch_rows<MODE_APPLY, STATS>(m, r, true, in(r), r.X[r.cur].p, out(r), 1.0, dot(r));
+    }
+}
+
 // BiCGStab iterations (BiCGStab.zig:303-366) on the row-scaled system until both components report done.
-void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st, double2* x, const double2* xc) {
+void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     cudaStream_t s = m->stream;
-    const int64_t N = m->N;
     const int check_every = 8;
     for (uint64_t k = 0;; ++k) {
         if (k % check_every == 0) {
             fetch_ctl(m);
             if (m->h_ctl->done[0] && m->h_ctl->done[1]) break;
         }
-        LAUNCH(bicg_p_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->kr.p, m->kp.p, m->kv.p);
-        sync_slaves(m, m->kp.p, 0);
-        launch_rows<MODE_APPLY, 2>(m, true, m->kp.p, xc, m->kv.p, 1.0, m->krhat.p);   // v = A p, partial rhat.v
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            LAUNCH(bicg_p_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const SolveCtl*)r.d_ctl.p, (const double2*)r.kr.p, r.kp.p, (const double2*)r.kv.p);
+        }
+        apply_operator<2>(m, [](RankMesh& r) { return r.kp.p; }, [](RankMesh& r) { return r.kv.p; }, [](RankMesh& r) { return (const double2*)r.krhat.p; });  // v = A p, rhat.v
         launch_reduce(m, RED_ALPHA, o, true);
-        LAUNCH(bicg_s_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->kr.p, m->kv.p, m->ks.p, x, m->kp.p, m->part_vec.p);
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            LAUNCH(bicg_s_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const SolveCtl*)r.d_ctl.p, (const double2*)r.kr.p, (const double2*)r.kv.p, r.ks.p,
+                   r.X[1 - r.cur].p, (const double2*)r.kp.p, r.part_vec.p);
+        }
         launch_reduce(m, RED_NORM_S, o, false);
-        sync_slaves(m, m->ks.p, 0);
-        launch_rows<MODE_APPLY, 3>(m, true, m->ks.p, xc, m->kt.p, 1.0, m->ks.p);      // t = A s, partials t.s and t.t
-        sync_slaves(m, m->ks.p, 2);
+        apply_operator<3>(m, [](RankMesh& r) { return r.ks.p; }, [](RankMesh& r) { return r.kt.p; }, [](RankMesh& r) { return (const double2*)r.ks.p; });  // t = A s, t.s, t.t
+        for (auto& rp : m->ranks) sync_slaves(m, *rp, rp->ks.p, 2);
         launch_reduce(m, RED_OMEGA, o, true);
-        LAUNCH(bicg_r_kernel, m->vec_grid, VEC_THREADS, s, N, m->d_ctl.p, m->ks.p, m->kt.p, m->kr.p, x, m->krhat.p, m->part_vec.p);
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            LAUNCH(bicg_r_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const SolveCtl*)r.d_ctl.p, (const double2*)r.ks.p, (const double2*)r.kt.p, r.kr.p,
+                   r.X[1 - r.cur].p, (const double2*)r.krhat.p, r.part_vec.p);
+        }
         launch_reduce(m, RED_NORM_R, o, false);
         st->operator_applications += 2;
     }
@@ -316,35 +484,50 @@ void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st,
 void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     ensure_krylov(m);
     cudaStream_t s = m->stream;
-    const int64_t N = m->N;
-    const size_t bytes = size_t(N) * sizeof(double2);
     const int max_restarts = 40;
     st->converged = 1;
+    auto xnew = [](RankMesh& r) { return r.X[1 - r.cur].p; };
+    auto refresh_x = [&]() {  // ghosts and copies of the iterate
+        exchange(m, xnew);
+        for (auto& rp : m->ranks) sync_slaves(m, *rp, xnew(*rp), 1);
+    };
     for (uint64_t it = 0; it < o->iterations; ++it) {
         if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true);
-        const double2* xc = m->X[m->cur].p;      // lagged coordinates: the mesh before this iteration
-        double2* x = m->X[1 - m->cur].p;         // x_new / y_new, warm-started from the mesh (GMRES.zig:157-174)
-        CUDA_TRY(cudaMemcpyAsync(x, xc, bytes, cudaMemcpyDeviceToDevice, s));
+        // X[cur] = lagged coordinates (the mesh before this iteration); X[1-cur] = x_new / y_new, warm-started from the
+        // mesh (GMRES.zig:157-174)
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            CUDA_TRY(cudaMemcpyAsync(r.X[1 - r.cur].p, r.X[r.cur].p, size_t(r.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        }
         for (int cycle = 0;; ++cycle) {
-            if (cycle > 0) sync_slaves(m, x, 1);
-            launch_rows<MODE_RESID, 4>(m, true, x, xc, m->kr.p, 1.0, nullptr);        // r = D^-1 (b - A x)
+            if (cycle > 0) refresh_x();
+            for (auto& rp : m->ranks) {
+                RankMesh& r = *rp;
+                launch_rows<MODE_RESID, 4>(m, r, true, xnew(r), r.X[r.cur].p, r.kr.p, 1.0, nullptr);  // r = D^-1 (b - A x)
+            }
             st->operator_applications += 1;
             launch_reduce(m, cycle == 0 ? RED_INIT : RED_RESTART, o, true);
             fetch_ctl(m);
             const int d0 = m->h_ctl->done[0], d1 = m->h_ctl->done[1];
             if ((d0 == 1 && d1 == 1) || d0 == 3 || d1 == 3 || cycle > max_restarts) break;
-            CUDA_TRY(cudaMemcpyAsync(m->krhat.p, m->kr.p, bytes, cudaMemcpyDeviceToDevice, s));
-            m->kp.zero(s);
-            m->kv.zero(s);
-            bicgstab_cycle(m, o, st, x, xc);
+            for (auto& rp : m->ranks) {
+                RankMesh& r = *rp;
+                CUDA_TRY(cudaMemcpyAsync(r.krhat.p, r.kr.p, size_t(r.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+                r.kp.zero(s);
+                r.kv.zero(s);
+            }
+            bicgstab_cycle(m, o, st);
         }
-        sync_slaves(m, x, 1);
+        refresh_x();
         st->inner_iterations += uint64_t(m->h_ctl->iters[0]) + uint64_t(m->h_ctl->iters[1]);
         st->last_inner_residual = std::fmax(m->h_ctl->norm_r[0], m->h_ctl->norm_r[1]);
         if (m->h_ctl->done[0] != 1 || m->h_ctl->done[1] != 1) st->converged = 0;  // log.warn "did not converge", BiCGStab.zig:368-369
-        LAUNCH(diff_stats_kernel, m->vec_grid, VEC_THREADS, s, N, xc, (const double2*)x, m->part_vec.p);
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            LAUNCH(diff_stats_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const double2*)r.X[r.cur].p, (const double2*)r.X[1 - r.cur].p, r.part_vec.p);
+        }
         launch_reduce(m, RED_UPDATE_STATS, o, false);
-        m->cur = 1 - m->cur;  // copy-back (smooth.zig:139-153) is a buffer swap
+        for (auto& rp : m->ranks) rp->cur = 1 - rp->cur;  // copy-back (smooth.zig:139-153) is a buffer swap
         m->outer_done += 1;
         st->outer_iterations += 1;
         if (o->stop_max_update > 0.0) {
@@ -371,9 +554,78 @@ int guarded(F&& f) {
 void check_mesh(const tm_mesh* m) {
     if (!m) TM_THROW(TM_ERR_INVALID_ARGUMENT, "mesh handle is NULL");
 }
-void check_block(const tm_mesh* m, size_t block) {
+// the rank (held by this process) that owns a global block, and the block's position in its own-block list
+RankMesh& owner_of_block(tm_mesh* m, size_t block, size_t* pos = nullptr) {
     check_mesh(m);
     if (block >= m->topo.blocks.size()) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block index %zu out of range", block);
+    for (auto& rp : m->ranks) {
+        if (rp->L.rank != m->owner[block]) continue;
+        const auto& ob = rp->L.own_blocks;
+        const auto it = std::lower_bound(ob.begin(), ob.end(), int32_t(block));
+        if (pos) *pos = size_t(it - ob.begin());
+        return *rp;
+    }
+    TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %zu is owned by rank %d, not by this process", block, m->owner[block]);
+}
+
+void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections,
+                   const tm_condition* conditions, size_t n_conditions, int device, void* stream) {
+    if ((n_connections && !connections) || (n_conditions && !conditions)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "NULL connection / condition array");
+    require_device(device);
+    if (device < 0) CUDA_TRY(cudaGetDevice(&m->device)); else m->device = device;
+    m->topo.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
+    if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
+    if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
+    if (stream) m->stream = (cudaStream_t)stream;
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
+    CUDA_TRY(cudaEventCreate(&m->ev0));
+    CUDA_TRY(cudaEventCreate(&m->ev1));
+    CUDA_TRY(cudaMallocHost(&m->h_ctl, sizeof(SolveCtl)));
+    std::memset(m->h_ctl, 0, sizeof(SolveCtl));
+}
+
+void upload_initial(tm_mesh* m, const tm_block* blocks, size_t n_blocks) {
+    for (size_t b = 0; b < n_blocks; ++b) {
+        if (!blocks[b].xy) continue;
+        bool mine = false;
+        for (auto& rp : m->ranks) mine = mine || rp->L.rank == m->owner[b];
+        if (!mine) continue;
+        size_t pos = 0;
+        RankMesh& r = owner_of_block(m, b, &pos);
+        CUDA_TRY(cudaMemcpyAsync(r.X[r.cur].p + r.L.loff[b], blocks[b].xy, size_t(blocks[b].ni * blocks[b].nj) * sizeof(double2), cudaMemcpyHostToDevice, m->stream));
+        r.have_coords[pos] = 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+}
+
+void tfi_launch(tm_mesh* m, RankMesh& r, size_t block, size_t pos) {
+    const auto& B = m->topo.blocks[block];
+    const int ni = int(B.ni), nj = int(B.nj);
+    const double* e = r.edges[pos].buf.p;
+    // layout of the cache: x_i_min[2ni] x_i_max[2ni] x_j_min[2nj] x_j_max[2nj] s1[ni] s2[ni] t1[nj] t2[nj]
+    const double2* x_i_min = (const double2*)e;
+    const double2* x_i_max = x_i_min + ni;
+    const double2* x_j_min = x_i_max + ni;
+    const double2* x_j_max = x_j_min + nj;
+    const double* s1 = (const double*)(x_j_max + nj);
+    const double *s2 = s1 + ni, *t1 = s2 + ni, *t2 = t1 + nj;
+    dim3 grid((nj + TILE_J - 1) / TILE_J, (ni + TFI_ROWS - 1) / TFI_ROWS);
+    LAUNCH(tfi_kernel, grid, TILE_J, m->stream, ni, nj, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2, r.X[r.cur].p + r.L.loff[block]);
+    r.have_coords[pos] = 1;
+    m->begun = false;
+}
+
+void tfi_validate_host(uint64_t ni, uint64_t nj, const double* x_i_min, const double* x_i_max, const double* x_j_min, const double* x_j_max,
+                       const double* s1, const double* s2, const double* t1, const double* t2) {
+    if (!x_i_min || !x_i_max || !x_j_min || !x_j_max || !s1 || !s2 || !t1 || !t2) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: NULL edge array");
+    if (ni < 2 || nj < 2) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: a block needs at least 2x2 nodes");
+    // what tfi.zig:135-162 asserts: clustering runs from exactly 0 to exactly 1, corners agree within 1e-10
+    if (s1[0] != 0 || s1[ni - 1] != 1.0 || s2[0] != 0 || s2[ni - 1] != 1.0 || t1[0] != 0 || t1[nj - 1] != 1.0 || t2[0] != 0 || t2[nj - 1] != 1.0)
+        TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: clustering must start at 0 and end at 1 (tfi.zig:135-145)");
+    auto near = [](const double* a, const double* b) { return std::fabs(a[0] - b[0]) <= 1e-10 && std::fabs(a[1] - b[1]) <= 1e-10; };
+    if (!near(x_i_min, x_j_min) || !near(x_i_min + 2 * (ni - 1), x_j_max) || !near(x_j_min + 2 * (nj - 1), x_i_max) ||
+        !near(x_i_max + 2 * (ni - 1), x_j_max + 2 * (nj - 1)))
+        TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: edge corner points are not consistent (tfi.zig:150-162)");
 }
 
 }  // namespace
@@ -423,58 +675,63 @@ int tm_mesh_create(const tm_block* blocks, size_t n_blocks, const tm_connection*
     tm_mesh* m = nullptr;
     int rc = guarded([&] {
         if (!out) TM_THROW(TM_ERR_INVALID_ARGUMENT, "out is NULL");
-        if ((n_connections && !connections) || (n_conditions && !conditions)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "NULL connection / condition array");
-        require_device(device);
         m = new tm_mesh();
-        if (device < 0) CUDA_TRY(cudaGetDevice(&m->device)); else m->device = device;
-        m->topo.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
-        if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
-        if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
-        if (stream) m->stream = (cudaStream_t)stream;
-        else { CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
-        CUDA_TRY(cudaEventCreate(&m->ev0));
-        CUDA_TRY(cudaEventCreate(&m->ev1));
-        m->N = m->topo.n_nodes;
-        m->X[0].alloc(size_t(m->N));
-        m->X[1].alloc(size_t(m->N));
-        build_tiles(m);
-        m->d_srows.upload(m->topo.smoothed, m->stream);
-        m->d_jrows.upload(m->topo.junction_rows, m->stream);
-        m->d_lrows.upload(m->topo.sliding, m->stream);
-        m->d_slaves.upload(m->topo.slaves, m->stream);
-        m->d_cslaves.upload(m->topo.const_slaves, m->stream);
-        m->d_fo.upload(m->topo.fixed_overrides, m->stream);
-        m->d_pairs.upload(m->topo.pairs, m->stream);
-        {
-            std::vector<RhsTerm> terms;
-            build_rhs_terms(m, terms);
-            for (const auto& c : m->topo.connected_rhs) terms.push_back(RhsTerm{c.self, c.x, c.y, 0, 0});  // smooth.zig:904-915
-            m->d_rhs_terms.upload(terms, m->stream);
-        }
-        m->n_bnd_rows = int(m->topo.smoothed.size() + m->topo.junction_rows.size() + m->topo.sliding.size());
-        m->n_bnd_ctas = bnd_ctas(m->n_bnd_rows);
-        int sms = 148;
-        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
-        const int64_t want = (m->N + VEC_THREADS - 1) / VEC_THREADS;
-        m->vec_grid = int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(sms) * 8)));
-        m->part_int.alloc(size_t(std::max(m->n_tiles, 1)) * 5);
-        m->part_bnd.alloc(size_t(std::max(m->n_bnd_ctas, 1)) * 5);
-        m->part_vec.alloc(size_t(m->vec_grid) * 5);
-        m->part_int.zero(m->stream); m->part_bnd.zero(m->stream); m->part_vec.zero(m->stream);
-        m->bconst.alloc(2); m->bconst.zero(m->stream);
-        m->d_worst.alloc(1);
-        m->d_ctl.alloc(1); m->d_ctl.zero(m->stream);
-        CUDA_TRY(cudaMallocHost(&m->h_ctl, sizeof(SolveCtl)));
-        std::memset(m->h_ctl, 0, sizeof(SolveCtl));
-        m->edges.resize(n_blocks);
-        m->have_coords.assign(n_blocks, 0);
-        for (size_t b = 0; b < n_blocks; ++b) {
-            if (blocks[b].xy) {
-                CUDA_TRY(cudaMemcpyAsync(m->X[0].p + m->topo.blocks[b].off, blocks[b].xy, size_t(blocks[b].ni * blocks[b].nj) * sizeof(double2), cudaMemcpyHostToDevice, m->stream));
-                m->have_coords[b] = 1;
+        create_common(m, blocks, n_blocks, connections, n_connections, conditions, n_conditions, device, stream);
+        m->n_ranks = 1;
+        m->owner.assign(n_blocks, 0);
+        m->ranks.emplace_back(new RankMesh());
+        build_rank(m, *m->ranks[0], 0);
+        upload_initial(m, blocks, n_blocks);
+        *out = m;
+    });
+    if (rc != TM_OK) delete m;
+    return rc;
+}
+
+int tm_dist_get_unique_id(uint8_t* id) {
+    return guarded([&] {
+        if (!id) TM_THROW(TM_ERR_INVALID_ARGUMENT, "id is NULL");
+        static_assert(sizeof(ncclUniqueId) <= TM_UNIQUE_ID_BYTES, "unique id does not fit");
+        g_nccl.load();
+        ncclUniqueId uid;
+        NCCL_TRY(g_nccl.GetUniqueId(&uid));
+        std::memset(id, 0, TM_UNIQUE_ID_BYTES);
+        std::memcpy(id, &uid, sizeof uid);
+    });
+}
+
+int tm_mesh_create_distributed(const tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections,
+                               const tm_condition* conditions, size_t n_conditions, const int32_t* block_owner, int rank, int n_ranks,
+                               const uint8_t* unique_id, int device, void* stream, tm_mesh** out) {
+    if (out) *out = nullptr;
+    tm_mesh* m = nullptr;
+    int rc = guarded([&] {
+        if (!out || !block_owner) TM_THROW(TM_ERR_INVALID_ARGUMENT, "out / block_owner is NULL");
+        if (n_ranks < 1 || n_ranks > 16) TM_THROW(TM_ERR_INVALID_ARGUMENT, "n_ranks must be in [1, 16]");
+        m = new tm_mesh();
+        create_common(m, blocks, n_blocks, connections, n_connections, conditions, n_conditions, device, stream);
+        m->n_ranks = n_ranks;
+        m->owner.assign(block_owner, block_owner + n_blocks);
+        validate_owner(m->topo, m->owner, n_ranks);
+        if (rank < 0) {  // all ranks emulated in this process on one GPU
+            m->emulated = n_ranks > 1;
+            for (int r = 0; r < n_ranks; ++r) {
+                m->ranks.emplace_back(new RankMesh());
+                build_rank(m, *m->ranks.back(), r);
             }
+        } else {
+            if (rank >= n_ranks) TM_THROW(TM_ERR_INVALID_ARGUMENT, "rank %d out of range", rank);
+            if (n_ranks > 1) {
+                if (!unique_id) TM_THROW(TM_ERR_INVALID_ARGUMENT, "unique_id is NULL");
+                g_nccl.load();
+                ncclUniqueId uid;
+                std::memcpy(&uid, unique_id, sizeof uid);
+                NCCL_TRY(g_nccl.CommInitRank(&m->comm, n_ranks, uid, rank));
+            }
+            m->ranks.emplace_back(new RankMesh());
+            build_rank(m, *m->ranks[0], rank);
         }
-        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        upload_initial(m, blocks, n_blocks);
         *out = m;
     });
     if (rc != TM_OK) delete m;
@@ -490,67 +747,39 @@ void tm_mesh_destroy(tm_mesh* mesh) {
 
 int tm_mesh_upload_block(tm_mesh* m, size_t block, const double* xy) {
     return guarded([&] {
-        check_block(m, block);
+        size_t pos = 0;
+        RankMesh& r = owner_of_block(m, block, &pos);
         if (!xy) TM_THROW(TM_ERR_INVALID_ARGUMENT, "xy is NULL");
         CUDA_TRY(cudaSetDevice(m->device));
         const auto& B = m->topo.blocks[block];
-        CUDA_TRY(cudaMemcpyAsync(m->X[m->cur].p + B.off, xy, size_t(B.ni * B.nj) * sizeof(double2), cudaMemcpyHostToDevice, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(r.X[r.cur].p + r.L.loff[block], xy, size_t(B.ni * B.nj) * sizeof(double2), cudaMemcpyHostToDevice, m->stream));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
-        m->have_coords[block] = 1;
+        r.have_coords[pos] = 1;
         m->begun = false;
     });
 }
 
 int tm_mesh_download_block(tm_mesh* m, size_t block, double* xy) {
     return guarded([&] {
-        check_block(m, block);
+        RankMesh& r = owner_of_block(m, block);
         if (!xy) TM_THROW(TM_ERR_INVALID_ARGUMENT, "xy is NULL");
         CUDA_TRY(cudaSetDevice(m->device));
         const auto& B = m->topo.blocks[block];
-        CUDA_TRY(cudaMemcpyAsync(xy, m->X[m->cur].p + B.off, size_t(B.ni * B.nj) * sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(xy, r.X[r.cur].p + r.L.loff[block], size_t(B.ni * B.nj) * sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
     });
-}
-
-static void tfi_launch(tm_mesh* m, size_t block) {
-    const auto& B = m->topo.blocks[block];
-    const int ni = int(B.ni), nj = int(B.nj);
-    const double* e = m->edges[block].buf.p;
-    // layout of the cache: x_i_min[2ni] x_i_max[2ni] x_j_min[2nj] x_j_max[2nj] s1[ni] s2[ni] t1[nj] t2[nj]
-    const double2* x_i_min = (const double2*)e;
-    const double2* x_i_max = x_i_min + ni;
-    const double2* x_j_min = x_i_max + ni;
-    const double2* x_j_max = x_j_min + nj;
-    const double* s1 = (const double*)(x_j_max + nj);
-    const double *s2 = s1 + ni, *t1 = s2 + ni, *t2 = t1 + nj;
-    dim3 grid((nj + TILE_J - 1) / TILE_J, (ni + TFI_ROWS - 1) / TFI_ROWS);
-    LAUNCH(tfi_kernel, grid, TILE_J, m->stream, ni, nj, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2, m->X[m->cur].p + B.off);
-    m->have_coords[block] = 1;
-    m->begun = false;
-}
-
-static void tfi_validate_host(uint64_t ni, uint64_t nj, const double* x_i_min, const double* x_i_max, const double* x_j_min, const double* x_j_max,
-                              const double* s1, const double* s2, const double* t1, const double* t2) {
-    if (!x_i_min || !x_i_max || !x_j_min || !x_j_max || !s1 || !s2 || !t1 || !t2) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: NULL edge array");
-    if (ni < 2 || nj < 2) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: a block needs at least 2x2 nodes");
-    // what tfi.zig:135-162 asserts: clustering runs from exactly 0 to exactly 1, corners agree within 1e-10
-    if (s1[0] != 0 || s1[ni - 1] != 1.0 || s2[0] != 0 || s2[ni - 1] != 1.0 || t1[0] != 0 || t1[nj - 1] != 1.0 || t2[0] != 0 || t2[nj - 1] != 1.0)
-        TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: clustering must start at 0 and end at 1 (tfi.zig:135-145)");
-    auto near = [](const double* a, const double* b) { return std::fabs(a[0] - b[0]) <= 1e-10 && std::fabs(a[1] - b[1]) <= 1e-10; };
-    if (!near(x_i_min, x_j_min) || !near(x_i_min + 2 * (ni - 1), x_j_max) || !near(x_j_min + 2 * (nj - 1), x_i_max) ||
-        !near(x_i_max + 2 * (ni - 1), x_j_max + 2 * (nj - 1)))
-        TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: edge corner points are not consistent (tfi.zig:150-162)");
 }
 
 int tm_mesh_tfi_block(tm_mesh* m, size_t block, const double* x_i_min, const double* x_i_max, const double* x_j_min, const double* x_j_max,
                       const double* s1, const double* s2, const double* t1, const double* t2) {
     return guarded([&] {
-        check_block(m, block);
+        size_t pos = 0;
+        RankMesh& r = owner_of_block(m, block, &pos);
         CUDA_TRY(cudaSetDevice(m->device));
         const auto& B = m->topo.blocks[block];
         const size_t ni = size_t(B.ni), nj = size_t(B.nj);
         tfi_validate_host(ni, nj, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2);
-        EdgeCache& ec = m->edges[block];
+        EdgeCache& ec = r.edges[pos];
         const size_t total = 6 * (ni + nj);
         if (ec.buf.n != total) ec.buf.alloc(total);
         double* d = ec.buf.p;
@@ -561,17 +790,18 @@ int tm_mesh_tfi_block(tm_mesh* m, size_t block, const double* x_i_min, const dou
             d += cnt[k];
         }
         ec.valid = true;
-        tfi_launch(m, block);
+        tfi_launch(m, r, block, pos);
         CUDA_TRY(cudaStreamSynchronize(m->stream));  // the host edge arrays may be freed after return
     });
 }
 
 int tm_mesh_tfi_block_resident(tm_mesh* m, size_t block) {
     return guarded([&] {
-        check_block(m, block);
+        size_t pos = 0;
+        RankMesh& r = owner_of_block(m, block, &pos);
         CUDA_TRY(cudaSetDevice(m->device));
-        if (!m->edges[block].valid) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %zu has no cached edges; call tm_mesh_tfi_block first", block);
-        tfi_launch(m, block);
+        if (!r.edges[pos].valid) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %zu has no cached edges; call tm_mesh_tfi_block first", block);
+        tfi_launch(m, r, block, pos);
     });
 }
 
@@ -580,45 +810,68 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
         check_mesh(m);
         validate_options(o);
         CUDA_TRY(cudaSetDevice(m->device));
-        for (size_t b = 0; b < m->have_coords.size(); ++b)
-            if (!m->have_coords[b]) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %zu has no coordinates yet", b);
         cudaStream_t s = m->stream;
-        double2* x = m->X[m->cur].p;
-        // connectionDataCheck (smooth.zig:220-275)
-        const int np = int(m->topo.pairs.size());
-        if (np > 0) {
-            CUDA_TRY(cudaMemsetAsync(m->d_worst.p, 0, sizeof(unsigned long long), s));
-            LAUNCH(pair_check_kernel, (np + 255) / 256, 256, s, m->d_pairs.p, np, (const double2*)x, 1e-15, m->d_worst.p);
+        for (auto& rp : m->ranks)
+            for (size_t k = 0; k < rp->have_coords.size(); ++k)
+                if (!rp->have_coords[k]) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %d has no coordinates yet", int(rp->L.own_blocks[k]));
+        auto xcur = [](RankMesh& r) { return r.X[r.cur].p; };
+        exchange(m, xcur);  // ghosts of the initial mesh
+        // connectionDataCheck (smooth.zig:220-275); each pair is checked by the rank that owns its side-1 node
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            CUDA_TRY(cudaMemsetAsync(r.d_worst.p, 0, sizeof(unsigned long long), s));
+            const int np = int(r.L.pairs.size());
+            if (np > 0) LAUNCH(pair_check_kernel, (np + 255) / 256, 256, s, (const PairCheck*)r.d_pairs.p, np, (const double2*)xcur(r), 1e-15, r.d_worst.p);
+        }
+        int bad_conn = -1, bad_point = -1;
+        for (auto& rp : m->ranks) {
             unsigned long long worst = 0;
-            CUDA_TRY(cudaMemcpyAsync(&worst, m->d_worst.p, sizeof worst, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(&worst, rp->d_worst.p, sizeof worst, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaStreamSynchronize(s));
-            if (worst != 0) {
-                const PairCheck& p = m->topo.pairs[size_t(worst & 0xffffffffull)];
-                TM_THROW(TM_ERR_TOPOLOGY, "non matching points for connection %d point %d (tolerance 1e-15 abs, smooth.zig:220-275)", p.conn, p.point);
+            if (worst != 0 && bad_conn < 0) {
+                const PairCheck& p = rp->L.pairs[size_t(worst & 0xffffffffull)];
+                bad_conn = p.conn; bad_point = p.point;
             }
         }
-        // rhs of fixed / sliding rows is captured from the initial mesh (smooth.zig:790-796, 853-858)
-        const int n_l = int(m->topo.sliding.size()), n_fo = int(m->topo.fixed_overrides.size());
-        if (n_l + n_fo > 0) LAUNCH(capture_boundary_kernel, (n_l + n_fo + 127) / 128, 128, s, m->d_lrows.p, n_l, m->d_fo.p, n_fo, x);
-        const int n_cs = int(m->topo.const_slaves.size());
-        if (n_cs > 0) LAUNCH(sync_slaves_kernel, (n_cs + 127) / 128, 128, s, m->d_cslaves.p, n_cs, x, 1);
-        CUDA_TRY(cudaMemcpyAsync(m->X[1 - m->cur].p, x, size_t(m->N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-        // constant part of ||b||^2 (the term table was uploaded by tm_mesh_create)
-        if (m->d_rhs_terms.n > 0) LAUNCH(rhs_const_kernel, 1, VEC_THREADS, s, m->d_rhs_terms.p, int(m->d_rhs_terms.n), (const double2*)x, m->bconst.p);
-        else m->bconst.zero(s);
+        if (bad_conn >= 0) TM_THROW(TM_ERR_TOPOLOGY, "non matching points for connection %d point %d (tolerance 1e-15 abs, smooth.zig:220-275)", bad_conn, bad_point);
+        // rhs of fixed / sliding rows is captured from the initial mesh (smooth.zig:790-796, 853-858); then every copy of
+        // a node is made exactly consistent with its root (x_copy = x_root + shift), constants included
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            const int n_l = int(r.L.sliding.size()), n_fo = int(r.L.fixed_overrides.size());
+            if (n_l + n_fo > 0) LAUNCH(capture_boundary_kernel, (n_l + n_fo + 127) / 128, 128, s, r.d_lrows.p, n_l, (const FixedOverride*)r.d_fo.p, n_fo, xcur(r));
+        }
+        exchange(m, xcur);
+        for (auto& rp : m->ranks) {
+            RankMesh& r = *rp;
+            const int n_cs = int(r.L.const_slaves.size());
+            if (n_cs > 0) LAUNCH(sync_slaves_kernel, (n_cs + 127) / 128, 128, s, (const SlaveRow*)r.d_cslaves.p, n_cs, xcur(r), 1);
+            sync_slaves(m, r, xcur(r), 1);
+            CUDA_TRY(cudaMemcpyAsync(r.X[1 - r.cur].p, xcur(r), size_t(r.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+            // this rank's constant part of ||b||^2
+            if (r.d_rhs_terms.n > 0) LAUNCH(rhs_const_kernel, 1, VEC_THREADS, s, (const RhsTerm*)r.d_rhs_terms.p, int(r.d_rhs_terms.n), (const double2*)xcur(r), r.bconst.p);
+            else r.bconst.zero(s);
+        }
         // control function (ControlFunction.init, wall_control_function.zig:27-42)
         m->cf = int(o->control_function);
+        for (auto& rp : m->ranks) rp->has_pq = false;
         if (m->cf == TM_CF_WHITE) {
             if (!m->topo.white_ok) TM_THROW(TM_ERR_UNSUPPORTED, "%s", m->topo.white_why.c_str());
-            const auto& B0 = m->topo.blocks[0];
-            const auto& B1 = m->topo.blocks[1];
-            m->wp.off0 = B0.off; m->wp.off1 = B1.off;
-            m->wp.ni0 = int32_t(B0.ni); m->wp.nj0 = int32_t(B0.nj); m->wp.ni1 = int32_t(B1.ni); m->wp.nj1 = int32_t(B1.nj);
-            m->wp.c_in0 = int32_t(B0.nj); m->wp.c_in1 = int32_t(B1.nj); m->wp.c_al0 = 1;  // j_min sides starting at node 0, running towards +j
-            m->wp.ds_target = o->white_ds_target; m->wp.theta_target = o->white_theta_target;
-            if (m->pq.n != size_t(m->N)) m->pq.alloc(size_t(m->N));
-            m->pq.zero(s);
-            m->wall_pq.alloc(size_t(B0.ni + B1.ni));
+            if (m->owner[0] != m->owner[1]) TM_THROW(TM_ERR_UNSUPPORTED, "White control function: blocks 0 and 1 must be owned by the same rank");
+            for (auto& rp : m->ranks) {
+                RankMesh& r = *rp;
+                if (!r.L.owns_white) continue;
+                const auto& B0 = m->topo.blocks[0];
+                const auto& B1 = m->topo.blocks[1];
+                r.wp.off0 = r.L.loff[0]; r.wp.off1 = r.L.loff[1];
+                r.wp.ni0 = int32_t(B0.ni); r.wp.nj0 = int32_t(B0.nj); r.wp.ni1 = int32_t(B1.ni); r.wp.nj1 = int32_t(B1.nj);
+                r.wp.c_in0 = int32_t(B0.nj); r.wp.c_in1 = int32_t(B1.nj); r.wp.c_al0 = 1;  // j_min sides starting at node 0, running towards +j
+                r.wp.ds_target = o->white_ds_target; r.wp.theta_target = o->white_theta_target;
+                if (r.pq.n != size_t(r.N)) r.pq.alloc(size_t(r.N));
+                r.pq.zero(s);
+                r.wall_pq.alloc(size_t(B0.ni + B1.ni));
+                r.has_pq = true;
+            }
             white_step(m, false);
         }
         m->outer_done = 0;
@@ -636,8 +889,9 @@ int tm_mesh_smooth(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* stat
         if (!m->begun) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tm_mesh_begin_smoothing has not been called for the current coordinates");
         if (int(o->control_function) != m->cf) TM_THROW(TM_ERR_INVALID_ARGUMENT, "control function differs from the one given to tm_mesh_begin_smoothing");
         CUDA_TRY(cudaSetDevice(m->device));
-        if (m->cf == TM_CF_WHITE) { m->wp.ds_target = o->white_ds_target; m->wp.theta_target = o->white_theta_target; }
-        st.nodes = uint64_t(m->N);
+        if (m->cf == TM_CF_WHITE)
+            for (auto& rp : m->ranks) { rp->wp.ds_target = o->white_ds_target; rp->wp.theta_target = o->white_theta_target; }
+        st.nodes = uint64_t(m->topo.n_nodes);
         st.converged = 1;
         CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
         if (o->solver == TM_SOLVER_RELAX) run_relax(m, o, &st);
@@ -667,36 +921,67 @@ int tm_mesh_synchronize(tm_mesh* m) {
 }
 
 uint64_t tm_mesh_block_count(const tm_mesh* m) { return m ? m->topo.blocks.size() : 0; }
-uint64_t tm_mesh_node_count(const tm_mesh* m) { return m ? uint64_t(m->N) : 0; }
+uint64_t tm_mesh_node_count(const tm_mesh* m) { return m ? uint64_t(m->topo.n_nodes) : 0; }
+uint64_t tm_mesh_local_node_count(const tm_mesh* m) {
+    uint64_t n = 0;
+    if (m) for (const auto& rp : m->ranks) n += uint64_t(rp->L.n_own);
+    return n;
+}
 int tm_mesh_block_size(const tm_mesh* m, size_t block, uint64_t* ni, uint64_t* nj) {
     return guarded([&] {
-        check_block(m, block);
+        check_mesh(m);
+        if (block >= m->topo.blocks.size()) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block index %zu out of range", block);
         if (ni) *ni = uint64_t(m->topo.blocks[block].ni);
         if (nj) *nj = uint64_t(m->topo.blocks[block].nj);
     });
 }
 double* tm_mesh_block_device_ptr(tm_mesh* m, size_t block) {
     if (!m || block >= m->topo.blocks.size()) return nullptr;
-    return reinterpret_cast<double*>(m->X[m->cur].p + m->topo.blocks[block].off);
+    for (auto& rp : m->ranks)
+        if (rp->L.rank == m->owner[block]) return reinterpret_cast<double*>(rp->X[rp->cur].p + rp->L.loff[block]);
+    return nullptr;
 }
 int tm_mesh_download_control_function(tm_mesh* m, size_t block, double* pqv) {
     return guarded([&] {
-        check_block(m, block);
+        RankMesh& r = owner_of_block(m, block);
         if (!pqv) TM_THROW(TM_ERR_INVALID_ARGUMENT, "pq is NULL");
         CUDA_TRY(cudaSetDevice(m->device));
         const auto& B = m->topo.blocks[block];
         const size_t bytes = size_t(B.ni * B.nj) * sizeof(double2);
-        if (m->cf != TM_CF_WHITE || !m->pq.p) { std::memset(pqv, 0, bytes); return; }  // laplace: all zero (wall_control_function.zig:29-33)
-        CUDA_TRY(cudaMemcpyAsync(pqv, m->pq.p + B.off, bytes, cudaMemcpyDeviceToHost, m->stream));
+        if (!r.has_pq || !r.pq.p) { std::memset(pqv, 0, bytes); return; }  // laplace: all zero (wall_control_function.zig:29-33)
+        CUDA_TRY(cudaMemcpyAsync(pqv, r.pq.p + r.L.loff[block], bytes, cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
     });
 }
 int tm_mesh_download_boundary_kinds(tm_mesh* m, size_t block, uint8_t* kinds) {
     return guarded([&] {
-        check_block(m, block);
+        check_mesh(m);
+        if (block >= m->topo.blocks.size()) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block index %zu out of range", block);
         if (!kinds) TM_THROW(TM_ERR_INVALID_ARGUMENT, "kinds is NULL");
         const auto& B = m->topo.blocks[block];
         std::memcpy(kinds, m->topo.kind.data() + B.bbuf, size_t(2 * (B.ni + B.nj - 2)));
+    });
+}
+
+// host-only view of the partition (no GPU needed): what rank `rank` owns, receives and sends
+int tm_dist_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections, const tm_condition* conditions,
+                 size_t n_conditions, const int32_t* block_owner, int rank, int n_ranks, tm_dist_plan_info* info, int64_t* ghost_ids, int64_t* send_ids,
+                 int64_t* counts) {
+    return guarded([&] {
+        if (!block_owner || !info) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block_owner / info is NULL");
+        if ((n_connections && !connections) || (n_conditions && !conditions)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "NULL connection / condition array");
+        Topology T;
+        T.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
+        std::vector<int32_t> owner(block_owner, block_owner + n_blocks);
+        const LocalTables L = localize(T, owner, rank, n_ranks);
+        info->n_own = uint64_t(L.n_own); info->n_ghost = uint64_t(L.n_ghost); info->n_synth = uint64_t(L.n_synth);
+        info->n_send = uint64_t(L.send_lidx.size());
+        info->n_smoothed = uint64_t(L.smoothed.size()); info->n_junction = uint64_t(L.junction_rows.size());
+        info->n_sliding = uint64_t(L.sliding.size()); info->n_slaves = uint64_t(L.slaves.size());
+        if (counts)
+            for (int p = 0; p < n_ranks; ++p) { counts[2 * p] = int64_t(L.ghost_ids[size_t(p)].size()); counts[2 * p + 1] = int64_t(L.send_ids[size_t(p)].size()); }
+        if (ghost_ids) { size_t k = 0; for (const auto& v : L.ghost_ids) for (int64_t g : v) ghost_ids[k++] = g; }
+        if (send_ids) { size_t k = 0; for (const auto& v : L.send_ids) for (int64_t g : v) send_ids[k++] = g; }
     });
 }
 

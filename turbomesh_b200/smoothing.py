@@ -167,15 +167,36 @@ mesh = smooth_mesh  # the reference's name: smoothing.smooth.mesh
 class DeviceMesh:
     """Device-resident mesh (``tm_mesh_*``): upload / TFI once, smooth repeatedly, download when needed."""
 
-    def __init__(self, mesh, device: int = -1, stream: int = 0, upload: bool = True):
+    def __init__(self, mesh, device: int = -1, stream: int = 0, upload: bool = True, owner=None, rank: Optional[int] = None,
+                 n_ranks: int = 1, unique_id: Optional[bytes] = None):
+        """``owner`` (one rank per block) makes the mesh distributed: ``rank`` = this process' rank (one process per GPU,
+        ``unique_id`` from :func:`dist_unique_id` shared by all ranks), or ``rank=None`` to emulate all ``n_ranks`` ranks
+        inside this process on one GPU (tests)."""
         self._L = _lib.load()
         self._cm = _CMesh(mesh, with_coords=upload)
         self.mesh = mesh
         h = C.c_void_p()
         cm = self._cm
-        check(self._L.tm_mesh_create(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        sp = C.c_void_p(stream) if stream else None
+        if owner is None:
+            self.owner, self.rank, self.n_ranks = [0] * cm.nb, 0, 1
+            check(self._L.tm_mesh_create(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, device, sp, C.byref(h)))
+        else:
+            assert len(owner) == cm.nb
+            self.owner, self.rank, self.n_ranks = [int(o) for o in owner], rank, int(n_ranks)
+            own = (C.c_int32 * cm.nb)(*self.owner)
+            uid = (C.c_uint8 * _lib.TM_UNIQUE_ID_BYTES)(*unique_id) if unique_id is not None else None
+            check(self._L.tm_mesh_create_distributed(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, own, -1 if rank is None else int(rank),
+                                                     int(n_ranks), uid, device, sp, C.byref(h)))
         self._h = h
         self._opts = None
+
+    def owns(self, block: int) -> bool:
+        return self.rank is None or self.owner[block] == self.rank
+
+    @property
+    def local_node_count(self) -> int:
+        return int(self._L.tm_mesh_local_node_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -218,9 +239,10 @@ class DeviceMesh:
         return out
 
     def download(self):
-        """Copies all blocks back into ``self.mesh`` (in place, like smooth.zig:139-153)."""
+        """Copies all blocks held by this process back into ``self.mesh`` (in place, like smooth.zig:139-153)."""
         for k, b in enumerate(self.mesh.blocks):
-            self.download_block(k, b.points)
+            if self.owns(k):
+                self.download_block(k, b.points)
         return self.mesh
 
     def begin_smoothing(self, solver: Optional[CudaSolver] = None, control_function=None):
@@ -252,6 +274,35 @@ class DeviceMesh:
 
     def block_device_ptr(self, block: int) -> int:
         return int(self._L.tm_mesh_block_device_ptr(self._h, block) or 0)
+
+
+def dist_unique_id() -> bytes:
+    """NCCL unique id (rank 0 creates it and broadcasts the bytes to the other ranks)."""
+    buf = (C.c_uint8 * _lib.TM_UNIQUE_ID_BYTES)()
+    check(_lib.load().tm_dist_get_unique_id(buf))
+    return bytes(buf)
+
+
+def dist_plan(mesh, owner, rank: int, n_ranks: int) -> dict:
+    """Host-only partition plan of one rank (``tm_dist_plan``): sizes plus the ghost / send id lists per peer."""
+    L = _lib.load()
+    cm = _CMesh(mesh, with_coords=False)
+    own = (C.c_int32 * cm.nb)(*[int(o) for o in owner])
+    info = _lib.TmDistPlanInfo()
+    counts = (C.c_int64 * (2 * n_ranks))()
+    check(L.tm_dist_plan(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, own, rank, n_ranks, C.byref(info), None, None, counts))
+    ghost = (C.c_int64 * max(int(info.n_ghost), 1))()
+    send = (C.c_int64 * max(int(info.n_send), 1))()
+    check(L.tm_dist_plan(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, own, rank, n_ranks, C.byref(info), ghost, send, counts))
+    out = info.as_dict()
+    g, s_, ghost_ids, send_ids = 0, 0, [], []
+    for p in range(n_ranks):
+        ng, ns = int(counts[2 * p]), int(counts[2 * p + 1])
+        ghost_ids.append(np.array(ghost[g:g + ng], dtype=np.int64))
+        send_ids.append(np.array(send[s_:s_ + ns], dtype=np.int64))
+        g, s_ = g + ng, s_ + ns
+    out["ghost_ids"], out["send_ids"] = ghost_ids, send_ids
+    return out
 
 
 def kernel_launch_count() -> int:
