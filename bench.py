@@ -147,17 +147,30 @@ def run_gpu(args):
 
     sweeps = args.sweeps
     solver = smoothing.CudaSolver(method="relax", sweeps_per_iteration=sweeps, omega=args.omega, device=local)
-    if world == 1:
+    stream = torch.cuda.Stream()                         # the library launches on this stream, so torch events see its kernels
+    kind = args.workload or ("single" if world == 1 else "cascade")
+    if kind == "single":
+        if world != 1:
+            raise SystemExit("the single-block workload does not shard; use --workload cascade for N > 1")
         ni = nj = args.size
         spec = synthetic.single_block(ni, nj)
         workload = f"single_block_{ni}x{nj} (config 3: synthetic single-block fp64 grid, TFI + elliptic smoothing)"
-        stream = torch.cuda.Stream()                     # the library launches on this stream, so torch events see its kernels
         dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False)
         my_blocks = list(range(len(spec.blocks)))
     else:
-        raise SystemExit("multi-GPU bench path is not wired yet")
+        # config 4 in tiling form: one block column (8 blocks of block_ni x block_nj) per GPU; 8 x 8 blocks / 512 Mi nodes at N = 8
+        n_bj = args.blocks_per_gpu
+        spec = synthetic.cascade(world, n_bj, args.block_ni, args.block_nj)
+        owner = [bi for bi in range(world) for _ in range(n_bj)]
+        workload = (f"cascade_{world}x{n_bj}_blocks_of_{args.block_ni}x{args.block_nj} (config 4: synthetic multi-block cascade passage, "
+                    f"{n_bj} blocks per GPU, interface halo exchange once per sweep)")
+        uid = [smoothing.dist_unique_id() if (rank == 0 and world > 1) else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
+        dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False, owner=owner, rank=rank, n_ranks=world, unique_id=uid[0])
+        my_blocks = [b for b in range(len(spec.blocks)) if owner[b] == rank]
     nodes_local = sum(spec.blocks[b].size[0] * spec.blocks[b].size[1] for b in my_blocks)
-    nodes_total = nodes_local * world
+    nodes_total = sum(b.size[0] * b.size[1] for b in spec.blocks)
 
     for b in my_blocks:  # upload the edges once: afterwards the TFI inputs are resident in HBM
         dm.tfi_block(b, *spec.blocks[b].edge_args())
@@ -199,7 +212,7 @@ def run_gpu(args):
 
     # ---- end to end through the reference-facing calls with HOST buffers (Block2d.init -> smooth.mesh) ----
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if kind == "single" and not args.no_e2e:
         e2e = run_e2e(args, spec, solver, torch)
 
     peak, peak_src = measured_peak()
@@ -214,13 +227,13 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "nodes": nodes_total, "sweeps_per_step": sweeps, "omega": args.omega,
                        "step": "TFI of all blocks from device-resident edges + begin_smoothing + sweeps (damped Jacobi, coefficients from the current iterate)",
-                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2"},
+                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2", "nodes_per_gpu": nodes_local},
             "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall / args.steps * 1e3,
             "last_max_update": stats["last_max_update"] if stats else None}
     if e2e:
         line["e2e"] = e2e
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and kind == "single":
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_sample(args.ref_size).items() if k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     dm.close()
@@ -268,6 +281,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="turbomesh_b200", choices=["turbomesh_b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="single-block edge length (N=1)")
+    ap.add_argument("--workload", default=None, choices=["single", "cascade"], help="default: single for N=1, cascade for N>1")
+    ap.add_argument("--block-ni", type=int, default=4096)
+    ap.add_argument("--block-nj", type=int, default=2048)
+    ap.add_argument("--blocks-per-gpu", type=int, default=8)
     ap.add_argument("--sweeps", type=int, default=100, help="smoothing sweeps per step")
     ap.add_argument("--omega", type=float, default=0.9)
     ap.add_argument("--ref-size", type=int, default=512, help="edge length of the bounded CPU sample")

@@ -43,6 +43,12 @@ def test_t106_white(gpu_lib):
     _smooth_and_compare("t106_white", gpu_lib)
 
 
+def test_ls89_x4_white(gpu_lib):
+    """Config 2: examples/LS89 with every num_cells entry doubled (147 398 nodes), boundary-layer clustering, White."""
+    mesh, st = _smooth_and_compare("ls89x4_white", gpu_lib)
+    assert mesh.num_nodes() == 147398
+
+
 def test_t106_topology_kinds(gpu_lib, orc):
     """Identical block topology and node classification (bit-exact) on the T106 mesh."""
     from turbomesh_b200 import smoothing

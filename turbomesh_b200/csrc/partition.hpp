@@ -27,12 +27,15 @@ struct LocalTables {
     int rank = 0, n_ranks = 1;
     std::vector<int32_t> own_blocks;             // global block ids owned by this rank, ascending
     std::vector<int64_t> loff;                   // per global block: offset of its node (0,0) in the local field, -1 if remote
-    int64_t n_own = 0, n_ghost = 0, n_synth = 0, n_local = 0; // local field = [own nodes][ghosts from rank 0][from rank 1]...[synthesised copies]
+    int64_t n_own = 0, n_ghost = 0, n_synth = 0, n_check = 0, n_local = 0; // local field = [own][ghosts from rank 0][from rank 1]...[synthesised copies][check ghosts]
     std::vector<int64_t> synth_ids;              // sorted global ids of remote `connected` copies kept as synthesised slots
     std::vector<std::vector<int64_t>> ghost_ids; // per peer: sorted global ids read here, owned there
     std::vector<std::vector<int64_t>> send_ids;  // per peer: sorted global ids owned here, read there
     std::vector<int64_t> ghost_base, send_base;  // per peer (n_ranks+1 entries): offsets in the ghost region / send buffer
     std::vector<int64_t> send_lidx;              // local indices to pack, concatenated over peers
+    // one-time exchange of raw coordinates for connectionDataCheck (smooth.zig:220-275) across ranks
+    std::vector<std::vector<int64_t>> check_ghost_ids, check_send_ids;
+    std::vector<int64_t> check_ghost_base, check_send_base, check_send_lidx;
     // rows owned by this rank, all node references are local indices
     std::vector<SmoothedRow> smoothed;
     std::vector<JunctionRow> junction_rows;
@@ -75,14 +78,26 @@ inline ReadSets read_sets(const Topology& T, const std::vector<int32_t>& owner, 
     for (const auto* list : {&T.slaves, &T.const_slaves})
         for (const auto& s : *list)
             if (owner_of_node(T, owner, s.self) == r) need(s.root);
-    for (const auto& p : T.pairs)
-        if (owner_of_node(T, owner, p.g1) == r) need(p.g0);
     for (auto& v : out.recv) {
         std::sort(v.begin(), v.end());
         v.erase(std::unique(v.begin(), v.end()), v.end());
     }
     std::sort(out.synth.begin(), out.synth.end());
     out.synth.erase(std::unique(out.synth.begin(), out.synth.end()), out.synth.end());
+    return out;
+}
+
+// side-0 nodes of interface pairs whose side-1 node belongs to rank r but which live elsewhere (raw coordinates,
+// fetched once when smoothing begins)
+inline std::vector<std::vector<int64_t>> check_sets(const Topology& T, const std::vector<int32_t>& owner, int r, int n_ranks) {
+    std::vector<std::vector<int64_t>> out;
+    out.resize(size_t(n_ranks));
+    for (const auto& p : T.pairs)
+        if (owner_of_node(T, owner, p.g1) == r && owner_of_node(T, owner, p.g0) != r) out[size_t(owner_of_node(T, owner, p.g0))].push_back(p.g0);
+    for (auto& v : out) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
     return out;
 }
 
@@ -124,7 +139,18 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     }
     L.n_ghost = L.ghost_base[size_t(n_ranks)];
     L.n_synth = int64_t(L.synth_ids.size());
-    L.n_local = L.n_own + L.n_ghost + L.n_synth;
+    L.check_ghost_ids = check_sets(T, owner, rank, n_ranks);
+    L.check_send_ids.assign(size_t(n_ranks), {});
+    for (int p = 0; p < n_ranks; ++p)
+        if (p != rank) L.check_send_ids[size_t(p)] = check_sets(T, owner, p, n_ranks)[size_t(rank)];
+    L.check_ghost_base.assign(size_t(n_ranks) + 1, 0);
+    L.check_send_base.assign(size_t(n_ranks) + 1, 0);
+    for (int p = 0; p < n_ranks; ++p) {
+        L.check_ghost_base[size_t(p) + 1] = L.check_ghost_base[size_t(p)] + int64_t(L.check_ghost_ids[size_t(p)].size());
+        L.check_send_base[size_t(p) + 1] = L.check_send_base[size_t(p)] + int64_t(L.check_send_ids[size_t(p)].size());
+    }
+    L.n_check = L.check_ghost_base[size_t(n_ranks)];
+    L.n_local = L.n_own + L.n_ghost + L.n_synth + L.n_check;
 
     auto lidx = [&](int64_t g) -> int64_t {
         const size_t b = T.block_of(g);
@@ -142,6 +168,14 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
 
     for (int p = 0; p < n_ranks; ++p)
         for (int64_t g : L.send_ids[size_t(p)]) L.send_lidx.push_back(lidx(g));
+    for (int p = 0; p < n_ranks; ++p)
+        for (int64_t g : L.check_send_ids[size_t(p)]) L.check_send_lidx.push_back(lidx(g));
+    auto check_idx = [&](int64_t g) -> int64_t {  // raw copy of a remote side-0 node
+        const int o = owner_of_node(T, owner, g);
+        const auto& v = L.check_ghost_ids[size_t(o)];
+        const auto it = std::lower_bound(v.begin(), v.end(), g);
+        return L.n_own + L.n_ghost + L.n_synth + L.check_ghost_base[size_t(o)] + int64_t(it - v.begin());
+    };
 
     // slaves owned here: those whose root row is also here are written by the root's thread
     std::map<int64_t, std::vector<SlaveRow>> by_root;  // keyed by the root's global id
@@ -193,7 +227,7 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     for (const auto& f : T.fixed_overrides)
         if (mine(f.self)) L.fixed_overrides.push_back({lidx(f.self), f.x, f.y});
     for (const auto& p : T.pairs)
-        if (mine(p.g1)) L.pairs.push_back({lidx(p.g0), lidx(p.g1), p.px, p.py, p.conn, p.point});
+        if (mine(p.g1)) L.pairs.push_back({mine(p.g0) ? lidx(p.g0) : check_idx(p.g0), lidx(p.g1), p.px, p.py, p.conn, p.point});
 
     // rows of the reference system with a non-zero rhs (smooth.zig:780-921), restricted to this rank
     std::vector<uint8_t> over(size_t(T.n_boundary), 0);

@@ -162,7 +162,7 @@ struct RankMesh {
     DevBuf<FixedOverride> d_fo;
     DevBuf<PairCheck> d_pairs;
     DevBuf<RhsTerm> d_rhs_terms;
-    DevBuf<int64_t> d_send_idx;
+    DevBuf<int64_t> d_send_idx, d_check_send_idx;
     DevBuf<double2> sendbuf;
     DevBuf<double> part_int, part_bnd, part_vec, bconst, red;
     DevBuf<unsigned long long> d_worst;
@@ -243,7 +243,8 @@ void build_rank(tm_mesh* m, RankMesh& r, int rank) {
     r.d_pairs.upload(r.L.pairs, s);
     r.d_rhs_terms.upload(r.L.rhs_terms, s);
     r.d_send_idx.upload(r.L.send_lidx, s);
-    r.sendbuf.alloc(r.L.send_lidx.size());
+    r.d_check_send_idx.upload(r.L.check_send_lidx, s);
+    r.sendbuf.alloc(std::max(r.L.send_lidx.size(), r.L.check_send_lidx.size()));
     r.n_bnd_rows = int(r.L.smoothed.size() + r.L.junction_rows.size() + r.L.sliding.size());
     r.n_bnd_ctas = bnd_ctas(r.n_bnd_rows);
     int sms = 148;
@@ -275,23 +276,28 @@ void ensure_krylov(tm_mesh* m) {
 }
 
 // ---- halo exchange: every rank's ghost slots of `field` are refreshed from their owners ------------------------
+// check = true: the one-time exchange of raw side-0 coordinates for connectionDataCheck (separate slots).
 template <class Get>
-void exchange(tm_mesh* m, Get get) {
+void exchange(tm_mesh* m, Get get, bool check = false) {
     if (m->n_ranks == 1) return;
     cudaStream_t s = m->stream;
+    auto send_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_send_base : r.L.send_base; };
+    auto ghost_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_ghost_base : r.L.ghost_base; };
+    auto region = [&](RankMesh& r) { return check ? r.L.n_own + r.L.n_ghost + r.L.n_synth : r.L.n_own; };
     for (auto& rp : m->ranks) {
         RankMesh& r = *rp;
-        const int64_t n = int64_t(r.L.send_lidx.size());
-        if (n > 0) LAUNCH(pack_kernel, unsigned((n + 255) / 256), 256, s, (const int64_t*)r.d_send_idx.p, n, (const double2*)get(r), r.sendbuf.p);
+        const int64_t n = send_base(r).back();
+        const int64_t* idx = check ? r.d_check_send_idx.p : r.d_send_idx.p;
+        if (n > 0) LAUNCH(pack_kernel, unsigned((n + 255) / 256), 256, s, idx, n, (const double2*)get(r), r.sendbuf.p);
     }
     if (m->emulated) {
         for (auto& rp : m->ranks) {
             RankMesh& r = *rp;
             for (int p = 0; p < m->n_ranks; ++p) {
-                const int64_t cnt = r.L.send_base[size_t(p) + 1] - r.L.send_base[size_t(p)];
+                const int64_t cnt = send_base(r)[size_t(p) + 1] - send_base(r)[size_t(p)];
                 if (cnt == 0) continue;
                 RankMesh& d = *m->ranks[size_t(p)];
-                CUDA_TRY(cudaMemcpyAsync(get(d) + d.L.n_own + d.L.ghost_base[size_t(r.L.rank)], r.sendbuf.p + r.L.send_base[size_t(p)],
+                CUDA_TRY(cudaMemcpyAsync(get(d) + region(d) + ghost_base(d)[size_t(r.L.rank)], r.sendbuf.p + send_base(r)[size_t(p)],
                                          size_t(cnt) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
             }
         }
@@ -299,10 +305,10 @@ void exchange(tm_mesh* m, Get get) {
         RankMesh& r = *m->ranks[0];
         NCCL_TRY(g_nccl.GroupStart());
         for (int p = 0; p < m->n_ranks; ++p) {
-            const int64_t ns = r.L.send_base[size_t(p) + 1] - r.L.send_base[size_t(p)];
-            const int64_t ng = r.L.ghost_base[size_t(p) + 1] - r.L.ghost_base[size_t(p)];
-            if (ns > 0) NCCL_TRY(g_nccl.Send(r.sendbuf.p + r.L.send_base[size_t(p)], size_t(ns) * 2, ncclDouble, p, m->comm, s));
-            if (ng > 0) NCCL_TRY(g_nccl.Recv(get(r) + r.L.n_own + r.L.ghost_base[size_t(p)], size_t(ng) * 2, ncclDouble, p, m->comm, s));
+            const int64_t ns = send_base(r)[size_t(p) + 1] - send_base(r)[size_t(p)];
+            const int64_t ng = ghost_base(r)[size_t(p) + 1] - ghost_base(r)[size_t(p)];
+            if (ns > 0) NCCL_TRY(g_nccl.Send(r.sendbuf.p + send_base(r)[size_t(p)], size_t(ns) * 2, ncclDouble, p, m->comm, s));
+            if (ng > 0) NCCL_TRY(g_nccl.Recv(get(r) + region(r) + ghost_base(r)[size_t(p)], size_t(ng) * 2, ncclDouble, p, m->comm, s));
         }
         NCCL_TRY(g_nccl.GroupEnd());
     }
@@ -815,7 +821,7 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
             for (size_t k = 0; k < rp->have_coords.size(); ++k)
                 if (!rp->have_coords[k]) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %d has no coordinates yet", int(rp->L.own_blocks[k]));
         auto xcur = [](RankMesh& r) { return r.X[r.cur].p; };
-        exchange(m, xcur);  // ghosts of the initial mesh
+        exchange(m, xcur, true);  // raw side-0 coordinates of cross-rank interface pairs
         // connectionDataCheck (smooth.zig:220-275); each pair is checked by the rank that owns its side-1 node
         for (auto& rp : m->ranks) {
             RankMesh& r = *rp;
