@@ -808,6 +808,18 @@ __global__ void __launch_bounds__(VEC_THREADS) bicg_r_kernel(int64_t n, const So
     block_reduce_store<4, VEC_THREADS>(sums, 0.0, partials + (size_t)blockIdx.x * 5);
 }
 
+// x += d  (end of a BiCGStab cycle: the correction accumulated from zero is added to the iterate once, so its
+// rounding errors scale with |d|, not |x| -- iterative refinement)
+__global__ void __launch_bounds__(VEC_THREADS) add_correction_kernel(int64_t n, double2* __restrict__ x, double2* __restrict__ d) {
+    for (int64_t k = (int64_t)blockIdx.x * VEC_THREADS + threadIdx.x; k < n; k += (int64_t)gridDim.x * VEC_THREADS) {
+        const double2 dd = d[k];
+        double2 xx = x[k];
+        xx.x += dd.x; xx.y += dd.y;
+        x[k] = xx;
+        d[k] = make_double2(0.0, 0.0);
+    }
+}
+
 // Constant part of ||b||^2 of the reference's full right-hand side (BiCGStab.zig:289-291): fixed rows carry their
 // coordinate, connected rows their (periodic) rhs, sliding rows (rhs_x, rhs_y), junction rows their periodic rhs.
 // Interior rows are 0 and periodic interface rows are added per solve (they depend on the lagged coordinates).

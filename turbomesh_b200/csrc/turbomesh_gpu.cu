@@ -167,7 +167,7 @@ struct RankMesh {
     DevBuf<double> part_int, part_bnd, part_vec, bconst, red;
     DevBuf<unsigned long long> d_worst;
     DevBuf<SolveCtl> d_ctl;
-    DevBuf<double2> kr, krhat, kp, kv, ks, kt;
+    DevBuf<double2> kr, krhat, kp, kv, ks, kt, kd;
     bool krylov_ready = false;
     std::vector<EdgeCache> edges;        // indexed by position in L.own_blocks
     std::vector<uint8_t> have_coords;
@@ -267,7 +267,7 @@ void ensure_krylov(tm_mesh* m) {
     for (auto& rp : m->ranks) {
         RankMesh& r = *rp;
         if (r.krylov_ready) continue;
-        for (DevBuf<double2>* v : {&r.kr, &r.krhat, &r.kp, &r.kv, &r.ks, &r.kt}) {
+        for (DevBuf<double2>* v : {&r.kr, &r.krhat, &r.kp, &r.kv, &r.ks, &r.kt, &r.kd}) {
             v->alloc(size_t(std::max<int64_t>(r.N, 1)));
             v->zero(m->stream);
         }
@@ -466,7 +466,7 @@ void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st)
         for (auto& rp : m->ranks) {
             RankMesh& r = *rp;
             LAUNCH(bicg_s_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const SolveCtl*)r.d_ctl.p, (const double2*)r.kr.p, (const double2*)r.kv.p, r.ks.p,
-                   r.X[1 - r.cur].p, (const double2*)r.kp.p, r.part_vec.p);
+                   r.kd.p, (const double2*)r.kp.p, r.part_vec.p);
         }
         launch_reduce(m, RED_NORM_S, o, false);
         apply_operator<3>(m, [](RankMesh& r) { return r.ks.p; }, [](RankMesh& r) { return r.kt.p; }, [](RankMesh& r) { return (const double2*)r.ks.p; });  // t = A s, t.s, t.t
@@ -475,7 +475,7 @@ void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st)
         for (auto& rp : m->ranks) {
             RankMesh& r = *rp;
             LAUNCH(bicg_r_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const SolveCtl*)r.d_ctl.p, (const double2*)r.ks.p, (const double2*)r.kt.p, r.kr.p,
-                   r.X[1 - r.cur].p, (const double2*)r.krhat.p, r.part_vec.p);
+                   r.kd.p, (const double2*)r.krhat.p, r.part_vec.p);
         }
         launch_reduce(m, RED_NORM_R, o, false);
         st->operator_applications += 2;
@@ -490,7 +490,7 @@ void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st)
 void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     ensure_krylov(m);
     cudaStream_t s = m->stream;
-    const int max_restarts = 40;
+    const int max_restarts = 60;
     st->converged = 1;
     auto xnew = [](RankMesh& r) { return r.X[1 - r.cur].p; };
     auto refresh_x = [&]() {  // ghosts and copies of the iterate
@@ -522,7 +522,11 @@ void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats
                 r.kp.zero(s);
                 r.kv.zero(s);
             }
-            bicgstab_cycle(m, o, st);
+            bicgstab_cycle(m, o, st);  // accumulates the correction d (from zero) with A d ~ r
+            for (auto& rp : m->ranks) {
+                RankMesh& r = *rp;
+                LAUNCH(add_correction_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, xnew(r), r.kd.p);
+            }
         }
         refresh_x();
         st->inner_iterations += uint64_t(m->h_ctl->iters[0]) + uint64_t(m->h_ctl->iters[1]);

@@ -1,0 +1,167 @@
+// cuda.zig -- Zig-side binding of the B200 back-end (include/turbomesh_gpu.h) for turbomesh's src/core.
+//
+// Drop this file next to src/core/smoothing/smooth.zig as src/core/smoothing/cuda.zig (see INTEGRATION.md).
+// NOTE: written without a Zig toolchain at hand (none exists in the build image); it mirrors the way the
+// reference binds its other foreign back-ends: `pub extern fn ... callconv(.c)` declarations as in
+// src/core/smoothing/petsc_import.zig:3021 and a thin solver-like wrapper as in src/core/smoothing/umfpack.zig:14-55.
+const std = @import("std");
+const discrete = @import("../discrete.zig");
+const boundary = @import("../boundary.zig");
+const types = @import("../types.zig");
+const wall_control_function = @import("wall_control_function.zig");
+
+const log = std.log.scoped(.cuda_backend);
+
+// ---- C ABI (include/turbomesh_gpu.h) ----------------------------------------------------------------
+pub const tm_block = extern struct { ni: u64, nj: u64, xy: ?[*]f64 };
+pub const tm_range = extern struct { block: u64, side: u32, _pad: u32 = 0, start: u64, end: u64 };
+pub const tm_connection = extern struct { ranges: [2]tm_range, has_periodicity: i32, _pad: i32 = 0, periodicity: [2]f64 };
+pub const tm_condition = extern struct { range: tm_range, kind: u32, _pad: u32 = 0 };
+pub const tm_smooth_options = extern struct {
+    struct_size: u32,
+    solver: u32, // 0 = picard_bicgstab, 1 = relax
+    iterations: u64,
+    control_function: u32, // 0 = laplace, 1 = white
+    fail_on_no_convergence: u32,
+    white_ds_target: f64,
+    white_theta_target: f64,
+    rtol: f64,
+    atol: f64,
+    max_inner_iterations: u64,
+    omega: f64,
+    sweeps_per_iteration: u64,
+    stop_max_update: f64,
+    device: i32,
+    _pad: i32 = 0,
+};
+pub const tm_smooth_stats = extern struct {
+    outer_iterations: u64,
+    inner_iterations: u64,
+    operator_applications: u64,
+    nodes: u64,
+    last_sumsq_x: f64,
+    last_sumsq_y: f64,
+    last_residual: f64,
+    last_max_update: f64,
+    last_inner_residual: f64,
+    gpu_seconds: f64,
+    converged: i32,
+    _pad: i32 = 0,
+};
+
+pub extern fn tm_tfi_block(ni: u64, nj: u64, x_i_min: [*]const f64, x_i_max: [*]const f64, x_j_min: [*]const f64, x_j_max: [*]const f64, s1: [*]const f64, s2: [*]const f64, t1: [*]const f64, t2: [*]const f64, out_xy: [*]f64) callconv(.c) c_int;
+pub extern fn tm_smooth_mesh(blocks: [*]tm_block, n_blocks: usize, connections: ?[*]const tm_connection, n_connections: usize, conditions: ?[*]const tm_condition, n_conditions: usize, opts: *const tm_smooth_options, stats: ?*tm_smooth_stats) callconv(.c) c_int;
+pub extern fn tm_smooth_options_default(opts: *tm_smooth_options) callconv(.c) void;
+pub extern fn tm_last_error() callconv(.c) [*:0]const u8;
+
+pub const Error = error{ CudaBackendFailed, CudaNoDevice, CudaBadTopology, CudaNotConverged };
+
+fn check(rc: c_int) Error!void {
+    if (rc == 0) return;
+    log.err("turbomesh_gpu: {s}", .{std.mem.span(tm_last_error())});
+    return switch (rc) {
+        -2 => error.CudaNoDevice,
+        -4, -5 => error.CudaBadTopology,
+        -6 => error.CudaNotConverged,
+        else => error.CudaBackendFailed,
+    };
+}
+
+/// Options of the `"cuda"` variant of `solver.Option` (JSON: `"solver": {"cuda": {"method": "picard_bicgstab"}}`).
+pub const Option = struct {
+    method: enum { picard_bicgstab, relax } = .picard_bicgstab,
+    rtol: f64 = 1e-6, // BiCGStab.zig:20
+    atol: f64 = 1e-8, // BiCGStab.zig:21
+    max_inner_iterations: u64 = 1000, // BiCGStab.zig:19
+    omega: f64 = 1.0,
+    sweeps_per_iteration: u64 = 1,
+    device: i32 = -1,
+};
+
+/// Replacement for the body of `tfi.linear2dBoundaryBlendedControlFunction` as called from
+/// `discrete.Block2d.init` (discrete.zig:147-158): same arguments, result written into `data`.
+pub fn tfi(
+    data: *types.Mat2d,
+    x_i_min: []const types.Vec2d,
+    x_i_max: []const types.Vec2d,
+    x_j_min: []const types.Vec2d,
+    x_j_max: []const types.Vec2d,
+    s1: []const types.Float,
+    s2: []const types.Float,
+    t1: []const types.Float,
+    t2: []const types.Float,
+) Error!void {
+    // Vec2d is `struct { data: [2]f64 }` (types.zig:16-27): a slice of it is the interleaved x,y array the ABI expects
+    try check(tm_tfi_block(
+        data.size[0],
+        data.size[1],
+        @ptrCast(x_i_min.ptr),
+        @ptrCast(x_i_max.ptr),
+        @ptrCast(x_j_min.ptr),
+        @ptrCast(x_j_max.ptr),
+        s1.ptr,
+        s2.ptr,
+        t1.ptr,
+        t2.ptr,
+        @ptrCast(data.data.ptr),
+    ));
+}
+
+/// Replacement for `smooth.mesh` (smooth.zig:74-166) when `solver_option == .cuda`: smooths all blocks in place.
+pub fn mesh(
+    allocator: std.mem.Allocator,
+    mesh_data: *discrete.Mesh,
+    iterations: usize,
+    option: Option,
+    control_function_algorithm: wall_control_function.Algorithm,
+) !void {
+    const blocks = try allocator.alloc(tm_block, mesh_data.blocks.items.len);
+    defer allocator.free(blocks);
+    for (mesh_data.blocks.items, blocks) |b, *out| {
+        out.* = .{ .ni = b.points.size[0], .nj = b.points.size[1], .xy = @ptrCast(b.points.data.ptr) };
+    }
+
+    const connections = try allocator.alloc(tm_connection, mesh_data.connections.items.len);
+    defer allocator.free(connections);
+    for (mesh_data.connections.items, connections) |c, *out| {
+        out.* = .{
+            .ranges = .{ toRange(c.ranges[0]), toRange(c.ranges[1]) },
+            .has_periodicity = if (c.periodicity != null) 1 else 0,
+            .periodicity = if (c.periodicity) |p| p.data else .{ 0, 0 },
+        };
+    }
+
+    const conditions = try allocator.alloc(tm_condition, mesh_data.boundary_conditions.items.len);
+    defer allocator.free(conditions);
+    for (mesh_data.boundary_conditions.items, conditions) |bc, *out| {
+        out.* = .{ .range = toRange(bc.range), .kind = @intFromEnum(bc.kind) }; // wall = 0, inlet = 1, outlet = 2 (boundary.zig:172-176)
+    }
+
+    var opts: tm_smooth_options = undefined;
+    tm_smooth_options_default(&opts);
+    opts.solver = @intFromEnum(option.method);
+    opts.iterations = iterations;
+    opts.rtol = option.rtol;
+    opts.atol = option.atol;
+    opts.max_inner_iterations = option.max_inner_iterations;
+    opts.omega = option.omega;
+    opts.sweeps_per_iteration = option.sweeps_per_iteration;
+    opts.device = option.device;
+    switch (control_function_algorithm) {
+        .laplace => opts.control_function = 0,
+        .white => |w| {
+            opts.control_function = 1;
+            opts.white_ds_target = w.ds_target;
+            opts.white_theta_target = w.theta_target;
+        },
+    }
+
+    var stats: tm_smooth_stats = undefined;
+    try check(tm_smooth_mesh(blocks.ptr, blocks.len, connections.ptr, connections.len, conditions.ptr, conditions.len, &opts, &stats));
+    log.info("\tresidual: {} ({} outer, {} inner iterations, {d:.3} s on the GPU)", .{ stats.last_residual, stats.outer_iterations, stats.inner_iterations, stats.gpu_seconds });
+}
+
+fn toRange(r: boundary.Range) tm_range {
+    // boundary.Side is declared i_min, i_max, j_min, j_max (boundary.zig:8-13) = 0..3, the ABI's tm_side
+    return .{ .block = r.block, .side = @intFromEnum(r.side), .start = r.start, .end = r.end };
+}
