@@ -134,23 +134,30 @@ __global__ void __launch_bounds__(TILE_J) tfi_kernel(int ni, int nj, const doubl
 //   with D_r = u[r][j+1]-u[r][j-1] and R_r = (u[r][j+1]-u[r][j]) + (u[r][j-1]-u[r][j]).  Evaluating the row this
 //   way is translation invariant: its rounding error scales with the cell size, not with |x|.
 // ---------------------------------------------------------------------------------------------------
-struct Metric {
-    double g11, g22, g12;
+struct Metric {  // 4x the reference's g11, g22, g12: built from undivided central differences (the common factor
+    double g11, g22, g12;  // cancels in every row result, and scaling by 4 is exact in binary floating point)
 };
 __device__ __forceinline__ Metric metric_terms(double2 W, double2 E, double2 Deta /* N - S */) {
-    const double x_xi = 0.5 * (E.x - W.x), y_xi = 0.5 * (E.y - W.y);
-    const double x_eta = 0.5 * Deta.x, y_eta = 0.5 * Deta.y;
+    const double ax = E.x - W.x, ay = E.y - W.y;  // 2 x_xi, 2 y_xi
     Metric m;
-    m.g22 = x_eta * x_eta + y_eta * y_eta;
-    m.g12 = x_xi * x_eta + y_xi * y_eta;
-    m.g11 = x_xi * x_xi + y_xi * y_xi;
+    m.g22 = Deta.x * Deta.x + Deta.y * Deta.y;
+    m.g12 = ax * Deta.x + ay * Deta.y;
+    m.g11 = ax * ax + ay * ay;
     return m;
 }
-// rel = (row applied to u) + 2(g11+g22) C - ... i.e. sum_k a_k (u_k - C) over the 8 neighbours
+// rel = sum_k a_k (u_k - C) over the 8 neighbours (times the common factor 4)
+template <bool HAS_PQ>
 __device__ __forceinline__ double2 row_rel(const Metric& m, double P, double Q, double2 C, double2 W, double2 E, double2 Rj, double2 Deta, double2 Dp, double2 Dm) {
+    double ex = (E.x - C.x) + (W.x - C.x), ey = (E.y - C.y) + (W.y - C.y);
+    double nx = Rj.x, ny = Rj.y;
+    if (HAS_PQ) {
+        ex += 0.5 * P * (E.x - W.x); ey += 0.5 * P * (E.y - W.y);
+        nx += 0.5 * Q * Deta.x; ny += 0.5 * Q * Deta.y;
+    }
+    const double h = 0.5 * m.g12;
     double2 r;
-    r.x = m.g22 * (((E.x - C.x) + (W.x - C.x)) + 0.5 * P * (E.x - W.x)) + m.g11 * (Rj.x + 0.5 * Q * Deta.x) - 0.5 * m.g12 * (Dp.x - Dm.x);
-    r.y = m.g22 * (((E.y - C.y) + (W.y - C.y)) + 0.5 * P * (E.y - W.y)) + m.g11 * (Rj.y + 0.5 * Q * Deta.y) - 0.5 * m.g12 * (Dp.y - Dm.y);
+    r.x = m.g22 * ex + m.g11 * nx - h * (Dp.x - Dm.x);
+    r.y = m.g22 * ey + m.g11 * ny - h * (Dp.y - Dm.y);
     return r;
 }
 
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
             const double2 f = ldg2(pq + b.off + idx);
             P = f.x; Q = f.y;
         }
-        const double2 rel = row_rel(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
+        const double2 rel = row_rel<HAS_PQ>(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
         const double2 res = row_result<MODE>(m, rel, C0, omega);
         if (active) {
             ob[idx] = res;
@@ -270,6 +277,23 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
 // Consumers read a node and its j-1/j+1 neighbours from shared memory (3 x LDS.128), keep the 3-row window in
 // registers and store results straight from registers (coalesced 16 B per thread).
 // ---------------------------------------------------------------------------------------------------
+constexpr int BND_THREADS = 128;
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
+__device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows, int n_j,
+                                              const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
+                                              const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
+                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials);
+// The boundary rows ride in the same launch as the interior tiles (the first n_ctas CTAs of the grid): they are few
+// and latency-bound, so they hide behind the interior work instead of costing a launch of their own.
+struct BndArgs {
+    const SmoothedRow* srows;
+    const JunctionRow* jrows;
+    const SlidingRow* lrows;
+    const SlaveRow* slaves;
+    double* partials;
+    int n_s, n_j, n_l, n_ctas;
+};
+
 constexpr int BULK_R = 4;    // rows per pipeline stage
 constexpr int BULK_NS = 3;   // stages
 constexpr int BULK_ROW = TILE_J + 2;
@@ -302,10 +326,16 @@ template <int MODE, bool HAS_PQ, int STATS>
 __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Tile* __restrict__ tiles, const DevBlock* __restrict__ blocks,
                                                                         const double2* __restrict__ u, const double2* __restrict__ pq,
                                                                         double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
-                                                                        double* __restrict__ partials) {
+                                                                        double* __restrict__ partials, const BndArgs bnd) {
     __shared__ __align__(128) double2 ring[BULK_NS][BULK_R][BULK_ROW];
     __shared__ __align__(8) uint64_t full[BULK_NS];
-    const Tile t = tiles[blockIdx.x];
+    if ((int)blockIdx.x < bnd.n_ctas) {
+        boundary_rows<MODE, false, HAS_PQ, STATS>(blockIdx.x, bnd.srows, bnd.n_s, bnd.jrows, bnd.n_j, bnd.lrows, bnd.n_l, bnd.slaves, u, u, pq, out, omega, dot_a,
+                                                  bnd.partials);
+        return;
+    }
+    const int tile_id = (int)blockIdx.x - bnd.n_ctas;
+    const Tile t = tiles[tile_id];
     const DevBlock b = blocks[t.block];
     const int nj = b.nj;
     const int tid = threadIdx.x;
@@ -340,49 +370,55 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Til
     double2 Cm = make_double2(0, 0), Dm = Cm, C0 = Cm, D0 = Cm, R0 = Cm;
     const int tl = active ? tid : 0;  // inactive lanes read a valid column, never store
     long long idx = (long long)(i_begin - 2) * nj + (active ? j : t.j0);  // block-local index of the row being finished (k-2)
-    for (int k = 0; k < n_rows; ++k) {
-        const int c = k / BULK_R, slot = k - c * BULK_R, s = c % BULK_NS;
-        if (slot == 0) mbar_wait(&full[s], (uint32_t)((c / BULK_NS) & 1));
-        const double2 lp = ring[s][slot][tl], Cp = ring[s][slot][tl + 1], rp = ring[s][slot][tl + 2];
-        const double2 Dp = rp - lp, Rp = (rp - Cp) + (lp - Cp);
-        if (k >= 2) {
-            const Metric m = metric_terms(Cm, Cp, D0);
-            double P = 0.0, Q = 0.0;
-            if (HAS_PQ) {
-                const double2 f = ldg2(pq + b.off + idx);
-                P = f.x; Q = f.y;
-            }
-            const double2 rel = row_rel(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
-            const double2 res = row_result<MODE>(m, rel, C0, omega);
-            if (active) {
-                ob[idx] = res;
-                if (STATS == 1) {
-                    const double dx = res.x - C0.x, dy = res.y - C0.y;
-                    s0 += dx * dx; s1 += dy * dy;
-                    mx = fmax(mx, fmax(fabs(dx), fabs(dy)));
-                } else if (STATS == 2) {
-                    const double2 a = ld2(dot_a + b.off + idx);
-                    s0 += a.x * res.x; s1 += a.y * res.y;
-                } else if (STATS == 3) {
-                    const double2 a = ld2(dot_a + b.off + idx);
-                    s0 += a.x * res.x; s1 += a.y * res.y;
-                    s2 += res.x * res.x; s3 += res.y * res.y;
-                } else if (STATS == 4) {
-                    s0 += res.x * res.x; s1 += res.y * res.y;
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(&full[stage], parity);
+#pragma unroll
+        for (int slot = 0; slot < BULK_R; ++slot) {
+            const int k = c * BULK_R + slot;
+            if (k < n_rows) {  // uniform over the CTA
+                const double2 lp = ring[stage][slot][tl], Cp = ring[stage][slot][tl + 1], rp = ring[stage][slot][tl + 2];
+                const double2 Dp = rp - lp, Rp = (rp - Cp) + (lp - Cp);
+                if (k >= 2) {
+                    const Metric m = metric_terms(Cm, Cp, D0);
+                    double P = 0.0, Q = 0.0;
+                    if (HAS_PQ) {
+                        const double2 f = ldg2(pq + b.off + idx);
+                        P = f.x; Q = f.y;
+                    }
+                    const double2 rel = row_rel<HAS_PQ>(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
+                    const double2 res = row_result<MODE>(m, rel, C0, omega);
+                    if (active) {
+                        ob[idx] = res;
+                        if (STATS == 1) {
+                            const double dx = res.x - C0.x, dy = res.y - C0.y;
+                            s0 += dx * dx; s1 += dy * dy;
+                            mx = fmax(mx, fmax(fabs(dx), fabs(dy)));
+                        } else if (STATS == 2) {
+                            const double2 a = ld2(dot_a + b.off + idx);
+                            s0 += a.x * res.x; s1 += a.y * res.y;
+                        } else if (STATS == 3) {
+                            const double2 a = ld2(dot_a + b.off + idx);
+                            s0 += a.x * res.x; s1 += a.y * res.y;
+                            s2 += res.x * res.x; s3 += res.y * res.y;
+                        } else if (STATS == 4) {
+                            s0 += res.x * res.x; s1 += res.y * res.y;
+                        }
+                    }
                 }
+                Cm = C0; Dm = D0;
+                C0 = Cp; D0 = Dp; R0 = Rp;
+                idx += nj;
             }
         }
-        Cm = C0; Dm = D0;
-        C0 = Cp; D0 = Dp; R0 = Rp;
-        idx += nj;
-        if (slot == BULK_R - 1 || k == n_rows - 1) {
-            __syncthreads();  // every thread has copied this stage into registers: the stage may be refilled
-            if (tid == 0 && c + BULK_NS < n_chunks) issue_chunk(c + BULK_NS);
-        }
+        __syncthreads();  // every thread has copied this stage into registers: the stage may be refilled
+        if (tid == 0 && c + BULK_NS < n_chunks) issue_chunk(c + BULK_NS);
+        if (++stage == BULK_NS) { stage = 0; parity ^= 1u; }
     }
     if (STATS != 0) {
         double sums[4] = {s0, s1, s2, s3};
-        block_reduce_store<4, TILE_J>(sums, mx, partials + (size_t)blockIdx.x * 5);
+        block_reduce_store<4, TILE_J>(sums, mx, partials + (size_t)tile_id * 5);
     }
 }
 
@@ -390,16 +426,12 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Til
 // Boundary rows: one thread per free boundary row (smoothed interface rows, then junction rows, then sliding
 // rows).  RELAX additionally writes the row's `connected` copies (x_slave = x_root + shift).
 // ---------------------------------------------------------------------------------------------------
-constexpr int BND_THREADS = 128;
-
 template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
-__global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows,
-                                                                       int n_j, const SlidingRow* __restrict__ lrows, int n_l,
-                                                                       const SlaveRow* __restrict__ slaves, const double2* __restrict__ u,
-                                                                       const double2* __restrict__ xc, const double2* __restrict__ pq,
-                                                                       double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
-                                                                       double* __restrict__ partials) {
-    const int r = blockIdx.x * BND_THREADS + threadIdx.x;
+__device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows, int n_j,
+                                              const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
+                                              const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
+                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials) {
+    const int r = cta * BND_THREADS + threadIdx.x;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
     double2 res = make_double2(0.0, 0.0), old = make_double2(0.0, 0.0);
     int64_t self = -1;
@@ -430,11 +462,11 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
             const double2 f = ldg2(pq + row.g0);
             if (row.periodic) { P = f.x; Q = f.y; } else { P = f.y; Q = f.x; }  // smooth.zig:1040-1041 vs 1082-1083
         }
-        const double2 rel = row_rel(m, P, Q, C, W, E, (N - C) + (S - C), N - S, NE - SE, NW - SW);
+        const double2 rel = row_rel<HAS_PQ>(m, P, Q, C, W, E, (N - C) + (S - C), N - S, NE - SE, NW - SW);
         res = row_result<MODE>(m, rel, C, omega);
         old = C;
         if (STATS == 4 && row.periodic) {  // rhs of the reference's row: p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)) = p * g11 (1 + Q/2)
-            const double a = m.g11 * (1.0 + 0.5 * Q);
+            const double a = 0.25 * m.g11 * (1.0 + 0.5 * Q);  // Metric holds 4 g11
             s2 = (row.px * a) * (row.px * a); s3 = (row.py * a) * (row.py * a);
         }
     } else if (r < n_s + n_j) {
@@ -494,8 +526,18 @@ __global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const Smo
     }
     if (STATS != 0) {
         double sums[4] = {s0, s1, s2, s3};
-        block_reduce_store<4, BND_THREADS>(sums, mx, partials + (size_t)blockIdx.x * 5);
+        block_reduce_store<4, BND_THREADS>(sums, mx, partials + (size_t)cta * 5);
     }
+}
+
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
+__global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows,
+                                                                       int n_j, const SlidingRow* __restrict__ lrows, int n_l,
+                                                                       const SlaveRow* __restrict__ slaves, const double2* __restrict__ u,
+                                                                       const double2* __restrict__ xc, const double2* __restrict__ pq,
+                                                                       double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
+                                                                       double* __restrict__ partials) {
+    boundary_rows<MODE, LAGGED, HAS_PQ, STATS>(blockIdx.x, srows, n_s, jrows, n_j, lrows, n_l, slaves, u, xc, pq, out, omega, dot_a, partials);
 }
 
 // mode 0: v[slave] = v[root]; mode 1: v[slave] = v[root] + shift (keeps `connected` copies consistent,

@@ -341,10 +341,11 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
     } while (0)
 #define TM_ROWS_BULK(PQ)                                                                                                                          \
     do {                                                                                                                                          \
-        if (r.n_tiles > 0)                                                                                                                        \
-            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), r.n_tiles, TILE_J, s, (const Tile*)r.d_tiles.p, (const DevBlock*)r.d_blocks.p, \
-                   u, pq, out, omega, dot_a, r.part_int.p);                                                                                       \
-        TM_BND(false, PQ);                                                                                                                        \
+        const BndArgs bnd{r.d_srows.p, r.d_jrows.p, r.d_lrows.p, r.d_slaves.p, r.part_bnd.p, int(r.L.smoothed.size()),                            \
+                          int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};                                                  \
+        if (r.n_tiles + r.n_bnd_ctas > 0)                                                                                                         \
+            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), r.n_tiles + r.n_bnd_ctas, TILE_J, s, (const Tile*)r.d_tiles.p,                \
+                   (const DevBlock*)r.d_blocks.p, u, pq, out, omega, dot_a, r.part_int.p, bnd);                                                   \
     } while (0)
     if (lagged) { if (has_pq) TM_ROWS(true, true); else TM_ROWS(true, false); }
     else if (m->use_bulk) { if (has_pq) TM_ROWS_BULK(true); else TM_ROWS_BULK(false); }
