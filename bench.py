@@ -30,7 +30,7 @@ UNIT = "node-updates/s"
 BYTES_PER_NODE_UPDATE = 32.0  # read own x,y (16 B) + write new x,y (16 B), Laplace control function
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of winslow_interior_kernel on the 8192^2 block, from the
 # committed ncu capture (profiles/); None until measured.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 2.150e9  # profiles/r1_ncu_winslow_interior_bulk_8192.txt: 1.1287 GB read + 1.0214 GB written
 
 
 def measured_peak():
@@ -219,7 +219,7 @@ def run_gpu(args):
     per_launch = sweep_seconds / max(sweep_launches, 1)
     achieved = BYTES_PER_NODE_UPDATE * nodes_local / per_launch / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "winslow_interior_kernel<RELAX>",
+                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (kind == "single" and args.size == 8192) else None, "kernel": "winslow_interior_bulk_kernel<RELAX>",
                 "algorithmic_bytes_per_launch": BYTES_PER_NODE_UPDATE * nodes_local, "avg_launch_ms": per_launch * 1e3,
                 "peak_source": peak_src + ", sustained copy figure"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
