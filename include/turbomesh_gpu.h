@@ -88,8 +88,12 @@ typedef enum tm_control_function { TM_CF_LAPLACE = 0, TM_CF_WHITE = 1 } tm_contr
  *  TM_SOLVER_RELAX  throughput path: `sweeps_per_iteration` damped-Jacobi sweeps of the same 9-point
  *      operator with the coefficients recomputed from the current iterate (32 B/node-update); converges
  *      to the same fixed point as the Picard iteration.
+ *  TM_SOLVER_FAS_MULTIGRID  time-to-converged path for a single block whose boundary nodes are all fixed (config 3):
+ *      `iterations` V(nu,nu) cycles of a geometric full-approximation-scheme multigrid (nu = sweeps_per_iteration) with
+ *      the same damped-Jacobi sweep as smoother on every level, stopped early by stop_max_update (max-norm of the last
+ *      fine-level Jacobi update).  Same fixed point as the two other solvers.  Other meshes: TM_ERR_UNSUPPORTED.
  */
-typedef enum tm_solver { TM_SOLVER_PICARD_BICGSTAB = 0, TM_SOLVER_RELAX = 1 } tm_solver;
+typedef enum tm_solver { TM_SOLVER_PICARD_BICGSTAB = 0, TM_SOLVER_RELAX = 1, TM_SOLVER_FAS_MULTIGRID = 2 } tm_solver;
 
 typedef struct tm_smooth_options {
     uint32_t struct_size;          /* sizeof(tm_smooth_options), for ABI evolution               */

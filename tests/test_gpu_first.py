@@ -75,3 +75,27 @@ def test_relax_converges_to_picard_fixed_point(orc, gpu_lib):
     st = smoothing.smooth_mesh(gpu, 400, smoothing.CudaSolver(method="relax", sweeps_per_iteration=50, omega=0.9, stop_max_update=1e-14))
     orc.smooth_mesh(cpu, 30, orc.tight_options())
     assert _max_diff(gpu, cpu) <= 1e-9, st
+
+
+@pytest.mark.parametrize("shape", [(129, 129), (130, 75), (257, 64)])
+def test_multigrid_converges_to_the_oracle_fixed_point(orc, gpu_lib, shape):
+    """FAS multigrid (time-to-converged path) reaches the fixed point of the reference's Picard iteration; the levels are
+    non-nested for (130, 75), semi-coarsened for (257, 64)."""
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.single_block(*shape)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    st = smoothing.smooth_mesh(gpu, 80, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-13))
+    orc.smooth_mesh(cpu, 40, orc.tight_options())
+    assert st["last_max_update"] <= 1e-13 and st["outer_iterations"] < 80, st
+    assert _max_diff(gpu, cpu) <= 1e-9, st
+
+
+def test_multigrid_rejects_multi_block_meshes(orc, gpu_lib):
+    from turbomesh_b200 import _lib, smoothing
+
+    mesh = synthetic.materialize(synthetic.cascade(2, 2, 12, 9), orc.tfi)
+    with pytest.raises(_lib.TurbomeshGpuError) as e:
+        smoothing.smooth_mesh(mesh, 2, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=2))
+    assert e.value.code == _lib.TM_ERR_UNSUPPORTED

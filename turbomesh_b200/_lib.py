@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libturbomesh_gpu.so")
 TM_OK = 0
 TM_ERR_INVALID_ARGUMENT, TM_ERR_NO_DEVICE, TM_ERR_CUDA, TM_ERR_TOPOLOGY = -1, -2, -3, -4
 TM_ERR_UNSUPPORTED, TM_ERR_NOT_CONVERGED, TM_ERR_OUT_OF_MEMORY = -5, -6, -7
-TM_SOLVER_PICARD_BICGSTAB, TM_SOLVER_RELAX = 0, 1
+TM_SOLVER_PICARD_BICGSTAB, TM_SOLVER_RELAX, TM_SOLVER_FAS_MULTIGRID = 0, 1, 2
 TM_CF_LAPLACE, TM_CF_WHITE = 0, 1
 
 

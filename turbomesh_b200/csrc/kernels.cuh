@@ -30,7 +30,7 @@ struct Tile {
 constexpr int TILE_J = 128;  // threads per CTA = nodes along j per tile
 constexpr int TILE_I = 32;   // default rows marched per CTA (the host balances waves, see build_tiles)
 
-enum Mode : int { MODE_RELAX = 0, MODE_APPLY = 1, MODE_RESID = 2 };
+enum Mode : int { MODE_RELAX = 0, MODE_APPLY = 1, MODE_RESID = 2, MODE_REL = 3 };
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
@@ -176,8 +176,10 @@ __device__ __forceinline__ double2 row_result(const Metric& m, double2 rel, doub
         return make_double2(C.x + omega * (rel.x * inv), C.y + omega * (rel.y * inv));
     } else if (MODE == MODE_APPLY) {
         return make_double2(-(rel.x * inv), -(rel.y * inv));
-    } else {
+    } else if (MODE == MODE_RESID) {
         return make_double2(rel.x * inv, rel.y * inv);
+    } else {
+        return rel;  // MODE_REL: the unscaled row (minus the multigrid right-hand side), see mg_* kernels
     }
 }
 
@@ -322,11 +324,12 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                  : "memory");
 }
 
-template <int MODE, bool HAS_PQ, int STATS>
+template <int MODE, bool HAS_PQ, int STATS, bool HAS_RHS = false>
 __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Tile* __restrict__ tiles, const DevBlock* __restrict__ blocks,
                                                                         const double2* __restrict__ u, const double2* __restrict__ pq,
                                                                         double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
-                                                                        double* __restrict__ partials, const BndArgs bnd) {
+                                                                        double* __restrict__ partials, const BndArgs bnd,
+                                                                        const double2* __restrict__ rhs /* HAS_RHS: multigrid tau term, in row units */) {
     __shared__ __align__(128) double2 ring[BULK_NS][BULK_R][BULK_ROW];
     __shared__ __align__(8) uint64_t full[BULK_NS];
     if ((int)blockIdx.x < bnd.n_ctas) {
@@ -387,7 +390,11 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Til
                         const double2 f = ldg2(pq + b.off + idx);
                         P = f.x; Q = f.y;
                     }
-                    const double2 rel = row_rel<HAS_PQ>(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
+                    double2 rel = row_rel<HAS_PQ>(m, P, Q, C0, Cm, Cp, R0, D0, Dp, Dm);
+                    if (HAS_RHS) {
+                        const double2 f = ld2(rhs + b.off + idx);
+                        rel.x -= f.x; rel.y -= f.y;
+                    }
                     const double2 res = row_result<MODE>(m, rel, C0, omega);
                     if (active) {
                         ob[idx] = res;
@@ -891,6 +898,90 @@ __global__ void __launch_bounds__(VEC_THREADS) diff_stats_kernel(int64_t n, cons
     }
     double sums[4] = {s0, s1, 0.0, 0.0};
     block_reduce_store<4, VEC_THREADS>(sums, mx, partials + (size_t)blockIdx.x * 5);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Geometric FAS multigrid for a block whose boundary nodes are all fixed (the single-block configuration).
+// Levels are NOT nested (8192 nodes = 8191 intervals is prime): a coarse level has about half the nodes per direction
+// and all transfers are bilinear interpolations in index space -- the coordinates are smooth functions of (xi, eta), and
+// the Winslow row (undivided differences) of a smooth field scales by (r_xi r_eta)^2 between levels.
+// ---------------------------------------------------------------------------------------------------
+struct MgLevelDims {
+    int ni_f, nj_f, ni_c, nj_c;
+    double r_i, r_j;  // (ni_f-1)/(ni_c-1), (nj_f-1)/(nj_c-1)
+};
+
+__device__ __forceinline__ double2 bilerp(const double2* __restrict__ f, int nj, int i0, int j0, double ti, double tj) {
+    const double2 a = f[(size_t)i0 * nj + j0], b = f[(size_t)i0 * nj + j0 + 1], c = f[(size_t)(i0 + 1) * nj + j0], d = f[(size_t)(i0 + 1) * nj + j0 + 1];
+    const double w00 = (1.0 - ti) * (1.0 - tj), w01 = (1.0 - ti) * tj, w10 = ti * (1.0 - tj), w11 = ti * tj;
+    return make_double2(w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x, w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y);
+}
+
+// coarse <- fine: the iterate by interpolation (boundary included); the residual by interpolation of its
+// [1 2 1]x[1 2 1]/16 average (full-weighting-like), scaled to coarse row units.  One thread per coarse node.
+__global__ void mg_restrict_kernel(MgLevelDims d, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
+                                   double2* __restrict__ e_c, double2* __restrict__ res_c, double scale) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x, I = blockIdx.y;
+    if (J >= d.nj_c || I >= d.ni_c) return;
+    const double xi = fmin(I * d.r_i, (double)(d.ni_f - 1)), eta = fmin(J * d.r_j, (double)(d.nj_f - 1));
+    const int i0 = min((int)xi, d.ni_f - 2), j0 = min((int)eta, d.nj_f - 2);
+    const double ti = xi - i0, tj = eta - j0;
+    const size_t k = (size_t)I * d.nj_c + J;
+    const double2 uc = bilerp(u_f, d.nj_f, i0, j0, ti, tj);
+    u_c[k] = uc;
+    e_c[k] = uc;
+    double2 r = make_double2(0.0, 0.0);
+    if (I > 0 && I < d.ni_c - 1 && J > 0 && J < d.nj_c - 1) {
+        // averaged residual at the four surrounding fine nodes (the fine residual is zero on the block boundary)
+        double2 acc[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int ic = i0 + a, jc = j0 + b;
+                double sx = 0.0, sy = 0.0;
+#pragma unroll
+                for (int p = -1; p <= 1; ++p)
+#pragma unroll
+                    for (int q = -1; q <= 1; ++q) {
+                        const int ii = ic + p, jj = jc + q;
+                        if (ii < 0 || ii >= d.ni_f || jj < 0 || jj >= d.nj_f) continue;
+                        const double w = (p == 0 ? 2.0 : 1.0) * (q == 0 ? 2.0 : 1.0) * (1.0 / 16.0);
+                        const double2 v = res_f[(size_t)ii * d.nj_f + jj];
+                        sx += w * v.x; sy += w * v.y;
+                    }
+                acc[a][b] = make_double2(sx, sy);
+            }
+        const double w00 = (1.0 - ti) * (1.0 - tj), w01 = (1.0 - ti) * tj, w10 = ti * (1.0 - tj), w11 = ti * tj;
+        r.x = scale * (w00 * acc[0][0].x + w01 * acc[0][1].x + w10 * acc[1][0].x + w11 * acc[1][1].x);
+        r.y = scale * (w00 * acc[0][0].y + w01 * acc[0][1].y + w10 * acc[1][0].y + w11 * acc[1][1].y);
+    }
+    res_c[k] = r;
+}
+
+// coarse right-hand side of FAS: tau_c = row_c(I u_f) + restricted residual.  `rel_c` holds row_c(I u_f) (MODE_REL output)
+// on interior nodes; `res_c` the scaled restricted residual; the result overwrites res_c.
+__global__ void mg_coarse_rhs_kernel(int ni, int nj, const double2* __restrict__ rel_c, double2* __restrict__ res_c) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= nj || i >= ni) return;
+    const size_t k = (size_t)i * nj + j;
+    if (i == 0 || i == ni - 1 || j == 0 || j == nj - 1) { res_c[k] = make_double2(0.0, 0.0); return; }
+    const double2 a = rel_c[k], r = res_c[k];
+    res_c[k] = make_double2(a.x + r.x, a.y + r.y);
+}
+
+// fine += interpolated coarse correction (u_c - e_c); interior fine nodes only.  One thread per fine node.
+__global__ void mg_prolong_kernel(MgLevelDims d, const double2* __restrict__ u_c, const double2* __restrict__ e_c, double2* __restrict__ u_f) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j <= 0 || j >= d.nj_f - 1 || i <= 0 || i >= d.ni_f - 1) return;
+    const double xi = i / d.r_i, eta = j / d.r_j;
+    const int i0 = min((int)xi, d.ni_c - 2), j0 = min((int)eta, d.nj_c - 2);
+    const double ti = xi - i0, tj = eta - j0;
+    const double2 a = bilerp(u_c, d.nj_c, i0, j0, ti, tj), b = bilerp(e_c, d.nj_c, i0, j0, ti, tj);
+    const size_t k = (size_t)i * d.nj_f + j;
+    double2 v = u_f[k];
+    v.x += a.x - b.x; v.y += a.y - b.y;
+    u_f[k] = v;
 }
 
 }  // namespace tmesh

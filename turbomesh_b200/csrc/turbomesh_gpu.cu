@@ -145,6 +145,16 @@ struct EdgeCache {  // device copies of the four edges + clusterings of one bloc
     bool valid = false;
 };
 
+// One level of the geometric multigrid hierarchy of a single block (level 0 aliases the mesh's own fields).
+struct MgLevel {
+    int ni = 0, nj = 0, n_tiles = 0;
+    MgLevelDims to_coarse{};                 // transfer to the next coarser level
+    double scale = 1.0;                      // (r_i r_j)^2: row units of the next coarser level per row unit here
+    DevBuf<double2> U, V, rhs, tmp, E;       // iterate ping-pong, tau term, scratch (row / residual), restricted iterate
+    DevBuf<Tile> tiles;
+    DevBuf<DevBlock> blk;
+};
+
 // Everything one rank keeps on its GPU.  A distributed mesh holds exactly one; the in-process emulation of several
 // ranks on one GPU (tests of the multi-rank logic) holds all of them.
 struct RankMesh {
@@ -174,6 +184,7 @@ struct RankMesh {
     int n_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
     bool has_pq = false;
     WhiteParams wp{};
+    std::vector<std::unique_ptr<MgLevel>> mg;  // built on first use of TM_SOLVER_FAS_MULTIGRID
 };
 
 }  // namespace
@@ -345,7 +356,7 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
                           int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};                                                  \
         if (r.n_tiles + r.n_bnd_ctas > 0)                                                                                                         \
             LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), r.n_tiles + r.n_bnd_ctas, TILE_J, s, (const Tile*)r.d_tiles.p,                \
-                   (const DevBlock*)r.d_blocks.p, u, pq, out, omega, dot_a, r.part_int.p, bnd);                                                   \
+                   (const DevBlock*)r.d_blocks.p, u, pq, out, omega, dot_a, r.part_int.p, bnd, (const double2*)nullptr);                          \
     } while (0)
     if (lagged) { if (has_pq) TM_ROWS(true, true); else TM_ROWS(true, false); }
     else if (m->use_bulk) { if (has_pq) TM_ROWS_BULK(true); else TM_ROWS_BULK(false); }
@@ -401,10 +412,10 @@ void white_step(tm_mesh* m, bool update) {
 void validate_options(const tm_smooth_options* o) {
     if (!o) TM_THROW(TM_ERR_INVALID_ARGUMENT, "options are NULL");
     if (o->struct_size != sizeof(tm_smooth_options)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tm_smooth_options.struct_size mismatch (ABI version?)");
-    if (o->solver > TM_SOLVER_RELAX) TM_THROW(TM_ERR_INVALID_ARGUMENT, "unknown solver %u", o->solver);
+    if (o->solver > TM_SOLVER_FAS_MULTIGRID) TM_THROW(TM_ERR_INVALID_ARGUMENT, "unknown solver %u", o->solver);
     if (o->control_function > TM_CF_WHITE) TM_THROW(TM_ERR_INVALID_ARGUMENT, "unknown control function %u", o->control_function);
     if (!(o->omega > 0.0 && o->omega <= 1.0)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "omega must be in (0, 1]");
-    if (o->solver == TM_SOLVER_RELAX && o->sweeps_per_iteration == 0) TM_THROW(TM_ERR_INVALID_ARGUMENT, "sweeps_per_iteration must be > 0");
+    if (o->solver != TM_SOLVER_PICARD_BICGSTAB && o->sweeps_per_iteration == 0) TM_THROW(TM_ERR_INVALID_ARGUMENT, "sweeps_per_iteration must be > 0");
     if (!(o->rtol >= 0.0) || !(o->atol >= 0.0)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tolerances must be non-negative");
 }
 
@@ -546,6 +557,162 @@ void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats
             if (m->h_ctl->max_update <= o->stop_max_update) break;
         }
     }
+}
+
+// ---- geometric FAS multigrid (single block, all boundary nodes fixed) ------------------------------------------
+void mg_build(tm_mesh* m, RankMesh& r) {
+    if (!r.mg.empty()) return;
+    cudaStream_t s = m->stream;
+    const auto& B = m->topo.blocks[0];
+    int ni = int(B.ni), nj = int(B.nj);
+    // Mean physical extents of the block along i and j (from its corner nodes) give the mean cell aspect ratio per level:
+    // with point relaxation, a direction whose spacing is much finer than the other's is strongly coupled and is the only
+    // one coarsened until the cells are roughly square (semi-coarsening).
+    double len_i = 1.0, len_j = 1.0;
+    {
+        double2 c[4];
+        const int64_t idx[4] = {0, int64_t(ni - 1) * nj, int64_t(nj - 1), int64_t(ni - 1) * nj + nj - 1};
+        for (int k = 0; k < 4; ++k) CUDA_TRY(cudaMemcpyAsync(&c[k], r.X[r.cur].p + r.L.loff[0] + idx[k], sizeof(double2), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        auto dist = [](double2 a, double2 b) { return std::hypot(a.x - b.x, a.y - b.y); };
+        len_i = 0.5 * (dist(c[0], c[1]) + dist(c[2], c[3]));
+        len_j = 0.5 * (dist(c[0], c[2]) + dist(c[1], c[3]));
+        if (!(len_i > 0.0) || !(len_j > 0.0)) len_i = len_j = 1.0;
+    }
+    for (int l = 0;; ++l) {
+        std::unique_ptr<MgLevel> L(new MgLevel());
+        L->ni = ni; L->nj = nj;
+        const size_t n = size_t(ni) * size_t(nj);
+        std::vector<Tile> tiles;
+        const int64_t interior_i = ni - 2;
+        const int64_t n_i = std::max<int64_t>(1, (interior_i + m->tile_rows - 1) / m->tile_rows);
+        const int64_t rows = (interior_i + n_i - 1) / n_i;
+        for (int64_t i0 = 1; i0 <= ni - 2; i0 += rows)
+            for (int64_t j0 = 1; j0 <= nj - 2; j0 += TILE_J) tiles.push_back(Tile{0, int32_t(i0), int32_t(j0), int32_t(rows)});
+        L->n_tiles = int(tiles.size());
+        L->tiles.upload(tiles, s);
+        L->blk.upload(std::vector<DevBlock>{DevBlock{0, ni, nj}}, s);
+        L->tmp.alloc(n); L->tmp.zero(s);
+        if (l == 0) L->E.alloc(n);
+        if (l > 0) {
+            L->U.alloc(n); L->V.alloc(n); L->rhs.alloc(n); L->E.alloc(n);
+            L->U.zero(s); L->V.zero(s); L->rhs.zero(s); L->E.zero(s);
+        }
+        const double hi = len_i / double(ni - 1), hj = len_j / double(nj - 1);
+        bool do_i = ni >= 9, do_j = nj >= 9;
+        if (do_i && do_j) {
+            if (hi < 0.6 * hj) do_j = false;       // i is the strongly coupled direction
+            else if (hj < 0.6 * hi) do_i = false;  // j is
+        }
+        const int ci = do_i ? (ni + 1) / 2 : ni, cj = do_j ? (nj + 1) / 2 : nj;
+        const bool last = (ci == ni && cj == nj);
+        if (!last) {
+            L->to_coarse = MgLevelDims{ni, nj, ci, cj, double(ni - 1) / double(ci - 1), double(nj - 1) / double(cj - 1)};
+            L->scale = (L->to_coarse.r_i * L->to_coarse.r_j) * (L->to_coarse.r_i * L->to_coarse.r_j);
+        }
+        r.mg.push_back(std::move(L));
+        if (last) break;
+        ni = ci; nj = cj;
+    }
+}
+
+// `sweeps` damped-Jacobi sweeps on one level; the fields ping-pong between *pu and *pv
+void mg_smooth(tm_mesh* m, RankMesh& r, MgLevel& L, double2** pu, double2** pv, int level, uint64_t sweeps, double omega, bool stats_on_last) {
+    const BndArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    for (uint64_t k = 0; k < sweeps; ++k) {
+        const bool st = stats_on_last && k + 1 == sweeps;
+        const double2* u = *pu;
+        double2* out = *pv;
+        if (level == 0) {
+            if (st) LAUNCH((winslow_interior_bulk_kernel<MODE_RELAX, false, 1, false>), L.n_tiles, TILE_J, m->stream, (const Tile*)L.tiles.p, (const DevBlock*)L.blk.p, u,
+                           (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, none, (const double2*)nullptr);
+            else LAUNCH((winslow_interior_bulk_kernel<MODE_RELAX, false, 0, false>), L.n_tiles, TILE_J, m->stream, (const Tile*)L.tiles.p, (const DevBlock*)L.blk.p, u,
+                        (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, none, (const double2*)nullptr);
+        } else {
+            LAUNCH((winslow_interior_bulk_kernel<MODE_RELAX, false, 0, true>), L.n_tiles, TILE_J, m->stream, (const Tile*)L.tiles.p, (const DevBlock*)L.blk.p, u,
+                   (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, none, (const double2*)L.rhs.p);
+        }
+        std::swap(*pu, *pv);
+    }
+}
+
+// tmp = row(u) - rhs on interior nodes (the rim of tmp is never written and stays 0); the restriction flips the sign
+void mg_residual(tm_mesh* m, RankMesh& r, MgLevel& L, const double2* u, int level) {
+    const BndArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    if (level == 0)
+        LAUNCH((winslow_interior_bulk_kernel<MODE_REL, false, 0, false>), L.n_tiles, TILE_J, m->stream, (const Tile*)L.tiles.p, (const DevBlock*)L.blk.p, u,
+               (const double2*)nullptr, L.tmp.p, 1.0, (const double2*)nullptr, r.part_int.p, none, (const double2*)nullptr);
+    else
+        LAUNCH((winslow_interior_bulk_kernel<MODE_REL, false, 0, true>), L.n_tiles, TILE_J, m->stream, (const Tile*)L.tiles.p, (const DevBlock*)L.blk.p, u,
+               (const double2*)nullptr, L.tmp.p, 1.0, (const double2*)nullptr, r.part_int.p, none, (const double2*)L.rhs.p);
+}
+
+// V(nu,nu) cycles of the full approximation scheme until the fine-level Jacobi update drops below stop_max_update
+void run_fas_multigrid(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
+    if (m->n_ranks != 1 || m->topo.blocks.size() != 1 || !m->topo.smoothed.empty() || !m->topo.junction_rows.empty() || !m->topo.sliding.empty() ||
+        !m->topo.slaves.empty() || m->cf != TM_CF_LAPLACE)
+        TM_THROW(TM_ERR_UNSUPPORTED, "the multigrid solver handles a single block with fixed boundary nodes and the Laplace control function "
+                                     "(multi-block meshes: use the relaxation or Picard/BiCGStab solvers)");
+    RankMesh& r = *m->ranks[0];
+    mg_build(m, r);
+    cudaStream_t s = m->stream;
+    const int n_levels = int(r.mg.size());
+    const uint64_t nu = o->sweeps_per_iteration;
+    const BndArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    std::vector<double2*> U, V;
+    U.resize(size_t(n_levels));
+    V.resize(size_t(n_levels));
+    double fine_work = 0.0;  // operator applications in units of one fine-grid application
+    for (uint64_t cyc = 0; cyc < o->iterations; ++cyc) {
+        U[0] = r.X[r.cur].p; V[0] = r.X[1 - r.cur].p;
+        for (int l = 1; l < n_levels; ++l) { U[size_t(l)] = r.mg[size_t(l)]->U.p; V[size_t(l)] = r.mg[size_t(l)]->V.p; }
+        const bool want_change = o->stop_max_update > 0.0 || cyc + 1 == o->iterations;  // mesh change over the whole cycle
+        if (want_change) CUDA_TRY(cudaMemcpyAsync(r.mg[0]->E.p, U[0], size_t(r.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        for (int l = 0; l + 1 < n_levels; ++l) {  // down: smooth, restrict iterate and residual, build the coarse tau term
+            MgLevel& F = *r.mg[size_t(l)];
+            MgLevel& C = *r.mg[size_t(l) + 1];
+            const double w = double(F.ni) * F.nj / (double(r.mg[0]->ni) * r.mg[0]->nj);
+            mg_smooth(m, r, F, &U[size_t(l)], &V[size_t(l)], l, nu, o->omega, false);
+            mg_residual(m, r, F, U[size_t(l)], l);
+            fine_work += w * double(nu + 1);
+            dim3 gc((C.nj + 127) / 128, C.ni);
+            LAUNCH(mg_restrict_kernel, gc, 128, s, F.to_coarse, (const double2*)U[size_t(l)], (const double2*)F.tmp.p, U[size_t(l) + 1], C.E.p, C.rhs.p, -F.scale);
+            CUDA_TRY(cudaMemcpyAsync(V[size_t(l) + 1], U[size_t(l) + 1], size_t(C.ni) * C.nj * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+            LAUNCH((winslow_interior_bulk_kernel<MODE_REL, false, 0, false>), C.n_tiles, TILE_J, s, (const Tile*)C.tiles.p, (const DevBlock*)C.blk.p,
+                   (const double2*)U[size_t(l) + 1], (const double2*)nullptr, C.tmp.p, 1.0, (const double2*)nullptr, r.part_int.p, none, (const double2*)nullptr);
+            LAUNCH(mg_coarse_rhs_kernel, gc, 128, s, C.ni, C.nj, (const double2*)C.tmp.p, C.rhs.p);
+        }
+        {   // coarsest level: relax (almost) to convergence
+            const int l = n_levels - 1;
+            MgLevel& C = *r.mg[size_t(l)];
+            const uint64_t nc = n_levels > 1 ? 4 * uint64_t(std::max(C.ni, C.nj)) : nu;
+            mg_smooth(m, r, C, &U[size_t(l)], &V[size_t(l)], l, nc, o->omega, false);
+            fine_work += double(nc) * double(C.ni) * C.nj / (double(r.mg[0]->ni) * r.mg[0]->nj);
+        }
+        for (int l = n_levels - 2; l >= 0; --l) {  // up: interpolate the coarse correction, smooth
+            MgLevel& F = *r.mg[size_t(l)];
+            MgLevel& C = *r.mg[size_t(l) + 1];
+            dim3 gf((F.nj + 127) / 128, F.ni);
+            LAUNCH(mg_prolong_kernel, gf, 128, s, F.to_coarse, (const double2*)U[size_t(l) + 1], (const double2*)C.E.p, U[size_t(l)]);
+            mg_smooth(m, r, F, &U[size_t(l)], &V[size_t(l)], l, nu, o->omega, false);
+            fine_work += double(nu) * double(F.ni) * F.nj / (double(r.mg[0]->ni) * r.mg[0]->nj);
+        }
+        if (U[0] != r.X[r.cur].p) r.cur = 1 - r.cur;  // the finest iterate lives in the mesh's own ping-pong pair
+        for (int l = 1; l < n_levels; ++l)
+            if (U[size_t(l)] != r.mg[size_t(l)]->U.p) std::swap(r.mg[size_t(l)]->U.p, r.mg[size_t(l)]->V.p);
+        if (want_change) {
+            LAUNCH(diff_stats_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const double2*)r.mg[0]->E.p, (const double2*)U[0], r.part_vec.p);
+            launch_reduce(m, RED_UPDATE_STATS, o, false);
+        }
+        m->outer_done += 1;
+        st->outer_iterations += 1;
+        st->inner_iterations += 1;
+        if (o->stop_max_update > 0.0) {
+            fetch_ctl(m);
+            if (m->h_ctl->max_update <= o->stop_max_update) break;
+        }
+    }
+    st->operator_applications += uint64_t(fine_work + 0.5);
 }
 
 template <class F>
@@ -885,6 +1052,7 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
             }
             white_step(m, false);
         }
+        if (o->solver == TM_SOLVER_FAS_MULTIGRID && m->n_ranks == 1 && m->topo.blocks.size() == 1) mg_build(m, *m->ranks[0]);
         m->outer_done = 0;
         m->begun = true;
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -906,6 +1074,7 @@ int tm_mesh_smooth(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* stat
         st.converged = 1;
         CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
         if (o->solver == TM_SOLVER_RELAX) run_relax(m, o, &st);
+        else if (o->solver == TM_SOLVER_FAS_MULTIGRID) run_fas_multigrid(m, o, &st);
         else run_picard_bicgstab(m, o, &st);
         CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
         fetch_ctl(m);

@@ -39,7 +39,8 @@ class CudaSolver:
 
     ``method``: ``"picard_bicgstab"`` reproduces the reference's outer/inner structure (lagged coefficients, linear
     solve per outer iteration, tolerances with the reference's defaults); ``"relax"`` runs ``sweeps_per_iteration``
-    damped-Jacobi sweeps of the nonlinear system per outer iteration.
+    damped-Jacobi sweeps of the nonlinear system per outer iteration; ``"multigrid"`` runs V(nu,nu) cycles of a
+    geometric FAS multigrid (nu = ``sweeps_per_iteration``) on a single block with fixed boundary nodes.
     """
 
     method: str = "picard_bicgstab"
@@ -70,7 +71,8 @@ def make_options(iterations: int, solver: Optional[CudaSolver] = None, control_f
     control_function = control_function or Laplace()
     o = TmSmoothOptions()
     _lib.load().tm_smooth_options_default(C.byref(o))
-    o.solver = {"picard_bicgstab": _lib.TM_SOLVER_PICARD_BICGSTAB, "relax": _lib.TM_SOLVER_RELAX}[solver.method]
+    o.solver = {"picard_bicgstab": _lib.TM_SOLVER_PICARD_BICGSTAB, "relax": _lib.TM_SOLVER_RELAX,
+                "multigrid": _lib.TM_SOLVER_FAS_MULTIGRID}[solver.method]
     o.iterations = int(iterations)
     o.rtol, o.atol, o.max_inner_iterations = solver.rtol, solver.atol, int(solver.max_inner_iterations)
     o.omega, o.sweeps_per_iteration, o.stop_max_update = solver.omega, int(solver.sweeps_per_iteration), solver.stop_max_update
