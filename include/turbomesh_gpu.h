@@ -174,6 +174,11 @@ int tm_mesh_tfi_block(tm_mesh *mesh, size_t block,
                       const double *x_j_min, const double *x_j_max,
                       const double *s1, const double *s2, const double *t1, const double *t2);
 int tm_mesh_tfi_block_resident(tm_mesh *mesh, size_t block);
+/* White control function groups (extension for batches of independent cuts in one mesh).  The reference applies White
+ * to blocks 0 and 1 and connection 0 only (wall_control_function.zig:72, 204-217) -- that is the default.  A batch names
+ * one pair (A, B) of O-grid half blocks per cut; each pair needs a connection A:j_min[0..] <-> B:j_min[0..].
+ * block_pairs holds 2*n_groups block indices.  Call before tm_mesh_begin_smoothing. */
+int tm_mesh_set_white_groups(tm_mesh *mesh, const uint64_t *block_pairs, size_t n_groups);
 /* Freezes the current coordinates as the initial mesh: checks interface coincidence
  * (connectionDataCheck, smooth.zig:220-275), captures fixed/sliding boundary values
  * (smooth.zig:790-796, 853-858) and initialises the control function (wall_control_function.zig:27-42). */

@@ -107,6 +107,7 @@ def load():
     L.tm_mesh_download_block.argtypes = [vp, C.c_size_t, dp]
     L.tm_mesh_tfi_block.argtypes = [vp, C.c_size_t] + [dp] * 8
     L.tm_mesh_tfi_block_resident.argtypes = [vp, C.c_size_t]
+    L.tm_mesh_set_white_groups.argtypes = [vp, C.POINTER(C.c_uint64), C.c_size_t]
     L.tm_mesh_begin_smoothing.argtypes = [vp, C.POINTER(TmSmoothOptions)]
     L.tm_mesh_smooth.argtypes = [vp, C.POINTER(TmSmoothOptions), C.POINTER(TmSmoothStats)]
     L.tm_mesh_synchronize.argtypes = [vp]

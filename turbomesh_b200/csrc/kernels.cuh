@@ -593,15 +593,20 @@ __global__ void pair_check_kernel(const PairCheck* __restrict__ pairs, int n, co
 }
 
 // ---------------------------------------------------------------------------------------------------
-// White wall control function (blocks 0 and 1, wall = line j = 0).  wall_control_function.zig:70-473
-// wall_pq holds the accumulated (P,Q) of every wall node: [block 0: ni0 entries][block 1: ni1 entries].
+// White wall control function (wall_control_function.zig:70-473).  The reference hard-codes it to blocks 0 and 1
+// (the two O-grid halves, wall = line j = 0) joined at the leading edge by connection 0; here every such pair of
+// blocks is a *group* (default: the reference's single group), so that a batch of independent cuts is handled in the
+// same launches.  wall_pq holds the accumulated (P,Q) of every wall node of a group:
+// [block A: niA entries][block B: niB entries] starting at wall_base.
 // ---------------------------------------------------------------------------------------------------
 struct WhiteParams {
-    int64_t off0, off1;        // global offsets of blocks 0, 1
+    int64_t off0, off1;           // local offsets of the group's two blocks
     int32_t ni0, nj0, ni1, nj1;
-    int32_t c_in0, c_in1, c_al0;  // connection 0: inward shifts on both sides, along shift on side 0
-    int32_t _pad;
-    double ds_target, theta_target;
+    int32_t c_in0, c_in1, c_al0;  // leading-edge connection: inward shifts on both sides, along shift on side 0
+    int32_t wall_base;            // first entry of the group in wall_pq
+};
+struct WhiteNode {
+    int32_t group, t;             // t in [0, ni0 + ni1): wall node of block A, then of block B
 };
 
 __device__ __forceinline__ void white_eq610(double x_xi, double y_xi, double x_xi2, double y_xi2, double x_eta, double y_eta, double x_eta2, double y_eta2,
@@ -611,23 +616,27 @@ __device__ __forceinline__ void white_eq610(double x_xi, double y_xi, double x_x
     p = -(x_xi * x_xi2 + y_xi * y_xi2) / g11 - (x_xi * x_eta2 + y_xi * y_eta2) / g22;
     q = -(x_eta * x_eta2 + y_eta * y_eta2) / g22 - (x_eta * x_xi2 + y_eta * y_xi2) / g11;
 }
-__device__ __forceinline__ void white_delta(const WhiteParams& w, double x_xi, double y_xi, double x_eta, double y_eta, double& p, double& q) {
+__device__ __forceinline__ void white_delta(double ds_target, double theta_target, double x_xi, double y_xi, double x_eta, double y_eta, double& p, double& q) {
     // White.computeUpdate, wall_control_function.zig:293-309
     const double g11 = x_xi * x_xi + y_xi * y_xi;
     const double g12 = x_xi * x_eta + y_xi * y_eta;
     const double g22 = x_eta * x_eta + y_eta * y_eta;
     const double ds = sqrt(g22);
     const double theta = acos(g12 / sqrt(g11 * g22));
-    const double delta_p = -atan2(w.theta_target - theta, w.theta_target);
-    const double delta_q = atan2(w.ds_target - ds, w.ds_target);
+    const double delta_p = -atan2(theta_target - theta, theta_target);
+    const double delta_q = atan2(ds_target - ds, ds_target);
     p += 0.1 * delta_p;
     q += 0.1 * delta_q;
 }
 
 // one thread per wall node; `update` = 0: initControlFunction, 1: update
-__global__ void white_wall_kernel(WhiteParams w, const double2* __restrict__ x, double2* __restrict__ wall_pq, int update) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= w.ni0 + w.ni1) return;
+__global__ void white_wall_kernel(const WhiteParams* __restrict__ groups, const WhiteNode* __restrict__ nodes, int n_nodes, double ds_target,
+                                  double theta_target, const double2* __restrict__ x, double2* __restrict__ wall_pq, int update) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_nodes) return;
+    const WhiteNode node = nodes[k];
+    const WhiteParams w = groups[node.group];
+    const int t = node.t;
     const int blk = t < w.ni0 ? 0 : 1;
     const int i = blk ? t - w.ni0 : t;
     const int ni = blk ? w.ni1 : w.ni0, nj = blk ? w.nj1 : w.nj0;
@@ -654,12 +663,12 @@ __global__ void white_wall_kernel(WhiteParams w, const double2* __restrict__ x, 
         const double2 e2 = d[l + 2];
         white_eq610(x_xi, y_xi, x_xi2, y_xi2, x_eta, y_eta, c.x - 2 * e1.x + e2.x, c.y - 2 * e1.y + e2.y, p, q);
     } else {
-        const double2 acc = wall_pq[t];
+        const double2 acc = wall_pq[w.wall_base + t];
         p = acc.x; q = acc.y;
-        white_delta(w, x_xi, y_xi, x_eta, y_eta, p, q);
+        white_delta(ds_target, theta_target, x_xi, y_xi, x_eta, y_eta, p, q);
     }
     if (t == 0) {
-        // connection 0 (block0:j_min <-> block1:j_min) shares the wall node 0; xi runs across the two blocks,
+        // the leading-edge connection (blockA:j_min <-> blockB:j_min) shares wall node 0; xi runs across the two blocks,
         // eta along the connection (wall_control_function.zig:203-279, 394-472)
         const double2* d1 = x + w.off1;
         const double2 ip1 = d[w.c_in0], im1 = d1[w.c_in1], jp1 = d[w.c_al0];
@@ -669,28 +678,32 @@ __global__ void white_wall_kernel(WhiteParams w, const double2* __restrict__ x, 
                         c.x - 2 * jp1.x + jp2.x, c.y - 2 * jp1.y + jp2.y, p, q);  // overwrites the corner value
         } else {
             // applied on top of the corner update above; note the sign flip of the xi derivative (:429-431)
-            white_delta(w, -0.5 * (ip1.x - im1.x), -0.5 * (ip1.y - im1.y), -c.x + jp1.x, -c.y + jp1.y, p, q);
+            white_delta(ds_target, theta_target, -0.5 * (ip1.x - im1.x), -0.5 * (ip1.y - im1.y), -c.x + jp1.x, -c.y + jp1.y, p, q);
         }
     }
-    wall_pq[t] = make_double2(p, q);
+    wall_pq[w.wall_base + t] = make_double2(p, q);
 }
 
-// blends the wall values linearly along j: factor = 1 - j/(nj-1)   (wall_control_function.zig:104-111)
-__global__ void white_blend_kernel(WhiteParams w, const double2* __restrict__ wall_pq, double2* __restrict__ pq) {
-    const int64_t n0 = (int64_t)w.ni0 * w.nj0, n1 = (int64_t)w.ni1 * w.nj1;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n0 + n1) return;
-    const int blk = t < n0 ? 0 : 1;
-    const int64_t l = blk ? t - n0 : t;
+// blends the wall values linearly along j: factor = 1 - j/(nj-1)   (wall_control_function.zig:104-111); one CTA per wall node
+__global__ void white_blend_kernel(const WhiteParams* __restrict__ groups, const WhiteNode* __restrict__ nodes, int n_nodes,
+                                   const double2* __restrict__ wall_pq, double2* __restrict__ pq) {
+    const int k = blockIdx.x;
+    if (k >= n_nodes) return;
+    const WhiteNode node = nodes[k];
+    const WhiteParams w = groups[node.group];
+    const int blk = node.t < w.ni0 ? 0 : 1;
+    const int i = blk ? node.t - w.ni0 : node.t;
     const int nj = blk ? w.nj1 : w.nj0;
-    const int i = (int)(l / nj), j = (int)(l - (int64_t)i * nj);
-    const double2 a = wall_pq[blk ? w.ni0 + i : i];
-    double2 r = a;
-    if (j > 0) {
-        const double factor = 1 - (double)j / ((double)nj - 1);
-        r = make_double2(factor * a.x, factor * a.y);
+    const double2 a = wall_pq[w.wall_base + node.t];
+    double2* line = pq + (blk ? w.off1 : w.off0) + (size_t)i * nj;
+    for (int j = threadIdx.x; j < nj; j += blockDim.x) {
+        double2 r = a;
+        if (j > 0) {
+            const double factor = 1 - (double)j / ((double)nj - 1);
+            r = make_double2(factor * a.x, factor * a.y);
+        }
+        line[j] = r;
     }
-    pq[(blk ? w.off1 : w.off0) + l] = r;
 }
 
 // ---------------------------------------------------------------------------------------------------

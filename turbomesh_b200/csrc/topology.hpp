@@ -106,8 +106,12 @@ struct Topology {
     std::vector<FixedOverride> fixed_overrides;
     std::vector<FixedOverride> connected_rhs; // non-zero rhs of `connected` rows (periodic copies), for ||b||
     std::vector<PairCheck> pairs;
-    bool white_ok = false;                // connection 0 has the shape White requires
+    // White control function groups: pairs of O-grid half blocks (A, B) joined by a connection A:j_min[0..] <-> B:j_min[0..].
+    // Default = the reference's hard-coded single group (blocks 0 and 1 with connection 0).
+    std::vector<std::pair<int64_t, int64_t>> white_groups;
+    bool white_ok = false;
     std::string white_why;
+    std::vector<tm_connection> conns_copy;  // kept for set_white_groups
 
     // ---- helpers -------------------------------------------------------------------------------
     static int64_t range_len(const tm_range& r) { return r.start > r.end ? int64_t(r.start - r.end) + 1 : int64_t(r.end - r.start) + 1; }
@@ -464,16 +468,42 @@ struct Topology {
         }
     }
 
-    void check_white(const tm_connection* conns, size_t nc) { // wall_control_function.zig:72, 204-217
+    static bool le_connection(const tm_connection& c, int64_t a, int64_t b) {  // wall_control_function.zig:212-217
+        return int64_t(c.ranges[0].block) == a && c.ranges[0].start == 0 && c.ranges[0].side == TM_SIDE_J_MIN && int64_t(c.ranges[1].block) == b &&
+               c.ranges[1].start == 0 && c.ranges[1].side == TM_SIDE_J_MIN && !c.has_periodicity && c.ranges[0].end > 1;
+    }
+
+    void check_white(const tm_connection* conns, size_t nc) {  // wall_control_function.zig:72, 204-217
+        conns_copy.assign(conns, conns + nc);
         white_ok = false;
+        white_groups.clear();
         if (blocks.size() < 2 || nc < 1) { white_why = "the White control function needs blocks 0 and 1 (O-grid halves) and connection 0"; return; }
-        const tm_connection& c = conns[0];
-        if (!(c.ranges[0].block == 0 && c.ranges[0].start == 0 && c.ranges[0].side == TM_SIDE_J_MIN && c.ranges[1].block == 1 &&
-              c.ranges[1].start == 0 && c.ranges[1].side == TM_SIDE_J_MIN && !c.has_periodicity)) {
+        if (!le_connection(conns[0], 0, 1)) {
             white_why = "White: connection 0 must be block0:j_min[0..] <-> block1:j_min[0..], non periodic (wall_control_function.zig:212-217)";
             return;
         }
+        white_groups.push_back({0, 1});
         white_ok = true;
+    }
+
+  public:
+    // Extension for batches of cuts: several (A, B) groups, each needing its own leading-edge connection.
+    void set_white_groups(const uint64_t* pairs, size_t n) {
+        std::vector<std::pair<int64_t, int64_t>> g;
+        for (size_t k = 0; k < n; ++k) {
+            const int64_t a = int64_t(pairs[2 * k]), b = int64_t(pairs[2 * k + 1]);
+            if (a < 0 || b < 0 || size_t(a) >= blocks.size() || size_t(b) >= blocks.size() || a == b)
+                TM_THROW(TM_ERR_INVALID_ARGUMENT, "white group %zu: invalid block pair", k);
+            bool found = false;
+            for (const auto& c : conns_copy) found = found || le_connection(c, a, b);
+            if (!found) TM_THROW(TM_ERR_UNSUPPORTED, "white group %zu: no connection block%lld:j_min[0..] <-> block%lld:j_min[0..] (non periodic)", k, (long long)a, (long long)b);
+            if (blocks[size_t(a)].ni < 3 || blocks[size_t(b)].ni < 3 || blocks[size_t(a)].nj < 3 || blocks[size_t(b)].nj < 3)
+                TM_THROW(TM_ERR_UNSUPPORTED, "white group %zu: blocks too small", k);
+            g.push_back({a, b});
+        }
+        white_groups = std::move(g);
+        white_ok = !white_groups.empty();
+        if (!white_ok) white_why = "no White groups set";
     }
 };
 

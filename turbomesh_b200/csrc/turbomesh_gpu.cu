@@ -183,7 +183,9 @@ struct RankMesh {
     std::vector<uint8_t> have_coords;
     int n_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
     bool has_pq = false;
-    WhiteParams wp{};
+    DevBuf<WhiteParams> d_wgroups;           // White groups handled by this rank
+    DevBuf<WhiteNode> d_wnodes;
+    int n_wnodes = 0;
     std::vector<std::unique_ptr<MgLevel>> mg;  // built on first use of TM_SOLVER_FAS_MULTIGRID
 };
 
@@ -398,14 +400,14 @@ void fetch_ctl(tm_mesh* m) {  // the solver scalars are identical on all ranks a
     CUDA_TRY(cudaStreamSynchronize(m->stream));
 }
 
-void white_step(tm_mesh* m, bool update) {
+void white_step(tm_mesh* m, bool update, double ds_target, double theta_target) {
     for (auto& rp : m->ranks) {
         RankMesh& r = *rp;
-        if (!r.has_pq) continue;
-        const int nw = r.wp.ni0 + r.wp.ni1;
-        LAUNCH(white_wall_kernel, (nw + 127) / 128, 128, m->stream, r.wp, (const double2*)r.X[r.cur].p, r.wall_pq.p, update ? 1 : 0);
-        const int64_t nn = int64_t(r.wp.ni0) * r.wp.nj0 + int64_t(r.wp.ni1) * r.wp.nj1;
-        LAUNCH(white_blend_kernel, unsigned((nn + 255) / 256), 256, m->stream, r.wp, (const double2*)r.wall_pq.p, r.pq.p);
+        if (!r.has_pq || r.n_wnodes == 0) continue;
+        LAUNCH(white_wall_kernel, (r.n_wnodes + 127) / 128, 128, m->stream, (const WhiteParams*)r.d_wgroups.p, (const WhiteNode*)r.d_wnodes.p, r.n_wnodes,
+               ds_target, theta_target, (const double2*)r.X[r.cur].p, r.wall_pq.p, update ? 1 : 0);
+        LAUNCH(white_blend_kernel, r.n_wnodes, 64, m->stream, (const WhiteParams*)r.d_wgroups.p, (const WhiteNode*)r.d_wnodes.p, r.n_wnodes,
+               (const double2*)r.wall_pq.p, r.pq.p);
     }
 }
 
@@ -422,7 +424,7 @@ void validate_options(const tm_smooth_options* o) {
 // ---- the two ways of advancing one outer iteration -------------------------------------------------
 void run_relax(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
     for (uint64_t it = 0; it < o->iterations; ++it) {
-        if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true);
+        if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true, o->white_ds_target, o->white_theta_target);
         for (uint64_t sw = 0; sw < o->sweeps_per_iteration; ++sw) {
             const bool last = sw + 1 == o->sweeps_per_iteration;
             for (auto& rp : m->ranks) {
@@ -510,7 +512,7 @@ void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats
         for (auto& rp : m->ranks) sync_slaves(m, *rp, xnew(*rp), 1);
     };
     for (uint64_t it = 0; it < o->iterations; ++it) {
-        if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true);
+        if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true, o->white_ds_target, o->white_theta_target);
         // X[cur] = lagged coordinates (the mesh before this iteration); X[1-cur] = x_new / y_new, warm-started from the
         // mesh (GMRES.zig:157-174)
         for (auto& rp : m->ranks) {
@@ -1035,22 +1037,37 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
         for (auto& rp : m->ranks) rp->has_pq = false;
         if (m->cf == TM_CF_WHITE) {
             if (!m->topo.white_ok) TM_THROW(TM_ERR_UNSUPPORTED, "%s", m->topo.white_why.c_str());
-            if (m->owner[0] != m->owner[1]) TM_THROW(TM_ERR_UNSUPPORTED, "White control function: blocks 0 and 1 must be owned by the same rank");
+            for (const auto& g : m->topo.white_groups)
+                if (m->owner[size_t(g.first)] != m->owner[size_t(g.second)])
+                    TM_THROW(TM_ERR_UNSUPPORTED, "White control function: blocks %lld and %lld must be owned by the same rank", (long long)g.first, (long long)g.second);
             for (auto& rp : m->ranks) {
                 RankMesh& r = *rp;
-                if (!r.L.owns_white) continue;
-                const auto& B0 = m->topo.blocks[0];
-                const auto& B1 = m->topo.blocks[1];
-                r.wp.off0 = r.L.loff[0]; r.wp.off1 = r.L.loff[1];
-                r.wp.ni0 = int32_t(B0.ni); r.wp.nj0 = int32_t(B0.nj); r.wp.ni1 = int32_t(B1.ni); r.wp.nj1 = int32_t(B1.nj);
-                r.wp.c_in0 = int32_t(B0.nj); r.wp.c_in1 = int32_t(B1.nj); r.wp.c_al0 = 1;  // j_min sides starting at node 0, running towards +j
-                r.wp.ds_target = o->white_ds_target; r.wp.theta_target = o->white_theta_target;
+                std::vector<WhiteParams> groups;
+                std::vector<WhiteNode> nodes;
+                int32_t wall_base = 0;
+                for (const auto& g : m->topo.white_groups) {
+                    if (m->owner[size_t(g.first)] != r.L.rank) continue;
+                    const auto& B0 = m->topo.blocks[size_t(g.first)];
+                    const auto& B1 = m->topo.blocks[size_t(g.second)];
+                    WhiteParams w{};
+                    w.off0 = r.L.loff[size_t(g.first)]; w.off1 = r.L.loff[size_t(g.second)];
+                    w.ni0 = int32_t(B0.ni); w.nj0 = int32_t(B0.nj); w.ni1 = int32_t(B1.ni); w.nj1 = int32_t(B1.nj);
+                    w.c_in0 = int32_t(B0.nj); w.c_in1 = int32_t(B1.nj); w.c_al0 = 1;  // j_min sides starting at node 0, running towards +j
+                    w.wall_base = wall_base;
+                    for (int32_t t = 0; t < w.ni0 + w.ni1; ++t) nodes.push_back(WhiteNode{int32_t(groups.size()), t});
+                    wall_base += w.ni0 + w.ni1;
+                    groups.push_back(w);
+                }
+                r.n_wnodes = int(nodes.size());
+                if (groups.empty()) continue;
+                r.d_wgroups.upload(groups, s);
+                r.d_wnodes.upload(nodes, s);
                 if (r.pq.n != size_t(r.N)) r.pq.alloc(size_t(r.N));
                 r.pq.zero(s);
-                r.wall_pq.alloc(size_t(B0.ni + B1.ni));
+                r.wall_pq.alloc(size_t(wall_base));
                 r.has_pq = true;
             }
-            white_step(m, false);
+            white_step(m, false, o->white_ds_target, o->white_theta_target);
         }
         if (o->solver == TM_SOLVER_FAS_MULTIGRID && m->n_ranks == 1 && m->topo.blocks.size() == 1) mg_build(m, *m->ranks[0]);
         m->outer_done = 0;
@@ -1068,8 +1085,6 @@ int tm_mesh_smooth(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* stat
         if (!m->begun) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tm_mesh_begin_smoothing has not been called for the current coordinates");
         if (int(o->control_function) != m->cf) TM_THROW(TM_ERR_INVALID_ARGUMENT, "control function differs from the one given to tm_mesh_begin_smoothing");
         CUDA_TRY(cudaSetDevice(m->device));
-        if (m->cf == TM_CF_WHITE)
-            for (auto& rp : m->ranks) { rp->wp.ds_target = o->white_ds_target; rp->wp.theta_target = o->white_theta_target; }
         st.nodes = uint64_t(m->topo.n_nodes);
         st.converged = 1;
         CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
@@ -1097,6 +1112,15 @@ int tm_mesh_synchronize(tm_mesh* m) {
         check_mesh(m);
         CUDA_TRY(cudaSetDevice(m->device));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
+    });
+}
+
+int tm_mesh_set_white_groups(tm_mesh* m, const uint64_t* block_pairs, size_t n_groups) {
+    return guarded([&] {
+        check_mesh(m);
+        if (n_groups && !block_pairs) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block_pairs is NULL");
+        m->topo.set_white_groups(block_pairs, n_groups);
+        m->begun = false;
     });
 }
 

@@ -247,6 +247,12 @@ class DeviceMesh:
                 self.download_block(k, b.points)
         return self.mesh
 
+    def set_white_groups(self, block_pairs):
+        """One (A, B) pair of O-grid half blocks per cut of a batch (``tm_mesh_set_white_groups``)."""
+        flat = [int(v) for pair in block_pairs for v in pair]
+        arr = (C.c_uint64 * max(len(flat), 1))(*flat)
+        check(self._L.tm_mesh_set_white_groups(self._h, arr, len(flat) // 2))
+
     def begin_smoothing(self, solver: Optional[CudaSolver] = None, control_function=None):
         self._opts = make_options(0, solver, control_function)
         check(self._L.tm_mesh_begin_smoothing(self._h, C.byref(self._opts)))

@@ -149,3 +149,31 @@ def materialize(mesh: Mesh, tfi) -> Mesh:
     for b in mesh.blocks:
         out.blocks.append(Block2d(tfi(*b.edge_args())) if isinstance(b, EdgeBlock) else b)
     return out
+
+
+def batch_of_cuts(base: Mesh, scales) -> Tuple[Mesh, List[Tuple[int, int]]]:
+    """Config 5: a batch of independent 2D cuts meshed in one go (the roadmap's 3D-from-2D-cuts path).
+
+    Every cut is the O4H block set of `base` (a mesh of ``EdgeBlock``s, e.g. the T106 inputs) scaled by ``scales[k]``
+    (span-wise variation of the blade size; the pitch scales alike).  The cuts are concatenated into ONE mesh with
+    block / connection indices offset per cut, so all of them advance in the same kernel launches; there is no
+    connection between cuts.  Returns the mesh and the White groups (the two O-grid half blocks of every cut).
+    """
+    nb = len(base.blocks)
+    out = Mesh()
+    groups = []
+    for k, sc in enumerate(scales):
+        sc = float(sc)
+        for name, b in zip(base.names, base.blocks):
+            def scaled(e: Edge) -> Edge:
+                return Edge(e.points * sc, e.clustering.copy())
+            out.add_block(f"cut{k}_{name}", EdgeBlock(scaled(b.i_min), scaled(b.i_max), scaled(b.j_min), scaled(b.j_max)))
+        for c in base.connections:
+            r0, r1 = c.ranges
+            per = None if c.periodicity is None else (c.periodicity[0] * sc, c.periodicity[1] * sc)
+            out.connections.append(Connection((Range(r0.block + k * nb, r0.side, r0.start, r0.end), Range(r1.block + k * nb, r1.side, r1.start, r1.end)), per))
+        for bc in base.boundary_conditions:
+            r = bc.range
+            out.boundary_conditions.append(Condition(Range(r.block + k * nb, r.side, r.start, r.end), bc.kind))
+        groups.append((k * nb, k * nb + 1))
+    return out, groups
