@@ -145,6 +145,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "cuts":
+        return run_cuts(args, torch, dist, rank, world, local, barrier)
     sweeps = args.sweeps
     solver = smoothing.CudaSolver(method="relax", sweeps_per_iteration=sweeps, omega=args.omega, device=local)
     stream = torch.cuda.Stream()                         # the library launches on this stream, so torch events see its kernels
@@ -265,6 +267,67 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_cuts(args, torch, dist, rank, world, local, barrier):
+    """Config 5: a batch of independent T106 cuts per GPU (replicas only, no collective): TFI of all blocks + the
+    reference's smoothing settings (10 outer iterations, White control function, default tolerances) per step."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import load_fixture
+
+    from turbomesh_b200 import smoothing, synthetic
+
+    base, z, meta = load_fixture("t106_white")
+    n_cuts = args.cuts_per_gpu
+    total_cuts = n_cuts * world
+    scales = [1.0 + 0.2 * (rank * n_cuts + k) / max(total_cuts - 1, 1) for k in range(n_cuts)]
+    batch, groups = synthetic.batch_of_cuts(base, scales)
+    stream = torch.cuda.Stream()
+    t0 = time.perf_counter()
+    dm = smoothing.DeviceMesh(batch, device=local, stream=stream.cuda_stream, upload=False)
+    t_create = time.perf_counter() - t0
+    for k, b in enumerate(batch.blocks):
+        dm.tfi_block(k, *b.edge_args())
+    dm.set_white_groups(groups)
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    sol = smoothing.CudaSolver(method="picard_bicgstab", rtol=1e-6, atol=1e-8, max_inner_iterations=1000, device=local)
+
+    def step():
+        for k in range(len(batch.blocks)):
+            dm.tfi_block_resident(k)
+        dm.begin_smoothing(sol, cf)
+        return dm.smooth(meta["iterations"], sol, cf)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = smoothing.kernel_launch_count()
+    ev0.record(stream)
+    ops = 0
+    for _ in range(args.steps):
+        st = step()
+        ops += st["operator_applications"]
+    ev1.record(stream)
+    dm.synchronize()
+    barrier()
+    elapsed = ev0.elapsed_time(ev1) * 1e-3
+    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    nodes_local = dm.node_count
+    line = {"metric": METRIC, "value": nodes_local * world * ops / elapsed, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"batch of {total_cuts} T106 cuts ({n_cuts} per GPU, 8 blocks / 25118 nodes each, scaled 1.0..1.2; config 5), no communication",
+                       "step": "TFI of all blocks + 10 outer iterations, White control function, BiCGStab rtol 1e-6 (reference defaults)",
+                       "nodes": nodes_local * world, "cuts_per_second": total_cuts * args.steps / elapsed, "create_seconds": t_create},
+            "gpu_launches": smoothing.kernel_launch_count() - launches0, "converged": st["converged"], "last_inner_residual": st["last_inner_residual"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_e2e(args, spec, solver, torch):
     """Same step through tm_tfi_block + tm_smooth_mesh with pinned HOST buffers: H2D/D2H inside the timed region."""
     from turbomesh_b200 import smoothing
@@ -305,7 +368,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="turbomesh_b200", choices=["turbomesh_b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="single-block edge length (N=1)")
-    ap.add_argument("--workload", default=None, choices=["single", "cascade"], help="default: single for N=1, cascade for N>1")
+    ap.add_argument("--workload", default=None, choices=["single", "cascade", "cuts"], help="default: single for N=1, cascade for N>1")
+    ap.add_argument("--cuts-per-gpu", type=int, default=128, help="--workload cuts: T106 cuts per GPU (1024 cuts on 8 GPUs)")
     ap.add_argument("--block-ni", type=int, default=4096)
     ap.add_argument("--block-nj", type=int, default=2048)
     ap.add_argument("--blocks-per-gpu", type=int, default=8)
