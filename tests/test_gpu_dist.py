@@ -40,6 +40,24 @@ def test_emulated_ranks_match_single_rank_relax(gpu_lib, orc, args, n_ranks):
     assert abs(st1["last_sumsq_x"] - stn["last_sumsq_x"]) <= 1e-12 * max(st1["last_sumsq_x"], 1e-30)
 
 
+@pytest.mark.parametrize("args,n_ranks,owner_kind", [((4, 2, 33, 17), 2, "columns"), ((4, 4, 17, 17), 4, "columns"), ((4, 2, 33, 17), 2, "interleaved")])
+def test_emulated_ranks_match_single_rank_multigrid(gpu_lib, orc, args, n_ranks, owner_kind):
+    """Every multigrid level is sharded like the fine mesh (ghost rows, copies re-derived from their roots after every
+    transfer): an N-rank V-cycle reproduces the 1-rank V-cycle to rounding."""
+    from turbomesh_b200 import smoothing
+
+    n_bi, n_bj = args[0], args[1]
+    nb = n_bi * n_bj
+    mesh0 = synthetic.materialize(synthetic.cascade(*args), orc.tfi)
+    owner = [bi * n_ranks // n_bi for bi in range(n_bi) for _ in range(n_bj)] if owner_kind == "columns" else [b % n_ranks for b in range(nb)]
+    sol = smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8)
+    one, st1 = _run(mesh0, None, 1, sol, 6)
+    many, stn = _run(mesh0, owner, n_ranks, sol, 6)
+    assert _md(one, many) <= 1e-13
+    assert abs(st1["last_max_update"] - stn["last_max_update"]) <= 1e-14
+    assert st1["last_max_update"] < 1e-3
+
+
 @pytest.mark.parametrize("owner_kind", ["columns", "interleaved"])
 def test_emulated_ranks_match_single_rank_picard(gpu_lib, orc, owner_kind):
     from turbomesh_b200 import smoothing

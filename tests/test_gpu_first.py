@@ -92,10 +92,38 @@ def test_multigrid_converges_to_the_oracle_fixed_point(orc, gpu_lib, shape):
     assert _max_diff(gpu, cpu) <= 1e-9, st
 
 
-def test_multigrid_rejects_multi_block_meshes(orc, gpu_lib):
+@pytest.mark.parametrize("args", [(2, 2, 33, 17), (4, 2, 33, 17), (4, 1, 17, 33), (4, 4, 17, 9)])
+def test_multiblock_multigrid_converges_to_the_oracle_fixed_point(orc, gpu_lib, args):
+    """Multi-block FAS multigrid (interfaces, periodic rows, junctions, plate ends, sliding inlet / outlet on every level)
+    reaches the fixed point of the reference's Picard iteration."""
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.cascade(*args)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    st = smoothing.smooth_mesh(gpu, 80, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-13))
+    orc.smooth_mesh(cpu, 40, orc.tight_options())
+    assert st["last_max_update"] <= 1e-13 and st["outer_iterations"] < 80, st
+    assert _max_diff(gpu, cpu) <= 1e-9, st
+
+
+def test_multiblock_multigrid_without_coarsenable_direction(orc, gpu_lib):
+    """11 x 8 intervals per block: only j can be halved (three times); the cycle degrades gracefully and keeps the fixed point."""
+    from turbomesh_b200 import smoothing
+
+    spec = synthetic.cascade(2, 2, 12, 9)
+    gpu = synthetic.materialize(spec, smoothing.tfi_block)
+    cpu = synthetic.materialize(spec, orc.tfi)
+    st = smoothing.smooth_mesh(gpu, 400, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-13))
+    orc.smooth_mesh(cpu, 40, orc.tight_options())
+    assert st["last_max_update"] <= 1e-13, st
+    assert _max_diff(gpu, cpu) <= 1e-9, st
+
+
+def test_multigrid_rejects_the_white_control_function(orc, gpu_lib):
     from turbomesh_b200 import _lib, smoothing
 
-    mesh = synthetic.materialize(synthetic.cascade(2, 2, 12, 9), orc.tfi)
+    mesh = synthetic.materialize(synthetic.cascade(2, 2, 17, 9), orc.tfi)
     with pytest.raises(_lib.TurbomeshGpuError) as e:
-        smoothing.smooth_mesh(mesh, 2, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=2))
+        smoothing.smooth_mesh(mesh, 2, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=2), smoothing.White(1e-4))
     assert e.value.code == _lib.TM_ERR_UNSUPPORTED

@@ -280,11 +280,12 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
 // registers and store results straight from registers (coalesced 16 B per thread).
 // ---------------------------------------------------------------------------------------------------
 constexpr int BND_THREADS = 128;
-template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS, bool HAS_RHS = false>
 __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows, int n_j,
                                               const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
                                               const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
-                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials);
+                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials,
+                                              const double2* __restrict__ rhs = nullptr);
 // The boundary rows ride in the same launch as the interior tiles (the first n_ctas CTAs of the grid): they are few
 // and latency-bound, so they hide behind the interior work instead of costing a launch of their own.
 struct BndArgs {
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Til
     __shared__ __align__(128) double2 ring[BULK_NS][BULK_R][BULK_ROW];
     __shared__ __align__(8) uint64_t full[BULK_NS];
     if ((int)blockIdx.x < bnd.n_ctas) {
-        boundary_rows<MODE, false, HAS_PQ, STATS>(blockIdx.x, bnd.srows, bnd.n_s, bnd.jrows, bnd.n_j, bnd.lrows, bnd.n_l, bnd.slaves, u, u, pq, out, omega, dot_a,
-                                                  bnd.partials);
+        boundary_rows<MODE, false, HAS_PQ, STATS, HAS_RHS>(blockIdx.x, bnd.srows, bnd.n_s, bnd.jrows, bnd.n_j, bnd.lrows, bnd.n_l, bnd.slaves, u, u, pq, out, omega,
+                                                           dot_a, bnd.partials, rhs);
         return;
     }
     const int tile_id = (int)blockIdx.x - bnd.n_ctas;
@@ -433,11 +434,14 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Til
 // Boundary rows: one thread per free boundary row (smoothed interface rows, then junction rows, then sliding
 // rows).  RELAX additionally writes the row's `connected` copies (x_slave = x_root + shift).
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
+// HAS_RHS (coarse multigrid levels): rhs[self] is the FAS tau term of the row -- in row units for the Winslow
+// interface rows, in update units (lengths) for junction and sliding rows.
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS, bool HAS_RHS>
 __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows, int n_j,
                                               const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
                                               const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
-                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials) {
+                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials,
+                                              const double2* __restrict__ rhs) {
     const int r = cta * BND_THREADS + threadIdx.x;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
     double2 res = make_double2(0.0, 0.0), old = make_double2(0.0, 0.0);
@@ -450,7 +454,7 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
         const double2 per = make_double2(row.px, row.py);
         // values the row is applied to; block-1 columns are shifted by -periodicity in the affine modes
         // (equivalent to the reference's rhs = p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)), smooth.zig:1060-1061)
-        const bool affine = (MODE == MODE_RELAX || MODE == MODE_RESID);
+        const bool affine = (MODE == MODE_RELAX || MODE == MODE_RESID || MODE == MODE_REL);
         const double2 sh = affine ? per : make_double2(0.0, 0.0);
         const double2 C = ld2(u + row.g0);
         const double2 W = ld2(u + row.g0 - row.d0), E = ld2(u + row.g0 + row.d0);
@@ -469,7 +473,8 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
             const double2 f = ldg2(pq + row.g0);
             if (row.periodic) { P = f.x; Q = f.y; } else { P = f.y; Q = f.x; }  // smooth.zig:1040-1041 vs 1082-1083
         }
-        const double2 rel = row_rel<HAS_PQ>(m, P, Q, C, W, E, (N - C) + (S - C), N - S, NE - SE, NW - SW);
+        double2 rel = row_rel<HAS_PQ>(m, P, Q, C, W, E, (N - C) + (S - C), N - S, NE - SE, NW - SW);
+        if (HAS_RHS) { const double2 f = ld2(rhs + row.g0); rel.x -= f.x; rel.y -= f.y; }
         res = row_result<MODE>(m, rel, C, omega);
         old = C;
         if (STATS == 4 && row.periodic) {  // rhs of the reference's row: p * (a(i-1,j+1)+a(i,j+1)+a(i+1,j+1)) = p * g11 (1 + Q/2)
@@ -484,12 +489,14 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
         double2 sum = make_double2(0.0, 0.0);  // sum_k (x_k - C): translation invariant like the Winslow rows
         for (int k = 0; k < row.n; ++k) sum = sum + (ld2(u + row.nbr[k]) - C);
         const double n = (double)row.n;
+        double2 tau = make_double2(0.0, 0.0);
+        if (HAS_RHS) tau = ld2(rhs + row.self);
         if (MODE == MODE_RELAX) {
-            res = make_double2(C.x + omega * ((sum.x - row.rhs_x) / n), C.y + omega * ((sum.y - row.rhs_y) / n));
+            res = make_double2(C.x + omega * ((sum.x - row.rhs_x) / n - tau.x), C.y + omega * ((sum.y - row.rhs_y) / n - tau.y));
         } else if (MODE == MODE_APPLY) {  // row / a_ii with a_ii = -n
             res = make_double2(-(sum.x / n), -(sum.y / n));
         } else {
-            res = make_double2((sum.x - row.rhs_x) / n, (sum.y - row.rhs_y) / n);
+            res = make_double2((sum.x - row.rhs_x) / n - tau.x, (sum.y - row.rhs_y) / n - tau.y);
         }
         old = C;
     } else if (r < n_s + n_j + n_l) {
@@ -498,10 +505,14 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
         sb = row.slave_begin; se = row.slave_end; n_copies = row.n_copies;
         const double2 C = ld2(u + row.self), I = ld2(u + row.inner);
         const double ys = (double)row.ysign;
+        double tau_y = 0.0;
+        if (HAS_RHS) tau_y = ld2(rhs + row.self).y;
         if (MODE == MODE_RELAX) {
-            res = make_double2(row.rhs_x, I.y + ys * row.rhs_y);
+            res = make_double2(row.rhs_x, I.y + ys * row.rhs_y - tau_y);
         } else if (MODE == MODE_APPLY) {  // a_ii = 1 (x) and ysign (y)
             res = make_double2(C.x, C.y - I.y);
+        } else if (MODE == MODE_REL) {    // multigrid residual in update units; x is a Dirichlet value (no residual)
+            res = make_double2(0.0, ys * row.rhs_y - (C.y - I.y) - tau_y);
         } else {
             res = make_double2(row.rhs_x - C.x, ys * row.rhs_y - (C.y - I.y));
         }
@@ -995,6 +1006,158 @@ __global__ void mg_prolong_kernel(MgLevelDims d, const double2* __restrict__ u_c
     double2 v = u_f[k];
     v.x += a.x - b.x; v.y += a.y - b.y;
     u_f[k] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-block / multi-GPU FAS multigrid: NESTED coarsening (every coarse node is a fine node), per block by a factor
+// f_i, f_j in {1, 2} per direction.  Block-local transfers; rows that straddle blocks (interface, junction, sliding
+// rows) are restricted by a flat table (RestrictRow), and the copies of a node are re-derived from their root after
+// every transfer, so all copies stay bit-consistent on every level.
+// ---------------------------------------------------------------------------------------------------
+struct BlockXfer {
+    int64_t off_f, off_c;          // local offsets of the block on the fine / coarse level
+    int32_t ni_f, nj_f, ni_c, nj_c;
+    int32_t fi, fj;                // fine index = f * coarse index
+    int32_t slide, _pad;           // bit 0..3: the whole side j_min (i = 0) / j_max (i = ni-1) / i_min (j = 0) / i_max (j = nj-1) slides
+};
+struct RestrictRow {               // rhs_c[dst] = sum_k w[k] * res_f[src[k]]  (scale and sign folded into w)
+    int64_t dst;
+    int64_t src[9];
+    double w[9];
+    int32_t n, _pad;
+};
+
+// coarse <- fine for one block: iterate by injection (all nodes, so that copies stay exact copies); residual of the
+// interior rows by full weighting in the coarsened directions, times `scale` (= -(f_i f_j)^2: the undivided Winslow row
+// of a smooth field scales like h_xi^2 h_eta^2, and the restricted quantity is the negative residual).
+__global__ void mgb_restrict_kernel(BlockXfer b, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
+                                    double2* __restrict__ e_c, double2* __restrict__ rhs_c, double scale) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x, I = blockIdx.y;
+    if (J >= b.nj_c || I >= b.ni_c) return;
+    const int i = I * b.fi, j = J * b.fj;
+    const size_t kc = (size_t)b.off_c + (size_t)I * b.nj_c + J;
+    const size_t kf = (size_t)b.off_f + (size_t)i * b.nj_f + j;
+    const double2 uc = u_f[kf];
+    u_c[kc] = uc;
+    e_c[kc] = uc;
+    double2 r = make_double2(0.0, 0.0);
+    if (I > 0 && I < b.ni_c - 1 && J > 0 && J < b.nj_c - 1) {
+        // Next to a sliding (Neumann-type) side the boundary unknown follows its inner neighbour, so the coarse boundary
+        // node carries no row of its own: the quarter of the first interior row's residual that full weighting would
+        // send there belongs to this row instead (the Galerkin restriction after eliminating y_0 = y_1).  That residual
+        // is what drives the sliding modes; with the plain weights the coarse correction is half of what is needed.
+        const int pi = b.fi == 2 ? 1 : 0, pj = b.fj == 2 ? 1 : 0;
+        const double wim = (I == 1 && (b.slide & 1)) ? 0.5 : 0.25, wip = (I == b.ni_c - 2 && (b.slide & 2)) ? 0.5 : 0.25;
+        const double wjm = (J == 1 && (b.slide & 4)) ? 0.5 : 0.25, wjp = (J == b.nj_c - 2 && (b.slide & 8)) ? 0.5 : 0.25;
+        for (int p = -pi; p <= pi; ++p)
+            for (int q = -pj; q <= pj; ++q) {
+                const double w = (pi ? (p == 0 ? 0.5 : (p < 0 ? wim : wip)) : 1.0) * (pj ? (q == 0 ? 0.5 : (q < 0 ? wjm : wjp)) : 1.0);
+                const double2 v = res_f[kf + (long long)p * b.nj_f + q];
+                r.x += w * v.x; r.y += w * v.y;
+            }
+        r.x *= scale; r.y *= scale;
+    }
+    rhs_c[kc] = r;
+}
+
+__global__ void mgb_restrict_rows_kernel(const RestrictRow* __restrict__ rows, int n, const double2* __restrict__ res_f, double2* __restrict__ rhs_c) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const RestrictRow row = rows[k];
+    double2 r = make_double2(0.0, 0.0);
+    for (int q = 0; q < row.n; ++q) {
+        const double2 v = res_f[row.src[q]];
+        r.x += row.w[q] * v.x; r.y += row.w[q] * v.y;
+    }
+    rhs_c[row.dst] = r;
+}
+
+// b += a  (tau_c = row_c(I u_f) + restricted residual; `a` is zero wherever no free row lives)
+__global__ void __launch_bounds__(256) mgb_add_kernel(int64_t n, const double2* __restrict__ a, double2* __restrict__ b) {
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        const double2 x = a[k];
+        double2 y = b[k];
+        y.x += x.x; y.y += x.y;
+        b[k] = y;
+    }
+}
+
+// fine += bilinear interpolation of the coarse correction (u_c - e_c).  Interior nodes per block; the free rows on
+// block boundaries (interface, junction, sliding rows) by table, interpolating along their boundary line.  Fixed nodes
+// are never touched (a fixed wall node next to a moving junction must not pick up half of its correction), and copies
+// are re-derived from their roots afterwards.
+__device__ __forceinline__ double2 mgb_correction(const BlockXfer& b, int i, int j, const double2* __restrict__ u_c, const double2* __restrict__ e_c) {
+    const int I0 = i / b.fi, J0 = j / b.fj;
+    const bool hi = (i % b.fi) != 0, hj = (j % b.fj) != 0;  // halfway between two coarse nodes
+    const double2* uc = u_c + b.off_c;
+    const double2* ec = e_c + b.off_c;
+    auto corr = [&](int I, int J) {
+        const size_t k = (size_t)I * b.nj_c + J;
+        const double2 a = uc[k], e = ec[k];
+        return make_double2(a.x - e.x, a.y - e.y);
+    };
+    double2 c = corr(I0, J0);
+    if (hi && hj) {
+        const double2 c1 = corr(I0 + 1, J0), c2 = corr(I0, J0 + 1), c3 = corr(I0 + 1, J0 + 1);
+        c = make_double2(0.25 * ((c.x + c3.x) + (c1.x + c2.x)), 0.25 * ((c.y + c3.y) + (c1.y + c2.y)));
+    } else if (hi) {
+        const double2 c1 = corr(I0 + 1, J0);
+        c = make_double2(0.5 * (c.x + c1.x), 0.5 * (c.y + c1.y));
+    } else if (hj) {
+        const double2 c2 = corr(I0, J0 + 1);
+        c = make_double2(0.5 * (c.x + c2.x), 0.5 * (c.y + c2.y));
+    }
+    return c;
+}
+__global__ void mgb_prolong_kernel(BlockXfer b, const double2* __restrict__ u_c, const double2* __restrict__ e_c, double2* __restrict__ u_f) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j <= 0 || j >= b.nj_f - 1 || i <= 0 || i >= b.ni_f - 1) return;
+    const double2 c = mgb_correction(b, i, j, u_c, e_c);
+    const size_t k = (size_t)b.off_f + (size_t)i * b.nj_f + j;
+    double2 v = u_f[k];
+    v.x += c.x; v.y += c.y;
+    u_f[k] = v;
+}
+__global__ void mgb_prolong_rows_kernel(const BlockXfer* __restrict__ blocks, int n_blocks, const SmoothedRow* __restrict__ srows, int n_s,
+                                        const JunctionRow* __restrict__ jrows, int n_j, const SlidingRow* __restrict__ lrows, int n_l,
+                                        const double2* __restrict__ u_c, const double2* __restrict__ e_c, double2* __restrict__ u_f) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_s + n_j + n_l) return;
+    const int64_t self = r < n_s ? srows[r].g0 : (r < n_s + n_j ? jrows[r - n_s].self : lrows[r - n_s - n_j].self);
+    int lo = 0, hi = n_blocks - 1;  // own blocks are stored in ascending offset order
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (blocks[mid].off_f <= self) lo = mid; else hi = mid - 1;
+    }
+    const BlockXfer b = blocks[lo];
+    const int64_t local = self - b.off_f;
+    const int i = (int)(local / b.nj_f), j = (int)(local - (int64_t)i * b.nj_f);
+    const double2 c = mgb_correction(b, i, j, u_c, e_c);
+    double2 v = u_f[self];
+    v.x += c.x; v.y += c.y;
+    u_f[self] = v;
+}
+
+// polyline length of one side of a block (multigrid: mean cell size per direction decides the semi-coarsening);
+// one CTA per (own block, side); out[4 * global block + side]
+struct SideLenJob { int64_t off; int32_t ni, nj, block; };
+__global__ void __launch_bounds__(256) side_length_kernel(const SideLenJob* __restrict__ jobs, const double2* __restrict__ x, double* __restrict__ out) {
+    const SideLenJob jb = jobs[blockIdx.x >> 2];
+    const int side = blockIdx.x & 3;  // tm_side order: i_min (j = 0), i_max (j = nj-1), j_min (i = 0), j_max (i = ni-1)
+    const int n = side < 2 ? jb.ni : jb.nj;
+    const long long stride = side < 2 ? jb.nj : 1;
+    const long long base = side == 0 ? 0 : side == 1 ? jb.nj - 1 : side == 2 ? 0 : (long long)(jb.ni - 1) * jb.nj;
+    const double2* p = x + jb.off + base;
+    double s = 0.0;
+    for (int k = threadIdx.x; k + 1 < n; k += 256) {
+        const double2 a = p[(long long)k * stride], b = p[(long long)(k + 1) * stride];
+        s += sqrt((b.x - a.x) * (b.x - a.x) + (b.y - a.y) * (b.y - a.y));
+    }
+    __shared__ double red[5];
+    double sums[4] = {s, 0.0, 0.0, 0.0};
+    block_reduce_store<4, 256>(sums, 0.0, red);
+    __syncthreads();
+    if (threadIdx.x == 0) out[4 * (size_t)jb.block + side] = red[0];
 }
 
 }  // namespace tmesh

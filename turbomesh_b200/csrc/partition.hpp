@@ -101,6 +101,20 @@ inline std::vector<std::vector<int64_t>> check_sets(const Topology& T, const std
     return out;
 }
 
+// local index (position in the rank's field) of global node g: owned, synthesised copy or ghost
+inline int64_t local_index(const Topology& T, const std::vector<int32_t>& owner, const LocalTables& L, int64_t g) {
+    const size_t b = T.block_of(g);
+    if (owner[b] == L.rank) return L.loff[b] + (g - T.blocks[b].off);
+    {
+        const auto it = std::lower_bound(L.synth_ids.begin(), L.synth_ids.end(), g);
+        if (it != L.synth_ids.end() && *it == g) return L.n_own + L.n_ghost + int64_t(it - L.synth_ids.begin());
+    }
+    const auto& v = L.ghost_ids[size_t(owner[b])];
+    const auto it = std::lower_bound(v.begin(), v.end(), g);
+    if (it == v.end() || *it != g) TM_THROW(TM_ERR_TOPOLOGY, "internal: node %lld is not in the ghost set of rank %d", (long long)g, L.rank);
+    return L.n_own + L.ghost_base[size_t(owner[b])] + int64_t(it - v.begin());
+}
+
 inline void validate_owner(const Topology& T, const std::vector<int32_t>& owner, int n_ranks) {
     if (owner.size() != T.blocks.size()) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block_owner must have one entry per block");
     for (size_t b = 0; b < owner.size(); ++b)
@@ -152,18 +166,7 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     L.n_check = L.check_ghost_base[size_t(n_ranks)];
     L.n_local = L.n_own + L.n_ghost + L.n_synth + L.n_check;
 
-    auto lidx = [&](int64_t g) -> int64_t {
-        const size_t b = T.block_of(g);
-        if (owner[b] == rank) return L.loff[b] + (g - T.blocks[b].off);
-        {
-            const auto it = std::lower_bound(L.synth_ids.begin(), L.synth_ids.end(), g);
-            if (it != L.synth_ids.end() && *it == g) return L.n_own + L.n_ghost + int64_t(it - L.synth_ids.begin());
-        }
-        const auto& v = L.ghost_ids[size_t(owner[b])];
-        const auto it = std::lower_bound(v.begin(), v.end(), g);
-        if (it == v.end() || *it != g) TM_THROW(TM_ERR_TOPOLOGY, "internal: node %lld is not in the ghost set of rank %d", (long long)g, rank);
-        return L.n_own + L.ghost_base[size_t(owner[b])] + int64_t(it - v.begin());
-    };
+    auto lidx = [&](int64_t g) -> int64_t { return local_index(T, owner, L, g); };
     auto mine = [&](int64_t g) { return owner_of_node(T, owner, g) == rank; };
 
     for (int p = 0; p < n_ranks; ++p)

@@ -112,6 +112,7 @@ struct Topology {
     bool white_ok = false;
     std::string white_why;
     std::vector<tm_connection> conns_copy;  // kept for set_white_groups
+    int64_t min_conn_nodes = 6;             // smooth.zig:631 (lenInternal() > 3); coarse multigrid levels relax this to 3
 
     // ---- helpers -------------------------------------------------------------------------------
     static int64_t range_len(const tm_range& r) { return r.start > r.end ? int64_t(r.start - r.end) + 1 : int64_t(r.end - r.start) + 1; }
@@ -323,7 +324,7 @@ struct Topology {
             if (cn.ranges[0].block == cn.ranges[1].block && !(cn.ranges[0].side == TM_SIDE_I_MIN && cn.ranges[1].side == TM_SIDE_I_MAX))
                 TM_THROW(TM_ERR_UNSUPPORTED, "connection %zu: same-block connections are only supported as i_min -> i_max (smooth.zig:522-559)", c);
             const int64_t n = range_len(cn.ranges[0]);
-            if (!(n > 5)) TM_THROW(TM_ERR_UNSUPPORTED, "connection %zu: needs at least 6 nodes (smooth.zig:631)", c);
+            if (n < min_conn_nodes) TM_THROW(TM_ERR_UNSUPPORTED, "connection %zu: needs at least %lld nodes (smooth.zig:631)", c, (long long)min_conn_nodes);
             int64_t b0, a0, n0, b1, a1, n1;
             walk(cn.ranges[0], b0, a0, n0);
             walk(cn.ranges[1], b1, a1, n1);

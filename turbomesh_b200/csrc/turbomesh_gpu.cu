@@ -186,7 +186,24 @@ struct RankMesh {
     DevBuf<WhiteParams> d_wgroups;           // White groups handled by this rank
     DevBuf<WhiteNode> d_wnodes;
     int n_wnodes = 0;
-    std::vector<std::unique_ptr<MgLevel>> mg;  // built on first use of TM_SOLVER_FAS_MULTIGRID
+    std::vector<std::unique_ptr<MgLevel>> mg;  // built on first use of TM_SOLVER_FAS_MULTIGRID (single fixed-boundary block)
+    // multi-block multigrid (one RankMesh per rank per level): FAS tau term, residual scratch, restricted iterate
+    DevBuf<double2> mg_rhs, mg_tmp, mg_E;
+    std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
+    DevBuf<BlockXfer> d_xfer_blocks;
+    DevBuf<RestrictRow> d_rrows;             // boundary rows of the next coarser level <- residuals of this level
+    int n_rrows = 0;
+};
+
+// One level of the multi-block multigrid hierarchy; level 0 aliases the mesh's own topology and rank data.
+struct MgbLevel {
+    Topology topo;                                   // levels >= 1
+    std::vector<tm_block> blocks;
+    std::vector<tm_connection> conns;
+    std::vector<tm_condition> bcs;
+    std::vector<std::unique_ptr<RankMesh>> ranks;    // levels >= 1
+    std::vector<int> fi, fj;                         // per block: coarsening factors towards the next level (empty on the coarsest)
+    double work = 1.0;                               // nodes relative to level 0
 };
 
 }  // namespace
@@ -206,10 +223,15 @@ struct tm_mesh {
     int cf = TM_CF_LAPLACE;
     uint64_t outer_done = 0;  // outer iterations since begin_smoothing (the `n` of system.fill(n), smooth.zig:1107-1110)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<tm_block> h_blocks;              // host copies of the topology description (xy = NULL): multigrid coarsening
+    std::vector<tm_connection> h_conns;
+    std::vector<tm_condition> h_bcs;
+    std::vector<std::unique_ptr<MgbLevel>> mgb;  // multi-block multigrid hierarchy, built on first use
     int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
     bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
 
     ~tm_mesh() {
+        mgb.clear();
         ranks.clear();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (h_ctl) cudaFreeHost(h_ctl);
@@ -223,19 +245,19 @@ namespace {
 
 int bnd_ctas(int rows) { return (rows + BND_THREADS - 1) / BND_THREADS; }
 
-void build_rank(tm_mesh* m, RankMesh& r, int rank) {
+void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank) {
     cudaStream_t s = m->stream;
-    r.L = localize(m->topo, m->owner, rank, m->n_ranks);
+    r.L = localize(topo, m->owner, rank, m->n_ranks);
     r.N = r.L.n_local;
     r.X[0].alloc(size_t(std::max<int64_t>(r.N, 1)));
     r.X[1].alloc(size_t(std::max<int64_t>(r.N, 1)));
     r.X[0].zero(s);
     r.X[1].zero(s);
     std::vector<Tile> tiles;
-    std::vector<DevBlock> blocks(m->topo.blocks.size(), DevBlock{0, 0, 0});
+    std::vector<DevBlock> blocks(topo.blocks.size(), DevBlock{0, 0, 0});
     for (size_t k = 0; k < r.L.own_blocks.size(); ++k) {
         const size_t b = size_t(r.L.own_blocks[k]);
-        const auto& B = m->topo.blocks[b];
+        const auto& B = topo.blocks[b];
         blocks[b] = DevBlock{r.L.loff[b], int32_t(B.ni), int32_t(B.nj)};
         // rows per CTA: about tile_rows, evened out over the block so that no CTA gets a short remainder
         const int64_t interior_i = B.ni - 2;
@@ -290,32 +312,33 @@ void ensure_krylov(tm_mesh* m) {
 
 // ---- halo exchange: every rank's ghost slots of `field` are refreshed from their owners ------------------------
 // check = true: the one-time exchange of raw side-0 coordinates for connectionDataCheck (separate slots).
+using RankList = std::vector<std::unique_ptr<RankMesh>>;
 template <class Get>
-void exchange(tm_mesh* m, Get get, bool check = false) {
+void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false) {
     if (m->n_ranks == 1) return;
     cudaStream_t s = m->stream;
     auto send_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_send_base : r.L.send_base; };
     auto ghost_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_ghost_base : r.L.ghost_base; };
     auto region = [&](RankMesh& r) { return check ? r.L.n_own + r.L.n_ghost + r.L.n_synth : r.L.n_own; };
-    for (auto& rp : m->ranks) {
+    for (auto& rp : ranks) {
         RankMesh& r = *rp;
         const int64_t n = send_base(r).back();
         const int64_t* idx = check ? r.d_check_send_idx.p : r.d_send_idx.p;
         if (n > 0) LAUNCH(pack_kernel, unsigned((n + 255) / 256), 256, s, idx, n, (const double2*)get(r), r.sendbuf.p);
     }
     if (m->emulated) {
-        for (auto& rp : m->ranks) {
+        for (auto& rp : ranks) {
             RankMesh& r = *rp;
             for (int p = 0; p < m->n_ranks; ++p) {
                 const int64_t cnt = send_base(r)[size_t(p) + 1] - send_base(r)[size_t(p)];
                 if (cnt == 0) continue;
-                RankMesh& d = *m->ranks[size_t(p)];
+                RankMesh& d = *ranks[size_t(p)];
                 CUDA_TRY(cudaMemcpyAsync(get(d) + region(d) + ghost_base(d)[size_t(r.L.rank)], r.sendbuf.p + send_base(r)[size_t(p)],
                                          size_t(cnt) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
             }
         }
     } else {
-        RankMesh& r = *m->ranks[0];
+        RankMesh& r = *ranks[0];
         NCCL_TRY(g_nccl.GroupStart());
         for (int p = 0; p < m->n_ranks; ++p) {
             const int64_t ns = send_base(r)[size_t(p) + 1] - send_base(r)[size_t(p)];
@@ -326,6 +349,9 @@ void exchange(tm_mesh* m, Get get, bool check = false) {
         NCCL_TRY(g_nccl.GroupEnd());
     }
 }
+
+template <class Get>
+void exchange(tm_mesh* m, Get get, bool check = false) { exchange_on(m, m->ranks, get, check); }
 
 // copies of nodes: mode 0 homogeneous / 1 affine / 2 zero; `only_remote_root` restricts to copies whose root is a ghost
 void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root = false) {
@@ -366,6 +392,21 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
 #undef TM_ROWS
 #undef TM_ROWS_BULK
 #undef TM_BND
+}
+
+// multigrid levels: all rows of the rank (interior tiles + boundary CTAs) through the bulk kernel, Laplace control
+// function, optional FAS right-hand side
+template <int MODE, int STATS>
+void launch_rows_mg(tm_mesh* m, RankMesh& r, const double2* u, double2* out, double omega, const double2* rhs) {
+    const BndArgs bnd{r.d_srows.p, r.d_jrows.p, r.d_lrows.p, r.d_slaves.p, r.part_bnd.p, int(r.L.smoothed.size()),
+                      int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};
+    if (r.n_tiles + r.n_bnd_ctas == 0) return;
+    if (rhs)
+        LAUNCH((winslow_interior_bulk_kernel<MODE, false, STATS, true>), r.n_tiles + r.n_bnd_ctas, TILE_J, m->stream, (const Tile*)r.d_tiles.p,
+               (const DevBlock*)r.d_blocks.p, u, (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, bnd, rhs);
+    else
+        LAUNCH((winslow_interior_bulk_kernel<MODE, false, STATS, false>), r.n_tiles + r.n_bnd_ctas, TILE_J, m->stream, (const Tile*)r.d_tiles.p,
+               (const DevBlock*)r.d_blocks.p, u, (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, bnd, (const double2*)nullptr);
 }
 
 // rank-local reduction of the per-CTA partials, all-reduce over ranks, solver scalars
@@ -650,11 +691,13 @@ void mg_residual(tm_mesh* m, RankMesh& r, MgLevel& L, const double2* u, int leve
 }
 
 // V(nu,nu) cycles of the full approximation scheme until the fine-level Jacobi update drops below stop_max_update
+void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st);
+bool mg_single_block_case(const tm_mesh* m) {
+    return m->n_ranks == 1 && m->topo.blocks.size() == 1 && m->topo.smoothed.empty() && m->topo.junction_rows.empty() && m->topo.sliding.empty() &&
+           m->topo.slaves.empty() && m->cf == TM_CF_LAPLACE && !std::getenv("TM_MG_NESTED");
+}
 void run_fas_multigrid(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
-    if (m->n_ranks != 1 || m->topo.blocks.size() != 1 || !m->topo.smoothed.empty() || !m->topo.junction_rows.empty() || !m->topo.sliding.empty() ||
-        !m->topo.slaves.empty() || m->cf != TM_CF_LAPLACE)
-        TM_THROW(TM_ERR_UNSUPPORTED, "the multigrid solver handles a single block with fixed boundary nodes and the Laplace control function "
-                                     "(multi-block meshes: use the relaxation or Picard/BiCGStab solvers)");
+    if (!mg_single_block_case(m)) { run_fas_multigrid_blocks(m, o, st); return; }
     RankMesh& r = *m->ranks[0];
     mg_build(m, r);
     cudaStream_t s = m->stream;
@@ -717,6 +760,335 @@ void run_fas_multigrid(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* 
     st->operator_applications += uint64_t(fine_work + 0.5);
 }
 
+// =====================================================================================================
+// Multi-block / multi-GPU geometric FAS multigrid (config 4: time to converged mesh on the cascade).
+//
+// Coarse levels are complete multi-block meshes of their own: the block sizes and all connection / condition ranges are
+// halved (NESTED coarsening: every coarse node is a fine node), the topology analysis and the rank-local tables are
+// rebuilt per level with the very same code as the fine level (Topology::build + localize), and the smoother of a level
+// is the same sweep launch (interior tiles + interface / junction / sliding rows) with the FAS tau term as right-hand
+// side.  Directions are tied into classes by the connections (the along and the normal direction of the two sides of a
+// connection must coarsen together); a class coarsens when every extent and every range end point in it is even, and
+// only while its mean cell size is not much larger than the smallest one (semi-coarsening).
+// =====================================================================================================
+int along_dir(uint32_t side) { return (side == TM_SIDE_I_MIN || side == TM_SIDE_I_MAX) ? 0 : 1; }
+
+// mean cell size per (block, direction), all blocks of the mesh (all-reduced over the ranks)
+std::vector<double> block_cell_sizes(tm_mesh* m) {
+    cudaStream_t s = m->stream;
+    const size_t nb = m->h_blocks.size();
+    DevBuf<double> d_len;
+    d_len.alloc(4 * nb);
+    d_len.zero(s);
+    for (auto& rp : m->ranks) {
+        RankMesh& r = *rp;
+        std::vector<SideLenJob> jobs;
+        for (int32_t b : r.L.own_blocks) jobs.push_back(SideLenJob{r.L.loff[size_t(b)], int32_t(m->topo.blocks[size_t(b)].ni), int32_t(m->topo.blocks[size_t(b)].nj), b});
+        if (jobs.empty()) continue;
+        DevBuf<SideLenJob> d_jobs;
+        d_jobs.upload(jobs, s);
+        LAUNCH(side_length_kernel, unsigned(4 * jobs.size()), 256, s, (const SideLenJob*)d_jobs.p, (const double2*)r.X[r.cur].p, d_len.p);
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    if (m->n_ranks > 1 && !m->emulated) NCCL_TRY(g_nccl.AllReduce(d_len.p, d_len.p, 4 * nb, ncclDouble, ncclSum, m->comm, s));
+    std::vector<double> len(4 * nb, 0.0), h(2 * nb, 0.0);
+    CUDA_TRY(cudaMemcpyAsync(len.data(), d_len.p, 4 * nb * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (size_t b = 0; b < nb; ++b) {
+        h[2 * b] = 0.5 * (len[4 * b] + len[4 * b + 1]) / double(m->h_blocks[b].ni - 1);      // sides i_min / i_max run along i
+        h[2 * b + 1] = 0.5 * (len[4 * b + 2] + len[4 * b + 3]) / double(m->h_blocks[b].nj - 1);
+    }
+    return h;
+}
+
+// residual restriction of the rows that straddle blocks: coarse row <- full weighting of the fine residuals around it
+void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankMesh& rf, const Topology& TC, const MgbLevel& C, RankMesh& rc) {
+    const int rank = rf.L.rank;
+    const auto& owner = m->owner;
+    rf.xfer_blocks.clear();
+    for (int32_t b : rf.L.own_blocks) {
+        const size_t k = size_t(b);
+        if (TF.blocks[k].ni > 65535 || TF.blocks[k].nj > 0x7fffffff) TM_THROW(TM_ERR_UNSUPPORTED, "multigrid: block %d too large for the transfer kernels", b);
+        const int64_t ni = TF.blocks[k].ni, nj = TF.blocks[k].nj;
+        auto slides = [&](int64_t base, int64_t stride, int64_t n) {  // every node strictly inside the side is a sliding node
+            for (int64_t q = 1; q + 1 < n; ++q)
+                if (TF.kind[size_t(TF.bid(k, base + q * stride))] != K_SLIDING) return false;
+            return n > 2;
+        };
+        const int32_t slide = (slides(0, 1, nj) ? 1 : 0) | (slides((ni - 1) * nj, 1, nj) ? 2 : 0) | (slides(0, nj, ni) ? 4 : 0) | (slides(nj - 1, nj, ni) ? 8 : 0);
+        rf.xfer_blocks.push_back(BlockXfer{rf.L.loff[k], rc.L.loff[k], int32_t(ni), int32_t(nj), int32_t(TC.blocks[k].ni), int32_t(TC.blocks[k].nj), F.fi[k],
+                                           F.fj[k], slide, 0});
+    }
+    std::vector<RestrictRow> rows;
+    auto lf = [&](int64_t g) { return local_index(TF, owner, rf.L, g); };
+    auto lc = [&](int64_t g) { return local_index(TC, owner, rc.L, g); };
+    auto add = [](RestrictRow& row, int64_t src, double w) { row.src[row.n] = src; row.w[row.n] = w; ++row.n; };
+    for (size_t c = 0; c < C.conns.size(); ++c) {
+        const tm_connection& cc = C.conns[c];
+        const tm_connection& cf = F.conns[c];
+        const size_t b0 = size_t(cc.ranges[0].block), b1 = size_t(cc.ranges[1].block);
+        if (owner[b0] != rank) continue;
+        int64_t B0, A0, N0, f0, a0, n0, f1, a1, n1;
+        TC.walk(cc.ranges[0], B0, A0, N0);
+        TF.walk(cf.ranges[0], f0, a0, n0);
+        TF.walk(cf.ranges[1], f1, a1, n1);
+        const int al = along_dir(cc.ranges[0].side);
+        const int fa = al == 0 ? F.fi[b0] : F.fj[b0], fn = al == 0 ? F.fj[b0] : F.fi[b0];
+        const double scale = -double(fa * fn) * double(fa * fn);
+        const int64_t nC = Topology::range_len(cc.ranges[0]);
+        for (int64_t K = 1; K + 1 < nC; ++K) {
+            const int64_t g0c = TC.blocks[b0].off + B0 + K * A0;
+            if (TC.kind[size_t(TC.bid_of_global(g0c))] != K_SMOOTHED) continue;
+            const int64_t k = K * fa;
+            const int64_t g0f = TF.blocks[b0].off + f0 + k * a0, g1f = TF.blocks[b1].off + f1 + k * a1;
+            RestrictRow row{};
+            row.dst = lc(g0c);
+            const int pa = fa == 2 ? 1 : 0;
+            // an end point of the connection that slides carries no Winslow row: its share of the neighbouring residual
+            // stays with this row (see mgb_restrict_kernel)
+            auto end_slides = [&](int64_t Kend) { return TC.kind[size_t(TC.bid_of_global(TC.blocks[b0].off + B0 + Kend * A0))] == K_SLIDING; };
+            const double w_lo = (K == 1 && end_slides(0)) ? 0.5 : 0.25, w_hi = (K == nC - 2 && end_slides(nC - 1)) ? 0.5 : 0.25;
+            for (int da = -pa; da <= pa; ++da) {
+                const double wa = pa ? (da == 0 ? 0.5 : (da < 0 ? w_lo : w_hi)) : 1.0;
+                if (fn == 2) {
+                    add(row, lf(g0f + da * a0), scale * wa * 0.5);
+                    add(row, lf(g0f + da * a0 + n0), scale * wa * 0.25);
+                    add(row, lf(g1f + da * a1 + n1), scale * wa * 0.25);
+                } else {
+                    add(row, lf(g0f + da * a0), scale * wa);
+                }
+            }
+            rows.push_back(row);
+        }
+    }
+    auto fine_of = [&](int64_t gc, size_t& b) {  // the fine node a coarse node coincides with
+        b = TC.block_of(gc);
+        const int64_t local = gc - TC.blocks[b].off, I = local / TC.blocks[b].nj, J = local - I * TC.blocks[b].nj;
+        return TF.blocks[b].off + (I * F.fi[b]) * TF.blocks[b].nj + J * F.fj[b];
+    };
+    for (const auto& jr : TC.junction_rows) {  // update units (lengths): second differences over the diagonal neighbours
+        size_t b;
+        const int64_t gf = fine_of(jr.self, b);
+        if (owner[b] != rank) continue;
+        RestrictRow row{};
+        row.dst = lc(jr.self);
+        add(row, lf(gf), -double(F.fi[b] * F.fj[b]));
+        rows.push_back(row);
+    }
+    for (const auto& sr : TC.sliding) {       // update units: a first difference along the inward normal
+        size_t b;
+        const int64_t gf = fine_of(sr.self, b);
+        if (owner[b] != rank) continue;
+        const int64_t inward = sr.inner - sr.self;
+        const int fn = (inward == 1 || inward == -1) ? F.fj[b] : F.fi[b];
+        RestrictRow row{};
+        row.dst = lc(sr.self);
+        add(row, lf(gf), -double(fn));
+        rows.push_back(row);
+    }
+    rf.n_rrows = int(rows.size());
+    rf.d_rrows.upload(rows, m->stream);
+    rf.d_xfer_blocks.upload(rf.xfer_blocks, m->stream);
+}
+
+void mgb_build(tm_mesh* m) {
+    if (!m->mgb.empty()) return;
+    cudaStream_t s = m->stream;
+    const size_t nb = m->h_blocks.size();
+    // direction classes
+    std::vector<int> parent(2 * nb);
+    for (size_t k = 0; k < parent.size(); ++k) parent[k] = int(k);
+    auto find = [&](int k) { while (parent[size_t(k)] != k) { parent[size_t(k)] = parent[size_t(parent[size_t(k)])]; k = parent[size_t(k)]; } return k; };
+    auto unite = [&](int a, int b) { a = find(a); b = find(b); if (a != b) parent[size_t(std::max(a, b))] = std::min(a, b); };
+    for (const auto& c : m->h_conns) {
+        const int b0 = int(c.ranges[0].block), b1 = int(c.ranges[1].block), a0 = along_dir(c.ranges[0].side), a1 = along_dir(c.ranges[1].side);
+        unite(2 * b0 + a0, 2 * b1 + a1);
+        unite(2 * b0 + 1 - a0, 2 * b1 + 1 - a1);
+    }
+    std::vector<double> hc(2 * nb, 0.0);  // per class root: mean cell size
+    {
+        const std::vector<double> h = block_cell_sizes(m);
+        std::vector<int> cnt(2 * nb, 0);
+        for (size_t k = 0; k < 2 * nb; ++k) { hc[size_t(find(int(k)))] += h[k]; cnt[size_t(find(int(k)))] += 1; }
+        for (size_t k = 0; k < 2 * nb; ++k) if (cnt[k]) hc[k] /= double(cnt[k]);
+    }
+    {
+        std::unique_ptr<MgbLevel> L0(new MgbLevel());
+        L0->blocks = m->h_blocks; L0->conns = m->h_conns; L0->bcs = m->h_bcs;
+        m->mgb.push_back(std::move(L0));
+    }
+    for (auto& rp : m->ranks) {
+        rp->mg_tmp.alloc(size_t(std::max<int64_t>(rp->N, 1))); rp->mg_tmp.zero(s);
+        rp->mg_E.alloc(size_t(std::max<int64_t>(rp->N, 1))); rp->mg_E.zero(s);
+    }
+    const double n0 = double(m->topo.n_nodes);
+    for (int level = 0; level < 20; ++level) {
+        MgbLevel& F = *m->mgb.back();
+        std::vector<uint8_t> ok(2 * nb, 1);
+        auto veto = [&](size_t block, int dir) { ok[size_t(find(int(2 * block) + dir))] = 0; };
+        for (size_t b = 0; b < nb; ++b) {
+            if ((F.blocks[b].ni - 1) % 2 || (F.blocks[b].ni - 1) / 2 < 2) veto(b, 0);
+            if ((F.blocks[b].nj - 1) % 2 || (F.blocks[b].nj - 1) / 2 < 2) veto(b, 1);
+        }
+        auto check_range = [&](const tm_range& r, uint64_t min_span) {
+            const uint64_t span = r.start > r.end ? r.start - r.end : r.end - r.start;
+            if (r.start % 2 || r.end % 2 || span < min_span) veto(size_t(r.block), along_dir(r.side));
+        };
+        for (const auto& c : F.conns) { check_range(c.ranges[0], 4); check_range(c.ranges[1], 4); }
+        for (const auto& c : F.bcs) check_range(c.range, 2);
+        double h_min = 0.0;
+        for (size_t k = 0; k < 2 * nb; ++k)
+            if (find(int(k)) == int(k) && ok[k] && (h_min == 0.0 || hc[k] < h_min)) h_min = hc[k];
+        if (h_min == 0.0) break;  // nothing can be coarsened any further
+        std::vector<uint8_t> go(2 * nb, 0);
+        for (size_t k = 0; k < 2 * nb; ++k)
+            if (find(int(k)) == int(k) && ok[k] && hc[k] <= h_min / 0.6) go[k] = 1;
+        std::unique_ptr<MgbLevel> C(new MgbLevel());
+        F.fi.resize(nb); F.fj.resize(nb);
+        C->blocks.resize(nb);
+        for (size_t b = 0; b < nb; ++b) {
+            F.fi[b] = go[size_t(find(int(2 * b)))] ? 2 : 1;
+            F.fj[b] = go[size_t(find(int(2 * b) + 1))] ? 2 : 1;
+            C->blocks[b] = tm_block{(F.blocks[b].ni - 1) / uint64_t(F.fi[b]) + 1, (F.blocks[b].nj - 1) / uint64_t(F.fj[b]) + 1, nullptr};
+        }
+        auto coarse_range = [&](tm_range r) {
+            const uint64_t f = uint64_t(along_dir(r.side) == 0 ? F.fi[size_t(r.block)] : F.fj[size_t(r.block)]);
+            r.start /= f; r.end /= f;
+            return r;
+        };
+        C->conns = F.conns;
+        for (auto& c : C->conns) { c.ranges[0] = coarse_range(c.ranges[0]); c.ranges[1] = coarse_range(c.ranges[1]); }
+        C->bcs = F.bcs;
+        for (auto& c : C->bcs) c.range = coarse_range(c.range);
+        C->topo.min_conn_nodes = 3;
+        try {
+            C->topo.build(C->blocks.data(), nb, C->conns.data(), C->conns.size(), C->bcs.data(), C->bcs.size());
+        } catch (const Error&) {  // a topology the row construction cannot express at this resolution: stop coarsening here
+            F.fi.clear(); F.fj.clear();
+            break;
+        }
+        C->work = double(C->topo.n_nodes) / n0;
+        for (auto& rp : m->ranks) {
+            C->ranks.emplace_back(new RankMesh());
+            RankMesh& rc = *C->ranks.back();
+            build_rank(m, C->topo, rc, rp->L.rank);
+            for (DevBuf<double2>* v : {&rc.mg_rhs, &rc.mg_tmp, &rc.mg_E}) { v->alloc(size_t(std::max<int64_t>(rc.N, 1))); v->zero(s); }
+            std::fill(rc.have_coords.begin(), rc.have_coords.end(), uint8_t(1));
+        }
+        const Topology& TF = m->mgb.size() == 1 ? m->topo : F.topo;
+        RankList& RF = m->mgb.size() == 1 ? m->ranks : F.ranks;
+        for (size_t q = 0; q < RF.size(); ++q) mgb_build_transfer(m, TF, F, *RF[q], C->topo, *C, *C->ranks[q]);
+        for (size_t k = 0; k < 2 * nb; ++k) if (go[k]) hc[k] *= 2.0;
+        m->mgb.push_back(std::move(C));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
+    if (m->cf != TM_CF_LAPLACE) TM_THROW(TM_ERR_UNSUPPORTED, "the multigrid solver supports the Laplace control function only");
+    mgb_build(m);
+    cudaStream_t s = m->stream;
+    const int nl = int(m->mgb.size());
+    const uint64_t nu = o->sweeps_per_iteration;
+    auto ranks_of = [&](int l) -> RankList& { return l == 0 ? m->ranks : m->mgb[size_t(l)]->ranks; };
+    auto xcur = [](RankMesh& r) { return r.X[r.cur].p; };
+    auto tmp_of = [](RankMesh& r) { return r.mg_tmp.p; };
+    double fine_work = 0.0;
+    auto smooth = [&](int l, uint64_t sweeps) {
+        RankList& R = ranks_of(l);
+        for (uint64_t k = 0; k < sweeps; ++k) {
+            for (auto& rp : R) {
+                RankMesh& r = *rp;
+                launch_rows_mg<MODE_RELAX, 0>(m, r, r.X[r.cur].p, r.X[1 - r.cur].p, o->omega, l > 0 ? (const double2*)r.mg_rhs.p : nullptr);
+                r.cur = 1 - r.cur;
+            }
+            exchange_on(m, R, xcur);
+            if (m->n_ranks > 1)
+                for (auto& rp : R) sync_slaves(m, *rp, xcur(*rp), 1, true);
+        }
+        fine_work += double(sweeps) * m->mgb[size_t(l)]->work;
+    };
+    auto refresh = [&](int l) {  // ghosts, then every copy re-derived from its root
+        RankList& R = ranks_of(l);
+        exchange_on(m, R, xcur);
+        for (auto& rp : R) sync_slaves(m, *rp, xcur(*rp), 1);
+    };
+    uint64_t n_coarsest = nu;
+    if (nl > 1) {
+        const MgbLevel& C = *m->mgb.back();
+        uint64_t ext = 0;
+        for (const auto& b : C.blocks) ext = std::max<uint64_t>(ext, std::max(b.ni, b.nj));
+        n_coarsest = std::min<uint64_t>(400, 4 * ext * uint64_t(std::ceil(std::sqrt(double(C.blocks.size())))));
+    }
+    for (uint64_t cyc = 0; cyc < o->iterations; ++cyc) {
+        const bool want_change = o->stop_max_update > 0.0 || cyc + 1 == o->iterations;
+        if (want_change)
+            for (auto& rp : m->ranks) CUDA_TRY(cudaMemcpyAsync(rp->mg_E.p, xcur(*rp), size_t(rp->N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        for (int l = 0; l + 1 < nl; ++l) {
+            RankList& RF = ranks_of(l);
+            RankList& RC = ranks_of(l + 1);
+            smooth(l, nu);
+            for (auto& rp : RF) launch_rows_mg<MODE_REL, 0>(m, *rp, xcur(*rp), rp->mg_tmp.p, 1.0, l > 0 ? (const double2*)rp->mg_rhs.p : nullptr);
+            exchange_on(m, RF, tmp_of);
+            fine_work += m->mgb[size_t(l)]->work;
+            for (size_t q = 0; q < RF.size(); ++q) {
+                RankMesh& rf = *RF[q];
+                RankMesh& rc = *RC[q];
+                for (const BlockXfer& b : rf.xfer_blocks) {
+                    dim3 g((b.nj_c + 127) / 128, b.ni_c);
+                    LAUNCH(mgb_restrict_kernel, g, 128, s, b, (const double2*)xcur(rf), (const double2*)rf.mg_tmp.p, xcur(rc), rc.mg_E.p, rc.mg_rhs.p,
+                           -double(b.fi * b.fj) * double(b.fi * b.fj));
+                }
+                if (rf.n_rrows > 0)
+                    LAUNCH(mgb_restrict_rows_kernel, (rf.n_rrows + 127) / 128, 128, s, (const RestrictRow*)rf.d_rrows.p, rf.n_rrows, (const double2*)rf.mg_tmp.p, rc.mg_rhs.p);
+            }
+            refresh(l + 1);
+            for (auto& rp : RC) {
+                RankMesh& rc = *rp;
+                const int n_l = int(rc.L.sliding.size());
+                if (n_l > 0) LAUNCH(capture_boundary_kernel, (n_l + 127) / 128, 128, s, rc.d_lrows.p, n_l, (const FixedOverride*)nullptr, 0, xcur(rc));
+                CUDA_TRY(cudaMemcpyAsync(rc.X[1 - rc.cur].p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+                CUDA_TRY(cudaMemcpyAsync(rc.mg_E.p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+                launch_rows_mg<MODE_REL, 0>(m, rc, xcur(rc), rc.mg_tmp.p, 1.0, nullptr);  // row_c(I u_f); zero wherever no free row lives
+                LAUNCH(mgb_add_kernel, rc.vec_grid, 256, s, rc.L.n_own, (const double2*)rc.mg_tmp.p, rc.mg_rhs.p);
+            }
+            fine_work += m->mgb[size_t(l) + 1]->work;
+        }
+        smooth(nl - 1, nl > 1 ? n_coarsest : nu);
+        for (int l = nl - 2; l >= 0; --l) {
+            RankList& RF = ranks_of(l);
+            RankList& RC = ranks_of(l + 1);
+            for (size_t q = 0; q < RF.size(); ++q) {
+                RankMesh& rf = *RF[q];
+                RankMesh& rc = *RC[q];
+                for (const BlockXfer& b : rf.xfer_blocks) {
+                    dim3 g((b.nj_f + 127) / 128, b.ni_f);
+                    LAUNCH(mgb_prolong_kernel, g, 128, s, b, (const double2*)xcur(rc), (const double2*)rc.mg_E.p, xcur(rf));
+                }
+                if (rf.n_bnd_rows > 0)
+                    LAUNCH(mgb_prolong_rows_kernel, (rf.n_bnd_rows + 127) / 128, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, int(rf.xfer_blocks.size()),
+                           (const SmoothedRow*)rf.d_srows.p, int(rf.L.smoothed.size()), (const JunctionRow*)rf.d_jrows.p, int(rf.L.junction_rows.size()),
+                           (const SlidingRow*)rf.d_lrows.p, int(rf.L.sliding.size()), (const double2*)xcur(rc), (const double2*)rc.mg_E.p, xcur(rf));
+            }
+            refresh(l);  // nodes no row writes (fixed ones) got a zero correction: both ping-pong buffers still agree there
+            smooth(l, nu);
+        }
+        if (want_change) {
+            for (auto& rp : m->ranks)
+                LAUNCH(diff_stats_kernel, rp->vec_grid, VEC_THREADS, s, rp->L.n_own, (const double2*)rp->mg_E.p, (const double2*)xcur(*rp), rp->part_vec.p);
+            launch_reduce(m, RED_UPDATE_STATS, o, false);
+        }
+        m->outer_done += 1;
+        st->outer_iterations += 1;
+        st->inner_iterations += 1;
+        if (o->stop_max_update > 0.0) {
+            fetch_ctl(m);
+            if (m->h_ctl->max_update <= o->stop_max_update) break;
+        }
+    }
+    st->operator_applications += uint64_t(fine_work + 0.5);
+}
+
 template <class F>
 int guarded(F&& f) {
     try {
@@ -754,6 +1126,10 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     require_device(device);
     if (device < 0) CUDA_TRY(cudaGetDevice(&m->device)); else m->device = device;
     m->topo.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
+    m->h_blocks.assign(blocks, blocks + n_blocks);
+    for (auto& b : m->h_blocks) b.xy = nullptr;
+    if (n_connections) m->h_conns.assign(connections, connections + n_connections);
+    if (n_conditions) m->h_bcs.assign(conditions, conditions + n_conditions);
     if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
     if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
     if (stream) m->stream = (cudaStream_t)stream;
@@ -860,7 +1236,7 @@ int tm_mesh_create(const tm_block* blocks, size_t n_blocks, const tm_connection*
         m->n_ranks = 1;
         m->owner.assign(n_blocks, 0);
         m->ranks.emplace_back(new RankMesh());
-        build_rank(m, *m->ranks[0], 0);
+        build_rank(m, m->topo, *m->ranks[0], 0);
         upload_initial(m, blocks, n_blocks);
         *out = m;
     });
@@ -897,7 +1273,7 @@ int tm_mesh_create_distributed(const tm_block* blocks, size_t n_blocks, const tm
             m->emulated = n_ranks > 1;
             for (int r = 0; r < n_ranks; ++r) {
                 m->ranks.emplace_back(new RankMesh());
-                build_rank(m, *m->ranks.back(), r);
+                build_rank(m, m->topo, *m->ranks.back(), r);
             }
         } else {
             if (rank >= n_ranks) TM_THROW(TM_ERR_INVALID_ARGUMENT, "rank %d out of range", rank);
@@ -909,7 +1285,7 @@ int tm_mesh_create_distributed(const tm_block* blocks, size_t n_blocks, const tm
                 NCCL_TRY(g_nccl.CommInitRank(&m->comm, n_ranks, uid, rank));
             }
             m->ranks.emplace_back(new RankMesh());
-            build_rank(m, *m->ranks[0], rank);
+            build_rank(m, m->topo, *m->ranks[0], rank);
         }
         upload_initial(m, blocks, n_blocks);
         *out = m;
