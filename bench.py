@@ -7,8 +7,8 @@
 A *step* is one pass of the hot path over one synthetic mesh: TFI of every block from its (device-resident) edges,
 then `--sweeps` smoothing sweeps of the whole mesh (interior rows, interface/junction/sliding rows, residual
 reduction).  node-updates = nodes x sweeps.  Workload: N=1 -> BASELINE.json config 3 (single block 8192 x 8192, the
-largest single-GPU configuration); N>1 -> config 4 in tiling form, 8 blocks of 4096 x 2048 per GPU (64 blocks / 512 Mi
-nodes at N=8), weak scaling.  Prints ONE JSON line on rank 0.
+largest single-GPU configuration); N>1 -> config 4 in tiling form, 8 blocks of 4097 x 2049 per GPU (64 blocks / 512 Mi
+nodes at N=8), weak scaling.  Both also report the time to a converged mesh (TFI + FAS multigrid).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -162,7 +162,9 @@ def run_gpu(args):
     else:
         # config 4 in tiling form: one block column (8 blocks of block_ni x block_nj) per GPU; 8 x 8 blocks / 512 Mi nodes at N = 8
         n_bj = args.blocks_per_gpu
-        spec = synthetic.cascade(world, n_bj, args.block_ni, args.block_nj)
+        # the passage grows with N (length = N/8) so that the cells stay square: 8 x 8 blocks on a 1 x 0.5 passage at N = 8
+        # (the waviness scales with it, so the grid lines have the same inclination at every N)
+        spec = synthetic.cascade(world, n_bj, args.block_ni, args.block_nj, length=world / 8.0, ay=0.015 * world / 8.0)
         owner = [bi for bi in range(world) for _ in range(n_bj)]
         workload = (f"cascade_{world}x{n_bj}_blocks_of_{args.block_ni}x{args.block_nj} (config 4: synthetic multi-block cascade passage, "
                     f"{n_bj} blocks per GPU, interface halo exchange once per sweep)")
@@ -214,10 +216,10 @@ def run_gpu(args):
 
     # ---- time to converged mesh (single block): TFI + FAS multigrid V(3,3) until the mesh changes by <= 1e-10 chord per cycle ----
     ttc = None
-    if kind == "single":
+    if not args.no_ttc:
         mg = smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-10, device=local)
         best = None
-        for _ in range(3):
+        for _ in range(3 if kind == "single" else 2):
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             evs[0].record(stream)
             for b in my_blocks:
@@ -226,13 +228,20 @@ def run_gpu(args):
             st_mg = dm.smooth(100, mg)
             evs[1].record(stream)
             dm.synchronize()
-            t_all = evs[0].elapsed_time(evs[1]) * 1e-3
+            tt = torch.tensor([evs[0].elapsed_time(evs[1]) * 1e-3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_all = float(tt.item())
             if best is None or t_all < best[0]:
                 best = (t_all, st_mg)
+        ops = best[1]["operator_applications"]
         ttc = {"seconds": best[0], "solver_seconds": best[1]["gpu_seconds"], "cycles": best[1]["outer_iterations"],
-               "criterion": "max-norm change of the mesh over one V(3,3) cycle <= 1e-10 chord", "last_max_update": best[1]["last_max_update"],
-               "fine_grid_operator_applications": best[1]["operator_applications"], "solver": "TFI + geometric FAS multigrid, damped-Jacobi smoother (omega 0.8)",
-               "note": "best of 3; includes TFI and begin_smoothing"}
+               "criterion": "max-norm change of the mesh over one V(3,3) cycle <= 1e-10 (chord / passage height are O(1))", "last_max_update": best[1]["last_max_update"],
+               "fine_grid_operator_applications": ops,
+               "solver": "TFI + geometric FAS multigrid over the whole block topology, damped-Jacobi smoother (omega 0.8)",
+               "equivalent_node_updates_per_s": nodes_total * ops / best[1]["gpu_seconds"],
+               "hbm_fraction_of_equivalent_sweeps": nodes_total * ops / best[1]["gpu_seconds"] * BYTES_PER_NODE_UPDATE / 1e9 / (measured_peak()[0] * world),
+               "note": "best of %d; includes TFI and begin_smoothing; max over ranks" % (3 if kind == "single" else 2)}
 
     # ---- end to end through the reference-facing calls with HOST buffers (Block2d.init -> smooth.mesh) ----
     e2e = None
@@ -256,8 +265,7 @@ def run_gpu(args):
             "last_max_update": stats["last_max_update"] if stats else None}
     if e2e:
         line["e2e"] = e2e
-    line["time_to_converged"] = ttc if ttc else {"seconds": None, "note": "multi-block meshes: the multigrid solver covers single fixed-boundary blocks this round; "
-                                                                            "see DESIGN.md section 4 for the Picard/BiCGStab timings on T106 / LS89"}
+    line["time_to_converged"] = ttc if ttc else {"seconds": None, "note": "skipped (--no-ttc)"}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1 and kind == "single":
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline_sample(args.ref_size).items() if k in ("value", "unit", "cores", "kind", "sample")}
@@ -370,13 +378,14 @@ def main():
     ap.add_argument("--size", type=int, default=8192, help="single-block edge length (N=1)")
     ap.add_argument("--workload", default=None, choices=["single", "cascade", "cuts"], help="default: single for N=1, cascade for N>1")
     ap.add_argument("--cuts-per-gpu", type=int, default=128, help="--workload cuts: T106 cuts per GPU (1024 cuts on 8 GPUs)")
-    ap.add_argument("--block-ni", type=int, default=4096)
-    ap.add_argument("--block-nj", type=int, default=2048)
+    ap.add_argument("--block-ni", type=int, default=4097, help="cascade: nodes per block along i (2^k + 1 keeps every multigrid level nested)")
+    ap.add_argument("--block-nj", type=int, default=2049)
     ap.add_argument("--blocks-per-gpu", type=int, default=8)
     ap.add_argument("--sweeps", type=int, default=100, help="smoothing sweeps per step")
     ap.add_argument("--omega", type=float, default=0.9)
     ap.add_argument("--ref-size", type=int, default=512, help="edge length of the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ttc", action="store_true", help="skip the time-to-converged (multigrid) measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

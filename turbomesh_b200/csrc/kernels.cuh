@@ -22,6 +22,10 @@ namespace tmesh {
 struct DevBlock {
     int64_t off;
     int32_t ni, nj;
+    // coarse multigrid levels only (HAS_RHS kernels): sides that slide as a whole (bit 0..3: i = 0, i = ni-1, j = 0, j = nj-1)
+    // and the weight of the tangential second difference in the rows next to them (see mgb_restrict_kernel)
+    int32_t slide = 0, _pad = 0;
+    double tan_i = 1.0, tan_j = 1.0;
 };
 struct Tile {
     int32_t block, i0, j0, rows;  // rows marched by the CTA starting at interior row i0
@@ -385,7 +389,12 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_bulk_kernel(const Til
                 const double2 lp = ring[stage][slot][tl], Cp = ring[stage][slot][tl + 1], rp = ring[stage][slot][tl + 2];
                 const double2 Dp = rp - lp, Rp = (rp - Cp) + (lp - Cp);
                 if (k >= 2) {
-                    const Metric m = metric_terms(Cm, Cp, D0);
+                    Metric m = metric_terms(Cm, Cp, D0);
+                    if (HAS_RHS && b.slide) {  // coarse level, row next to a sliding side: Galerkin weight of the tangential term
+                        const int irow = i_begin - 2 + k;
+                        if ((irow == 1 && (b.slide & 1)) || (irow == b.ni - 2 && (b.slide & 2))) m.g11 *= b.tan_i;
+                        if ((j == 1 && (b.slide & 4)) || (j == nj - 2 && (b.slide & 8))) m.g22 *= b.tan_j;
+                    }
                     double P = 0.0, Q = 0.0;
                     if (HAS_PQ) {
                         const double2 f = ldg2(pq + b.off + idx);

@@ -188,7 +188,7 @@ struct RankMesh {
     int n_wnodes = 0;
     std::vector<std::unique_ptr<MgLevel>> mg;  // built on first use of TM_SOLVER_FAS_MULTIGRID (single fixed-boundary block)
     // multi-block multigrid (one RankMesh per rank per level): FAS tau term, residual scratch, restricted iterate
-    DevBuf<double2> mg_rhs, mg_tmp, mg_E;
+    DevBuf<double2> mg_rhs, mg_tmp, mg_E, mg_zero;
     std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
     DevBuf<BlockXfer> d_xfer_blocks;
     DevBuf<RestrictRow> d_rrows;             // boundary rows of the next coarser level <- residuals of this level
@@ -203,6 +203,7 @@ struct MgbLevel {
     std::vector<tm_condition> bcs;
     std::vector<std::unique_ptr<RankMesh>> ranks;    // levels >= 1
     std::vector<int> fi, fj;                         // per block: coarsening factors towards the next level (empty on the coarsest)
+    std::vector<double> tan_i, tan_j;                // per block: weight of the tangential term next to sliding sides (1 on level 0)
     double work = 1.0;                               // nodes relative to level 0
 };
 
@@ -801,6 +802,17 @@ std::vector<double> block_cell_sizes(tm_mesh* m) {
     return h;
 }
 
+// bit 0..3: every node strictly inside the side i = 0 / i = ni-1 / j = 0 / j = nj-1 of the block is a sliding node
+int32_t side_slide_mask(const Topology& T, size_t k) {
+    const int64_t ni = T.blocks[k].ni, nj = T.blocks[k].nj;
+    auto slides = [&](int64_t base, int64_t stride, int64_t n) {
+        for (int64_t q = 1; q + 1 < n; ++q)
+            if (T.kind[size_t(T.bid(k, base + q * stride))] != K_SLIDING) return false;
+        return n > 2;
+    };
+    return (slides(0, 1, nj) ? 1 : 0) | (slides((ni - 1) * nj, 1, nj) ? 2 : 0) | (slides(0, nj, ni) ? 4 : 0) | (slides(nj - 1, nj, ni) ? 8 : 0);
+}
+
 // residual restriction of the rows that straddle blocks: coarse row <- full weighting of the fine residuals around it
 void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankMesh& rf, const Topology& TC, const MgbLevel& C, RankMesh& rc) {
     const int rank = rf.L.rank;
@@ -810,12 +822,7 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
         const size_t k = size_t(b);
         if (TF.blocks[k].ni > 65535 || TF.blocks[k].nj > 0x7fffffff) TM_THROW(TM_ERR_UNSUPPORTED, "multigrid: block %d too large for the transfer kernels", b);
         const int64_t ni = TF.blocks[k].ni, nj = TF.blocks[k].nj;
-        auto slides = [&](int64_t base, int64_t stride, int64_t n) {  // every node strictly inside the side is a sliding node
-            for (int64_t q = 1; q + 1 < n; ++q)
-                if (TF.kind[size_t(TF.bid(k, base + q * stride))] != K_SLIDING) return false;
-            return n > 2;
-        };
-        const int32_t slide = (slides(0, 1, nj) ? 1 : 0) | (slides((ni - 1) * nj, 1, nj) ? 2 : 0) | (slides(0, nj, ni) ? 4 : 0) | (slides(nj - 1, nj, ni) ? 8 : 0);
+        const int32_t slide = side_slide_mask(TF, k);
         rf.xfer_blocks.push_back(BlockXfer{rf.L.loff[k], rc.L.loff[k], int32_t(ni), int32_t(nj), int32_t(TC.blocks[k].ni), int32_t(TC.blocks[k].nj), F.fi[k],
                                            F.fj[k], slide, 0});
     }
@@ -915,6 +922,7 @@ void mgb_build(tm_mesh* m) {
     {
         std::unique_ptr<MgbLevel> L0(new MgbLevel());
         L0->blocks = m->h_blocks; L0->conns = m->h_conns; L0->bcs = m->h_bcs;
+        L0->tan_i.assign(nb, 1.0); L0->tan_j.assign(nb, 1.0);
         m->mgb.push_back(std::move(L0));
     }
     for (auto& rp : m->ranks) {
@@ -968,12 +976,25 @@ void mgb_build(tm_mesh* m) {
             break;
         }
         C->work = double(C->topo.n_nodes) / n0;
+        // Rows next to a sliding side: the Galerkin coarse operator (restriction weights 1/2, 1/2, 1/4 over the first three
+        // rows, boundary unknown eliminated) carries 5/4 of the tangential term of the level below; f' = f/2 + 3/4.
+        C->tan_i.resize(nb); C->tan_j.resize(nb);
+        for (size_t b = 0; b < nb; ++b) {
+            C->tan_i[b] = F.fi[b] == 2 ? 0.5 * F.tan_i[b] + 0.75 : F.tan_i[b];
+            C->tan_j[b] = F.fj[b] == 2 ? 0.5 * F.tan_j[b] + 0.75 : F.tan_j[b];
+        }
         for (auto& rp : m->ranks) {
             C->ranks.emplace_back(new RankMesh());
             RankMesh& rc = *C->ranks.back();
             build_rank(m, C->topo, rc, rp->L.rank);
-            for (DevBuf<double2>* v : {&rc.mg_rhs, &rc.mg_tmp, &rc.mg_E}) { v->alloc(size_t(std::max<int64_t>(rc.N, 1))); v->zero(s); }
+            for (DevBuf<double2>* v : {&rc.mg_rhs, &rc.mg_tmp, &rc.mg_E, &rc.mg_zero}) { v->alloc(size_t(std::max<int64_t>(rc.N, 1))); v->zero(s); }
             std::fill(rc.have_coords.begin(), rc.have_coords.end(), uint8_t(1));
+            std::vector<DevBlock> blocks(nb, DevBlock{0, 0, 0});
+            for (int32_t b : rc.L.own_blocks) {
+                const size_t k = size_t(b);
+                blocks[k] = DevBlock{rc.L.loff[k], int32_t(C->topo.blocks[k].ni), int32_t(C->topo.blocks[k].nj), side_slide_mask(C->topo, k), 0, C->tan_i[k], C->tan_j[k]};
+            }
+            rc.d_blocks.upload(blocks, s);
         }
         const Topology& TF = m->mgb.size() == 1 ? m->topo : F.topo;
         RankList& RF = m->mgb.size() == 1 ? m->ranks : F.ranks;
@@ -1019,6 +1040,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
         uint64_t ext = 0;
         for (const auto& b : C.blocks) ext = std::max<uint64_t>(ext, std::max(b.ni, b.nj));
         n_coarsest = std::min<uint64_t>(400, 4 * ext * uint64_t(std::ceil(std::sqrt(double(C.blocks.size())))));
+        if (const char* e = std::getenv("TM_MG_COARSEST_SWEEPS")) n_coarsest = uint64_t(std::max(1, std::atoi(e)));
     }
     for (uint64_t cyc = 0; cyc < o->iterations; ++cyc) {
         const bool want_change = o->stop_max_update > 0.0 || cyc + 1 == o->iterations;
@@ -1049,7 +1071,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 if (n_l > 0) LAUNCH(capture_boundary_kernel, (n_l + 127) / 128, 128, s, rc.d_lrows.p, n_l, (const FixedOverride*)nullptr, 0, xcur(rc));
                 CUDA_TRY(cudaMemcpyAsync(rc.X[1 - rc.cur].p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
                 CUDA_TRY(cudaMemcpyAsync(rc.mg_E.p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-                launch_rows_mg<MODE_REL, 0>(m, rc, xcur(rc), rc.mg_tmp.p, 1.0, nullptr);  // row_c(I u_f); zero wherever no free row lives
+                launch_rows_mg<MODE_REL, 0>(m, rc, xcur(rc), rc.mg_tmp.p, 1.0, (const double2*)rc.mg_zero.p);  // row_c(I u_f) with the level's (HAS_RHS) operator
                 LAUNCH(mgb_add_kernel, rc.vec_grid, 256, s, rc.L.n_own, (const double2*)rc.mg_tmp.p, rc.mg_rhs.p);
             }
             fine_work += m->mgb[size_t(l) + 1]->work;

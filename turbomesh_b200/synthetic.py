@@ -66,7 +66,8 @@ def _channel(xi: np.ndarray, eta: np.ndarray, length: float, height: float, ax: 
     return x, y
 
 
-def cascade(n_bi: int = 8, n_bj: int = 8, ni: int = 4096, nj: int = 2048, length: float = 1.0, height: float = 0.5) -> Mesh:
+def cascade(n_bi: int = 8, n_bj: int = 8, ni: int = 4096, nj: int = 2048, length: float = 1.0, height: float = 0.5,
+            ax: Optional[float] = None, ay: Optional[float] = None) -> Mesh:
     """Config 4 (tiling form): n_bi x n_bj blocks of ni x nj nodes tiling one cascade passage.
 
     A wavy channel with inlet at x = 0 and outlet at x = `length`, pitch-wise periodic (period `height`) like the T106
@@ -81,7 +82,9 @@ def cascade(n_bi: int = 8, n_bj: int = 8, ni: int = 4096, nj: int = 2048, length
     gi, gj = n_bi * (ni - 1) + 1, n_bj * (nj - 1) + 1
     xi_all = np.arange(gi, dtype=np.float64) / (gi - 1)
     eta_all = np.arange(gj, dtype=np.float64) / (gj - 1)
-    ax, ay = 0.02 * length, 0.03 * height
+    # amplitudes of the waviness; the grid lines j = const are inclined by up to atan(2 pi ay / length) against the x axis
+    ax = 0.02 * length if ax is None else ax
+    ay = 0.03 * height if ay is None else ay
     u_i = Uniform().compute(ni)
     u_j = Uniform().compute(nj)
     mesh = Mesh()
