@@ -260,7 +260,8 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "nodes": nodes_total, "sweeps_per_step": sweeps, "omega": args.omega,
                        "step": "TFI of all blocks from device-resident edges + begin_smoothing + sweeps (damped Jacobi, coefficients from the current iterate)",
-                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2", "nodes_per_gpu": nodes_local},
+                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2", "nodes_per_gpu": nodes_local,
+                       "halo_exchange": dm.halo_path},
             "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall / args.steps * 1e3,
             "last_max_update": stats["last_max_update"] if stats else None}
     if e2e:

@@ -224,6 +224,12 @@ int tm_mesh_create_distributed(const tm_block *blocks, size_t n_blocks,
                                const uint8_t *unique_id /* TM_UNIQUE_ID_BYTES; may be NULL when n_ranks == 1 or rank == -1 */,
                                int device, void *stream, tm_mesh **out);
 uint64_t tm_mesh_local_node_count(const tm_mesh *mesh); /* nodes of the blocks held by this process */
+/* How the per-sweep halo exchange of this mesh travels.  TM_HALO_PEER_MEMORY: the owner pushes the nodes its neighbours
+ * ghost straight into their fields over NVLink (buffers mapped with CUDA IPC, one gather+store+signal kernel per
+ * exchange); chosen when every rank could map its neighbours' buffers (TM_P2P=0 in the environment forces NCCL).
+ * TM_HALO_NCCL: pack kernel + ncclSend/ncclRecv group. */
+typedef enum tm_halo_path { TM_HALO_NONE = 0, TM_HALO_EMULATED = 1, TM_HALO_NCCL = 2, TM_HALO_PEER_MEMORY = 3 } tm_halo_path;
+int tm_mesh_halo_path(const tm_mesh *mesh);
 
 /* Host-only view of the partition (needs no GPU): sizes of rank `rank`'s local field and its exchange lists.
  * ghost_ids / send_ids (may be NULL) receive the global node ids grouped by peer rank in ascending rank order;

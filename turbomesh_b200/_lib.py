@@ -98,6 +98,8 @@ def load():
                                              C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, vp, C.POINTER(vp)]
     L.tm_mesh_local_node_count.argtypes = [vp]
     L.tm_mesh_local_node_count.restype = C.c_uint64
+    L.tm_mesh_halo_path.argtypes = [vp]
+    L.tm_mesh_halo_path.restype = C.c_int
     L.tm_dist_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t,
                                C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(TmDistPlanInfo), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int64)]

@@ -584,6 +584,70 @@ __global__ void pack_kernel(const int64_t* __restrict__ idx, int64_t n, const do
     if (k < n) out[k] = v[idx[k]];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Halo exchange over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): the owner PUSHES the nodes
+// its neighbours ghost straight into the tail of their fields -- gather and remote store in one kernel, no staging buffer,
+// no NCCL launch -- and the last CTA to finish raises the rank's slot of every neighbour's flag array to the exchange
+// counter (release at system scope, after every writer fenced its stores).  The consumer side is p2p_wait_kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int P2P_MAX_RANKS = 16;
+struct PushArgs {
+    double2* dst[P2P_MAX_RANKS];                 // peer field + offset of this rank's ghost segment there
+    int64_t base[P2P_MAX_RANKS + 1];             // send list offsets per peer
+    unsigned long long* flag[P2P_MAX_RANKS];     // this rank's slot in the peer's flag array (NULL: not a neighbour)
+    int n_ranks;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// One launch per exchange, at most one CTA per SM (all CTAs are co-resident, so spinning cannot starve a CTA that still
+// has to push): every CTA pushes its share (grid-stride) and fences; the last CTA to finish signals the neighbours; then
+// ALL CTAs wait until the neighbours' pushes number `epoch` have landed here (bounded spin: a rank that never arrives
+// makes the wait give up and raise *err instead of hanging the GPU) and re-derive their share of the copies whose root is
+// a ghost (mode as in sync_slaves_kernel; n_slaves = 0 for fields without copies).
+__global__ void __launch_bounds__(256) p2p_exchange_kernel(const int64_t* __restrict__ idx, int64_t n, double2* __restrict__ v, PushArgs a,
+                                                           unsigned long long epoch, unsigned int* __restrict__ counter,
+                                                           const unsigned long long* __restrict__ flags, unsigned int nb_mask, int* __restrict__ err,
+                                                           const SlaveRow* __restrict__ slaves, int n_slaves, int slave_mode) {
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        int p = 0;
+        while (k >= a.base[p + 1]) ++p;
+        a.dst[p][k - a.base[p]] = v[idx[k]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        if (ticket == gridDim.x - 1) {
+            *counter = 0u;
+            __threadfence_system();
+            for (int p = 0; p < a.n_ranks; ++p)
+                if (a.flag[p]) st_release_sys(a.flag[p], epoch);
+        }
+    }
+    const int p = threadIdx.x;
+    if (p < P2P_MAX_RANKS && ((nb_mask >> p) & 1u)) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + p) < epoch) {
+            if (clock64() - t0 > 8000000000ll) { *err = 1; break; }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < n_slaves; q += gridDim.x * 256) {
+        const SlaveRow s = slaves[q];
+        if (slave_mode == 2) { v[s.self] = make_double2(0.0, 0.0); continue; }
+        // the root is a ghost written by a peer GPU: read it past the (non-coherent) L1
+        const double2 r = __ldcg(v + s.root);
+        v[s.self] = slave_mode == 1 ? make_double2(r.x + s.sx, r.y + s.sy) : r;
+    }
+}
+
 // begin_smoothing: capture rhs_x of sliding rows from the initial mesh (smooth.zig:853-857), apply the
 // (normally empty) fixed overrides.
 __global__ void capture_boundary_kernel(SlidingRow* __restrict__ lrows, int n_l, const FixedOverride* __restrict__ fo, int n_fo, double2* __restrict__ x) {

@@ -33,6 +33,7 @@ struct LocalTables {
     std::vector<std::vector<int64_t>> send_ids;  // per peer: sorted global ids owned here, read there
     std::vector<int64_t> ghost_base, send_base;  // per peer (n_ranks+1 entries): offsets in the ghost region / send buffer
     std::vector<int64_t> send_lidx;              // local indices to pack, concatenated over peers
+    std::vector<int64_t> peer_ghost_offset;      // per peer p: where this rank's segment starts in p's local field (peer-memory push)
     // one-time exchange of raw coordinates for connectionDataCheck (smooth.zig:220-275) across ranks
     std::vector<std::vector<int64_t>> check_ghost_ids, check_send_ids;
     std::vector<int64_t> check_ghost_base, check_send_base, check_send_lidx;
@@ -141,9 +142,18 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
         L.synth_ids = std::move(mine_sets.synth);
     }
     L.send_ids.assign(size_t(n_ranks), {});
+    L.peer_ghost_offset.assign(size_t(n_ranks), 0);
     for (int p = 0; p < n_ranks; ++p) {
         if (p == rank) continue;
-        L.send_ids[size_t(p)] = read_sets(T, owner, p, n_ranks, root_of).recv[size_t(rank)];
+        ReadSets theirs = read_sets(T, owner, p, n_ranks, root_of);
+        // p's local field is [own nodes of p | ghosts from rank 0 | from rank 1 | ...]: my segment starts after p's own nodes
+        // and the ghosts p receives from the ranks below me
+        int64_t off = 0;
+        for (size_t b = 0; b < T.blocks.size(); ++b)
+            if (owner[b] == p) off += T.blocks[b].ni * T.blocks[b].nj;
+        for (int q = 0; q < rank; ++q) off += int64_t(theirs.recv[size_t(q)].size());
+        L.peer_ghost_offset[size_t(p)] = off;
+        L.send_ids[size_t(p)] = std::move(theirs.recv[size_t(rank)]);
     }
     L.ghost_base.assign(size_t(n_ranks) + 1, 0);
     L.send_base.assign(size_t(n_ranks) + 1, 0);

@@ -191,6 +191,23 @@ struct RankMesh {
     DevBuf<double2> mg_rhs, mg_tmp, mg_E, mg_zero;
     std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
     DevBuf<BlockXfer> d_xfer_blocks;
+    // NVLink peer-memory halo exchange (real multi-rank meshes): peers' fields mapped with CUDA IPC
+    struct P2P {
+        bool ready = false;                          // flags + X[0] + X[1] mapped on every rank
+        bool have[3] = {false, false, false};        // X[0], X[1], mg_tmp
+        double2* peer[3][P2P_MAX_RANKS] = {};        // mapped base pointers of the peers' buffers
+        unsigned long long* peer_flags[P2P_MAX_RANKS] = {};
+        std::vector<void*> opened;                   // for cudaIpcCloseMemHandle
+        DevBuf<unsigned long long> flags;            // slot p: number of pushes rank p has completed into this rank's buffers
+        DevBuf<unsigned int> counter;
+        DevBuf<int> err;
+        unsigned int nb_mask = 0;
+        unsigned long long epoch = 0;
+    } p2p;
+    ~RankMesh() {
+        for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
+    }
+    RankMesh() = default;
     DevBuf<RestrictRow> d_rrows;             // boundary rows of the next coarser level <- residuals of this level
     int n_rrows = 0;
 };
@@ -228,6 +245,7 @@ struct tm_mesh {
     std::vector<tm_connection> h_conns;
     std::vector<tm_condition> h_bcs;
     std::vector<std::unique_ptr<MgbLevel>> mgb;  // multi-block multigrid hierarchy, built on first use
+    int sm_count = 148;
     int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
     bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
 
@@ -299,6 +317,88 @@ void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank) {
     r.have_coords.assign(r.L.own_blocks.size(), 0);
 }
 
+// ---- CUDA IPC plumbing of the peer-memory exchange ---------------------------------------------------------------
+// All ranks call these in lock-step (they contain NCCL collectives).  Handles travel through an all-reduce of bytes in
+// which every rank fills only its own slot; a rank on which anything fails votes the feature off for everybody, so the
+// ranks can never disagree about the exchange path (the NCCL send/recv path stays as the alternative).
+bool p2p_vote(tm_mesh* m, bool ok) {
+    DevBuf<double> d;
+    d.alloc(1);
+    const double mine = ok ? 1.0 : 0.0;
+    CUDA_TRY(cudaMemcpyAsync(d.p, &mine, sizeof mine, cudaMemcpyHostToDevice, m->stream));
+    NCCL_TRY(g_nccl.AllReduce(d.p, d.p, 1, ncclDouble, ncclMin, m->comm, m->stream));
+    double all = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&all, d.p, sizeof all, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return all > 0.5;
+}
+
+// exports `ptr` of every rank and maps the neighbours' copies into out[p]; returns false (on every rank) if any rank failed
+bool p2p_share(tm_mesh* m, RankMesh& r, void* ptr, void** out) {
+    const int n = m->n_ranks, me = r.L.rank;
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    std::vector<unsigned char> all(size_t(n) * hs, 0);
+    bool ok = ptr != nullptr;
+    if (ok) {
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) { (void)cudaGetLastError(); ok = false; }
+        else std::memcpy(all.data() + size_t(me) * hs, &h, hs);
+    }
+    DevBuf<unsigned char> d;
+    d.alloc(all.size());
+    CUDA_TRY(cudaMemcpyAsync(d.p, all.data(), all.size(), cudaMemcpyHostToDevice, m->stream));
+    NCCL_TRY(g_nccl.AllReduce(d.p, d.p, all.size(), ncclUint8, ncclSum, m->comm, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d.p, all.size(), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    ok = p2p_vote(m, ok);
+    if (ok) {
+        for (int p = 0; p < n; ++p) {
+            out[p] = nullptr;
+            if (p == me || !((r.p2p.nb_mask >> p) & 1u)) continue;
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, all.data() + size_t(p) * hs, hs);
+            void* q = nullptr;
+            if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); ok = false; break; }
+            r.p2p.opened.push_back(q);
+            out[p] = q;
+        }
+    }
+    return p2p_vote(m, ok);
+}
+
+void p2p_setup(tm_mesh* m, RankMesh& r) {
+    if (m->n_ranks < 2 || m->emulated || m->n_ranks > P2P_MAX_RANKS) return;
+    if (const char* e = std::getenv("TM_P2P")) if (std::atoi(e) == 0) return;
+    const int n = m->n_ranks, me = r.L.rank;
+    r.p2p.nb_mask = 0;
+    for (int p = 0; p < n; ++p)
+        if (p != me && (r.L.send_base[size_t(p) + 1] > r.L.send_base[size_t(p)] || r.L.ghost_base[size_t(p) + 1] > r.L.ghost_base[size_t(p)])) r.p2p.nb_mask |= 1u << p;
+    r.p2p.flags.alloc(size_t(n)); r.p2p.flags.zero(m->stream);
+    r.p2p.counter.alloc(1); r.p2p.counter.zero(m->stream);
+    r.p2p.err.alloc(1); r.p2p.err.zero(m->stream);
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    void* tmp[P2P_MAX_RANKS];
+    bool ok = p2p_share(m, r, r.p2p.flags.p, tmp);
+    if (ok) for (int p = 0; p < n; ++p) r.p2p.peer_flags[p] = static_cast<unsigned long long*>(tmp[p]);
+    for (int w = 0; w < 2 && ok; ++w) {
+        ok = p2p_share(m, r, r.X[w].p, tmp);
+        if (ok) { for (int p = 0; p < n; ++p) r.p2p.peer[w][p] = static_cast<double2*>(tmp[p]); r.p2p.have[w] = true; }
+    }
+    r.p2p.ready = ok;
+}
+void p2p_add_tmp(tm_mesh* m, RankMesh& r) {  // the residual scratch field of a multigrid level
+    if (!r.p2p.ready || r.p2p.have[2]) return;
+    void* tmp[P2P_MAX_RANKS];
+    if (p2p_share(m, r, r.mg_tmp.p, tmp)) { for (int p = 0; p < m->n_ranks; ++p) r.p2p.peer[2][p] = static_cast<double2*>(tmp[p]); r.p2p.have[2] = true; }
+}
+void p2p_check(tm_mesh* m, RankMesh& r) {  // after a synchronisation point: did a wait give up?
+    if (!r.p2p.ready) return;
+    int e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, r.p2p.err.p, sizeof e, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (e) TM_THROW(TM_ERR_CUDA, "peer-memory halo exchange timed out waiting for a neighbour rank");
+}
+
 void ensure_krylov(tm_mesh* m) {
     for (auto& rp : m->ranks) {
         RankMesh& r = *rp;
@@ -314,14 +414,25 @@ void ensure_krylov(tm_mesh* m) {
 // ---- halo exchange: every rank's ghost slots of `field` are refreshed from their owners ------------------------
 // check = true: the one-time exchange of raw side-0 coordinates for connectionDataCheck (separate slots).
 using RankList = std::vector<std::unique_ptr<RankMesh>>;
+void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root = false);
+// slave_mode >= 0: afterwards the copies whose root is a ghost are re-derived from it (mode as in sync_slaves_kernel)
 template <class Get>
-void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false) {
+void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false, int slave_mode = -1) {
     if (m->n_ranks == 1) return;
     cudaStream_t s = m->stream;
     auto send_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_send_base : r.L.send_base; };
     auto ghost_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_ghost_base : r.L.ghost_base; };
     auto region = [&](RankMesh& r) { return check ? r.L.n_own + r.L.n_ghost + r.L.n_synth : r.L.n_own; };
+    bool p2p = false;
+    int which = -1;
+    if (!m->emulated && !check) {
+        RankMesh& r = *ranks[0];
+        double2* f = get(r);
+        which = f == r.X[0].p ? 0 : f == r.X[1].p ? 1 : (r.mg_tmp.p && f == r.mg_tmp.p) ? 2 : -1;
+        p2p = r.p2p.ready && which >= 0 && r.p2p.have[which];
+    }
     for (auto& rp : ranks) {
+        if (p2p) break;
         RankMesh& r = *rp;
         const int64_t n = send_base(r).back();
         const int64_t* idx = check ? r.d_check_send_idx.p : r.d_send_idx.p;
@@ -340,6 +451,25 @@ void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false) {
         }
     } else {
         RankMesh& r = *ranks[0];
+        if (p2p) {
+            // peer-memory push: gather + remote store + signal in one launch, then wait for the neighbours' pushes
+            PushArgs a{};
+            a.n_ranks = m->n_ranks;
+            for (int p = 0; p <= m->n_ranks; ++p) a.base[p] = r.L.send_base[size_t(p)];
+            for (int p = 0; p < m->n_ranks; ++p) {
+                a.dst[p] = r.p2p.peer[which][p] ? r.p2p.peer[which][p] + r.L.peer_ghost_offset[size_t(p)] : nullptr;
+                a.flag[p] = ((r.p2p.nb_mask >> p) & 1u) ? r.p2p.peer_flags[p] + r.L.rank : nullptr;
+            }
+            r.p2p.epoch += 1;
+            const int64_t n = r.L.send_base.back();
+            const int64_t first = r.L.n_slaves_local_root;
+            const int n_sl = slave_mode >= 0 ? int(int64_t(r.L.slaves.size()) - first) : 0;
+            const int64_t want = (std::max<int64_t>(n, n_sl) + 255) / 256;
+            LAUNCH(p2p_exchange_kernel, unsigned(std::max<int64_t>(1, std::min<int64_t>(want, m->sm_count))), 256, s, (const int64_t*)r.d_send_idx.p, n, get(r), a, r.p2p.epoch,
+                   r.p2p.counter.p, (const unsigned long long*)r.p2p.flags.p, r.p2p.nb_mask, r.p2p.err.p, (const SlaveRow*)(r.d_slaves.p + first), n_sl,
+                   std::max(slave_mode, 0));
+            return;
+        }
         NCCL_TRY(g_nccl.GroupStart());
         for (int p = 0; p < m->n_ranks; ++p) {
             const int64_t ns = send_base(r)[size_t(p) + 1] - send_base(r)[size_t(p)];
@@ -349,13 +479,15 @@ void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false) {
         }
         NCCL_TRY(g_nccl.GroupEnd());
     }
+    if (slave_mode >= 0)
+        for (auto& rp : ranks) sync_slaves(m, *rp, get(*rp), slave_mode, true);
 }
 
 template <class Get>
-void exchange(tm_mesh* m, Get get, bool check = false) { exchange_on(m, m->ranks, get, check); }
+void exchange(tm_mesh* m, Get get, bool check = false, int slave_mode = -1) { exchange_on(m, m->ranks, get, check, slave_mode); }
 
 // copies of nodes: mode 0 homogeneous / 1 affine / 2 zero; `only_remote_root` restricts to copies whose root is a ghost
-void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root = false) {
+void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root) {
     const int64_t first = only_remote_root ? r.L.n_slaves_local_root : 0;
     const int n = int(int64_t(r.L.slaves.size()) - first);
     if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, m->stream, (const SlaveRow*)(r.d_slaves.p + first), n, v, mode);
@@ -477,9 +609,7 @@ void run_relax(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
                 else launch_rows<MODE_RELAX, 0>(m, r, false, u, u, out, o->omega, nullptr);
                 r.cur = 1 - r.cur;
             }
-            exchange(m, [](RankMesh& r) { return r.X[r.cur].p; });
-            if (m->n_ranks > 1)
-                for (auto& rp : m->ranks) sync_slaves(m, *rp, rp->X[rp->cur].p, 1, true);
+            exchange(m, [](RankMesh& r) { return r.X[r.cur].p; }, false, 1);
             st->inner_iterations += 1;
             st->operator_applications += 1;
         }
@@ -928,6 +1058,8 @@ void mgb_build(tm_mesh* m) {
     for (auto& rp : m->ranks) {
         rp->mg_tmp.alloc(size_t(std::max<int64_t>(rp->N, 1))); rp->mg_tmp.zero(s);
         rp->mg_E.alloc(size_t(std::max<int64_t>(rp->N, 1))); rp->mg_E.zero(s);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        p2p_add_tmp(m, *rp);
     }
     const double n0 = double(m->topo.n_nodes);
     for (int level = 0; level < 20; ++level) {
@@ -995,6 +1127,9 @@ void mgb_build(tm_mesh* m) {
                 blocks[k] = DevBlock{rc.L.loff[k], int32_t(C->topo.blocks[k].ni), int32_t(C->topo.blocks[k].nj), side_slide_mask(C->topo, k), 0, C->tan_i[k], C->tan_j[k]};
             }
             rc.d_blocks.upload(blocks, s);
+            CUDA_TRY(cudaStreamSynchronize(s));
+            p2p_setup(m, rc);
+            p2p_add_tmp(m, rc);
         }
         const Topology& TF = m->mgb.size() == 1 ? m->topo : F.topo;
         RankList& RF = m->mgb.size() == 1 ? m->ranks : F.ranks;
@@ -1023,9 +1158,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 launch_rows_mg<MODE_RELAX, 0>(m, r, r.X[r.cur].p, r.X[1 - r.cur].p, o->omega, l > 0 ? (const double2*)r.mg_rhs.p : nullptr);
                 r.cur = 1 - r.cur;
             }
-            exchange_on(m, R, xcur);
-            if (m->n_ranks > 1)
-                for (auto& rp : R) sync_slaves(m, *rp, xcur(*rp), 1, true);
+            exchange_on(m, R, xcur, false, 1);
         }
         fine_work += double(sweeps) * m->mgb[size_t(l)]->work;
     };
@@ -1147,6 +1280,7 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     if ((n_connections && !connections) || (n_conditions && !conditions)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "NULL connection / condition array");
     require_device(device);
     if (device < 0) CUDA_TRY(cudaGetDevice(&m->device)); else m->device = device;
+    CUDA_TRY(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
     m->topo.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
     m->h_blocks.assign(blocks, blocks + n_blocks);
     for (auto& b : m->h_blocks) b.xy = nullptr;
@@ -1308,6 +1442,7 @@ int tm_mesh_create_distributed(const tm_block* blocks, size_t n_blocks, const tm
             }
             m->ranks.emplace_back(new RankMesh());
             build_rank(m, m->topo, *m->ranks[0], rank);
+            p2p_setup(m, *m->ranks[0]);
         }
         upload_initial(m, blocks, n_blocks);
         *out = m;
@@ -1491,6 +1626,8 @@ int tm_mesh_smooth(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* stat
         else run_picard_bicgstab(m, o, &st);
         CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
         fetch_ctl(m);
+        for (auto& rp : m->ranks) p2p_check(m, *rp);
+        for (auto& lv : m->mgb) for (auto& rp : lv->ranks) p2p_check(m, *rp);
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         st.gpu_seconds = 1e-3 * double(ms);
@@ -1524,6 +1661,11 @@ int tm_mesh_set_white_groups(tm_mesh* m, const uint64_t* block_pairs, size_t n_g
 
 uint64_t tm_mesh_block_count(const tm_mesh* m) { return m ? m->topo.blocks.size() : 0; }
 uint64_t tm_mesh_node_count(const tm_mesh* m) { return m ? uint64_t(m->topo.n_nodes) : 0; }
+int tm_mesh_halo_path(const tm_mesh* m) {
+    if (!m || m->n_ranks < 2) return TM_HALO_NONE;
+    if (m->emulated) return TM_HALO_EMULATED;
+    return (!m->ranks.empty() && m->ranks[0]->p2p.ready) ? TM_HALO_PEER_MEMORY : TM_HALO_NCCL;
+}
 uint64_t tm_mesh_local_node_count(const tm_mesh* m) {
     uint64_t n = 0;
     if (m) for (const auto& rp : m->ranks) n += uint64_t(rp->L.n_own);

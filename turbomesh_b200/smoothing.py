@@ -197,6 +197,11 @@ class DeviceMesh:
         return self.rank is None or self.owner[block] == self.rank
 
     @property
+    def halo_path(self) -> str:
+        """How the per-sweep halo exchange travels (``tm_mesh_halo_path``)."""
+        return {0: "none", 1: "emulated (one process)", 2: "nccl send/recv", 3: "nvlink peer memory (cuda ipc push)"}[int(self._L.tm_mesh_halo_path(self._h))]
+
+    @property
     def local_node_count(self) -> int:
         return int(self._L.tm_mesh_local_node_count(self._h))
 
