@@ -1103,34 +1103,61 @@ struct RestrictRow {               // rhs_c[dst] = sum_k w[k] * res_f[src[k]]  (
 // coarse <- fine for one block: iterate by injection (all nodes, so that copies stay exact copies); residual of the
 // interior rows by full weighting in the coarsened directions, times `scale` (= -(f_i f_j)^2: the undivided Winslow row
 // of a smooth field scales like h_xi^2 h_eta^2, and the restricted quantity is the negative residual).
-__global__ void mgb_restrict_kernel(BlockXfer b, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
-                                    double2* __restrict__ e_c, double2* __restrict__ rhs_c, double scale) {
-    const int J = blockIdx.x * blockDim.x + threadIdx.x, I = blockIdx.y;
-    if (J >= b.nj_c || I >= b.ni_c) return;
-    const int i = I * b.fi, j = J * b.fj;
-    const size_t kc = (size_t)b.off_c + (size_t)I * b.nj_c + J;
-    const size_t kf = (size_t)b.off_f + (size_t)i * b.nj_f + j;
-    const double2 uc = u_f[kf];
-    u_c[kc] = uc;
-    e_c[kc] = uc;
-    double2 r = make_double2(0.0, 0.0);
-    if (I > 0 && I < b.ni_c - 1 && J > 0 && J < b.nj_c - 1) {
+constexpr int MGB_ROWS = 1;  // rows per CTA in the block transfer kernels (marching several rows per thread measured slower: less memory-level parallelism)
+__global__ void __launch_bounds__(128) mgb_restrict_kernel(BlockXfer b, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
+                                                           double2* __restrict__ e_c, double2* __restrict__ rhs_c, double scale,
+                                                           unsigned long long* __restrict__ change /* may be NULL */) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I_end = min((int)(blockIdx.y + 1) * MGB_ROWS, b.ni_c);
+    double dmax = 0.0;
+    if (J < b.nj_c) {
+        const int j = J * b.fj;
+        const int pi = b.fi == 2 ? 1 : 0, pj = b.fj == 2 ? 1 : 0;
         // Next to a sliding (Neumann-type) side the boundary unknown follows its inner neighbour, so the coarse boundary
         // node carries no row of its own: the quarter of the first interior row's residual that full weighting would
         // send there belongs to this row instead (the Galerkin restriction after eliminating y_0 = y_1).  That residual
         // is what drives the sliding modes; with the plain weights the coarse correction is half of what is needed.
-        const int pi = b.fi == 2 ? 1 : 0, pj = b.fj == 2 ? 1 : 0;
-        const double wim = (I == 1 && (b.slide & 1)) ? 0.5 : 0.25, wip = (I == b.ni_c - 2 && (b.slide & 2)) ? 0.5 : 0.25;
         const double wjm = (J == 1 && (b.slide & 4)) ? 0.5 : 0.25, wjp = (J == b.nj_c - 2 && (b.slide & 8)) ? 0.5 : 0.25;
-        for (int p = -pi; p <= pi; ++p)
-            for (int q = -pj; q <= pj; ++q) {
-                const double w = (pi ? (p == 0 ? 0.5 : (p < 0 ? wim : wip)) : 1.0) * (pj ? (q == 0 ? 0.5 : (q < 0 ? wjm : wjp)) : 1.0);
-                const double2 v = res_f[kf + (long long)p * b.nj_f + q];
-                r.x += w * v.x; r.y += w * v.y;
+        for (int I = blockIdx.y * MGB_ROWS; I < I_end; ++I) {
+            const int i = I * b.fi;
+            const size_t kc = (size_t)b.off_c + (size_t)I * b.nj_c + J;
+            const size_t kf = (size_t)b.off_f + (size_t)i * b.nj_f + j;
+            const double2 uc = u_f[kf];
+            if (change) {  // how far this node moved since the previous cycle's restriction (the cycle's convergence measure)
+                const double2 old = e_c[kc];
+                dmax = fmax(dmax, fmax(fabs(uc.x - old.x), fabs(uc.y - old.y)));
             }
-        r.x *= scale; r.y *= scale;
+            u_c[kc] = uc;
+            e_c[kc] = uc;
+            double2 r = make_double2(0.0, 0.0);
+            if (I > 0 && I < b.ni_c - 1 && J > 0 && J < b.nj_c - 1) {
+                const double wim = (I == 1 && (b.slide & 1)) ? 0.5 : 0.25, wip = (I == b.ni_c - 2 && (b.slide & 2)) ? 0.5 : 0.25;
+                for (int p = -pi; p <= pi; ++p)
+                    for (int q = -pj; q <= pj; ++q) {
+                        const double w = (pi ? (p == 0 ? 0.5 : (p < 0 ? wim : wip)) : 1.0) * (pj ? (q == 0 ? 0.5 : (q < 0 ? wjm : wjp)) : 1.0);
+                        const double2 v = res_f[kf + (long long)p * b.nj_f + q];
+                        r.x += w * v.x; r.y += w * v.y;
+                    }
+                r.x *= scale; r.y *= scale;
+            }
+            rhs_c[kc] = r;
+        }
     }
-    rhs_c[kc] = r;
+    if (change) {
+        dmax = warp_max(dmax);
+        // non-negative doubles order like integers; the plain (possibly stale) read filters out nearly every atomic
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(dmax);
+        if ((threadIdx.x & 31) == 0 && bits > *(volatile unsigned long long*)change) atomicMax(change, bits);
+    }
+}
+
+// the cycle's convergence measure as one record of per-CTA partials (reduce_kernel / all-reduce take it from there)
+__global__ void mgb_change_kernel(unsigned long long* __restrict__ change, double* __restrict__ partials, int n_records) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_records) return;
+    double* p = partials + (size_t)k * 5;
+    p[0] = p[1] = p[2] = p[3] = 0.0;
+    p[4] = k == 0 ? __longlong_as_double((long long)*change) : 0.0;
 }
 
 __global__ void mgb_restrict_rows_kernel(const RestrictRow* __restrict__ rows, int n, const double2* __restrict__ res_f, double2* __restrict__ rhs_c) {
@@ -1182,14 +1209,17 @@ __device__ __forceinline__ double2 mgb_correction(const BlockXfer& b, int i, int
     }
     return c;
 }
-__global__ void mgb_prolong_kernel(BlockXfer b, const double2* __restrict__ u_c, const double2* __restrict__ e_c, double2* __restrict__ u_f) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j <= 0 || j >= b.nj_f - 1 || i <= 0 || i >= b.ni_f - 1) return;
-    const double2 c = mgb_correction(b, i, j, u_c, e_c);
-    const size_t k = (size_t)b.off_f + (size_t)i * b.nj_f + j;
-    double2 v = u_f[k];
-    v.x += c.x; v.y += c.y;
-    u_f[k] = v;
+__global__ void __launch_bounds__(128) mgb_prolong_kernel(BlockXfer b, const double2* __restrict__ u_c, const double2* __restrict__ e_c, double2* __restrict__ u_f) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= 0 || j >= b.nj_f - 1) return;
+    const int i_begin = max(1, (int)blockIdx.y * MGB_ROWS), i_end = min((int)(blockIdx.y + 1) * MGB_ROWS, b.ni_f - 1);
+    for (int i = i_begin; i < i_end; ++i) {
+        const double2 c = mgb_correction(b, i, j, u_c, e_c);
+        const size_t k = (size_t)b.off_f + (size_t)i * b.nj_f + j;
+        double2 v = u_f[k];
+        v.x += c.x; v.y += c.y;
+        u_f[k] = v;
+    }
 }
 __global__ void mgb_prolong_rows_kernel(const BlockXfer* __restrict__ blocks, int n_blocks, const SmoothedRow* __restrict__ srows, int n_s,
                                         const JunctionRow* __restrict__ jrows, int n_j, const SlidingRow* __restrict__ lrows, int n_l,

@@ -191,6 +191,8 @@ struct RankMesh {
     DevBuf<double2> mg_rhs, mg_tmp, mg_E, mg_zero;
     std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
     DevBuf<BlockXfer> d_xfer_blocks;
+    DevBuf<unsigned long long> d_change;     // level 0: max-norm movement of the level-1 nodes between two restrictions
+    bool mg_primed = false;                  // coarse levels: both ping-pong buffers hold the (constant) fixed-node values
     // NVLink peer-memory halo exchange (real multi-rank meshes): peers' fields mapped with CUDA IPC
     struct P2P {
         bool ready = false;                          // flags + X[0] + X[1] mapped on every rank
@@ -1058,6 +1060,7 @@ void mgb_build(tm_mesh* m) {
     for (auto& rp : m->ranks) {
         rp->mg_tmp.alloc(size_t(std::max<int64_t>(rp->N, 1))); rp->mg_tmp.zero(s);
         rp->mg_E.alloc(size_t(std::max<int64_t>(rp->N, 1))); rp->mg_E.zero(s);
+        rp->d_change.alloc(1); rp->d_change.zero(s);
         CUDA_TRY(cudaStreamSynchronize(s));
         p2p_add_tmp(m, *rp);
     }
@@ -1176,9 +1179,15 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
         if (const char* e = std::getenv("TM_MG_COARSEST_SWEEPS")) n_coarsest = uint64_t(std::max(1, std::atoi(e)));
     }
     for (uint64_t cyc = 0; cyc < o->iterations; ++cyc) {
+        // Convergence measure of a cycle.  With coarse levels: how far the level-1 nodes moved between this cycle's and the
+        // previous cycle's restriction (taken inside the restriction kernel, no extra pass over the mesh; the very first
+        // cycle after begin_smoothing compares against the initial mesh).  Without: the change of the whole mesh.
         const bool want_change = o->stop_max_update > 0.0 || cyc + 1 == o->iterations;
-        if (want_change)
+        const bool track = nl > 1;
+        if (want_change && !track)
             for (auto& rp : m->ranks) CUDA_TRY(cudaMemcpyAsync(rp->mg_E.p, xcur(*rp), size_t(rp->N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        if (track)
+            for (auto& rp : m->ranks) CUDA_TRY(cudaMemsetAsync(rp->d_change.p, 0, sizeof(unsigned long long), s));
         for (int l = 0; l + 1 < nl; ++l) {
             RankList& RF = ranks_of(l);
             RankList& RC = ranks_of(l + 1);
@@ -1190,9 +1199,9 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 RankMesh& rf = *RF[q];
                 RankMesh& rc = *RC[q];
                 for (const BlockXfer& b : rf.xfer_blocks) {
-                    dim3 g((b.nj_c + 127) / 128, b.ni_c);
+                    dim3 g((b.nj_c + 127) / 128, (b.ni_c + MGB_ROWS - 1) / MGB_ROWS);
                     LAUNCH(mgb_restrict_kernel, g, 128, s, b, (const double2*)xcur(rf), (const double2*)rf.mg_tmp.p, xcur(rc), rc.mg_E.p, rc.mg_rhs.p,
-                           -double(b.fi * b.fj) * double(b.fi * b.fj));
+                           -double(b.fi * b.fj) * double(b.fi * b.fj), l == 0 ? rf.d_change.p : (unsigned long long*)nullptr);
                 }
                 if (rf.n_rrows > 0)
                     LAUNCH(mgb_restrict_rows_kernel, (rf.n_rrows + 127) / 128, 128, s, (const RestrictRow*)rf.d_rrows.p, rf.n_rrows, (const double2*)rf.mg_tmp.p, rc.mg_rhs.p);
@@ -1202,8 +1211,10 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 RankMesh& rc = *rp;
                 const int n_l = int(rc.L.sliding.size());
                 if (n_l > 0) LAUNCH(capture_boundary_kernel, (n_l + 127) / 128, 128, s, rc.d_lrows.p, n_l, (const FixedOverride*)nullptr, 0, xcur(rc));
-                CUDA_TRY(cudaMemcpyAsync(rc.X[1 - rc.cur].p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
-                CUDA_TRY(cudaMemcpyAsync(rc.mg_E.p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+                if (!rc.mg_primed) {  // nodes no row writes (fixed ones) never change after the first restriction
+                    CUDA_TRY(cudaMemcpyAsync(rc.X[1 - rc.cur].p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+                    rc.mg_primed = true;
+                }
                 launch_rows_mg<MODE_REL, 0>(m, rc, xcur(rc), rc.mg_tmp.p, 1.0, (const double2*)rc.mg_zero.p);  // row_c(I u_f) with the level's (HAS_RHS) operator
                 LAUNCH(mgb_add_kernel, rc.vec_grid, 256, s, rc.L.n_own, (const double2*)rc.mg_tmp.p, rc.mg_rhs.p);
             }
@@ -1217,7 +1228,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 RankMesh& rf = *RF[q];
                 RankMesh& rc = *RC[q];
                 for (const BlockXfer& b : rf.xfer_blocks) {
-                    dim3 g((b.nj_f + 127) / 128, b.ni_f);
+                    dim3 g((b.nj_f + 127) / 128, (b.ni_f + MGB_ROWS - 1) / MGB_ROWS);
                     LAUNCH(mgb_prolong_kernel, g, 128, s, b, (const double2*)xcur(rc), (const double2*)rc.mg_E.p, xcur(rf));
                 }
                 if (rf.n_bnd_rows > 0)
@@ -1229,8 +1240,10 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             smooth(l, nu);
         }
         if (want_change) {
-            for (auto& rp : m->ranks)
-                LAUNCH(diff_stats_kernel, rp->vec_grid, VEC_THREADS, s, rp->L.n_own, (const double2*)rp->mg_E.p, (const double2*)xcur(*rp), rp->part_vec.p);
+            for (auto& rp : m->ranks) {
+                if (track) LAUNCH(mgb_change_kernel, (rp->vec_grid + 127) / 128, 128, s, rp->d_change.p, rp->part_vec.p, rp->vec_grid);
+                else LAUNCH(diff_stats_kernel, rp->vec_grid, VEC_THREADS, s, rp->L.n_own, (const double2*)rp->mg_E.p, (const double2*)xcur(*rp), rp->part_vec.p);
+            }
             launch_reduce(m, RED_UPDATE_STATS, o, false);
         }
         m->outer_done += 1;
@@ -1603,6 +1616,8 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
             white_step(m, false, o->white_ds_target, o->white_theta_target);
         }
         if (o->solver == TM_SOLVER_FAS_MULTIGRID && m->n_ranks == 1 && m->topo.blocks.size() == 1) mg_build(m, *m->ranks[0]);
+        for (auto& lv : m->mgb)
+            for (auto& rp : lv->ranks) { rp->mg_primed = false; rp->mg_E.zero(s); }
         m->outer_done = 0;
         m->begun = true;
         CUDA_TRY(cudaStreamSynchronize(s));
