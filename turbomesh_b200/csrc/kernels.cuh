@@ -1104,9 +1104,12 @@ struct RestrictRow {               // rhs_c[dst] = sum_k w[k] * res_f[src[k]]  (
 // interior rows by full weighting in the coarsened directions, times `scale` (= -(f_i f_j)^2: the undivided Winslow row
 // of a smooth field scales like h_xi^2 h_eta^2, and the restricted quantity is the negative residual).
 constexpr int MGB_ROWS = 1;  // rows per CTA in the block transfer kernels (marching several rows per thread measured slower: less memory-level parallelism)
-__global__ void __launch_bounds__(128) mgb_restrict_kernel(BlockXfer b, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
-                                                           double2* __restrict__ e_c, double2* __restrict__ rhs_c, double scale,
-                                                           unsigned long long* __restrict__ change /* may be NULL */) {
+__global__ void __launch_bounds__(128) mgb_restrict_kernel(const BlockXfer* __restrict__ blocks /* one per blockIdx.z */, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
+                                                           double2* e_c, double2* __restrict__ rhs_c,
+                                                           unsigned long long* __restrict__ change /* may be NULL */,
+                                                           const double2* e_prev /* the previous cycle's restricted iterate (may alias e_c) */) {
+    const BlockXfer b = blocks[blockIdx.z];
+    const double scale = -(double)(b.fi * b.fj) * (double)(b.fi * b.fj);
     const int J = blockIdx.x * blockDim.x + threadIdx.x;
     const int I_end = min((int)(blockIdx.y + 1) * MGB_ROWS, b.ni_c);
     double dmax = 0.0;
@@ -1124,7 +1127,7 @@ __global__ void __launch_bounds__(128) mgb_restrict_kernel(BlockXfer b, const do
             const size_t kf = (size_t)b.off_f + (size_t)i * b.nj_f + j;
             const double2 uc = u_f[kf];
             if (change) {  // how far this node moved since the previous cycle's restriction (the cycle's convergence measure)
-                const double2 old = e_c[kc];
+                const double2 old = e_prev[kc];
                 dmax = fmax(dmax, fmax(fabs(uc.x - old.x), fabs(uc.y - old.y)));
             }
             u_c[kc] = uc;
@@ -1209,7 +1212,9 @@ __device__ __forceinline__ double2 mgb_correction(const BlockXfer& b, int i, int
     }
     return c;
 }
-__global__ void __launch_bounds__(128) mgb_prolong_kernel(BlockXfer b, const double2* __restrict__ u_c, const double2* __restrict__ e_c, double2* __restrict__ u_f) {
+__global__ void __launch_bounds__(128) mgb_prolong_kernel(const BlockXfer* __restrict__ blocks /* one per blockIdx.z */, const double2* __restrict__ u_c,
+                                                          const double2* __restrict__ e_c, double2* __restrict__ u_f) {
+    const BlockXfer b = blocks[blockIdx.z];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j <= 0 || j >= b.nj_f - 1) return;
     const int i_begin = max(1, (int)blockIdx.y * MGB_ROWS), i_end = min((int)(blockIdx.y + 1) * MGB_ROWS, b.ni_f - 1);
@@ -1239,6 +1244,121 @@ __global__ void mgb_prolong_rows_kernel(const BlockXfer* __restrict__ blocks, in
     double2 v = u_f[self];
     v.x += c.x; v.y += c.y;
     u_f[self] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Anderson acceleration of the multigrid cycle on level-1 samples.  The slow modes of the cycle are smooth (on the
+// cascade: the global shift anchored only by the plate, whose tip singularity every level resolves differently), so their
+// history is kept where it is cheap -- on the nodes of level 1, a quarter of the mesh.  One "iteration" runs from the
+// restriction point of a cycle to that of the next: X_j = the (accelerated) iterate sampled there, G_j = what the cycle
+// made of it one cycle later, F_j = G_j - X_j.  alpha minimises |sum alpha_j F_j| subject to sum alpha_j = 1 over the
+// last q <= 3 iterations and the new iterate is sum alpha_j G_j: the difference to the current one lives on level 1 and is
+// interpolated to the fine mesh like a coarse-grid correction.
+// ---------------------------------------------------------------------------------------------------
+constexpr int AA_MAX = 3;
+struct AaFields { double2* G[AA_MAX]; double2* F[AA_MAX]; int q; };  // chronological, index q-1 = newest
+// samples the fine iterate on the level-1 nodes of one block: G_new = sample, F_new = sample - X_prev
+__global__ void __launch_bounds__(128) aa_sample_kernel(const BlockXfer* __restrict__ blocks /* one per blockIdx.z */, const double2* __restrict__ u_f,
+                                                        const double2* __restrict__ x_prev, double2* __restrict__ g_new, double2* __restrict__ f_new) {
+    const BlockXfer b = blocks[blockIdx.z];
+    const int J = blockIdx.x * blockDim.x + threadIdx.x, I = blockIdx.y;
+    if (J >= b.nj_c || I >= b.ni_c) return;
+    const size_t kc = (size_t)b.off_c + (size_t)I * b.nj_c + J;
+    const double2 g = u_f[(size_t)b.off_f + (size_t)(I * b.fi) * b.nj_f + (size_t)J * b.fj];
+    const double2 x = x_prev[kc];
+    g_new[kc] = g;
+    f_new[kc] = make_double2(g.x - x.x, g.y - x.y);
+}
+__global__ void __launch_bounds__(256) aa_gram_kernel(int64_t n, AaFields h, double* __restrict__ partials /* grid x 6 */) {
+    double g[6] = {0, 0, 0, 0, 0, 0};  // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        double2 f[AA_MAX];
+#pragma unroll
+        for (int i = 0; i < AA_MAX; ++i) f[i] = i < h.q ? h.F[i][k] : make_double2(0.0, 0.0);
+        g[0] += f[0].x * f[0].x + f[0].y * f[0].y; g[1] += f[0].x * f[1].x + f[0].y * f[1].y; g[2] += f[0].x * f[2].x + f[0].y * f[2].y;
+        g[3] += f[1].x * f[1].x + f[1].y * f[1].y; g[4] += f[1].x * f[2].x + f[1].y * f[2].y; g[5] += f[2].x * f[2].x + f[2].y * f[2].y;
+    }
+    __shared__ double sh[6][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { g[i] = warp_sum(g[i]); if (lane == 0) sh[i][w] = g[i]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += sh[threadIdx.x][q];
+        partials[(size_t)blockIdx.x * 6 + threadIdx.x] = s;
+    }
+}
+__global__ void aa_reduce_kernel(const double* __restrict__ partials, int n_part, double* __restrict__ gram) {  // one CTA of 192 threads, fixed order
+    __shared__ double sh[6][32];
+    const int e = threadIdx.x / 32, l = threadIdx.x & 31;
+    double s = 0.0;
+    for (int k = l; k < n_part; k += 32) s += partials[(size_t)k * 6 + e];
+    sh[e][l] = s;
+    __syncthreads();
+    if (l == 0) { double t = 0.0; for (int q = 0; q < 32; ++q) t += sh[e][q]; gram[e] = t; }
+}
+struct SumPtrs { double* p[16]; };
+__global__ void combine_sum_kernel(SumPtrs v, int n_ranks, int count) {  // in-process emulation of the all-reduce
+    const int k = threadIdx.x;
+    if (k >= count) return;
+    double s = 0.0;
+    for (int r = 0; r < n_ranks; ++r) s += v.p[r][k];
+    __syncthreads();
+    for (int r = 0; r < n_ranks; ++r) v.p[r][k] = s;
+}
+// alpha_0..alpha_{q-1} (sum 1); falls back to "newest only" (no extrapolation) when the window is short, the
+// least-squares problem is degenerate, the weights are wild or the newest residual grew
+__global__ void aa_solve_kernel(const double* __restrict__ gram, int q, double* __restrict__ alpha) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = 0; i < AA_MAX; ++i) alpha[i] = 0.0;
+    alpha[q - 1] = 1.0;
+    if (q < 2) return;
+    double G[3][3] = {{gram[0], gram[1], gram[2]}, {gram[1], gram[3], gram[4]}, {gram[2], gram[4], gram[5]}};
+    if (G[q - 1][q - 1] > 4.0 * G[q - 2][q - 2]) return;  // the residual doubled: the history is not trustworthy
+    double z[3] = {1.0, 1.0, 1.0};
+    double tr = 0.0;
+    for (int i = 0; i < q; ++i) tr += G[i][i];
+    if (!(tr > 0.0)) return;
+    for (int i = 0; i < q; ++i) G[i][i] += 1e-12 * tr;   // Tikhonov guard against a degenerate window
+    for (int c = 0; c < q; ++c) {                        // Gaussian elimination with partial pivoting, G z = 1
+        int piv = c;
+        for (int r = c + 1; r < q; ++r) if (fabs(G[r][c]) > fabs(G[piv][c])) piv = r;
+        if (fabs(G[piv][c]) < 1e-300) return;
+        if (piv != c) { for (int k = 0; k < q; ++k) { const double t = G[c][k]; G[c][k] = G[piv][k]; G[piv][k] = t; } const double t = z[c]; z[c] = z[piv]; z[piv] = t; }
+        for (int r = c + 1; r < q; ++r) {
+            const double f = G[r][c] / G[c][c];
+            for (int k = c; k < q; ++k) G[r][k] -= f * G[c][k];
+            z[r] -= f * z[c];
+        }
+    }
+    for (int r = q - 1; r >= 0; --r) {
+        double t = z[r];
+        for (int k = r + 1; k < q; ++k) t -= G[r][k] * z[k];
+        z[r] = t / G[r][r];
+    }
+    double sum = 0.0;
+    for (int i = 0; i < q; ++i) sum += z[i];
+    if (!(fabs(sum) > 1e-300)) return;
+    double a[3];
+    for (int i = 0; i < q; ++i) { a[i] = z[i] / sum; if (!(fabs(a[i]) < 20.0)) return; }
+    for (int i = 0; i < q; ++i) alpha[i] = a[i];
+}
+// x_new = sum alpha_j G_j ; d = x_new - G_newest (the extrapolation, interpolated to the fine mesh next) ; x_store = x_new
+__global__ void __launch_bounds__(256) aa_combine_kernel(int64_t n, AaFields h, const double* __restrict__ alpha, double2* __restrict__ d, double2* __restrict__ x_store) {
+    double a[AA_MAX];
+#pragma unroll
+    for (int i = 0; i < AA_MAX; ++i) a[i] = alpha[i];
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        const double2 gn = h.G[h.q - 1][k];
+        // written as newest + sum alpha_j (G_j - newest): exactly zero wherever all samples agree (fixed nodes)
+        double dx = 0.0, dy = 0.0;
+#pragma unroll
+        for (int i = 0; i < AA_MAX; ++i)
+            if (i < h.q - 1) { const double2 t = h.G[i][k]; dx += a[i] * (t.x - gn.x); dy += a[i] * (t.y - gn.y); }
+        d[k] = make_double2(dx, dy);
+        x_store[k] = make_double2(gn.x + dx, gn.y + dy);
+    }
 }
 
 // polyline length of one side of a block (multigrid: mean cell size per direction decides the semi-coarsening);

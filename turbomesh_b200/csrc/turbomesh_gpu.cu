@@ -191,8 +191,16 @@ struct RankMesh {
     DevBuf<double2> mg_rhs, mg_tmp, mg_E, mg_zero;
     std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
     DevBuf<BlockXfer> d_xfer_blocks;
+    int xf_ni_f = 0, xf_nj_f = 0, xf_ni_c = 0, xf_nj_c = 0;  // largest extents over the own blocks (grid of the batched transfer kernels)
     DevBuf<unsigned long long> d_change;     // level 0: max-norm movement of the level-1 nodes between two restrictions
     bool mg_primed = false;                  // coarse levels: both ping-pong buffers hold the (constant) fixed-node values
+    // level 1 only: Anderson acceleration history (rings of AA_MAX samples G_j and residuals F_j, the accelerated state X)
+    std::vector<std::unique_ptr<DevBuf<double2>>> aa_G, aa_F;
+    DevBuf<double2> aa_X, aa_D;
+    int aa_head = -1, aa_count = 0;          // newest slot, entries in the rings
+    bool aa_have_x = false;
+    DevBuf<double> aa_part, aa_gram, aa_coef;
+    double2* E() { return mg_E.p; }
     // NVLink peer-memory halo exchange (real multi-rank meshes): peers' fields mapped with CUDA IPC
     struct P2P {
         bool ready = false;                          // flags + X[0] + X[1] mapped on every rank
@@ -248,6 +256,7 @@ struct tm_mesh {
     std::vector<tm_condition> h_bcs;
     std::vector<std::unique_ptr<MgbLevel>> mgb;  // multi-block multigrid hierarchy, built on first use
     int sm_count = 148;
+    bool mg_aa = true;        // Anderson acceleration of the multi-block multigrid cycle (TM_MG_AA=0 switches it off)
     int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
     bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
 
@@ -1028,6 +1037,12 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
     rf.n_rrows = int(rows.size());
     rf.d_rrows.upload(rows, m->stream);
     rf.d_xfer_blocks.upload(rf.xfer_blocks, m->stream);
+    rf.xf_ni_f = rf.xf_nj_f = rf.xf_ni_c = rf.xf_nj_c = 0;
+    for (const BlockXfer& b : rf.xfer_blocks) {
+        rf.xf_ni_f = std::max(rf.xf_ni_f, b.ni_f); rf.xf_nj_f = std::max(rf.xf_nj_f, b.nj_f);
+        rf.xf_ni_c = std::max(rf.xf_ni_c, b.ni_c); rf.xf_nj_c = std::max(rf.xf_nj_c, b.nj_c);
+    }
+    if (rf.xfer_blocks.size() > 65535) TM_THROW(TM_ERR_UNSUPPORTED, "multigrid: more than 65535 blocks per rank");
 }
 
 void mgb_build(tm_mesh* m) {
@@ -1130,6 +1145,19 @@ void mgb_build(tm_mesh* m) {
                 blocks[k] = DevBlock{rc.L.loff[k], int32_t(C->topo.blocks[k].ni), int32_t(C->topo.blocks[k].nj), side_slide_mask(C->topo, k), 0, C->tan_i[k], C->tan_j[k]};
             }
             rc.d_blocks.upload(blocks, s);
+            if (m->mgb.size() == 1 && m->mg_aa) {  // this is level 1
+                for (int k = 0; k < AA_MAX; ++k)
+                    for (auto* ring : {&rc.aa_G, &rc.aa_F}) {
+                        ring->emplace_back(new DevBuf<double2>());
+                        ring->back()->alloc(size_t(std::max<int64_t>(rc.N, 1)));
+                        ring->back()->zero(s);
+                    }
+                rc.aa_X.alloc(size_t(std::max<int64_t>(rc.N, 1))); rc.aa_X.zero(s);
+                rc.aa_D.alloc(size_t(std::max<int64_t>(rc.N, 1))); rc.aa_D.zero(s);
+                rc.aa_part.alloc(size_t(rc.vec_grid) * 6);
+                rc.aa_gram.alloc(6); rc.aa_gram.zero(s);
+                rc.aa_coef.alloc(AA_MAX); rc.aa_coef.zero(s);
+            }
             CUDA_TRY(cudaStreamSynchronize(s));
             p2p_setup(m, rc);
             p2p_add_tmp(m, rc);
@@ -1141,6 +1169,71 @@ void mgb_build(tm_mesh* m) {
         m->mgb.push_back(std::move(C));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
+}
+
+// Anderson acceleration at the restriction point of a cycle (see kernels.cuh): sample, least squares over the last <= 3
+// iterations, interpolate the extrapolation to the fine mesh.
+void anderson_step(tm_mesh* m, RankList& RF, RankList& RC) {
+    cudaStream_t s = m->stream;
+    auto xcur = [](RankMesh& r) { return r.X[r.cur].p; };
+    const bool have_x = RC[0]->aa_have_x;
+    for (size_t q = 0; q < RF.size(); ++q) {
+        RankMesh& rf = *RF[q];
+        RankMesh& rc = *RC[q];
+        if (have_x) { rc.aa_head = (rc.aa_head + 1) % AA_MAX; rc.aa_count = std::min(rc.aa_count + 1, AA_MAX); }
+        // without a previous state there is no residual yet: the sample only becomes the state X
+        double2* g_new = have_x ? rc.aa_G[size_t(rc.aa_head)]->p : rc.aa_X.p;
+        double2* f_new = have_x ? rc.aa_F[size_t(rc.aa_head)]->p : rc.aa_D.p;
+        if (!rf.xfer_blocks.empty()) {
+            dim3 g((rf.xf_nj_c + 127) / 128, rf.xf_ni_c, unsigned(rf.xfer_blocks.size()));
+            LAUNCH(aa_sample_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)xcur(rf), (const double2*)rc.aa_X.p, g_new, f_new);
+        }
+        rc.aa_have_x = true;
+    }
+    if (!have_x) return;
+    const int q_res = RC[0]->aa_count;
+    auto fields = [&](RankMesh& rc) {
+        AaFields h{};
+        h.q = q_res;
+        for (int i = 0; i < q_res; ++i) {
+            const size_t slot = size_t((rc.aa_head + AA_MAX - (q_res - 1) + i) % AA_MAX);
+            h.G[i] = rc.aa_G[slot]->p; h.F[i] = rc.aa_F[slot]->p;
+        }
+        return h;
+    };
+    for (auto& rp : RC) {
+        RankMesh& rc = *rp;
+        LAUNCH(aa_gram_kernel, rc.vec_grid, 256, s, rc.L.n_own, fields(rc), rc.aa_part.p);
+        LAUNCH(aa_reduce_kernel, 1, 192, s, (const double*)rc.aa_part.p, rc.vec_grid, rc.aa_gram.p);
+    }
+    if (m->n_ranks > 1) {
+        if (m->emulated) {
+            SumPtrs ptrs{};
+            for (size_t k = 0; k < RC.size(); ++k) ptrs.p[k] = RC[k]->aa_gram.p;
+            LAUNCH(combine_sum_kernel, 1, 32, s, ptrs, int(RC.size()), 6);
+        } else {
+            NCCL_TRY(g_nccl.AllReduce(RC[0]->aa_gram.p, RC[0]->aa_gram.p, 6, ncclDouble, ncclSum, m->comm, s));
+        }
+    }
+    for (size_t q = 0; q < RF.size(); ++q) {
+        RankMesh& rf = *RF[q];
+        RankMesh& rc = *RC[q];
+        LAUNCH(aa_solve_kernel, 1, 32, s, (const double*)rc.aa_gram.p, q_res, rc.aa_coef.p);
+        LAUNCH(aa_combine_kernel, rc.vec_grid, 256, s, rc.L.n_own, fields(rc), (const double*)rc.aa_coef.p, rc.aa_D.p, rc.aa_X.p);
+        if (q_res < 2) continue;  // nothing to extrapolate from yet (d = 0)
+        if (!rf.xfer_blocks.empty()) {
+            dim3 g((rf.xf_nj_f + 127) / 128, (rf.xf_ni_f + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
+            LAUNCH(mgb_prolong_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)rc.aa_D.p, (const double2*)rc.mg_zero.p, xcur(rf));
+        }
+        if (rf.n_bnd_rows > 0)
+            LAUNCH(mgb_prolong_rows_kernel, (rf.n_bnd_rows + 127) / 128, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, int(rf.xfer_blocks.size()),
+                   (const SmoothedRow*)rf.d_srows.p, int(rf.L.smoothed.size()), (const JunctionRow*)rf.d_jrows.p, int(rf.L.junction_rows.size()),
+                   (const SlidingRow*)rf.d_lrows.p, int(rf.L.sliding.size()), (const double2*)rc.aa_D.p, (const double2*)rc.mg_zero.p, xcur(rf));
+    }
+    if (q_res >= 2) {
+        exchange_on(m, RF, xcur);
+        for (auto& rp : RF) sync_slaves(m, *rp, xcur(*rp), 1);
+    }
 }
 
 void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
@@ -1192,16 +1285,18 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             RankList& RF = ranks_of(l);
             RankList& RC = ranks_of(l + 1);
             smooth(l, nu);
+            if (l == 0 && !RC.empty() && !RC[0]->aa_G.empty()) anderson_step(m, RF, RC);
             for (auto& rp : RF) launch_rows_mg<MODE_REL, 0>(m, *rp, xcur(*rp), rp->mg_tmp.p, 1.0, l > 0 ? (const double2*)rp->mg_rhs.p : nullptr);
             exchange_on(m, RF, tmp_of);
             fine_work += m->mgb[size_t(l)]->work;
             for (size_t q = 0; q < RF.size(); ++q) {
                 RankMesh& rf = *RF[q];
                 RankMesh& rc = *RC[q];
-                for (const BlockXfer& b : rf.xfer_blocks) {
-                    dim3 g((b.nj_c + 127) / 128, (b.ni_c + MGB_ROWS - 1) / MGB_ROWS);
-                    LAUNCH(mgb_restrict_kernel, g, 128, s, b, (const double2*)xcur(rf), (const double2*)rf.mg_tmp.p, xcur(rc), rc.mg_E.p, rc.mg_rhs.p,
-                           -double(b.fi * b.fj) * double(b.fi * b.fj), l == 0 ? rf.d_change.p : (unsigned long long*)nullptr);
+                const double2* e_prev = rc.E();
+                if (!rf.xfer_blocks.empty()) {  // all own blocks in one launch (blockIdx.z = block)
+                    dim3 g((rf.xf_nj_c + 127) / 128, (rf.xf_ni_c + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
+                    LAUNCH(mgb_restrict_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)xcur(rf), (const double2*)rf.mg_tmp.p, xcur(rc), rc.E(),
+                           rc.mg_rhs.p, l == 0 ? rf.d_change.p : (unsigned long long*)nullptr, e_prev);
                 }
                 if (rf.n_rrows > 0)
                     LAUNCH(mgb_restrict_rows_kernel, (rf.n_rrows + 127) / 128, 128, s, (const RestrictRow*)rf.d_rrows.p, rf.n_rrows, (const double2*)rf.mg_tmp.p, rc.mg_rhs.p);
@@ -1227,14 +1322,14 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             for (size_t q = 0; q < RF.size(); ++q) {
                 RankMesh& rf = *RF[q];
                 RankMesh& rc = *RC[q];
-                for (const BlockXfer& b : rf.xfer_blocks) {
-                    dim3 g((b.nj_f + 127) / 128, (b.ni_f + MGB_ROWS - 1) / MGB_ROWS);
-                    LAUNCH(mgb_prolong_kernel, g, 128, s, b, (const double2*)xcur(rc), (const double2*)rc.mg_E.p, xcur(rf));
+                if (!rf.xfer_blocks.empty()) {
+                    dim3 g((rf.xf_nj_f + 127) / 128, (rf.xf_ni_f + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
+                    LAUNCH(mgb_prolong_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)xcur(rc), (const double2*)rc.E(), xcur(rf));
                 }
                 if (rf.n_bnd_rows > 0)
                     LAUNCH(mgb_prolong_rows_kernel, (rf.n_bnd_rows + 127) / 128, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, int(rf.xfer_blocks.size()),
                            (const SmoothedRow*)rf.d_srows.p, int(rf.L.smoothed.size()), (const JunctionRow*)rf.d_jrows.p, int(rf.L.junction_rows.size()),
-                           (const SlidingRow*)rf.d_lrows.p, int(rf.L.sliding.size()), (const double2*)xcur(rc), (const double2*)rc.mg_E.p, xcur(rf));
+                           (const SlidingRow*)rf.d_lrows.p, int(rf.L.sliding.size()), (const double2*)xcur(rc), (const double2*)rc.E(), xcur(rf));
             }
             refresh(l);  // nodes no row writes (fixed ones) got a zero correction: both ping-pong buffers still agree there
             smooth(l, nu);
@@ -1299,6 +1394,7 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     for (auto& b : m->h_blocks) b.xy = nullptr;
     if (n_connections) m->h_conns.assign(connections, connections + n_connections);
     if (n_conditions) m->h_bcs.assign(conditions, conditions + n_conditions);
+    if (const char* e = std::getenv("TM_MG_AA")) m->mg_aa = std::atoi(e) != 0;
     if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
     if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
     if (stream) m->stream = (cudaStream_t)stream;
@@ -1617,7 +1713,11 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
         }
         if (o->solver == TM_SOLVER_FAS_MULTIGRID && m->n_ranks == 1 && m->topo.blocks.size() == 1) mg_build(m, *m->ranks[0]);
         for (auto& lv : m->mgb)
-            for (auto& rp : lv->ranks) { rp->mg_primed = false; rp->mg_E.zero(s); }
+            for (auto& rp : lv->ranks) {
+                rp->mg_primed = false;
+                rp->mg_E.zero(s);
+                rp->aa_head = -1; rp->aa_count = 0; rp->aa_have_x = false;
+            }
         m->outer_done = 0;
         m->begun = true;
         CUDA_TRY(cudaStreamSynchronize(s));
