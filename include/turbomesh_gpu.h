@@ -196,6 +196,13 @@ int tm_mesh_block_size(const tm_mesh *mesh, size_t block, uint64_t *ni, uint64_t
 double *tm_mesh_block_device_ptr(tm_mesh *mesh, size_t block);
 /* device pointer / host copy of the control function (P,Q per node, wall_control_function.zig:24) */
 int tm_mesh_download_control_function(tm_mesh *mesh, size_t block, double *pq);
+/* Structured output, the step right after the path: the block as two struct-of-arrays fields with i fastest
+ * (x[j*ni + i], y[j*ni + i]) -- exactly the buffers the reference's CGNS writer passes to cg_coord_write for
+ * CoordinateX / CoordinateY (src/core/cgns.zig:69-101) and, with TM_FIELD_CONTROL_FUNCTION, to cg_field_write for the
+ * P / Q solution fields (cgns.zig:110-161).  The transposition runs on the device; x and y receive ni*nj doubles each
+ * (host memory, ideally pinned). */
+typedef enum tm_field { TM_FIELD_COORDINATES = 0, TM_FIELD_CONTROL_FUNCTION = 1 } tm_field;
+int tm_mesh_download_block_soa(tm_mesh *mesh, size_t block, int field /* tm_field */, double *x, double *y);
 /* node kind per block-boundary node in the reference's flat boundary numbering (boundary.zig:248-285);
  * values: 0 fixed, 1 smoothed, 2 connected, 3 laplacian_smoothed, 4 sliding_circ (smooth.zig:1168-1174).
  * `kinds` receives 2*(ni+nj-2) bytes. */

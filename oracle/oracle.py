@@ -88,6 +88,8 @@ def lib():
         L.orc_system_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.orc_system_junction.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), dp, ip, dp]
         L.orc_csr_solve.argtypes = [C.c_uint64, ip, ip, dp, dp, dp, C.POINTER(Options), C.POINTER(Stats)]
+        L.orc_block_to_soa.argtypes = [C.c_uint64, C.c_uint64, dp, dp, dp]
+        L.orc_block_to_soa.restype = None
         _lib = L
     return _lib
 
@@ -268,3 +270,12 @@ def csr_solve(indptr, indices, values, rhs, x0=None, opts: Options = None):
     ip = C.POINTER(C.c_int32)
     _check(lib().orc_csr_solve(len(rhs), indptr.ctypes.data_as(ip), indices.ctypes.data_as(ip), _dp(values), _dp(rhs), _dp(x), C.byref(opts), C.byref(st)))
     return x, st.as_dict()
+
+
+def block_to_soa(points: np.ndarray):
+    """CoordinateX / CoordinateY arrays of a block as the reference's CGNS writer lays them out (cgns.zig:69-101): i fastest."""
+    a = np.ascontiguousarray(points, dtype=np.float64)
+    ni, nj = a.shape[0], a.shape[1]
+    x, y = np.empty(ni * nj), np.empty(ni * nj)
+    lib().orc_block_to_soa(ni, nj, _dp(a), _dp(x), _dp(y))
+    return x, y

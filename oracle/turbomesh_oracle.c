@@ -1340,3 +1340,17 @@ int orc_csr_solve(uint64_t dof, const int32_t *lhs_p, const int32_t *lhs_i, cons
     if (stats) *stats = S.stats;
     return rc;
 }
+
+/* Structured output: the AoS block (x,y interleaved, j fastest) as two SoA arrays with i fastest, the layout the
+ * reference hands to cg_coord_write for CoordinateX / CoordinateY (src/core/cgns.zig:69-101) and, for the control
+ * function, to cg_field_write (cgns.zig:110-161). */
+void orc_block_to_soa(uint64_t ni, uint64_t nj, const double *xy, double *x, double *y)
+{
+    uint64_t idx = 0;
+    for (uint64_t j = 0; j < nj; ++j)          /* cgns.zig:74-83 */
+        for (uint64_t i = 0; i < ni; ++i) {
+            x[idx] = xy[2 * (i * nj + j)];
+            y[idx] = xy[2 * (i * nj + j) + 1];
+            ++idx;
+        }
+}

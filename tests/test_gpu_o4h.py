@@ -60,3 +60,31 @@ def test_t106_topology_kinds(gpu_lib, orc):
         got = np.concatenate([dm.boundary_kinds(k) for k in range(len(mesh.blocks))])
     assert np.array_equal(ref, got)
     assert mesh.num_nodes() == 25118 and len(mesh.blocks) == 8 and len(mesh.connections) == 21
+
+
+@pytest.mark.parametrize("shape", [(3, 3), (33, 65), (100, 37), (257, 129)])
+def test_structured_output_matches_the_oracle(orc, gpu_lib, shape):
+    """SoA (i fastest) output of coordinates and control function: bit-exact with the oracle's cgns.zig:69-101 loop."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    mesh = synthetic.materialize(synthetic.single_block(*shape), smoothing.tfi_block)
+    with smoothing.DeviceMesh(mesh) as dm:
+        x, y = dm.block_soa(0)
+        px, py = dm.block_soa(0, "control_function")
+    ox, oy = orc.block_to_soa(mesh.blocks[0].points)
+    assert np.array_equal(x, ox) and np.array_equal(y, oy)
+    assert not px.any() and not py.any()
+
+
+def test_structured_output_of_the_white_control_function(orc, gpu_lib):
+    from turbomesh_b200 import smoothing, synthetic
+
+    spec, z, meta = load_fixture("t106_white")
+    mesh = synthetic.materialize(spec, smoothing.tfi_block)
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    with smoothing.DeviceMesh(mesh) as dm:
+        dm.begin_smoothing(smoothing.CudaSolver.tight(), cf)
+        p, q = dm.block_soa(0, "control_function")
+        aos = dm.control_function(0)
+    op, oq = orc.block_to_soa(aos)
+    assert np.array_equal(p, op) and np.array_equal(q, oq) and np.abs(p).max() > 0

@@ -189,3 +189,11 @@ def test_golden_t106_white_is_reproduced(orc):
     orc.smooth_mesh(mesh, meta["iterations"], orc.tight_options(max_iters=100000))
     err = max(float(np.abs(b.points - z[f"smooth_b{k}"]).max()) for k, b in enumerate(mesh.blocks))
     assert err < 1e-12
+
+
+def test_block_to_soa_is_the_cgns_layout(orc):
+    """cgns.zig:69-101: buffer[j*ni + i] = block(i, j) -- i fastest."""
+    ni, nj = 7, 5
+    a = np.arange(ni * nj * 2, dtype=np.float64).reshape(ni, nj, 2)
+    x, y = orc.block_to_soa(a)
+    assert np.array_equal(x, a[:, :, 0].T.ravel()) and np.array_equal(y, a[:, :, 1].T.ravel())

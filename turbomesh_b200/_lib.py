@@ -122,6 +122,7 @@ def load():
     L.tm_mesh_block_device_ptr.restype = vp
     L.tm_mesh_download_control_function.argtypes = [vp, C.c_size_t, dp]
     L.tm_mesh_download_boundary_kinds.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint8)]
+    L.tm_mesh_download_block_soa.argtypes = [vp, C.c_size_t, C.c_int, dp, dp]
     _lib = L
     return L
 

@@ -1383,4 +1383,28 @@ __global__ void __launch_bounds__(256) side_length_kernel(const SideLenJob* __re
     if (threadIdx.x == 0) out[4 * (size_t)jb.block + side] = red[0];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Structured output (the step right after the path, src/core/cgns.zig:69-101, 110-161): the AoS block (x,y interleaved,
+// j fastest) as two SoA arrays with i fastest -- what cg_coord_write / cg_field_write take.  A 32x32 tile transpose
+// through shared memory: coalesced 16 B loads along j, coalesced 8 B stores along i.  HBM-bound, 32 B per node.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(int ni, int nj, const double2* __restrict__ in, double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double2 tile[32][33];
+    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + tx;
+        if (i < ni && j < nj) tile[r][tx] = in[(size_t)i * nj + j];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, i = i0 + tx;
+        if (i < ni && j < nj) {
+            const double2 v = tile[tx][r];
+            x[(size_t)j * ni + i] = v.x;
+            y[(size_t)j * ni + i] = v.y;
+        }
+    }
+}
+
 }  // namespace tmesh

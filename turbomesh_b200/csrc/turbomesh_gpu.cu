@@ -192,6 +192,7 @@ struct RankMesh {
     std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
     DevBuf<BlockXfer> d_xfer_blocks;
     int xf_ni_f = 0, xf_nj_f = 0, xf_ni_c = 0, xf_nj_c = 0;  // largest extents over the own blocks (grid of the batched transfer kernels)
+    DevBuf<double> soa_stage;                // device staging of the structured (SoA) output
     DevBuf<unsigned long long> d_change;     // level 0: max-norm movement of the level-1 nodes between two restrictions
     bool mg_primed = false;                  // coarse levels: both ping-pong buffers hold the (constant) fixed-node values
     // level 1 only: Anderson acceleration history (rings of AA_MAX samples G_j and residuals F_j, the accelerated state X)
@@ -1809,6 +1810,28 @@ int tm_mesh_download_control_function(tm_mesh* m, size_t block, double* pqv) {
         const size_t bytes = size_t(B.ni * B.nj) * sizeof(double2);
         if (!r.has_pq || !r.pq.p) { std::memset(pqv, 0, bytes); return; }  // laplace: all zero (wall_control_function.zig:29-33)
         CUDA_TRY(cudaMemcpyAsync(pqv, r.pq.p + r.L.loff[block], bytes, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+    });
+}
+int tm_mesh_download_block_soa(tm_mesh* m, size_t block, int field, double* x, double* y) {
+    return guarded([&] {
+        RankMesh& r = owner_of_block(m, block);
+        if (!x || !y) TM_THROW(TM_ERR_INVALID_ARGUMENT, "x / y is NULL");
+        if (field != TM_FIELD_COORDINATES && field != TM_FIELD_CONTROL_FUNCTION) TM_THROW(TM_ERR_INVALID_ARGUMENT, "unknown field %d", field);
+        CUDA_TRY(cudaSetDevice(m->device));
+        const auto& B = m->topo.blocks[block];
+        const size_t n = size_t(B.ni * B.nj);
+        if (field == TM_FIELD_CONTROL_FUNCTION && (!r.has_pq || !r.pq.p)) {  // laplace: all zero (wall_control_function.zig:29-33)
+            std::memset(x, 0, n * sizeof(double));
+            std::memset(y, 0, n * sizeof(double));
+            return;
+        }
+        const double2* src = (field == TM_FIELD_COORDINATES ? r.X[r.cur].p : r.pq.p) + r.L.loff[block];
+        if (r.soa_stage.n < 2 * n) r.soa_stage.alloc(2 * n);
+        dim3 grid(unsigned((B.nj + 31) / 32), unsigned((B.ni + 31) / 32));
+        LAUNCH(aos_to_soa_kernel, grid, 256, m->stream, int(B.ni), int(B.nj), src, r.soa_stage.p, r.soa_stage.p + n);
+        CUDA_TRY(cudaMemcpyAsync(x, r.soa_stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(y, r.soa_stage.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
     });
 }

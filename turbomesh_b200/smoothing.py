@@ -278,6 +278,15 @@ class DeviceMesh:
         check(self._L.tm_mesh_download_control_function(self._h, block, _dp(out)))
         return out
 
+    def block_soa(self, block: int, field: str = "coordinates"):
+        """Structured output of one block (``tm_mesh_download_block_soa``): two flat arrays with i fastest, the buffers
+        ``cgns.write`` hands to ``cg_coord_write`` / ``cg_field_write`` (cgns.zig:69-101, 110-161)."""
+        ni, nj = C.c_uint64(), C.c_uint64()
+        check(self._L.tm_mesh_block_size(self._h, block, C.byref(ni), C.byref(nj)))
+        x, y = np.empty(ni.value * nj.value), np.empty(ni.value * nj.value)
+        check(self._L.tm_mesh_download_block_soa(self._h, block, {"coordinates": 0, "control_function": 1}[field], _dp(x), _dp(y)))
+        return x, y
+
     def boundary_kinds(self, block: int) -> np.ndarray:
         ni, nj = C.c_uint64(), C.c_uint64()
         check(self._L.tm_mesh_block_size(self._h, block, C.byref(ni), C.byref(nj)))
