@@ -72,6 +72,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
 
 
+def pin_to_gpu_numa_node(index: int):
+    """Runs this process on the CPUs NVML reports as closest to the GPU, so that pinned host buffers are allocated on the
+    GPU's NUMA node (host<->device copies of the e2e leg otherwise cross the socket interconnect)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -137,6 +155,7 @@ def run_gpu(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -361,6 +380,14 @@ def run_e2e(args, spec, solver, torch):
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     torch.cuda.synchronize()
+    # what the host link of this box delivers (explains the gap between `value` and `e2e`)
+    dev = torch.empty_like(pinned, device="cuda")
+    link = {}
+    for name, (dst, src) in {"h2d_gbs": (dev, pinned), "d2h_gbs": (pinned, dev)}.items():
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        t0 = time.perf_counter(); dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        link[name] = host.nbytes / (time.perf_counter() - t0) / 1e9
+    del dev
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -368,7 +395,7 @@ def run_e2e(args, spec, solver, torch):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     return {"value": ni * nj * solver.sweeps_per_iteration / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": dt * 1e3, "api": "tm_tfi_block + tm_smooth_mesh (host buffers in pinned memory)", "steps": steps,
+            "ms_per_step": dt * 1e3, "api": "tm_tfi_block + tm_smooth_mesh (host buffers in pinned memory)", "steps": steps, "host_link": link,
             "last_max_update": st["last_max_update"]}
 
 

@@ -255,6 +255,10 @@ int tm_dist_plan(const tm_block *blocks, size_t n_blocks,
  * Misc
  * ------------------------------------------------------------------------------------------------- */
 const char *tm_last_error(void);
+/* Device fields of 32 MiB and more (and the pinned scalar block of a mesh) are recycled through a process-wide cache
+ * when a mesh is destroyed, so that the one-shot entry points do not pay cudaMalloc / cudaFree of GB-sized fields per
+ * call; at most TM_CACHE_GB GiB (environment, default 8) are kept.  This returns everything to the driver. */
+void tm_release_cached_memory(void);
 int tm_abi_version(void);
 /* number of CUDA kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t tm_kernel_launch_count(void);

@@ -85,6 +85,7 @@ def load():
     L.tm_last_error.restype = C.c_char_p
     L.tm_abi_version.restype = C.c_int
     L.tm_kernel_launch_count.restype = C.c_uint64
+    L.tm_release_cached_memory.restype = None
     L.tm_device_info.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     L.tm_smooth_options_default.argtypes = [C.POINTER(TmSmoothOptions)]
     L.tm_smooth_options_default.restype = None

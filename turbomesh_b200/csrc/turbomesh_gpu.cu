@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -63,14 +64,67 @@ void require_device(int device) {
     if (device >= 0) CUDA_TRY(cudaSetDevice(device));
 }
 
+// Large device allocations are recycled through a small process-wide cache: the one-shot entry points (tm_tfi_block,
+// tm_smooth_mesh) create and destroy a device mesh per call, and cudaMalloc / cudaFree of GB-sized fields would otherwise
+// cost more than the kernels they bracket.  Exact-size reuse only; at most TM_CACHE_GB (default 8) GiB are kept;
+// tm_release_cached_memory() returns everything to the driver.
+struct DeviceCache {
+    struct Entry { void* p; size_t bytes; int device; };
+    std::mutex mu;
+    std::vector<Entry> free_list;
+    size_t held = 0;
+    static constexpr size_t kMinBytes = size_t(32) << 20;
+    size_t cap() const {
+        static const size_t c = [] { const char* e = std::getenv("TM_CACHE_GB"); return size_t((e ? std::atof(e) : 8.0) * double(size_t(1) << 30)); }();
+        return c;
+    }
+    void* take(size_t bytes, int device) {
+        std::lock_guard<std::mutex> lock(mu);
+        for (size_t k = 0; k < free_list.size(); ++k)
+            if (free_list[k].bytes == bytes && free_list[k].device == device) {
+                void* q = free_list[k].p;
+                held -= bytes;
+                free_list.erase(free_list.begin() + long(k));
+                return q;
+            }
+        return nullptr;
+    }
+    bool give(void* q, size_t bytes, int device) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (bytes < kMinBytes || held + bytes > cap()) return false;
+        free_list.push_back(Entry{q, bytes, device});
+        held += bytes;
+        return true;
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& e : free_list) cudaFree(e.p);
+        free_list.clear();
+        held = 0;
+    }
+};
+DeviceCache g_cache;
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    int device = 0;
     void alloc(size_t count) {
         release();
         if (count == 0) return;
-        CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+        const size_t bytes = count * sizeof(T);
+        CUDA_TRY(cudaGetDevice(&device));
+        if (bytes >= DeviceCache::kMinBytes) p = static_cast<T*>(g_cache.take(bytes, device));
+        if (!p) {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+                (void)cudaGetLastError();
+                g_cache.clear();
+                e = cudaMalloc(&p, bytes);
+            }
+            CUDA_TRY(e);
+        }
         n = count;
     }
     void upload(const std::vector<T>& h, cudaStream_t s) {
@@ -84,16 +138,16 @@ struct DevBuf {
         if (p) CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(T), s));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && !g_cache.give(p, n * sizeof(T), device)) cudaFree(p);
         p = nullptr;
         n = 0;
     }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), device(o.device) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; device = o.device; o.p = nullptr; o.n = 0; }
         return *this;
     }
     ~DevBuf() { release(); }
@@ -235,6 +289,23 @@ struct MgbLevel {
     double work = 1.0;                               // nodes relative to level 0
 };
 
+// the pinned scalar block a mesh polls (cudaMallocHost / cudaFreeHost cost milliseconds: recycled like the device fields)
+std::mutex g_pinned_mu;
+std::vector<SolveCtl*> g_pinned_free;
+SolveCtl* acquire_pinned_ctl() {
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mu);
+        if (!g_pinned_free.empty()) { SolveCtl* q = g_pinned_free.back(); g_pinned_free.pop_back(); return q; }
+    }
+    SolveCtl* q = nullptr;
+    CUDA_TRY(cudaMallocHost(&q, sizeof(SolveCtl)));
+    return q;
+}
+void release_pinned_ctl(SolveCtl* q) {
+    std::lock_guard<std::mutex> lock(g_pinned_mu);
+    if (g_pinned_free.size() < 8) g_pinned_free.push_back(q); else cudaFreeHost(q);
+}
+
 }  // namespace
 
 struct tm_mesh {
@@ -265,7 +336,7 @@ struct tm_mesh {
         mgb.clear();
         ranks.clear();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
-        if (h_ctl) cudaFreeHost(h_ctl);
+        if (h_ctl) release_pinned_ctl(h_ctl);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -1402,7 +1473,7 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     else { CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
     CUDA_TRY(cudaEventCreate(&m->ev0));
     CUDA_TRY(cudaEventCreate(&m->ev1));
-    CUDA_TRY(cudaMallocHost(&m->h_ctl, sizeof(SolveCtl)));
+    m->h_ctl = acquire_pinned_ctl();
     std::memset(m->h_ctl, 0, sizeof(SolveCtl));
 }
 
@@ -1460,6 +1531,12 @@ extern "C" {
 
 const char* tm_last_error(void) { return g_last_error.c_str(); }
 int tm_abi_version(void) { return TM_ABI_VERSION; }
+void tm_release_cached_memory(void) {
+    g_cache.clear();
+    std::lock_guard<std::mutex> lock(g_pinned_mu);
+    for (SolveCtl* q : g_pinned_free) cudaFreeHost(q);
+    g_pinned_free.clear();
+}
 uint64_t tm_kernel_launch_count(void) { return g_launches.load(); }
 
 int tm_device_info(int device, char* name, size_t name_len, int* sm_count, uint64_t* global_mem_bytes) {
