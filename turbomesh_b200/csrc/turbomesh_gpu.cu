@@ -235,7 +235,7 @@ struct RankMesh {
     bool krylov_ready = false;
     std::vector<EdgeCache> edges;        // indexed by position in L.own_blocks
     std::vector<uint8_t> have_coords;
-    int n_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
+    int n_tiles = 0, n_rim_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
     bool has_pq = false;
     DevBuf<WhiteParams> d_wgroups;           // White groups handled by this rank
     DevBuf<WhiteNode> d_wnodes;
@@ -323,6 +323,10 @@ struct tm_mesh {
     int cf = TM_CF_LAPLACE;
     uint64_t outer_done = 0;  // outer iterations since begin_smoothing (the `n` of system.fill(n), smooth.zig:1107-1110)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t comm_stream = nullptr;          // the halo exchange of a sweep runs here, next to the bulk of the interior
+    cudaEvent_t ev_rim = nullptr, ev_x = nullptr;
+    bool overlap = true;                         // TM_OVERLAP=0: exchange on the main stream after the whole sweep
+    bool ev_x_valid = false, overlap_pending = false;
     std::vector<tm_block> h_blocks;              // host copies of the topology description (xy = NULL): multigrid coarsening
     std::vector<tm_connection> h_conns;
     std::vector<tm_condition> h_bcs;
@@ -337,6 +341,9 @@ struct tm_mesh {
         ranks.clear();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         if (h_ctl) release_pinned_ctl(h_ctl);
+        if (ev_rim) cudaEventDestroy(ev_rim);
+        if (ev_x) cudaEventDestroy(ev_x);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -367,6 +374,41 @@ void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank) {
         const int64_t rows = (interior_i + n_i - 1) / n_i;
         for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += rows)
             for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += TILE_J) tiles.push_back(Tile{int32_t(b), int32_t(i0), int32_t(j0), int32_t(rows)});
+    }
+    // Rim tiles first: the tiles that write a node some peer ghosts, or read a copy whose root is a ghost.  Everything the
+    // halo exchange of a sweep needs is produced by the rim tiles (and the boundary CTAs), so the exchange can travel while
+    // the bulk of the interior is still being swept (relax_sweep).
+    r.n_rim_tiles = 0;
+    if (m->n_ranks > 1 && !tiles.empty()) {
+        std::vector<uint8_t> rim(tiles.size(), 0);
+        std::vector<size_t> first_tile(topo.blocks.size(), 0);  // index of a block's first tile
+        {
+            size_t t = 0;
+            for (int32_t b : r.L.own_blocks) {
+                first_tile[size_t(b)] = t;
+                while (t < tiles.size() && tiles[t].block == b) ++t;
+            }
+        }
+        auto mark_near = [&](int64_t lidx) {  // tiles holding an interior node within one node of local node lidx
+            if (lidx < 0 || lidx >= r.L.n_own) return;
+            size_t b = size_t(r.L.own_blocks.back());
+            for (int32_t cand : r.L.own_blocks)
+                if (lidx >= r.L.loff[size_t(cand)] && lidx < r.L.loff[size_t(cand)] + topo.blocks[size_t(cand)].ni * topo.blocks[size_t(cand)].nj) { b = size_t(cand); break; }
+            const int64_t ni = topo.blocks[b].ni, nj = topo.blocks[b].nj, local = lidx - r.L.loff[b], i = local / nj, j = local - i * nj;
+            const int64_t rows = tiles[first_tile[b]].rows, ncols = (nj - 2 + TILE_J - 1) / TILE_J;
+            for (int64_t di = -1; di <= 1; ++di)
+                for (int64_t dj = -1; dj <= 1; ++dj) {
+                    const int64_t ii = std::min<int64_t>(std::max<int64_t>(i + di, 1), ni - 2), jj = std::min<int64_t>(std::max<int64_t>(j + dj, 1), nj - 2);
+                    rim[first_tile[b] + size_t(((ii - 1) / rows) * ncols + (jj - 1) / TILE_J)] = 1;
+                }
+        };
+        for (int64_t l : r.L.send_lidx) mark_near(l);
+        for (size_t k = size_t(r.L.n_slaves_local_root); k < r.L.slaves.size(); ++k) mark_near(r.L.slaves[k].self);
+        std::vector<Tile> ordered;
+        for (size_t t = 0; t < tiles.size(); ++t) if (rim[t]) ordered.push_back(tiles[t]);
+        r.n_rim_tiles = int(ordered.size());
+        for (size_t t = 0; t < tiles.size(); ++t) if (!rim[t]) ordered.push_back(tiles[t]);
+        tiles.swap(ordered);
     }
     r.n_tiles = int(tiles.size());
     r.d_tiles.upload(tiles, s);
@@ -497,12 +539,12 @@ void ensure_krylov(tm_mesh* m) {
 // ---- halo exchange: every rank's ghost slots of `field` are refreshed from their owners ------------------------
 // check = true: the one-time exchange of raw side-0 coordinates for connectionDataCheck (separate slots).
 using RankList = std::vector<std::unique_ptr<RankMesh>>;
-void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root = false);
+void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root = false, cudaStream_t xs = nullptr);
 // slave_mode >= 0: afterwards the copies whose root is a ghost are re-derived from it (mode as in sync_slaves_kernel)
 template <class Get>
-void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false, int slave_mode = -1) {
+void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false, int slave_mode = -1, cudaStream_t xs = nullptr) {
     if (m->n_ranks == 1) return;
-    cudaStream_t s = m->stream;
+    cudaStream_t s = xs ? xs : m->stream;
     auto send_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_send_base : r.L.send_base; };
     auto ghost_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_ghost_base : r.L.ghost_base; };
     auto region = [&](RankMesh& r) { return check ? r.L.n_own + r.L.n_ghost + r.L.n_synth : r.L.n_own; };
@@ -548,7 +590,8 @@ void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false, int s
             const int64_t first = r.L.n_slaves_local_root;
             const int n_sl = slave_mode >= 0 ? int(int64_t(r.L.slaves.size()) - first) : 0;
             const int64_t want = (std::max<int64_t>(n, n_sl) + 255) / 256;
-            LAUNCH(p2p_exchange_kernel, unsigned(std::max<int64_t>(1, std::min<int64_t>(want, m->sm_count))), 256, s, (const int64_t*)r.d_send_idx.p, n, get(r), a, r.p2p.epoch,
+            const int64_t most = xs ? 32 : m->sm_count;  // next to a running sweep: few CTAs, they only move O(interface) nodes
+            LAUNCH(p2p_exchange_kernel, unsigned(std::max<int64_t>(1, std::min<int64_t>(want, most))), 256, s, (const int64_t*)r.d_send_idx.p, n, get(r), a, r.p2p.epoch,
                    r.p2p.counter.p, (const unsigned long long*)r.p2p.flags.p, r.p2p.nb_mask, r.p2p.err.p, (const SlaveRow*)(r.d_slaves.p + first), n_sl,
                    std::max(slave_mode, 0));
             return;
@@ -563,25 +606,34 @@ void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false, int s
         NCCL_TRY(g_nccl.GroupEnd());
     }
     if (slave_mode >= 0)
-        for (auto& rp : ranks) sync_slaves(m, *rp, get(*rp), slave_mode, true);
+        for (auto& rp : ranks) sync_slaves(m, *rp, get(*rp), slave_mode, true, s);
 }
 
 template <class Get>
 void exchange(tm_mesh* m, Get get, bool check = false, int slave_mode = -1) { exchange_on(m, m->ranks, get, check, slave_mode); }
 
 // copies of nodes: mode 0 homogeneous / 1 affine / 2 zero; `only_remote_root` restricts to copies whose root is a ghost
-void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root) {
+void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote_root, cudaStream_t xs) {
     const int64_t first = only_remote_root ? r.L.n_slaves_local_root : 0;
     const int n = int(int64_t(r.L.slaves.size()) - first);
-    if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, m->stream, (const SlaveRow*)(r.d_slaves.p + first), n, v, mode);
+    if (n > 0) LAUNCH(sync_slaves_kernel, (n + 127) / 128, 128, xs ? xs : m->stream, (const SlaveRow*)(r.d_slaves.p + first), n, v, mode);
 }
+
+// which rows of a rank one launch covers (bulk kernel only): tiles [first, first+count) and, optionally, the boundary CTAs
+struct RowPart {
+    int first = 0, count = -1;  // count < 0: all tiles
+    bool bnd = true;
+    cudaStream_t stream = nullptr;  // NULL: the mesh's stream
+};
 
 // ---- kernel dispatch over the (LAGGED, HAS_PQ) template space -------------------------------------
 template <int MODE, int STATS>
-void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const double2* xc, double2* out, double omega, const double2* dot_a) {
+void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const double2* xc, double2* out, double omega, const double2* dot_a,
+                 RowPart part = RowPart()) {
     const bool has_pq = r.has_pq;
     const double2* pq = r.pq.p;
-    cudaStream_t s = m->stream;
+    cudaStream_t s = part.stream ? part.stream : m->stream;
+    const int t_first = part.first, t_count = part.count < 0 ? r.n_tiles : part.count, b_ctas = part.bnd ? r.n_bnd_ctas : 0;
 #define TM_BND(LAG, PQ)                                                                                                                           \
     if (r.n_bnd_rows > 0)                                                                                                                         \
         LAUNCH((winslow_boundary_kernel<MODE, LAG, PQ, STATS>), r.n_bnd_ctas, BND_THREADS, s, (const SmoothedRow*)r.d_srows.p,                   \
@@ -597,10 +649,10 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
 #define TM_ROWS_BULK(PQ)                                                                                                                          \
     do {                                                                                                                                          \
         const BndArgs bnd{r.d_srows.p, r.d_jrows.p, r.d_lrows.p, r.d_slaves.p, r.part_bnd.p, int(r.L.smoothed.size()),                            \
-                          int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};                                                  \
-        if (r.n_tiles + r.n_bnd_ctas > 0)                                                                                                         \
-            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), r.n_tiles + r.n_bnd_ctas, TILE_J, s, (const Tile*)r.d_tiles.p,                \
-                   (const DevBlock*)r.d_blocks.p, u, pq, out, omega, dot_a, r.part_int.p, bnd, (const double2*)nullptr);                          \
+                          int(r.L.junction_rows.size()), int(r.L.sliding.size()), b_ctas};                                                        \
+        if (t_count + b_ctas > 0)                                                                                                                 \
+            LAUNCH((winslow_interior_bulk_kernel<MODE, PQ, STATS>), t_count + b_ctas, TILE_J, s, (const Tile*)r.d_tiles.p + t_first,              \
+                   (const DevBlock*)r.d_blocks.p, u, pq, out, omega, dot_a, r.part_int.p + size_t(t_first) * 5, bnd, (const double2*)nullptr);    \
     } while (0)
     if (lagged) { if (has_pq) TM_ROWS(true, true); else TM_ROWS(true, false); }
     else if (m->use_bulk) { if (has_pq) TM_ROWS_BULK(true); else TM_ROWS_BULK(false); }
@@ -613,16 +665,65 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
 // multigrid levels: all rows of the rank (interior tiles + boundary CTAs) through the bulk kernel, Laplace control
 // function, optional FAS right-hand side
 template <int MODE, int STATS>
-void launch_rows_mg(tm_mesh* m, RankMesh& r, const double2* u, double2* out, double omega, const double2* rhs) {
+void launch_rows_mg(tm_mesh* m, RankMesh& r, const double2* u, double2* out, double omega, const double2* rhs, RowPart part = RowPart()) {
+    const int t_first = part.first, t_count = part.count < 0 ? r.n_tiles : part.count, b_ctas = part.bnd ? r.n_bnd_ctas : 0;
     const BndArgs bnd{r.d_srows.p, r.d_jrows.p, r.d_lrows.p, r.d_slaves.p, r.part_bnd.p, int(r.L.smoothed.size()),
-                      int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};
-    if (r.n_tiles + r.n_bnd_ctas == 0) return;
+                      int(r.L.junction_rows.size()), int(r.L.sliding.size()), b_ctas};
+    if (t_count + b_ctas == 0) return;
     if (rhs)
-        LAUNCH((winslow_interior_bulk_kernel<MODE, false, STATS, true>), r.n_tiles + r.n_bnd_ctas, TILE_J, m->stream, (const Tile*)r.d_tiles.p,
-               (const DevBlock*)r.d_blocks.p, u, (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, bnd, rhs);
+        LAUNCH((winslow_interior_bulk_kernel<MODE, false, STATS, true>), t_count + b_ctas, TILE_J, part.stream ? part.stream : m->stream, (const Tile*)r.d_tiles.p + t_first,
+               (const DevBlock*)r.d_blocks.p, u, (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p + size_t(t_first) * 5, bnd, rhs);
     else
-        LAUNCH((winslow_interior_bulk_kernel<MODE, false, STATS, false>), r.n_tiles + r.n_bnd_ctas, TILE_J, m->stream, (const Tile*)r.d_tiles.p,
-               (const DevBlock*)r.d_blocks.p, u, (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p, bnd, (const double2*)nullptr);
+        LAUNCH((winslow_interior_bulk_kernel<MODE, false, STATS, false>), t_count + b_ctas, TILE_J, part.stream ? part.stream : m->stream, (const Tile*)r.d_tiles.p + t_first,
+               (const DevBlock*)r.d_blocks.p, u, (const double2*)nullptr, out, omega, (const double2*)nullptr, r.part_int.p + size_t(t_first) * 5, bnd,
+               (const double2*)nullptr);
+}
+
+// One damped-Jacobi sweep of every rank held by this process (X[cur] -> X[1-cur], swap) followed by the halo exchange of
+// the new iterate.  A real multi-GPU rank overlaps the two: the rim tiles and the boundary rows run on a second,
+// high-priority stream, immediately followed there by the exchange (push over NVLink / NCCL, wait, copies of ghost
+// roots), while the bulk of the interior is swept on the main stream at the same time:
+//     comm:  wait(bulk k-1)  rim(k)  exchange(k)                    main:  wait(exchange k-1)  bulk(k)
+// rim(k) may overwrite what bulk(k-1) still reads and bulk(k) what rim(k-1) read -- the two waits order exactly that.
+// `mg`: Laplace rows with optional FAS rhs.
+template <int STATS>
+void relax_sweep(tm_mesh* m, RankList& R, double omega, bool mg, bool with_rhs) {
+    auto xcur = [](RankMesh& r) { return r.X[r.cur].p; };
+    auto rows = [&](RankMesh& r, const double2* u, double2* out, RowPart part) {
+        if (mg) launch_rows_mg<MODE_RELAX, STATS>(m, r, u, out, omega, with_rhs ? (const double2*)r.mg_rhs.p : nullptr, part);
+        else launch_rows<MODE_RELAX, STATS>(m, r, false, u, u, out, omega, nullptr, part);
+    };
+    const bool overlap = m->overlap && m->n_ranks > 1 && !m->emulated && R.size() == 1 && (mg || m->use_bulk) && R[0]->n_rim_tiles * 4 < R[0]->n_tiles;
+    if (!overlap) {
+        for (auto& rp : R) {
+            RankMesh& r = *rp;
+            rows(r, r.X[r.cur].p, r.X[1 - r.cur].p, RowPart());
+            r.cur = 1 - r.cur;
+        }
+        exchange_on(m, R, xcur, false, 1);
+        return;
+    }
+    RankMesh& r = *R[0];
+    const double2* u = r.X[r.cur].p;
+    double2* out = r.X[1 - r.cur].p;
+    // everything queued on the main stream so far (the previous sweep's bulk in particular) precedes the rim
+    CUDA_TRY(cudaEventRecord(m->ev_rim, m->stream));
+    CUDA_TRY(cudaStreamWaitEvent(m->comm_stream, m->ev_rim, 0));
+    rows(r, u, out, RowPart{0, r.n_rim_tiles, true, m->comm_stream});
+    r.cur = 1 - r.cur;
+    // the previous exchange (queued on comm before the rim) precedes the bulk: ev_x still holds its record
+    if (m->ev_x_valid) CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x, 0));
+    rows(r, u, out, RowPart{r.n_rim_tiles, r.n_tiles - r.n_rim_tiles, false, nullptr});
+    exchange_on(m, R, xcur, false, 1, m->comm_stream);
+    CUDA_TRY(cudaEventRecord(m->ev_x, m->comm_stream));
+    m->ev_x_valid = true;
+    m->overlap_pending = true;
+}
+// after a run of overlapped sweeps: the main stream joins the last exchange
+void relax_join(tm_mesh* m) {
+    if (!m->overlap_pending) return;
+    CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_x, 0));
+    m->overlap_pending = false;
 }
 
 // rank-local reduction of the per-CTA partials, all-reduce over ranks, solver scalars
@@ -684,15 +785,9 @@ void run_relax(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
         if (m->cf == TM_CF_WHITE && m->outer_done > 0) white_step(m, true, o->white_ds_target, o->white_theta_target);
         for (uint64_t sw = 0; sw < o->sweeps_per_iteration; ++sw) {
             const bool last = sw + 1 == o->sweeps_per_iteration;
-            for (auto& rp : m->ranks) {
-                RankMesh& r = *rp;
-                const double2* u = r.X[r.cur].p;
-                double2* out = r.X[1 - r.cur].p;
-                if (last) launch_rows<MODE_RELAX, 1>(m, r, false, u, u, out, o->omega, nullptr);
-                else launch_rows<MODE_RELAX, 0>(m, r, false, u, u, out, o->omega, nullptr);
-                r.cur = 1 - r.cur;
-            }
-            exchange(m, [](RankMesh& r) { return r.X[r.cur].p; }, false, 1);
+            if (last) relax_sweep<1>(m, m->ranks, o->omega, false, false);
+            else relax_sweep<0>(m, m->ranks, o->omega, false, false);
+            if (last) relax_join(m);
             st->inner_iterations += 1;
             st->operator_applications += 1;
         }
@@ -1320,14 +1415,8 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
     double fine_work = 0.0;
     auto smooth = [&](int l, uint64_t sweeps) {
         RankList& R = ranks_of(l);
-        for (uint64_t k = 0; k < sweeps; ++k) {
-            for (auto& rp : R) {
-                RankMesh& r = *rp;
-                launch_rows_mg<MODE_RELAX, 0>(m, r, r.X[r.cur].p, r.X[1 - r.cur].p, o->omega, l > 0 ? (const double2*)r.mg_rhs.p : nullptr);
-                r.cur = 1 - r.cur;
-            }
-            exchange_on(m, R, xcur, false, 1);
-        }
+        for (uint64_t k = 0; k < sweeps; ++k) relax_sweep<0>(m, R, o->omega, true, l > 0);
+        relax_join(m);
         fine_work += double(sweeps) * m->mgb[size_t(l)]->work;
     };
     auto refresh = [&](int l) {  // ghosts, then every copy re-derived from its root
@@ -1471,6 +1560,14 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
     if (stream) m->stream = (cudaStream_t)stream;
     else { CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
+    {
+        int lo = 0, hi = 0;  // numerically lowest = highest priority: the few exchange CTAs must not queue behind the sweep's
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, hi));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_rim, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
+    if (const char* e = std::getenv("TM_OVERLAP")) m->overlap = std::atoi(e) != 0;
     CUDA_TRY(cudaEventCreate(&m->ev0));
     CUDA_TRY(cudaEventCreate(&m->ev1));
     m->h_ctl = acquire_pinned_ctl();
