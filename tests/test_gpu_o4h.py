@@ -88,3 +88,20 @@ def test_structured_output_of_the_white_control_function(orc, gpu_lib):
         aos = dm.control_function(0)
     op, oq = orc.block_to_soa(aos)
     assert np.array_equal(p, op) and np.array_equal(q, oq) and np.abs(p).max() > 0
+
+
+def test_multigrid_on_the_t106_o4h_mesh_reaches_the_picard_fixed_point(gpu_lib):
+    """The reference's own T106 topology (8 blocks, 21 connections with sub-range and reversed ranges, 3- and 5-block
+    junctions, periodic and sliding rows): every extent and range end point is even, so one nested level exists; the
+    accelerated cycle converges to the fixed point of the Picard iteration."""
+    from turbomesh_b200 import smoothing
+
+    spec, z, meta = load_fixture("t106_laplace")
+    a = synthetic.materialize(spec, smoothing.tfi_block)
+    b = synthetic.materialize(spec, smoothing.tfi_block)
+    st_mg = smoothing.smooth_mesh(a, 200, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-13))
+    st_pc = smoothing.smooth_mesh(b, 80, smoothing.CudaSolver.tight(stop_max_update=1e-13))
+    assert st_mg["last_max_update"] <= 1e-13 and st_mg["outer_iterations"] < 100, st_mg
+    assert st_pc["last_max_update"] <= 1e-13, st_pc
+    err = max(float(np.abs(x.points - y.points).max()) for x, y in zip(a.blocks, b.blocks))
+    assert err <= 1e-9 * chord_of(a), (err, st_mg)

@@ -289,7 +289,7 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
                                               const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
                                               const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
                                               double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials,
-                                              const double2* __restrict__ rhs = nullptr);
+                                              const double2* __restrict__ rhs = nullptr, int row_override = -1);
 // The boundary rows ride in the same launch as the interior tiles (the first n_ctas CTAs of the grid): they are few
 // and latency-bound, so they hide behind the interior work instead of costing a launch of their own.
 struct BndArgs {
@@ -450,8 +450,8 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
                                               const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
                                               const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
                                               double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials,
-                                              const double2* __restrict__ rhs) {
-    const int r = cta * BND_THREADS + threadIdx.x;
+                                              const double2* __restrict__ rhs, int row_override /* >= 0: this row (STATS == 0 callers only) */) {
+    const int r = row_override >= 0 ? row_override : cta * BND_THREADS + threadIdx.x;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, mx = 0.0;
     double2 res = make_double2(0.0, 0.0), old = make_double2(0.0, 0.0);
     int64_t self = -1;
@@ -1307,6 +1307,13 @@ __global__ void combine_sum_kernel(SumPtrs v, int n_ranks, int count) {  // in-p
     __syncthreads();
     for (int r = 0; r < n_ranks; ++r) v.p[r][k] = s;
 }
+__global__ void __launch_bounds__(256) combine_sum_fields_kernel(SumPtrs v, int n_ranks, int64_t count /* doubles */) {
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < count; k += (int64_t)gridDim.x * 256) {
+        double s = 0.0;
+        for (int r = 0; r < n_ranks; ++r) s += v.p[r][k];
+        for (int r = 0; r < n_ranks; ++r) v.p[r][k] = s;
+    }
+}
 // alpha_0..alpha_{q-1} (sum 1); falls back to "newest only" (no extrapolation) when the window is short, the
 // least-squares problem is degenerate, the weights are wild or the newest residual grew
 __global__ void aa_solve_kernel(const double* __restrict__ gram, int q, double* __restrict__ alpha) {
@@ -1358,6 +1365,44 @@ __global__ void __launch_bounds__(256) aa_combine_kernel(int64_t n, AaFields h, 
             if (i < h.q - 1) { const double2 t = h.G[i][k]; dx += a[i] * (t.x - gn.x); dy += a[i] * (t.y - gn.y); }
         d[k] = make_double2(dx, dy);
         x_store[k] = make_double2(gn.x + dx, gn.y + dy);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Tiny multigrid levels (a few thousand nodes: the coarsest levels of a block-structured hierarchy cannot get smaller
+// than 3x3 nodes per block): ALL sweeps of a visit in ONE launch of ONE CTA.  Launch latency, not bandwidth, is what
+// such levels cost; the level's data lives in L2 and __syncthreads() separates the sweeps.  Interior rows come from a flat
+// node list, boundary rows reuse boundary_rows(); ping-pong between xa and xb, the result is in xa after an even and
+// in xb after an odd number of sweeps.
+// ---------------------------------------------------------------------------------------------------
+struct SmallNode { int64_t idx; int32_t block, i, j, _pad; };  // an interior node: local index, owning block, (i, j)
+__global__ void __launch_bounds__(1024) winslow_small_level_kernel(const SmallNode* nodes, int n_nodes, const DevBlock* blocks, BndArgs bnd, double2* xa, double2* xb,
+                                                                   const double2* rhs /* may be NULL */, double omega, int sweeps) {
+    const int n_rows = bnd.n_s + bnd.n_j + bnd.n_l;
+    for (int sw = 0; sw < sweeps; ++sw) {
+        const double2* u = (sw & 1) ? xb : xa;
+        double2* out = (sw & 1) ? xa : xb;
+        for (int k = threadIdx.x; k < n_nodes; k += blockDim.x) {
+            const SmallNode nd = nodes[k];
+            const DevBlock b = blocks[nd.block];
+            const double2* c = u + nd.idx;
+            const int nj = b.nj;
+            const double2 C = c[0], W = c[-nj], E = c[nj], S = c[-1], N = c[1];
+            const double2 SW = c[-nj - 1], NW = c[-nj + 1], SE = c[nj - 1], NE = c[nj + 1];
+            Metric m = metric_terms(W, E, N - S);
+            if (rhs && b.slide) {
+                if ((nd.i == 1 && (b.slide & 1)) || (nd.i == b.ni - 2 && (b.slide & 2))) m.g11 *= b.tan_i;
+                if ((nd.j == 1 && (b.slide & 4)) || (nd.j == nj - 2 && (b.slide & 8))) m.g22 *= b.tan_j;
+            }
+            double2 rel = row_rel<false>(m, 0.0, 0.0, C, W, E, (N - C) + (S - C), N - S, NE - SE, NW - SW);
+            if (rhs) { const double2 f = rhs[nd.idx]; rel.x -= f.x; rel.y -= f.y; }
+            out[nd.idx] = row_result<MODE_RELAX>(m, rel, C, omega);
+        }
+        for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+            if (rhs) boundary_rows<MODE_RELAX, false, false, 0, true>(0, bnd.srows, bnd.n_s, bnd.jrows, bnd.n_j, bnd.lrows, bnd.n_l, bnd.slaves, u, u, nullptr, out, omega, nullptr, nullptr, rhs, r);
+            else boundary_rows<MODE_RELAX, false, false, 0, false>(0, bnd.srows, bnd.n_s, bnd.jrows, bnd.n_j, bnd.lrows, bnd.n_l, bnd.slaves, u, u, nullptr, out, omega, nullptr, nullptr, nullptr, r);
+        }
+        __syncthreads();
     }
 }
 

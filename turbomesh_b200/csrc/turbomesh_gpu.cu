@@ -247,6 +247,9 @@ struct RankMesh {
     DevBuf<BlockXfer> d_xfer_blocks;
     int xf_ni_f = 0, xf_nj_f = 0, xf_ni_c = 0, xf_nj_c = 0;  // largest extents over the own blocks (grid of the batched transfer kernels)
     DevBuf<double> soa_stage;                // device staging of the structured (SoA) output
+    bool replicated = false;                 // multigrid level held in full by every rank (no halo exchange, redundant work)
+    DevBuf<SmallNode> d_small;               // tiny levels: flat interior node list of winslow_small_level_kernel
+    int n_small = 0;
     DevBuf<unsigned long long> d_change;     // level 0: max-norm movement of the level-1 nodes between two restrictions
     bool mg_primed = false;                  // coarse levels: both ping-pong buffers hold the (constant) fixed-node values
     // level 1 only: Anderson acceleration history (rings of AA_MAX samples G_j and residuals F_j, the accelerated state X)
@@ -332,6 +335,8 @@ struct tm_mesh {
     std::vector<tm_condition> h_bcs;
     std::vector<std::unique_ptr<MgbLevel>> mgb;  // multi-block multigrid hierarchy, built on first use
     int sm_count = 148;
+    int64_t mg_replicate_nodes = 32768;  // multigrid levels up to this size are replicated on every rank (TM_MG_REPLICATE_NODES)
+    int64_t mg_small_nodes = 4096;       // ... and up to this size swept by the single-CTA kernel (TM_MG_SMALL_NODES)
     bool mg_aa = true;        // Anderson acceleration of the multi-block multigrid cycle (TM_MG_AA=0 switches it off)
     int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
     bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
@@ -354,9 +359,9 @@ namespace {
 
 int bnd_ctas(int rows) { return (rows + BND_THREADS - 1) / BND_THREADS; }
 
-void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank) {
+void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank, const std::vector<int32_t>* owner_override = nullptr) {
     cudaStream_t s = m->stream;
-    r.L = localize(topo, m->owner, rank, m->n_ranks);
+    r.L = localize(topo, owner_override ? *owner_override : m->owner, rank, m->n_ranks);
     r.N = r.L.n_local;
     r.X[0].alloc(size_t(std::max<int64_t>(r.N, 1)));
     r.X[1].alloc(size_t(std::max<int64_t>(r.N, 1)));
@@ -543,7 +548,7 @@ void sync_slaves(tm_mesh* m, RankMesh& r, double2* v, int mode, bool only_remote
 // slave_mode >= 0: afterwards the copies whose root is a ghost are re-derived from it (mode as in sync_slaves_kernel)
 template <class Get>
 void exchange_on(tm_mesh* m, RankList& ranks, Get get, bool check = false, int slave_mode = -1, cudaStream_t xs = nullptr) {
-    if (m->n_ranks == 1) return;
+    if (m->n_ranks == 1 || ranks.empty() || ranks[0]->replicated) return;  // (a replicated level has no remote roots either)
     cudaStream_t s = xs ? xs : m->stream;
     auto send_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_send_base : r.L.send_base; };
     auto ghost_base = [&](RankMesh& r) -> const std::vector<int64_t>& { return check ? r.L.check_ghost_base : r.L.ghost_base; };
@@ -693,7 +698,7 @@ void relax_sweep(tm_mesh* m, RankList& R, double omega, bool mg, bool with_rhs) 
         if (mg) launch_rows_mg<MODE_RELAX, STATS>(m, r, u, out, omega, with_rhs ? (const double2*)r.mg_rhs.p : nullptr, part);
         else launch_rows<MODE_RELAX, STATS>(m, r, false, u, u, out, omega, nullptr, part);
     };
-    const bool overlap = m->overlap && m->n_ranks > 1 && !m->emulated && R.size() == 1 && (mg || m->use_bulk) && R[0]->n_rim_tiles * 4 < R[0]->n_tiles;
+    const bool overlap = m->overlap && m->n_ranks > 1 && !m->emulated && R.size() == 1 && !R[0]->replicated && (mg || m->use_bulk) && R[0]->n_rim_tiles * 4 < R[0]->n_tiles;
     if (!overlap) {
         for (auto& rp : R) {
             RankMesh& r = *rp;
@@ -1124,7 +1129,10 @@ int32_t side_slide_mask(const Topology& T, size_t k) {
 // residual restriction of the rows that straddle blocks: coarse row <- full weighting of the fine residuals around it
 void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankMesh& rf, const Topology& TC, const MgbLevel& C, RankMesh& rc) {
     const int rank = rf.L.rank;
-    const auto& owner = m->owner;
+    // who computes what: the owner on the fine level (a replicated fine level: this rank, for every block)
+    const std::vector<int32_t> all_mine(m->owner.size(), int32_t(rank));
+    const std::vector<int32_t>& owner = rf.replicated ? all_mine : m->owner;
+    const std::vector<int32_t>& owner_c = rc.replicated ? all_mine : m->owner;
     rf.xfer_blocks.clear();
     for (int32_t b : rf.L.own_blocks) {
         const size_t k = size_t(b);
@@ -1136,7 +1144,7 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
     }
     std::vector<RestrictRow> rows;
     auto lf = [&](int64_t g) { return local_index(TF, owner, rf.L, g); };
-    auto lc = [&](int64_t g) { return local_index(TC, owner, rc.L, g); };
+    auto lc = [&](int64_t g) { return local_index(TC, owner_c, rc.L, g); };
     auto add = [](RestrictRow& row, int64_t src, double w) { row.src[row.n] = src; row.w[row.n] = w; ++row.n; };
     for (size_t c = 0; c < C.conns.size(); ++c) {
         const tm_connection& cc = C.conns[c];
@@ -1300,10 +1308,26 @@ void mgb_build(tm_mesh* m) {
             C->tan_i[b] = F.fi[b] == 2 ? 0.5 * F.tan_i[b] + 0.75 : F.tan_i[b];
             C->tan_j[b] = F.fj[b] == 2 ? 0.5 * F.tan_j[b] + 0.75 : F.tan_j[b];
         }
+        // Small levels are REPLICATED on every rank of a multi-GPU run (every rank holds all blocks and does the same work):
+        // their sweeps then need no halo exchange at all, which is what such levels cost.  Levels of a few thousand nodes
+        // additionally run all sweeps of a visit in one single-CTA launch (winslow_small_level_kernel).
+        const bool replicate = m->n_ranks > 1 && C->topo.n_nodes <= m->mg_replicate_nodes;
         for (auto& rp : m->ranks) {
             C->ranks.emplace_back(new RankMesh());
             RankMesh& rc = *C->ranks.back();
-            build_rank(m, C->topo, rc, rp->L.rank);
+            rc.replicated = replicate;
+            const std::vector<int32_t> all_mine(nb, int32_t(rp->L.rank));
+            build_rank(m, C->topo, rc, rp->L.rank, replicate ? &all_mine : nullptr);
+            if (C->topo.n_nodes <= m->mg_small_nodes && (replicate || m->n_ranks == 1)) {
+                std::vector<SmallNode> nodes;
+                for (int32_t b : rc.L.own_blocks) {
+                    const auto& B = C->topo.blocks[size_t(b)];
+                    for (int64_t i = 1; i + 1 < B.ni; ++i)
+                        for (int64_t j = 1; j + 1 < B.nj; ++j) nodes.push_back(SmallNode{rc.L.loff[size_t(b)] + i * B.nj + j, b, int32_t(i), int32_t(j), 0});
+                }
+                rc.n_small = int(nodes.size());
+                rc.d_small.upload(nodes, s);
+            }
             for (DevBuf<double2>* v : {&rc.mg_rhs, &rc.mg_tmp, &rc.mg_E, &rc.mg_zero}) { v->alloc(size_t(std::max<int64_t>(rc.N, 1))); v->zero(s); }
             std::fill(rc.have_coords.begin(), rc.have_coords.end(), uint8_t(1));
             std::vector<DevBlock> blocks(nb, DevBlock{0, 0, 0});
@@ -1326,8 +1350,10 @@ void mgb_build(tm_mesh* m) {
                 rc.aa_coef.alloc(AA_MAX); rc.aa_coef.zero(s);
             }
             CUDA_TRY(cudaStreamSynchronize(s));
-            p2p_setup(m, rc);
-            p2p_add_tmp(m, rc);
+            if (!replicate) {
+                p2p_setup(m, rc);
+                p2p_add_tmp(m, rc);
+            }
         }
         const Topology& TF = m->mgb.size() == 1 ? m->topo : F.topo;
         RankList& RF = m->mgb.size() == 1 ? m->ranks : F.ranks;
@@ -1415,6 +1441,18 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
     double fine_work = 0.0;
     auto smooth = [&](int l, uint64_t sweeps) {
         RankList& R = ranks_of(l);
+        if (l > 0 && !R.empty() && R[0]->n_small > 0) {  // a tiny level: all sweeps in one single-CTA launch per rank held here
+            for (auto& rp : R) {
+                RankMesh& r = *rp;
+                const BndArgs bnd{r.d_srows.p, r.d_jrows.p, r.d_lrows.p, r.d_slaves.p, r.part_bnd.p, int(r.L.smoothed.size()),
+                                  int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};
+                LAUNCH(winslow_small_level_kernel, 1, 1024, s, (const SmallNode*)r.d_small.p, r.n_small, (const DevBlock*)r.d_blocks.p, bnd, r.X[r.cur].p, r.X[1 - r.cur].p,
+                       (const double2*)r.mg_rhs.p, o->omega, int(sweeps));
+                if (sweeps & 1) r.cur = 1 - r.cur;
+            }
+            fine_work += double(sweeps) * m->mgb[size_t(l)]->work;
+            return;
+        }
         for (uint64_t k = 0; k < sweeps; ++k) relax_sweep<0>(m, R, o->omega, true, l > 0);
         relax_join(m);
         fine_work += double(sweeps) * m->mgb[size_t(l)]->work;
@@ -1450,6 +1488,12 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             for (auto& rp : RF) launch_rows_mg<MODE_REL, 0>(m, *rp, xcur(*rp), rp->mg_tmp.p, 1.0, l > 0 ? (const double2*)rp->mg_rhs.p : nullptr);
             exchange_on(m, RF, tmp_of);
             fine_work += m->mgb[size_t(l)]->work;
+            const bool gather = !RC.empty() && RC[0]->replicated && !RF[0]->replicated;  // every rank restricts its blocks, all need all
+            if (gather)
+                for (auto& rp : RC) {
+                    CUDA_TRY(cudaMemsetAsync(xcur(*rp), 0, size_t(rp->L.n_own) * sizeof(double2), s));
+                    CUDA_TRY(cudaMemsetAsync(rp->mg_rhs.p, 0, size_t(rp->L.n_own) * sizeof(double2), s));
+                }
             for (size_t q = 0; q < RF.size(); ++q) {
                 RankMesh& rf = *RF[q];
                 RankMesh& rc = *RC[q];
@@ -1461,6 +1505,18 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 }
                 if (rf.n_rrows > 0)
                     LAUNCH(mgb_restrict_rows_kernel, (rf.n_rrows + 127) / 128, 128, s, (const RestrictRow*)rf.d_rrows.p, rf.n_rrows, (const double2*)rf.mg_tmp.p, rc.mg_rhs.p);
+            }
+            if (gather) {  // sum of "mine, zero elsewhere" = everybody's blocks (exact: one non-zero contribution per node)
+                for (double2* (*field)(RankMesh&) : {+[](RankMesh& r) { return r.X[r.cur].p; }, +[](RankMesh& r) { return r.mg_rhs.p; }}) {
+                    if (m->emulated) {
+                        SumPtrs ptrs{};
+                        for (size_t k = 0; k < RC.size(); ++k) ptrs.p[k] = reinterpret_cast<double*>(field(*RC[k]));
+                        LAUNCH(combine_sum_fields_kernel, 64, 256, s, ptrs, int(RC.size()), 2 * RC[0]->L.n_own);
+                    } else {
+                        double* f = reinterpret_cast<double*>(field(*RC[0]));
+                        NCCL_TRY(g_nccl.AllReduce(f, f, size_t(2 * RC[0]->L.n_own), ncclDouble, ncclSum, m->comm, s));
+                    }
+                }
             }
             refresh(l + 1);
             for (auto& rp : RC) {
@@ -1556,6 +1612,8 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     if (n_connections) m->h_conns.assign(connections, connections + n_connections);
     if (n_conditions) m->h_bcs.assign(conditions, conditions + n_conditions);
     if (const char* e = std::getenv("TM_MG_AA")) m->mg_aa = std::atoi(e) != 0;
+    if (const char* e = std::getenv("TM_MG_REPLICATE_NODES")) m->mg_replicate_nodes = std::atoll(e);
+    if (const char* e = std::getenv("TM_MG_SMALL_NODES")) m->mg_small_nodes = std::atoll(e);
     if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
     if (const char* e = std::getenv("TM_INTERIOR")) m->use_bulk = std::strcmp(e, "regs") != 0;
     if (stream) m->stream = (cudaStream_t)stream;
