@@ -251,6 +251,16 @@ int tm_dist_plan(const tm_block *blocks, size_t n_blocks,
                  const int32_t *block_owner, int rank, int n_ranks,
                  tm_dist_plan_info *info, int64_t *ghost_ids, int64_t *send_ids, int64_t *counts);
 
+/* Host-only view of the multigrid hierarchy TM_SOLVER_FAS_MULTIGRID builds for a multi-block mesh (needs no GPU): nested
+ * coarsening of block sizes and connection / condition ranges, directions tied into classes by the connections.
+ * cell_size (may be NULL = all equal) holds the mean cell size per (block, direction), 2*n_blocks entries -- the solver
+ * measures it on the device.  *n_levels receives the number of levels (>= 1); sizes (may be NULL) receives (ni, nj) of
+ * every block on every level: sizes[(level*n_blocks + block)*2 + {0,1}] for level < max_levels. */
+int tm_mg_plan(const tm_block *blocks, size_t n_blocks,
+               const tm_connection *connections, size_t n_connections,
+               const tm_condition *conditions, size_t n_conditions,
+               const double *cell_size, size_t max_levels, uint64_t *n_levels, uint64_t *sizes);
+
 /* -------------------------------------------------------------------------------------------------
  * Misc
  * ------------------------------------------------------------------------------------------------- */

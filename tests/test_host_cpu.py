@@ -153,3 +153,43 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "turbomesh_oracle" not in text, f
+
+
+# ---- host-only planning of the multi-block multigrid hierarchy (tm_mg_plan) -----------------------------------------
+def test_mg_plan_cascade_halves_every_block_down_to_3x3(gpu_lib):
+    from turbomesh_b200 import smoothing, synthetic
+
+    plan = smoothing.mg_plan(synthetic.cascade(2, 2, 65, 33))
+    assert plan[0] == [(65, 33)] * 4
+    assert plan[1] == [(33, 17)] * 4 and plan[2] == [(17, 9)] * 4
+    assert plan[-1] == [(3, 3)] * 4
+    # 33 nodes along j bottom out first (2 intervals); i goes on alone for one more level
+    assert plan[-2] == [(5, 3)] * 4
+
+
+def test_mg_plan_semi_coarsening_follows_the_cell_sizes(gpu_lib):
+    from turbomesh_b200 import smoothing, synthetic
+
+    mesh = synthetic.cascade(2, 2, 65, 65)
+    iso = smoothing.mg_plan(mesh, cell_size=[1.0, 1.0] * 4)
+    assert iso[1] == [(33, 33)] * 4
+    thin_j = smoothing.mg_plan(mesh, cell_size=[1.0, 0.25] * 4)   # j spacing 4x finer: only j is halved until the cells are square
+    assert thin_j[1] == [(65, 33)] * 4 and thin_j[2] == [(65, 17)] * 4 and thin_j[3] == [(33, 9)] * 4
+
+
+def test_mg_plan_stops_at_odd_extents_and_odd_range_ends(gpu_lib):
+    from turbomesh_b200 import smoothing, synthetic
+
+    plan = smoothing.mg_plan(synthetic.cascade(2, 2, 12, 9))     # 11 x 8 intervals: i can never be halved
+    assert [lv[0] for lv in plan] == [(12, 9), (12, 5), (12, 3)]
+    t106, _, _ = __import__("util").load_fixture("t106_laplace")
+    plan = smoothing.mg_plan(t106)
+    assert len(plan) == 2                                         # 220 x 40 ... intervals halve once; then range ends become odd
+    assert plan[1][0] == ((221 - 1) // 2 + 1, (41 - 1) // 2 + 1)
+
+
+def test_mg_plan_single_block_without_connections(gpu_lib):
+    from turbomesh_b200 import smoothing, synthetic
+
+    plan = smoothing.mg_plan(synthetic.single_block(129, 65))
+    assert [lv[0] for lv in plan][:3] == [(129, 65), (65, 33), (33, 17)] and plan[-1][0] == (3, 3)

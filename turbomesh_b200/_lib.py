@@ -104,6 +104,8 @@ def load():
     L.tm_dist_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t,
                                C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(TmDistPlanInfo), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int64)]
+    L.tm_mg_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t, dp, C.c_size_t,
+                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tm_mesh_destroy.argtypes = [vp]
     L.tm_mesh_destroy.restype = None
     L.tm_mesh_upload_block.argtypes = [vp, C.c_size_t, dp]

@@ -21,6 +21,7 @@
 
 #include "../../include/turbomesh_gpu.h"
 #include "kernels.cuh"
+#include "mg_plan.hpp"
 #include "partition.hpp"
 
 using namespace tmesh;
@@ -1085,7 +1086,6 @@ void run_fas_multigrid(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* 
 // connection must coarsen together); a class coarsens when every extent and every range end point in it is even, and
 // only while its mean cell size is not much larger than the smallest one (semi-coarsening).
 // =====================================================================================================
-int along_dir(uint32_t side) { return (side == TM_SIDE_I_MIN || side == TM_SIDE_I_MAX) ? 0 : 1; }
 
 // mean cell size per (block, direction), all blocks of the mesh (all-reduced over the ranks)
 std::vector<double> block_cell_sizes(tm_mesh* m) {
@@ -1224,26 +1224,11 @@ void mgb_build(tm_mesh* m) {
     if (!m->mgb.empty()) return;
     cudaStream_t s = m->stream;
     const size_t nb = m->h_blocks.size();
-    // direction classes
-    std::vector<int> parent(2 * nb);
-    for (size_t k = 0; k < parent.size(); ++k) parent[k] = int(k);
-    auto find = [&](int k) { while (parent[size_t(k)] != k) { parent[size_t(k)] = parent[size_t(parent[size_t(k)])]; k = parent[size_t(k)]; } return k; };
-    auto unite = [&](int a, int b) { a = find(a); b = find(b); if (a != b) parent[size_t(std::max(a, b))] = std::min(a, b); };
-    for (const auto& c : m->h_conns) {
-        const int b0 = int(c.ranges[0].block), b1 = int(c.ranges[1].block), a0 = along_dir(c.ranges[0].side), a1 = along_dir(c.ranges[1].side);
-        unite(2 * b0 + a0, 2 * b1 + a1);
-        unite(2 * b0 + 1 - a0, 2 * b1 + 1 - a1);
-    }
-    std::vector<double> hc(2 * nb, 0.0);  // per class root: mean cell size
-    {
-        const std::vector<double> h = block_cell_sizes(m);
-        std::vector<int> cnt(2 * nb, 0);
-        for (size_t k = 0; k < 2 * nb; ++k) { hc[size_t(find(int(k)))] += h[k]; cnt[size_t(find(int(k)))] += 1; }
-        for (size_t k = 0; k < 2 * nb; ++k) if (cnt[k]) hc[k] /= double(cnt[k]);
-    }
+    // the hierarchy is planned on the host (mg_plan.hpp); here its levels get their device meshes and transfer tables
+    std::vector<MgPlanLevel> plan = plan_multigrid(m->h_blocks, m->h_conns, m->h_bcs, block_cell_sizes(m));
     {
         std::unique_ptr<MgbLevel> L0(new MgbLevel());
-        L0->blocks = m->h_blocks; L0->conns = m->h_conns; L0->bcs = m->h_bcs;
+        L0->blocks = plan[0].blocks; L0->conns = plan[0].conns; L0->bcs = plan[0].bcs;
         L0->tan_i.assign(nb, 1.0); L0->tan_j.assign(nb, 1.0);
         m->mgb.push_back(std::move(L0));
     }
@@ -1255,51 +1240,14 @@ void mgb_build(tm_mesh* m) {
         p2p_add_tmp(m, *rp);
     }
     const double n0 = double(m->topo.n_nodes);
-    for (int level = 0; level < 20; ++level) {
+    for (size_t level = 1; level < plan.size(); ++level) {
         MgbLevel& F = *m->mgb.back();
-        std::vector<uint8_t> ok(2 * nb, 1);
-        auto veto = [&](size_t block, int dir) { ok[size_t(find(int(2 * block) + dir))] = 0; };
-        for (size_t b = 0; b < nb; ++b) {
-            if ((F.blocks[b].ni - 1) % 2 || (F.blocks[b].ni - 1) / 2 < 2) veto(b, 0);
-            if ((F.blocks[b].nj - 1) % 2 || (F.blocks[b].nj - 1) / 2 < 2) veto(b, 1);
-        }
-        auto check_range = [&](const tm_range& r, uint64_t min_span) {
-            const uint64_t span = r.start > r.end ? r.start - r.end : r.end - r.start;
-            if (r.start % 2 || r.end % 2 || span < min_span) veto(size_t(r.block), along_dir(r.side));
-        };
-        for (const auto& c : F.conns) { check_range(c.ranges[0], 4); check_range(c.ranges[1], 4); }
-        for (const auto& c : F.bcs) check_range(c.range, 2);
-        double h_min = 0.0;
-        for (size_t k = 0; k < 2 * nb; ++k)
-            if (find(int(k)) == int(k) && ok[k] && (h_min == 0.0 || hc[k] < h_min)) h_min = hc[k];
-        if (h_min == 0.0) break;  // nothing can be coarsened any further
-        std::vector<uint8_t> go(2 * nb, 0);
-        for (size_t k = 0; k < 2 * nb; ++k)
-            if (find(int(k)) == int(k) && ok[k] && hc[k] <= h_min / 0.6) go[k] = 1;
+        F.fi = plan[level - 1].fi; F.fj = plan[level - 1].fj;
         std::unique_ptr<MgbLevel> C(new MgbLevel());
-        F.fi.resize(nb); F.fj.resize(nb);
-        C->blocks.resize(nb);
-        for (size_t b = 0; b < nb; ++b) {
-            F.fi[b] = go[size_t(find(int(2 * b)))] ? 2 : 1;
-            F.fj[b] = go[size_t(find(int(2 * b) + 1))] ? 2 : 1;
-            C->blocks[b] = tm_block{(F.blocks[b].ni - 1) / uint64_t(F.fi[b]) + 1, (F.blocks[b].nj - 1) / uint64_t(F.fj[b]) + 1, nullptr};
-        }
-        auto coarse_range = [&](tm_range r) {
-            const uint64_t f = uint64_t(along_dir(r.side) == 0 ? F.fi[size_t(r.block)] : F.fj[size_t(r.block)]);
-            r.start /= f; r.end /= f;
-            return r;
-        };
-        C->conns = F.conns;
-        for (auto& c : C->conns) { c.ranges[0] = coarse_range(c.ranges[0]); c.ranges[1] = coarse_range(c.ranges[1]); }
-        C->bcs = F.bcs;
-        for (auto& c : C->bcs) c.range = coarse_range(c.range);
-        C->topo.min_conn_nodes = 3;
-        try {
-            C->topo.build(C->blocks.data(), nb, C->conns.data(), C->conns.size(), C->bcs.data(), C->bcs.size());
-        } catch (const Error&) {  // a topology the row construction cannot express at this resolution: stop coarsening here
-            F.fi.clear(); F.fj.clear();
-            break;
-        }
+        C->blocks = std::move(plan[level].blocks);
+        C->conns = std::move(plan[level].conns);
+        C->bcs = std::move(plan[level].bcs);
+        C->topo = std::move(plan[level].topo);
         C->work = double(C->topo.n_nodes) / n0;
         // Rows next to a sliding side: the Galerkin coarse operator (restriction weights 1/2, 1/2, 1/4 over the first three
         // rows, boundary unknown eliminated) carries 5/4 of the tangential term of the level below; f' = f/2 + 3/4.
@@ -1358,7 +1306,6 @@ void mgb_build(tm_mesh* m) {
         const Topology& TF = m->mgb.size() == 1 ? m->topo : F.topo;
         RankList& RF = m->mgb.size() == 1 ? m->ranks : F.ranks;
         for (size_t q = 0; q < RF.size(); ++q) mgb_build_transfer(m, TF, F, *RF[q], C->topo, *C, *C->ranks[q]);
-        for (size_t k = 0; k < 2 * nb; ++k) if (go[k]) hc[k] *= 2.0;
         m->mgb.push_back(std::move(C));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -2096,6 +2043,29 @@ int tm_dist_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* c
             for (int p = 0; p < n_ranks; ++p) { counts[2 * p] = int64_t(L.ghost_ids[size_t(p)].size()); counts[2 * p + 1] = int64_t(L.send_ids[size_t(p)].size()); }
         if (ghost_ids) { size_t k = 0; for (const auto& v : L.ghost_ids) for (int64_t g : v) ghost_ids[k++] = g; }
         if (send_ids) { size_t k = 0; for (const auto& v : L.send_ids) for (int64_t g : v) send_ids[k++] = g; }
+    });
+}
+
+int tm_mg_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections, const tm_condition* conditions,
+               size_t n_conditions, const double* cell_size, size_t max_levels, uint64_t* n_levels, uint64_t* sizes) {
+    return guarded([&] {
+        if (!blocks || !n_levels) TM_THROW(TM_ERR_INVALID_ARGUMENT, "blocks / n_levels is NULL");
+        if ((n_connections && !connections) || (n_conditions && !conditions)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "NULL connection / condition array");
+        Topology T;  // validates the fine topology exactly like tm_mesh_create
+        T.build(blocks, n_blocks, connections, n_connections, conditions, n_conditions);
+        std::vector<tm_block> b(blocks, blocks + n_blocks);
+        std::vector<tm_connection> c(connections, connections + n_connections);
+        std::vector<tm_condition> k(conditions, conditions + n_conditions);
+        std::vector<double> h;
+        if (cell_size) h.assign(cell_size, cell_size + 2 * n_blocks);
+        const std::vector<MgPlanLevel> plan = plan_multigrid(b, c, k, h);
+        *n_levels = plan.size();
+        if (sizes)
+            for (size_t l = 0; l < plan.size() && l < max_levels; ++l)
+                for (size_t q = 0; q < n_blocks; ++q) {
+                    sizes[(l * n_blocks + q) * 2] = plan[l].blocks[q].ni;
+                    sizes[(l * n_blocks + q) * 2 + 1] = plan[l].blocks[q].nj;
+                }
     });
 }
 

@@ -327,6 +327,21 @@ def dist_plan(mesh, owner, rank: int, n_ranks: int) -> dict:
     return out
 
 
+def mg_plan(mesh, cell_size=None, max_levels: int = 32):
+    """Host-only plan of the multigrid hierarchy (``tm_mg_plan``): list over levels of the (ni, nj) of every block."""
+    L = _lib.load()
+    cm = _CMesh(mesh, with_coords=False)
+    n = C.c_uint64()
+    sizes = (C.c_uint64 * (max_levels * max(cm.nb, 1) * 2))()
+    h = None
+    if cell_size is not None:
+        hs = np.ascontiguousarray(cell_size, dtype=np.float64).ravel()
+        assert hs.size == 2 * cm.nb
+        h = _dp(hs)
+    check(L.tm_mg_plan(cm.blocks, cm.nb, cm.conns, cm.nc, cm.bcs, cm.nbc, h, max_levels, C.byref(n), sizes))
+    return [[(int(sizes[(l * cm.nb + b) * 2]), int(sizes[(l * cm.nb + b) * 2 + 1])) for b in range(cm.nb)] for l in range(min(int(n.value), max_levels))]
+
+
 def kernel_launch_count() -> int:
     return int(_lib.load().tm_kernel_launch_count())
 
