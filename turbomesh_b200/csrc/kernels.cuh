@@ -117,8 +117,17 @@ __global__ void __launch_bounds__(TILE_J) tfi_kernel(int ni, int nj, const doubl
         const double2 xi0 = ldg2(x_i_min + i), xim = ldg2(x_i_max + i);
         const double ds = __dsub_rn(s2_i, s1_i);
         // tfi.zig:185-186 (the two denominators are the same product with the factors swapped; IEEE multiplication commutes)
-        const double u = __ddiv_rn(__dadd_rn(__dmul_rn(omt1, s1_i), __dmul_rn(t1_j, s2_i)), __dsub_rn(1.0, __dmul_rn(ds, dt)));
-        const double v = __ddiv_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, s1_i), t1_j), __dmul_rn(s1_i, t2_j)), __dsub_rn(1.0, __dmul_rn(dt, ds)));
+        // When the two clusterings of a direction coincide (s1 == s2 or t1 == t2 -- every synthetic workload, most O4H
+        // blocks) the product is exactly 0, the denominator exactly 1 and x / 1 == x bit for bit: the two IEEE divisions,
+        // which otherwise make this kernel fp64-bound instead of store-bound, are skipped.  ds is warp-uniform.
+        const double prod = __dmul_rn(ds, dt);
+        double u = __dadd_rn(__dmul_rn(omt1, s1_i), __dmul_rn(t1_j, s2_i));
+        double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, s1_i), t1_j), __dmul_rn(s1_i, t2_j));
+        if (prod != 0.0) {
+            const double den = __dsub_rn(1.0, prod);
+            u = __ddiv_rn(u, den);
+            v = __ddiv_rn(v, den);
+        }
         const double omu = __dsub_rn(1.0, u), omv = __dsub_rn(1.0, v);
         const double uv = __dmul_rn(u, v), u_omv = __dmul_rn(u, omv), omu_v = __dmul_rn(omu, v), omu_omv = __dmul_rn(omu, omv);
         double2 r;
