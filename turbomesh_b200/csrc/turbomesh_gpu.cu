@@ -247,6 +247,7 @@ struct RankMesh {
     std::vector<BlockXfer> xfer_blocks;      // own blocks: this level -> next coarser level
     DevBuf<BlockXfer> d_xfer_blocks;
     int xf_ni_f = 0, xf_nj_f = 0, xf_ni_c = 0, xf_nj_c = 0;  // largest extents over the own blocks (grid of the batched transfer kernels)
+    bool xf_all_2x2 = false;                                 // every own block halves both directions
     DevBuf<double> soa_stage;                // device staging of the structured (SoA) output
     bool replicated = false;                 // multigrid level held in full by every rank (no halo exchange, redundant work)
     DevBuf<SmallNode> d_small;               // tiny levels: flat interior node list of winslow_small_level_kernel
@@ -1213,7 +1214,9 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
     rf.d_rrows.upload(rows, m->stream);
     rf.d_xfer_blocks.upload(rf.xfer_blocks, m->stream);
     rf.xf_ni_f = rf.xf_nj_f = rf.xf_ni_c = rf.xf_nj_c = 0;
+    rf.xf_all_2x2 = !rf.xfer_blocks.empty();
     for (const BlockXfer& b : rf.xfer_blocks) {
+        rf.xf_all_2x2 = rf.xf_all_2x2 && b.fi == 2 && b.fj == 2;
         rf.xf_ni_f = std::max(rf.xf_ni_f, b.ni_f); rf.xf_nj_f = std::max(rf.xf_nj_f, b.nj_f);
         rf.xf_ni_c = std::max(rf.xf_ni_c, b.ni_c); rf.xf_nj_c = std::max(rf.xf_nj_c, b.nj_c);
     }
@@ -1311,6 +1314,18 @@ void mgb_build(tm_mesh* m) {
     CUDA_TRY(cudaStreamSynchronize(s));
 }
 
+// fine += interpolated (u_c - e_c) on the interior nodes of every own block
+void launch_prolong_blocks(tm_mesh* m, RankMesh& rf, const double2* u_c, const double2* e_c, double2* u_f) {
+    if (rf.xfer_blocks.empty()) return;
+    if (rf.xf_all_2x2) {
+        dim3 g((rf.xf_nj_c - 1 + 127) / 128, rf.xf_ni_c - 1, unsigned(rf.xfer_blocks.size()));
+        LAUNCH(mgb_prolong_2x2_kernel, g, 128, m->stream, (const BlockXfer*)rf.d_xfer_blocks.p, u_c, e_c, u_f);
+    } else {
+        dim3 g((rf.xf_nj_f + 127) / 128, (rf.xf_ni_f + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
+        LAUNCH(mgb_prolong_kernel, g, 128, m->stream, (const BlockXfer*)rf.d_xfer_blocks.p, u_c, e_c, u_f);
+    }
+}
+
 // Anderson acceleration at the restriction point of a cycle (see kernels.cuh): sample, least squares over the last <= 3
 // iterations, interpolate the extrapolation to the fine mesh.
 void anderson_step(tm_mesh* m, RankList& RF, RankList& RC) {
@@ -1361,10 +1376,7 @@ void anderson_step(tm_mesh* m, RankList& RF, RankList& RC) {
         LAUNCH(aa_solve_kernel, 1, 32, s, (const double*)rc.aa_gram.p, q_res, rc.aa_coef.p);
         LAUNCH(aa_combine_kernel, rc.vec_grid, 256, s, rc.L.n_own, fields(rc), (const double*)rc.aa_coef.p, rc.aa_D.p, rc.aa_X.p);
         if (q_res < 2) continue;  // nothing to extrapolate from yet (d = 0)
-        if (!rf.xfer_blocks.empty()) {
-            dim3 g((rf.xf_nj_f + 127) / 128, (rf.xf_ni_f + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
-            LAUNCH(mgb_prolong_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)rc.aa_D.p, (const double2*)rc.mg_zero.p, xcur(rf));
-        }
+        launch_prolong_blocks(m, rf, (const double2*)rc.aa_D.p, (const double2*)rc.mg_zero.p, xcur(rf));
         if (rf.n_bnd_rows > 0)
             LAUNCH(mgb_prolong_rows_kernel, (rf.n_bnd_rows + 127) / 128, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, int(rf.xfer_blocks.size()),
                    (const SmoothedRow*)rf.d_srows.p, int(rf.L.smoothed.size()), (const JunctionRow*)rf.d_jrows.p, int(rf.L.junction_rows.size()),
@@ -1486,10 +1498,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             for (size_t q = 0; q < RF.size(); ++q) {
                 RankMesh& rf = *RF[q];
                 RankMesh& rc = *RC[q];
-                if (!rf.xfer_blocks.empty()) {
-                    dim3 g((rf.xf_nj_f + 127) / 128, (rf.xf_ni_f + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
-                    LAUNCH(mgb_prolong_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)xcur(rc), (const double2*)rc.E(), xcur(rf));
-                }
+                launch_prolong_blocks(m, rf, (const double2*)xcur(rc), (const double2*)rc.E(), xcur(rf));
                 if (rf.n_bnd_rows > 0)
                     LAUNCH(mgb_prolong_rows_kernel, (rf.n_bnd_rows + 127) / 128, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, int(rf.xfer_blocks.size()),
                            (const SmoothedRow*)rf.d_srows.p, int(rf.L.smoothed.size()), (const JunctionRow*)rf.d_jrows.p, int(rf.L.junction_rows.size()),
