@@ -1,3 +1,4 @@
+"""Convergence histories of the (Anderson-accelerated) multigrid on 8x8 / 2x8 / 4x4 block cascades; TM_MG_AA=0 for the plain cycle."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turbomesh_b200 import smoothing, synthetic

@@ -1,3 +1,4 @@
+"""GPU vs wall time per multigrid cycle on a 64-block mesh (launch-count sensitivity)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turbomesh_b200 import smoothing, synthetic

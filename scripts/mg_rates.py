@@ -1,3 +1,4 @@
+"""Convergence factor per V-cycle of the multi-block multigrid over a set of topologies and smoother settings (development aid)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -1,10 +1,11 @@
+"""Multigrid on the reference T106 O4H topology against the Picard fixed point (development aid; the test lives in tests/test_gpu_o4h.py)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from util import load_fixture, chord_of
 from turbomesh_b200 import smoothing, synthetic
-for name in ("t106_laplace", "ls89_x4_white"):
+for name in ("t106_laplace",):
     spec, z, meta = load_fixture(name)
     mesh = synthetic.materialize(spec, smoothing.tfi_block)
     with smoothing.DeviceMesh(mesh) as dm:

@@ -1,3 +1,4 @@
+"""Structured (SoA) output of an 8192^2 block: transpose on the device + D2H into pinned memory."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -1,3 +1,4 @@
+"""Sweep time of the cascade workload for two block sizes (alignment check)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from turbomesh_b200 import smoothing, synthetic

@@ -1065,6 +1065,21 @@ __global__ void mg_restrict_kernel(MgLevelDims d, const double2* __restrict__ u_
     res_c[k] = r;
 }
 
+// Anderson acceleration of the single-block cycle (see aa_* kernels below): the fine iterate sampled by interpolation on
+// the nodes of level 1; g_new = sample, f_new = sample - x_prev.  One thread per coarse node.
+__global__ void mg_sample_kernel(MgLevelDims d, const double2* __restrict__ u_f, const double2* __restrict__ x_prev, double2* __restrict__ g_new,
+                                 double2* __restrict__ f_new) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x, I = blockIdx.y;
+    if (J >= d.nj_c || I >= d.ni_c) return;
+    const double xi = fmin(I * d.r_i, (double)(d.ni_f - 1)), eta = fmin(J * d.r_j, (double)(d.nj_f - 1));
+    const int i0 = min((int)xi, d.ni_f - 2), j0 = min((int)eta, d.nj_f - 2);
+    const size_t k = (size_t)I * d.nj_c + J;
+    const double2 g = bilerp(u_f, d.nj_f, i0, j0, xi - i0, eta - j0);
+    const double2 x = x_prev[k];
+    g_new[k] = g;
+    f_new[k] = make_double2(g.x - x.x, g.y - x.y);
+}
+
 // coarse right-hand side of FAS: tau_c = row_c(I u_f) + restricted residual.  `rel_c` holds row_c(I u_f) (MODE_REL output)
 // on interior nodes; `res_c` the scaled restricted residual; the result overwrites res_c.
 __global__ void mg_coarse_rhs_kernel(int ni, int nj, const double2* __restrict__ rel_c, double2* __restrict__ res_c) {

@@ -208,6 +208,12 @@ struct MgLevel {
     DevBuf<double2> U, V, rhs, tmp, E;       // iterate ping-pong, tau term, scratch (row / residual), restricted iterate
     DevBuf<Tile> tiles;
     DevBuf<DevBlock> blk;
+    // level 1 only: Anderson acceleration history on this level's nodes (see anderson_step)
+    std::vector<std::unique_ptr<DevBuf<double2>>> aa_G, aa_F;
+    DevBuf<double2> aa_X, aa_D, aa_zero;
+    DevBuf<double> aa_part, aa_gram, aa_coef;
+    int aa_head = -1, aa_count = 0;
+    bool aa_have_x = false;
 };
 
 // Everything one rank keeps on its GPU.  A distributed mesh holds exactly one; the in-process emulation of several
@@ -957,6 +963,18 @@ void mg_build(tm_mesh* m, RankMesh& r) {
             L->U.alloc(n); L->V.alloc(n); L->rhs.alloc(n); L->E.alloc(n);
             L->U.zero(s); L->V.zero(s); L->rhs.zero(s); L->E.zero(s);
         }
+        if (l == 1 && m->mg_aa) {
+            for (int k = 0; k < AA_MAX; ++k)
+                for (auto* ring : {&L->aa_G, &L->aa_F}) {
+                    ring->emplace_back(new DevBuf<double2>());
+                    ring->back()->alloc(n);
+                    ring->back()->zero(s);
+                }
+            for (DevBuf<double2>* v : {&L->aa_X, &L->aa_D, &L->aa_zero}) { v->alloc(n); v->zero(s); }
+            L->aa_part.alloc(size_t(r.vec_grid) * 6);
+            L->aa_gram.alloc(6); L->aa_gram.zero(s);
+            L->aa_coef.alloc(AA_MAX); L->aa_coef.zero(s);
+        }
         const double hi = len_i / double(ni - 1), hj = len_j / double(nj - 1);
         bool do_i = ni >= 9, do_j = nj >= 9;
         if (do_i && do_j) {
@@ -1007,6 +1025,34 @@ void mg_residual(tm_mesh* m, RankMesh& r, MgLevel& L, const double2* u, int leve
 }
 
 // V(nu,nu) cycles of the full approximation scheme until the fine-level Jacobi update drops below stop_max_update
+// Anderson acceleration of the single-block cycle on the nodes of level 1 (same scheme as anderson_step for multi-block
+// meshes; the levels are not nested here, so the samples and the extrapolation travel by interpolation)
+void anderson_step_single(tm_mesh* m, RankMesh& r, MgLevel& F, MgLevel& C, double2* u_f) {
+    cudaStream_t s = m->stream;
+    const int64_t n = int64_t(C.ni) * C.nj;
+    const bool have_x = C.aa_have_x;
+    if (have_x) { C.aa_head = (C.aa_head + 1) % AA_MAX; C.aa_count = std::min(C.aa_count + 1, AA_MAX); }
+    double2* g_new = have_x ? C.aa_G[size_t(C.aa_head)]->p : C.aa_X.p;
+    double2* f_new = have_x ? C.aa_F[size_t(C.aa_head)]->p : C.aa_D.p;
+    dim3 gc((C.nj + 127) / 128, C.ni);
+    LAUNCH(mg_sample_kernel, gc, 128, s, F.to_coarse, (const double2*)u_f, (const double2*)C.aa_X.p, g_new, f_new);
+    C.aa_have_x = true;
+    if (!have_x) return;
+    AaFields h{};
+    h.q = C.aa_count;
+    for (int i = 0; i < h.q; ++i) {
+        const size_t slot = size_t((C.aa_head + AA_MAX - (h.q - 1) + i) % AA_MAX);
+        h.G[i] = C.aa_G[slot]->p; h.F[i] = C.aa_F[slot]->p;
+    }
+    LAUNCH(aa_gram_kernel, r.vec_grid, 256, s, n, h, C.aa_part.p);
+    LAUNCH(aa_reduce_kernel, 1, 192, s, (const double*)C.aa_part.p, r.vec_grid, C.aa_gram.p);
+    LAUNCH(aa_solve_kernel, 1, 32, s, (const double*)C.aa_gram.p, h.q, C.aa_coef.p);
+    LAUNCH(aa_combine_kernel, r.vec_grid, 256, s, n, h, (const double*)C.aa_coef.p, C.aa_D.p, C.aa_X.p);
+    if (h.q < 2) return;
+    dim3 gf((F.nj + 127) / 128, F.ni);
+    LAUNCH(mg_prolong_kernel, gf, 128, s, F.to_coarse, (const double2*)C.aa_D.p, (const double2*)C.aa_zero.p, u_f);
+}
+
 void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st);
 bool mg_single_block_case(const tm_mesh* m) {
     return m->n_ranks == 1 && m->topo.blocks.size() == 1 && m->topo.smoothed.empty() && m->topo.junction_rows.empty() && m->topo.sliding.empty() &&
@@ -1034,6 +1080,7 @@ void run_fas_multigrid(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* 
             MgLevel& C = *r.mg[size_t(l) + 1];
             const double w = double(F.ni) * F.nj / (double(r.mg[0]->ni) * r.mg[0]->nj);
             mg_smooth(m, r, F, &U[size_t(l)], &V[size_t(l)], l, nu, o->omega, false);
+            if (l == 0 && !C.aa_G.empty()) anderson_step_single(m, r, F, C, U[0]);
             mg_residual(m, r, F, U[size_t(l)], l);
             fine_work += w * double(nu + 1);
             dim3 gc((C.nj + 127) / 128, C.ni);
@@ -1901,6 +1948,8 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
             white_step(m, false, o->white_ds_target, o->white_theta_target);
         }
         if (o->solver == TM_SOLVER_FAS_MULTIGRID && m->n_ranks == 1 && m->topo.blocks.size() == 1) mg_build(m, *m->ranks[0]);
+        for (auto& rp : m->ranks)
+            for (auto& lv : rp->mg) { lv->aa_head = -1; lv->aa_count = 0; lv->aa_have_x = false; }
         for (auto& lv : m->mgb)
             for (auto& rp : lv->ranks) {
                 rp->mg_primed = false;

@@ -19,7 +19,7 @@ pub const tm_connection = extern struct { ranges: [2]tm_range, has_periodicity: 
 pub const tm_condition = extern struct { range: tm_range, kind: u32, _pad: u32 = 0 };
 pub const tm_smooth_options = extern struct {
     struct_size: u32,
-    solver: u32, // 0 = picard_bicgstab, 1 = relax
+    solver: u32, // 0 = picard_bicgstab, 1 = relax, 2 = multigrid (FAS V-cycles, any multi-block topology, Laplace control function)
     iterations: u64,
     control_function: u32, // 0 = laplace, 1 = white
     fail_on_no_convergence: u32,
@@ -53,6 +53,17 @@ pub extern fn tm_tfi_block(ni: u64, nj: u64, x_i_min: [*]const f64, x_i_max: [*]
 pub extern fn tm_smooth_mesh(blocks: [*]tm_block, n_blocks: usize, connections: ?[*]const tm_connection, n_connections: usize, conditions: ?[*]const tm_condition, n_conditions: usize, opts: *const tm_smooth_options, stats: ?*tm_smooth_stats) callconv(.c) c_int;
 pub extern fn tm_smooth_options_default(opts: *tm_smooth_options) callconv(.c) void;
 pub extern fn tm_last_error() callconv(.c) [*:0]const u8;
+
+// Device-resident handle (viewers, repeated smoothing, structured output without an AoS round trip); see the header.
+pub const tm_mesh = opaque {};
+pub extern fn tm_mesh_create(blocks: [*]const tm_block, n_blocks: usize, connections: ?[*]const tm_connection, n_connections: usize, conditions: ?[*]const tm_condition, n_conditions: usize, device: c_int, stream: ?*anyopaque, out: *?*tm_mesh) callconv(.c) c_int;
+pub extern fn tm_mesh_destroy(mesh: ?*tm_mesh) callconv(.c) void;
+pub extern fn tm_mesh_begin_smoothing(mesh: *tm_mesh, opts: *const tm_smooth_options) callconv(.c) c_int;
+pub extern fn tm_mesh_smooth(mesh: *tm_mesh, opts: *const tm_smooth_options, stats: ?*tm_smooth_stats) callconv(.c) c_int;
+pub extern fn tm_mesh_download_block(mesh: *tm_mesh, block: usize, xy: [*]f64) callconv(.c) c_int;
+/// cgns.zig:69-101 / 110-161 on the device: x[j*ni + i], y[j*ni + i] (field 0 = coordinates, 1 = control function P,Q)
+pub extern fn tm_mesh_download_block_soa(mesh: *tm_mesh, block: usize, field: c_int, x: [*]f64, y: [*]f64) callconv(.c) c_int;
+pub extern fn tm_release_cached_memory() callconv(.c) void;
 
 pub const Error = error{ CudaBackendFailed, CudaNoDevice, CudaBadTopology, CudaNotConverged };
 
