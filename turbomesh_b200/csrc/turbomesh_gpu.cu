@@ -336,6 +336,7 @@ struct tm_mesh {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t comm_stream = nullptr;          // the halo exchange of a sweep runs here, next to the bulk of the interior
     cudaEvent_t ev_rim = nullptr, ev_x = nullptr;
+    bool use_graph = true;                       // TM_GRAPH=0: launch the BiCGStab iteration kernel by kernel
     bool overlap = true;                         // TM_OVERLAP=0: exchange on the main stream after the whole sweep
     bool ev_x_valid = false, overlap_pending = false;
     std::vector<tm_block> h_blocks;              // host copies of the topology description (xy = NULL): multigrid coarsening
@@ -826,14 +827,10 @@ void apply_operator(tm_mesh* m, GetIn in, GetOut out, GetDot dot) {
 }
 
 // BiCGStab iterations (BiCGStab.zig:303-366) on the row-scaled system until both components report done.
-void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
+// one BiCGStab iteration (BiCGStab.zig:303-366): ~12 small launches, all scalars on the device
+void bicgstab_iteration(tm_mesh* m, const tm_smooth_options* o) {
     cudaStream_t s = m->stream;
-    const int check_every = 8;
-    for (uint64_t k = 0;; ++k) {
-        if (k % check_every == 0) {
-            fetch_ctl(m);
-            if (m->h_ctl->done[0] && m->h_ctl->done[1]) break;
-        }
+    {
         for (auto& rp : m->ranks) {
             RankMesh& r = *rp;
             LAUNCH(bicg_p_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const SolveCtl*)r.d_ctl.p, (const double2*)r.kr.p, r.kp.p, (const double2*)r.kv.p);
@@ -855,8 +852,53 @@ void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st)
                    r.kd.p, (const double2*)r.krhat.p, r.part_vec.p);
         }
         launch_reduce(m, RED_NORM_R, o, false);
-        st->operator_applications += 2;
     }
+}
+
+// Iterates until both components report done.  On one GPU the iteration is captured once into a CUDA graph and replayed:
+// on the reference's own mesh sizes (1e4..1e5 nodes) the solver is bound by launch cadence, not by bandwidth.
+void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st) {
+    cudaStream_t s = m->stream;
+    const int check_every = 8;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches_per_iteration = 0;
+    if (m->n_ranks == 1 && m->use_graph) {
+        const uint64_t before = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+            bicgstab_iteration(m, o);
+        } catch (...) {
+            cudaStreamEndCapture(s, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        CUDA_TRY(cudaStreamEndCapture(s, &graph));
+        launches_per_iteration = g_launches.load() - before;
+        g_launches.store(before);  // captured, not run
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CUDA_TRY(e);
+    }
+    try {
+        for (uint64_t k = 0;; ++k) {
+            if (k % check_every == 0) {
+                fetch_ctl(m);
+                if (m->h_ctl->done[0] && m->h_ctl->done[1]) break;
+            }
+            if (exec) {
+                CUDA_TRY(cudaGraphLaunch(exec, s));
+                g_launches.fetch_add(launches_per_iteration, std::memory_order_relaxed);
+            } else {
+                bicgstab_iteration(m, o);
+            }
+            st->operator_applications += 2;
+        }
+    } catch (...) {
+        if (exec) cudaGraphExecDestroy(exec);
+        throw;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
 }
 
 // One outer (Picard) iteration = the reference's fill + solve(x) + solve(y) (smooth.zig:104-154), with the two
@@ -1629,6 +1671,7 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_rim, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
     if (const char* e = std::getenv("TM_OVERLAP")) m->overlap = std::atoi(e) != 0;
+    if (const char* e = std::getenv("TM_GRAPH")) m->use_graph = std::atoi(e) != 0;
     CUDA_TRY(cudaEventCreate(&m->ev0));
     CUDA_TRY(cudaEventCreate(&m->ev1));
     m->h_ctl = acquire_pinned_ctl();
