@@ -1301,7 +1301,8 @@ __global__ void mgb_prolong_rows_kernel(const BlockXfer* __restrict__ blocks, in
 // last q <= 3 iterations and the new iterate is sum alpha_j G_j: the difference to the current one lives on level 1 and is
 // interpolated to the fine mesh like a coarse-grid correction.
 // ---------------------------------------------------------------------------------------------------
-constexpr int AA_MAX = 3;
+constexpr int AA_MAX = 5;                            // residuals in the window
+constexpr int AA_GRAM = AA_MAX * (AA_MAX + 1) / 2;   // upper triangle of the Gram matrix, row-major
 struct AaFields { double2* G[AA_MAX]; double2* F[AA_MAX]; int q; };  // chronological, index q-1 = newest
 // samples the fine iterate on the level-1 nodes of one block: G_new = sample, F_new = sample - X_prev
 __global__ void __launch_bounds__(128) aa_sample_kernel(const BlockXfer* __restrict__ blocks /* one per blockIdx.z */, const double2* __restrict__ u_f,
@@ -1315,31 +1316,36 @@ __global__ void __launch_bounds__(128) aa_sample_kernel(const BlockXfer* __restr
     g_new[kc] = g;
     f_new[kc] = make_double2(g.x - x.x, g.y - x.y);
 }
-__global__ void __launch_bounds__(256) aa_gram_kernel(int64_t n, AaFields h, double* __restrict__ partials /* grid x 6 */) {
-    double g[6] = {0, 0, 0, 0, 0, 0};  // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+__global__ void __launch_bounds__(256) aa_gram_kernel(int64_t n, AaFields h, double* __restrict__ partials /* grid x AA_GRAM */) {
+    double g[AA_GRAM];
+#pragma unroll
+    for (int e = 0; e < AA_GRAM; ++e) g[e] = 0.0;
     for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
         double2 f[AA_MAX];
 #pragma unroll
         for (int i = 0; i < AA_MAX; ++i) f[i] = i < h.q ? h.F[i][k] : make_double2(0.0, 0.0);
-        g[0] += f[0].x * f[0].x + f[0].y * f[0].y; g[1] += f[0].x * f[1].x + f[0].y * f[1].y; g[2] += f[0].x * f[2].x + f[0].y * f[2].y;
-        g[3] += f[1].x * f[1].x + f[1].y * f[1].y; g[4] += f[1].x * f[2].x + f[1].y * f[2].y; g[5] += f[2].x * f[2].x + f[2].y * f[2].y;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < AA_MAX; ++a)
+#pragma unroll
+            for (int c = a; c < AA_MAX; ++c) g[e++] += f[a].x * f[c].x + f[a].y * f[c].y;
     }
-    __shared__ double sh[6][8];
+    __shared__ double sh[AA_GRAM][8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { g[i] = warp_sum(g[i]); if (lane == 0) sh[i][w] = g[i]; }
+    for (int e = 0; e < AA_GRAM; ++e) { g[e] = warp_sum(g[e]); if (lane == 0) sh[e][w] = g[e]; }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < AA_GRAM) {
         double s = 0.0;
         for (int q = 0; q < 8; ++q) s += sh[threadIdx.x][q];
-        partials[(size_t)blockIdx.x * 6 + threadIdx.x] = s;
+        partials[(size_t)blockIdx.x * AA_GRAM + threadIdx.x] = s;
     }
 }
-__global__ void aa_reduce_kernel(const double* __restrict__ partials, int n_part, double* __restrict__ gram) {  // one CTA of 192 threads, fixed order
-    __shared__ double sh[6][32];
+__global__ void aa_reduce_kernel(const double* __restrict__ partials, int n_part, double* __restrict__ gram) {  // one CTA of 32 * AA_GRAM threads, fixed order
+    __shared__ double sh[AA_GRAM][32];
     const int e = threadIdx.x / 32, l = threadIdx.x & 31;
     double s = 0.0;
-    for (int k = l; k < n_part; k += 32) s += partials[(size_t)k * 6 + e];
+    for (int k = l; k < n_part; k += 32) s += partials[(size_t)k * AA_GRAM + e];
     sh[e][l] = s;
     __syncthreads();
     if (l == 0) { double t = 0.0; for (int q = 0; q < 32; ++q) t += sh[e][q]; gram[e] = t; }
@@ -1367,11 +1373,16 @@ __global__ void aa_solve_kernel(const double* __restrict__ gram, int q, double* 
     for (int i = 0; i < AA_MAX; ++i) alpha[i] = 0.0;
     alpha[q - 1] = 1.0;
     if (q < 2) return;
-    double G[3][3] = {{gram[0], gram[1], gram[2]}, {gram[1], gram[3], gram[4]}, {gram[2], gram[4], gram[5]}};
+    double G[AA_MAX][AA_MAX];
+    {
+        int e = 0;
+        for (int a = 0; a < AA_MAX; ++a)
+            for (int c = a; c < AA_MAX; ++c) { G[a][c] = gram[e]; G[c][a] = gram[e]; ++e; }
+    }
     if (G[q - 1][q - 1] > 4.0 * G[q - 2][q - 2]) return;  // the residual doubled: the history is not trustworthy
-    double z[3] = {1.0, 1.0, 1.0};
+    double z[AA_MAX];
     double tr = 0.0;
-    for (int i = 0; i < q; ++i) tr += G[i][i];
+    for (int i = 0; i < q; ++i) { z[i] = 1.0; tr += G[i][i]; }
     if (!(tr > 0.0)) return;
     for (int i = 0; i < q; ++i) G[i][i] += 1e-12 * tr;   // Tikhonov guard against a degenerate window
     for (int c = 0; c < q; ++c) {                        // Gaussian elimination with partial pivoting, G z = 1
@@ -1393,7 +1404,7 @@ __global__ void aa_solve_kernel(const double* __restrict__ gram, int q, double* 
     double sum = 0.0;
     for (int i = 0; i < q; ++i) sum += z[i];
     if (!(fabs(sum) > 1e-300)) return;
-    double a[3];
+    double a[AA_MAX];
     for (int i = 0; i < q; ++i) { a[i] = z[i] / sum; if (!(fabs(a[i]) < 20.0)) return; }
     for (int i = 0; i < q; ++i) alpha[i] = a[i];
 }

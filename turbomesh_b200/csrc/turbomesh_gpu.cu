@@ -260,7 +260,7 @@ struct RankMesh {
     int n_small = 0;
     DevBuf<unsigned long long> d_change;     // level 0: max-norm movement of the level-1 nodes between two restrictions
     bool mg_primed = false;                  // coarse levels: both ping-pong buffers hold the (constant) fixed-node values
-    // level 1 only: Anderson acceleration history (rings of AA_MAX samples G_j and residuals F_j, the accelerated state X)
+    // level 1 only: Anderson acceleration history (rings of mg_aa_window samples G_j and residuals F_j, the accelerated state X)
     std::vector<std::unique_ptr<DevBuf<double2>>> aa_G, aa_F;
     DevBuf<double2> aa_X, aa_D;
     int aa_head = -1, aa_count = 0;          // newest slot, entries in the rings
@@ -346,6 +346,7 @@ struct tm_mesh {
     int sm_count = 148;
     int64_t mg_replicate_nodes = 32768;  // multigrid levels up to this size are replicated on every rank (TM_MG_REPLICATE_NODES)
     int64_t mg_small_nodes = 4096;       // ... and up to this size swept by the single-CTA kernel (TM_MG_SMALL_NODES)
+    int mg_aa_window = 3;       // residuals kept by the Anderson acceleration (TM_MG_AA_WINDOW, 1..AA_MAX)
     bool mg_aa = true;        // Anderson acceleration of the multi-block multigrid cycle (TM_MG_AA=0 switches it off)
     int tile_rows = TILE_I;   // TM_TILE_ROWS overrides (tuning aid)
     bool use_bulk = true;     // TM_INTERIOR=regs selects the register-only interior kernel (tuning aid)
@@ -1006,15 +1007,15 @@ void mg_build(tm_mesh* m, RankMesh& r) {
             L->U.zero(s); L->V.zero(s); L->rhs.zero(s); L->E.zero(s);
         }
         if (l == 1 && m->mg_aa) {
-            for (int k = 0; k < AA_MAX; ++k)
+            for (int k = 0; k < m->mg_aa_window; ++k)
                 for (auto* ring : {&L->aa_G, &L->aa_F}) {
                     ring->emplace_back(new DevBuf<double2>());
                     ring->back()->alloc(n);
                     ring->back()->zero(s);
                 }
             for (DevBuf<double2>* v : {&L->aa_X, &L->aa_D, &L->aa_zero}) { v->alloc(n); v->zero(s); }
-            L->aa_part.alloc(size_t(r.vec_grid) * 6);
-            L->aa_gram.alloc(6); L->aa_gram.zero(s);
+            L->aa_part.alloc(size_t(r.vec_grid) * AA_GRAM);
+            L->aa_gram.alloc(AA_GRAM); L->aa_gram.zero(s);
             L->aa_coef.alloc(AA_MAX); L->aa_coef.zero(s);
         }
         const double hi = len_i / double(ni - 1), hj = len_j / double(nj - 1);
@@ -1073,7 +1074,7 @@ void anderson_step_single(tm_mesh* m, RankMesh& r, MgLevel& F, MgLevel& C, doubl
     cudaStream_t s = m->stream;
     const int64_t n = int64_t(C.ni) * C.nj;
     const bool have_x = C.aa_have_x;
-    if (have_x) { C.aa_head = (C.aa_head + 1) % AA_MAX; C.aa_count = std::min(C.aa_count + 1, AA_MAX); }
+    if (have_x) { C.aa_head = (C.aa_head + 1) % m->mg_aa_window; C.aa_count = std::min(C.aa_count + 1, m->mg_aa_window); }
     double2* g_new = have_x ? C.aa_G[size_t(C.aa_head)]->p : C.aa_X.p;
     double2* f_new = have_x ? C.aa_F[size_t(C.aa_head)]->p : C.aa_D.p;
     dim3 gc((C.nj + 127) / 128, C.ni);
@@ -1083,11 +1084,11 @@ void anderson_step_single(tm_mesh* m, RankMesh& r, MgLevel& F, MgLevel& C, doubl
     AaFields h{};
     h.q = C.aa_count;
     for (int i = 0; i < h.q; ++i) {
-        const size_t slot = size_t((C.aa_head + AA_MAX - (h.q - 1) + i) % AA_MAX);
+        const size_t slot = size_t((C.aa_head + m->mg_aa_window - (h.q - 1) + i) % m->mg_aa_window);
         h.G[i] = C.aa_G[slot]->p; h.F[i] = C.aa_F[slot]->p;
     }
     LAUNCH(aa_gram_kernel, r.vec_grid, 256, s, n, h, C.aa_part.p);
-    LAUNCH(aa_reduce_kernel, 1, 192, s, (const double*)C.aa_part.p, r.vec_grid, C.aa_gram.p);
+    LAUNCH(aa_reduce_kernel, 1, 32 * AA_GRAM, s, (const double*)C.aa_part.p, r.vec_grid, C.aa_gram.p);
     LAUNCH(aa_solve_kernel, 1, 32, s, (const double*)C.aa_gram.p, h.q, C.aa_coef.p);
     LAUNCH(aa_combine_kernel, r.vec_grid, 256, s, n, h, (const double*)C.aa_coef.p, C.aa_D.p, C.aa_X.p);
     if (h.q < 2) return;
@@ -1377,7 +1378,7 @@ void mgb_build(tm_mesh* m) {
             }
             rc.d_blocks.upload(blocks, s);
             if (m->mgb.size() == 1 && m->mg_aa) {  // this is level 1
-                for (int k = 0; k < AA_MAX; ++k)
+                for (int k = 0; k < m->mg_aa_window; ++k)
                     for (auto* ring : {&rc.aa_G, &rc.aa_F}) {
                         ring->emplace_back(new DevBuf<double2>());
                         ring->back()->alloc(size_t(std::max<int64_t>(rc.N, 1)));
@@ -1385,8 +1386,8 @@ void mgb_build(tm_mesh* m) {
                     }
                 rc.aa_X.alloc(size_t(std::max<int64_t>(rc.N, 1))); rc.aa_X.zero(s);
                 rc.aa_D.alloc(size_t(std::max<int64_t>(rc.N, 1))); rc.aa_D.zero(s);
-                rc.aa_part.alloc(size_t(rc.vec_grid) * 6);
-                rc.aa_gram.alloc(6); rc.aa_gram.zero(s);
+                rc.aa_part.alloc(size_t(rc.vec_grid) * AA_GRAM);
+                rc.aa_gram.alloc(AA_GRAM); rc.aa_gram.zero(s);
                 rc.aa_coef.alloc(AA_MAX); rc.aa_coef.zero(s);
             }
             CUDA_TRY(cudaStreamSynchronize(s));
@@ -1424,7 +1425,7 @@ void anderson_step(tm_mesh* m, RankList& RF, RankList& RC) {
     for (size_t q = 0; q < RF.size(); ++q) {
         RankMesh& rf = *RF[q];
         RankMesh& rc = *RC[q];
-        if (have_x) { rc.aa_head = (rc.aa_head + 1) % AA_MAX; rc.aa_count = std::min(rc.aa_count + 1, AA_MAX); }
+        if (have_x) { rc.aa_head = (rc.aa_head + 1) % m->mg_aa_window; rc.aa_count = std::min(rc.aa_count + 1, m->mg_aa_window); }
         // without a previous state there is no residual yet: the sample only becomes the state X
         double2* g_new = have_x ? rc.aa_G[size_t(rc.aa_head)]->p : rc.aa_X.p;
         double2* f_new = have_x ? rc.aa_F[size_t(rc.aa_head)]->p : rc.aa_D.p;
@@ -1440,7 +1441,7 @@ void anderson_step(tm_mesh* m, RankList& RF, RankList& RC) {
         AaFields h{};
         h.q = q_res;
         for (int i = 0; i < q_res; ++i) {
-            const size_t slot = size_t((rc.aa_head + AA_MAX - (q_res - 1) + i) % AA_MAX);
+            const size_t slot = size_t((rc.aa_head + m->mg_aa_window - (q_res - 1) + i) % m->mg_aa_window);
             h.G[i] = rc.aa_G[slot]->p; h.F[i] = rc.aa_F[slot]->p;
         }
         return h;
@@ -1448,15 +1449,15 @@ void anderson_step(tm_mesh* m, RankList& RF, RankList& RC) {
     for (auto& rp : RC) {
         RankMesh& rc = *rp;
         LAUNCH(aa_gram_kernel, rc.vec_grid, 256, s, rc.L.n_own, fields(rc), rc.aa_part.p);
-        LAUNCH(aa_reduce_kernel, 1, 192, s, (const double*)rc.aa_part.p, rc.vec_grid, rc.aa_gram.p);
+        LAUNCH(aa_reduce_kernel, 1, 32 * AA_GRAM, s, (const double*)rc.aa_part.p, rc.vec_grid, rc.aa_gram.p);
     }
     if (m->n_ranks > 1) {
         if (m->emulated) {
             SumPtrs ptrs{};
             for (size_t k = 0; k < RC.size(); ++k) ptrs.p[k] = RC[k]->aa_gram.p;
-            LAUNCH(combine_sum_kernel, 1, 32, s, ptrs, int(RC.size()), 6);
+            LAUNCH(combine_sum_kernel, 1, 32, s, ptrs, int(RC.size()), AA_GRAM);
         } else {
-            NCCL_TRY(g_nccl.AllReduce(RC[0]->aa_gram.p, RC[0]->aa_gram.p, 6, ncclDouble, ncclSum, m->comm, s));
+            NCCL_TRY(g_nccl.AllReduce(RC[0]->aa_gram.p, RC[0]->aa_gram.p, AA_GRAM, ncclDouble, ncclSum, m->comm, s));
         }
     }
     for (size_t q = 0; q < RF.size(); ++q) {
@@ -1657,6 +1658,7 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
     if (n_connections) m->h_conns.assign(connections, connections + n_connections);
     if (n_conditions) m->h_bcs.assign(conditions, conditions + n_conditions);
     if (const char* e = std::getenv("TM_MG_AA")) m->mg_aa = std::atoi(e) != 0;
+    if (const char* e = std::getenv("TM_MG_AA_WINDOW")) m->mg_aa_window = std::min(AA_MAX, std::max(1, std::atoi(e)));
     if (const char* e = std::getenv("TM_MG_REPLICATE_NODES")) m->mg_replicate_nodes = std::atoll(e);
     if (const char* e = std::getenv("TM_MG_SMALL_NODES")) m->mg_small_nodes = std::atoll(e);
     if (const char* e = std::getenv("TM_TILE_ROWS")) m->tile_rows = std::max(4, std::atoi(e));
