@@ -251,6 +251,37 @@ int tm_dist_plan(const tm_block *blocks, size_t n_blocks,
                  const int32_t *block_owner, int rank, int n_ranks,
                  tm_dist_plan_info *info, int64_t *ghost_ids, int64_t *send_ids, int64_t *counts);
 
+/* -------------------------------------------------------------------------------------------------
+ * Edge discretisation, the step right before the path (batched): discrete.Edge.init = clustering.create +
+ * Curve.interpolate (src/core/discrete.zig:17-31; clustering.zig:9-116, geometry.zig:26-40, spline.zig:74-139, 202-222)
+ * ------------------------------------------------------------------------------------------------- */
+typedef enum tm_clustering_kind { TM_CLUSTERING_UNIFORM = 0, TM_CLUSTERING_ROBERTS = 1, TM_CLUSTERING_SINGLE_HYPERBOLIC = 2 } tm_clustering_kind;
+typedef enum tm_curve_kind { TM_CURVE_LINE = 0, TM_CURVE_SPLINE = 1 } tm_curve_kind;
+/* views of the fields of an already fitted spline.FittingSpline(2) (spline.zig:24-40): the library borrows them */
+typedef struct tm_spline {
+    uint64_t n_points;            /* knots                                                            */
+    const double *params;         /* chord-length parameters, n_points                                */
+    const double *points;         /* interleaved x,y, 2*n_points                                      */
+    const double *second_derivs_x, *second_derivs_y; /* n_points each                                 */
+    uint64_t n_samples;           /* arc-length table entries (201 in the reference, spline.zig:22)   */
+    const double *sample_arc;     /* normalised arc length at the uniform parameters i/(n_samples-1)  */
+    double total_length;
+} tm_spline;
+typedef struct tm_edge_job {
+    uint64_t n;                   /* points of the edge                                               */
+    uint32_t curve_kind;          /* tm_curve_kind                                                    */
+    uint32_t clustering_kind;     /* tm_clustering_kind                                               */
+    double line_start[2], line_end[2]; /* TM_CURVE_LINE                                               */
+    const tm_spline *spline;      /* TM_CURVE_SPLINE                                                  */
+    double alpha, beta;           /* Roberts (clustering.zig:24-27)                                   */
+    double delta_s;               /* single hyperbolic (clustering.zig:56-59)                         */
+    double *points;               /* out: 2*n doubles, interleaved x,y (Edge.points), host memory     */
+    double *clustering;           /* out: n doubles (Edge.clustering), host memory                    */
+} tm_edge_job;
+/* All edges in one launch (one CTA per edge).  Curve arithmetic is bit-exact with the reference's operation order; the
+ * pow / tanh inside the Roberts and hyperbolic clusterings are CUDA's (a few ulp from any host libm). */
+int tm_edges_discretize(const tm_edge_job *jobs, size_t n_jobs, int device);
+
 /* Host-only view of the multigrid hierarchy TM_SOLVER_FAS_MULTIGRID builds for a multi-block mesh (needs no GPU): nested
  * coarsening of block sizes and connection / condition ranges, directions tied into classes by the connections.
  * cell_size (may be NULL = all equal) holds the mean cell size per (block, direction), 2*n_blocks entries -- the solver

@@ -90,6 +90,11 @@ def lib():
         L.orc_csr_solve.argtypes = [C.c_uint64, ip, ip, dp, dp, dp, C.POINTER(Options), C.POINTER(Stats)]
         L.orc_block_to_soa.argtypes = [C.c_uint64, C.c_uint64, dp, dp, dp]
         L.orc_block_to_soa.restype = None
+        L.orc_clustering.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, dp]
+        L.orc_line_interpolate.argtypes = [dp, dp, dp, C.c_uint64, dp]
+        L.orc_line_interpolate.restype = None
+        L.orc_spline_interpolate.argtypes = [C.c_uint64, dp, dp, dp, dp, C.c_uint64, dp, C.c_double, dp, C.c_uint64, dp]
+        L.orc_spline_interpolate.restype = None
         _lib = L
     return _lib
 
@@ -279,3 +284,28 @@ def block_to_soa(points: np.ndarray):
     x, y = np.empty(ni * nj), np.empty(ni * nj)
     lib().orc_block_to_soa(ni, nj, _dp(a), _dp(x), _dp(y))
     return x, y
+
+
+def clustering(kind: str, n: int, alpha: float = 0.0, beta: float = 0.0, delta_s: float = 0.0) -> np.ndarray:
+    """``clustering.create`` (clustering.zig:9-116): kind = uniform | roberts | single_hyperbolic_clustering."""
+    out = np.empty(n)
+    _check(lib().orc_clustering({"uniform": 0, "roberts": 1, "single_hyperbolic_clustering": 2}[kind], alpha, beta, delta_s, n, _dp(out)))
+    return out
+
+
+def line_interpolate(start, end, u) -> np.ndarray:
+    """``Line.interpolate`` (geometry.zig:26-40)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    a, b = np.array(start, dtype=np.float64), np.array(end, dtype=np.float64)
+    out = np.empty((len(u), 2))
+    lib().orc_line_interpolate(_dp(a), _dp(b), _dp(u), len(u), _dp(out))
+    return out
+
+
+def spline_interpolate(params, points, zx, zy, sample_arc, total_length: float, u) -> np.ndarray:
+    """``FittingSpline.interpolate`` (spline.zig:74-81, 112-139, 202-222) on the tables of an already fitted spline."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (params, points, zx, zy, sample_arc, u)]
+    out = np.empty((len(arrs[5]), 2))
+    lib().orc_spline_interpolate(len(arrs[0]), _dp(arrs[0]), _dp(arrs[1]), _dp(arrs[2]), _dp(arrs[3]), len(arrs[4]), _dp(arrs[4]), float(total_length),
+                                 _dp(arrs[5]), len(arrs[5]), _dp(out))
+    return out

@@ -1354,3 +1354,91 @@ void orc_block_to_soa(uint64_t ni, uint64_t nj, const double *xy, double *x, dou
             ++idx;
         }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Edge discretisation, the step right before the path: discrete.Edge.init = clustering.create + Curve.interpolate
+ * (src/core/discrete.zig:17-31).  The spline itself (chord parameters, second derivatives, arc-length table) is an input
+ * here: its construction (spline.zig:141-200, 87-110) is covered by the host-side mirror and the reference's known answers.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* clustering.zig:9-17 (uniform), :24-42 (roberts), :56-95 (single hyperbolic); kind 0 / 1 / 2 */
+int orc_clustering(int kind, double alpha, double beta, double delta_s, uint64_t n, double *out)
+{
+    if (n < 2) FAIL(-1, "clustering needs at least 2 points");
+    if (kind == 0) {
+        for (uint64_t i = 0; i < n; ++i) out[i] = (double)i / (double)(n - 1);
+    } else if (kind == 1) {
+        for (uint64_t i = 0; i < n; ++i) {
+            const double u = (double)i / (double)(n - 1);
+            const double tmp = pow((beta + 1.0) / (beta - 1.0), (u - alpha) / (1.0 - alpha));
+            const double tbar = (beta + 2.0 * alpha) * tmp - beta + 2.0 * alpha;
+            out[i] = tbar / ((2.0 * alpha + 1.0) * (1.0 + tmp));
+        }
+    } else if (kind == 2) {
+        const double n_1 = (double)(n - 1);
+        const double b = n_1 * delta_s;
+        const double y = 1.0 / b;
+        double delta;
+        if (y < 1.0) FAIL(-1, "single hyperbolic clustering needs (n-1)*delta_s <= 1 (clustering.zig:68-76)");
+        if (y < 2.7829681) {
+            const double y_bar = y - 1.0;
+            delta = sqrt(6.0 * y_bar) * (1.0 + y_bar * (-0.15 + y_bar * (0.057321429 + y_bar * (-0.024907295 + y_bar * (0.0077424461 - 0.0010794123 * y_bar)))));
+        } else {
+            const double w = 1.0 / y - 0.028527431;
+            const double v = log(y);
+            delta = v + (1.0 + 1.0 / v) * log(2.0 * v) - 0.02041793 + w * (0.24902722 + w * (1.9496443 + w * (-2.6294547 + 8.56795911 * w)));
+        }
+        for (uint64_t i = 0; i < n; ++i) out[i] = (double)i / n_1;
+        for (uint64_t i = 1; i < n; ++i) out[i] = 1.0 + tanh(0.5 * delta * (out[i] - 1.0)) / tanh(0.5 * delta);
+    } else {
+        FAIL(-1, "unknown clustering kind");
+    }
+    return 0;
+}
+
+/* geometry.zig:26-40 */
+void orc_line_interpolate(const double start[2], const double end[2], const double *u, uint64_t n, double *out)
+{
+    const double dx = end[0] - start[0], dy = end[1] - start[1];
+    for (uint64_t k = 0; k < n; ++k) {
+        out[2 * k] = start[0] + u[k] * dx;
+        out[2 * k + 1] = start[1] + u[k] * dy;
+    }
+}
+
+/* FittingSpline.interpolate (spline.zig:74-81) = eval(paramAtArcFraction(u)) (spline.zig:112-139, 202-222); the arc table
+ * has n_samples entries at the uniform parameters i / (n_samples - 1) (spline.zig:87-110, 201 in the reference) */
+void orc_spline_interpolate(uint64_t m, const double *params, const double *points, const double *zx, const double *zy,
+                            uint64_t n_samples, const double *sample_arc, double total_length, const double *u, uint64_t n, double *out)
+{
+    for (uint64_t k = 0; k < n; ++k) {
+        double param = 0.0;
+        if (total_length != 0.0) {
+            const double target = u[k] < 0.0 ? 0.0 : (u[k] > 1.0 ? 1.0 : u[k]);
+            uint64_t lo = 0, hi = n_samples - 1;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (sample_arc[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            if (lo == 0) {
+                param = 0.0;
+            } else {
+                const double a0 = sample_arc[lo - 1], a1 = sample_arc[lo];
+                const double p0 = (double)(lo - 1) / (double)(n_samples - 1), p1 = (double)lo / (double)(n_samples - 1);
+                const double t = a1 > a0 ? (target - a0) / (a1 - a0) : 0.0;
+                param = p0 + t * (p1 - p0);
+            }
+        }
+        const double uu = param < 0.0 ? 0.0 : (param > 1.0 ? 1.0 : param);
+        uint64_t idx = 0;
+        while (idx + 1 < m && params[idx + 1] < uu) ++idx;
+        if (idx >= m - 1) idx = m - 2;
+        const double h = params[idx + 1] - params[idx];
+        const double a = (params[idx + 1] - uu) / h, b = (uu - params[idx]) / h;
+        const double *z[2] = {zx, zy};
+        for (int d = 0; d < 2; ++d) {
+            const double y0 = points[2 * idx + d], y1 = points[2 * (idx + 1) + d];
+            const double z0 = z[d][idx], z1 = z[d][idx + 1];
+            out[2 * k + d] = a * y0 + b * y1 + ((a * a * a - a) * z0 + (b * b * b - b) * z1) * (h * h) / 6.0;
+        }
+    }
+}

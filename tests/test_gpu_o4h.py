@@ -105,3 +105,36 @@ def test_multigrid_on_the_t106_o4h_mesh_reaches_the_picard_fixed_point(gpu_lib):
     assert st_pc["last_max_update"] <= 1e-13, st_pc
     err = max(float(np.abs(x.points - y.points).max()) for x, y in zip(a.blocks, b.blocks))
     assert err <= 1e-9 * chord_of(a), (err, st_mg)
+
+
+def test_edge_discretisation_on_the_device(orc, gpu_lib):
+    """Edge.init batched on the GPU (tm_edges_discretize) against the oracle: bit-exact curve arithmetic (uniform
+    clustering), a few ulp through CUDA's pow / tanh for the Roberts and hyperbolic clusterings."""
+    from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform
+    from turbomesh_b200.discrete import Edge
+    from turbomesh_b200.geometry import Line
+    from turbomesh_b200.spline import FittingSpline
+
+    t = np.linspace(0.0, 1.0, 215)
+    blade = FittingSpline(np.stack([0.08 * t, 0.03 * np.sin(np.pi * t) + 0.01 * t ** 2], axis=1))   # a T106-sized suction side
+    other = FittingSpline(np.stack([0.08 * t, -0.012 * np.sin(np.pi * t)], axis=1))
+    line = Line((0.0, 0.0), (-0.04, 0.022))
+    specs = [(221, blade, Uniform()), (121, other, Uniform()), (41, line, Uniform()), (2, line, Uniform()),
+             (221, blade, Roberts(0.5, 1.03)), (41, line, SingleHyperbolicClustering(0.01)), (131, other, SingleHyperbolicClustering(1e-3)),
+             (91, line, Roberts(0.0, 1.2))]
+    got = Edge.init_batch(specs)
+    kinds = {Uniform: "uniform", Roberts: "roberts", SingleHyperbolicClustering: "single_hyperbolic_clustering"}
+    for (n, curve, cl), e in zip(specs, got):
+        ref_u = orc.clustering(kinds[type(cl)], n, alpha=getattr(cl, "alpha", 0.0), beta=getattr(cl, "beta", 0.0), delta_s=getattr(cl, "delta_s", 0.0))
+        if isinstance(curve, Line):
+            ref_p = orc.line_interpolate(curve.start, curve.end, ref_u)
+        else:
+            ref_p = orc.spline_interpolate(curve.params, curve.points, curve.second_derivs[0], curve.second_derivs[1], curve.sample_arc, curve.total_length, ref_u)
+        if isinstance(cl, Uniform):
+            assert np.array_equal(e.clustering, ref_u) and np.array_equal(e.points, ref_p)
+        else:
+            assert e.clustering[0] == 0.0 or isinstance(cl, Roberts)
+            assert np.abs(e.clustering - ref_u).max() <= 8 * np.finfo(float).eps      # values in [0, 1]: a few ulp of pow / tanh
+            assert np.abs(e.points - ref_p).max() <= 1e-14
+        if isinstance(cl, SingleHyperbolicClustering):
+            assert e.clustering[0] == 0.0 and e.clustering[-1] == 1.0                  # tfi.zig:135-145 needs exact end points

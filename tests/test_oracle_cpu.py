@@ -197,3 +197,29 @@ def test_block_to_soa_is_the_cgns_layout(orc):
     a = np.arange(ni * nj * 2, dtype=np.float64).reshape(ni, nj, 2)
     x, y = orc.block_to_soa(a)
     assert np.array_equal(x, a[:, :, 0].T.ravel()) and np.array_equal(y, a[:, :, 1].T.ravel())
+
+
+def test_edge_discretisation_oracle_matches_the_host_mirror(orc):
+    """clustering.create + Curve.interpolate (discrete.zig:17-31): the C restatement and the host-side mirror agree bit for
+    bit (same libm), incl. the reference's straight-line known answer for the spline (spline.zig:235-304)."""
+    from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform
+    from turbomesh_b200.geometry import Line
+    from turbomesh_b200.spline import FittingSpline
+
+    for n in (2, 5, 41, 200):
+        assert np.array_equal(orc.clustering("uniform", n), Uniform().compute(n))
+        assert np.array_equal(orc.clustering("roberts", n, alpha=0.5, beta=1.03), Roberts(0.5, 1.03).compute(n))
+    for n, ds in ((5, 0.2), (41, 0.01), (131, 1e-3)):
+        c = orc.clustering("single_hyperbolic_clustering", n, delta_s=ds)
+        assert np.array_equal(c, SingleHyperbolicClustering(ds).compute(n)) and c[0] == 0.0 and c[-1] == 1.0
+    t = np.linspace(0.0, 1.0, 37)
+    sp = FittingSpline(np.stack([t, 0.1 * np.sin(3 * t) + 0.2 * t ** 2], axis=1))
+    u = Roberts(0.5, 1.1).compute(60)
+    got = orc.spline_interpolate(sp.params, sp.points, sp.second_derivs[0], sp.second_derivs[1], sp.sample_arc, sp.total_length, u)
+    assert np.array_equal(got, sp.interpolate(u))
+    line = FittingSpline(np.array([[0.0, 0.0], [1.0, 2.0], [2.0, 4.0], [4.0, 8.0]]))   # spline.zig:235-260: a straight line is reproduced
+    uu = Uniform().compute(9)
+    pts = orc.spline_interpolate(line.params, line.points, line.second_derivs[0], line.second_derivs[1], line.sample_arc, line.total_length, uu)
+    assert np.allclose(pts, np.stack([4.0 * uu, 8.0 * uu], axis=1), atol=1e-9)
+    ln = Line((0.1, 0.2), (1.3, -0.4))
+    assert np.array_equal(orc.line_interpolate(ln.start, ln.end, uu), ln.interpolate(uu))

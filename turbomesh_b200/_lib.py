@@ -61,6 +61,19 @@ class TmDistPlanInfo(C.Structure):
 TM_UNIQUE_ID_BYTES = 128
 
 
+class TmSpline(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("params", C.POINTER(C.c_double)), ("points", C.POINTER(C.c_double)),
+                ("second_derivs_x", C.POINTER(C.c_double)), ("second_derivs_y", C.POINTER(C.c_double)),
+                ("n_samples", C.c_uint64), ("sample_arc", C.POINTER(C.c_double)), ("total_length", C.c_double)]
+
+
+class TmEdgeJob(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("curve_kind", C.c_uint32), ("clustering_kind", C.c_uint32),
+                ("line_start", C.c_double * 2), ("line_end", C.c_double * 2), ("spline", C.POINTER(TmSpline)),
+                ("alpha", C.c_double), ("beta", C.c_double), ("delta_s", C.c_double),
+                ("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double))]
+
+
 class TurbomeshGpuError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"turbomesh_gpu error {code}: {message}")
@@ -106,6 +119,7 @@ def load():
                                C.POINTER(C.c_int64)]
     L.tm_mg_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t, dp, C.c_size_t,
                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.tm_edges_discretize.argtypes = [C.POINTER(TmEdgeJob), C.c_size_t, C.c_int]
     L.tm_mesh_destroy.argtypes = [vp]
     L.tm_mesh_destroy.restype = None
     L.tm_mesh_upload_block.argtypes = [vp, C.c_size_t, dp]

@@ -1509,4 +1509,92 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(int ni, int nj, const d
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Edge discretisation, the step right before the path: discrete.Edge.init =
+// clustering.create + Curve.interpolate (src/core/discrete.zig:17-31), batched -- one CTA per edge, one thread per point.
+//   clustering   clustering.zig:9-17 (uniform), :24-42 (Roberts), :56-95 (Vinokur tanh; delta comes from the host)
+//   line         geometry.zig:26-40
+//   spline       FittingSpline.interpolate = eval(paramAtArcFraction(u)), spline.zig:74-81, 112-139, 202-222, on the tables of
+//                an already fitted spline (params, points, second derivatives, arc-length table)
+// The arithmetic of the curves uses round-to-nearest intrinsics in the reference's operation order (no FMA contraction):
+// with a uniform clustering the points are bit-exact; pow / tanh of the other clusterings are CUDA's libm (<= 2 ulp).
+// ---------------------------------------------------------------------------------------------------
+struct EdgeJob {
+    int64_t out_off;        // first point of the edge in the output arrays
+    int64_t spline_off;     // spline tables in `tables`: params[m], points[2m], zx[m], zy[m], arc[n_samples]
+    int32_t n, curve, clustering, spline_m, n_samples, _pad;
+    double line[4];         // start x,y ; end x,y
+    double alpha, beta, delta, total_length;
+};
+__device__ __forceinline__ double edge_clustering(const EdgeJob& e, int i) {
+    const double n_1 = (double)(e.n - 1);
+    const double u = __ddiv_rn((double)i, n_1);
+    if (e.clustering == 1) {  // Roberts
+        const double tmp = pow(__ddiv_rn(__dadd_rn(e.beta, 1.0), __dsub_rn(e.beta, 1.0)), __ddiv_rn(__dsub_rn(u, e.alpha), __dsub_rn(1.0, e.alpha)));
+        const double tbar = __dadd_rn(__dsub_rn(__dmul_rn(__dadd_rn(e.beta, __dmul_rn(2.0, e.alpha)), tmp), e.beta), __dmul_rn(2.0, e.alpha));
+        return __ddiv_rn(tbar, __dmul_rn(__dadd_rn(__dmul_rn(2.0, e.alpha), 1.0), __dadd_rn(1.0, tmp)));
+    }
+    if (e.clustering == 2 && i > 0)  // Vinokur: 1 + tanh(delta/2 (u - 1)) / tanh(delta/2)
+        return __dadd_rn(1.0, __ddiv_rn(tanh(__dmul_rn(__dmul_rn(0.5, e.delta), __dsub_rn(u, 1.0))), tanh(__dmul_rn(0.5, e.delta))));
+    return u;
+}
+__device__ __forceinline__ double2 edge_spline_point(const EdgeJob& e, const double* __restrict__ tables, double u) {
+    const int m = e.spline_m;
+    const double* params = tables + e.spline_off;
+    const double* points = params + m;
+    const double* zx = points + 2 * m;
+    const double* zy = zx + m;
+    const double* arc = zy + m;
+    double param = 0.0;
+    if (e.total_length != 0.0) {  // paramAtArcFraction
+        const double target = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        int lo = 0, hi = e.n_samples - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (arc[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        if (lo > 0) {
+            const double a0 = arc[lo - 1], a1 = arc[lo];
+            const double ns = (double)(e.n_samples - 1);
+            const double p0 = __ddiv_rn((double)(lo - 1), ns), p1 = __ddiv_rn((double)lo, ns);
+            const double t = a1 > a0 ? __ddiv_rn(__dsub_rn(target, a0), __dsub_rn(a1, a0)) : 0.0;
+            param = __dadd_rn(p0, __dmul_rn(t, __dsub_rn(p1, p0)));
+        }
+    }
+    const double uu = param < 0.0 ? 0.0 : (param > 1.0 ? 1.0 : param);
+    // idx = number of knots params[1..] below uu (the reference scans linearly), at most m-2
+    int lo = 0, hi = m - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (params[mid + 1] < uu) lo = mid + 1; else hi = mid;
+    }
+    const int idx = lo >= m - 1 ? m - 2 : lo;
+    const double h = __dsub_rn(params[idx + 1], params[idx]);
+    const double a = __ddiv_rn(__dsub_rn(params[idx + 1], uu), h), b = __ddiv_rn(__dsub_rn(uu, params[idx]), h);
+    const double a3 = __dsub_rn(__dmul_rn(__dmul_rn(a, a), a), a), b3 = __dsub_rn(__dmul_rn(__dmul_rn(b, b), b), b);
+    const double hh = __dmul_rn(h, h);
+    auto comp = [&](double y0, double y1, double z0, double z1) {
+        const double lin = __dadd_rn(__dmul_rn(a, y0), __dmul_rn(b, y1));
+        const double cub = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(a3, z0), __dmul_rn(b3, z1)), hh), 6.0);
+        return __dadd_rn(lin, cub);
+    };
+    return make_double2(comp(points[2 * idx], points[2 * idx + 2], zx[idx], zx[idx + 1]), comp(points[2 * idx + 1], points[2 * idx + 3], zy[idx], zy[idx + 1]));
+}
+__global__ void __launch_bounds__(128) edge_discretize_kernel(const EdgeJob* __restrict__ jobs, const double* __restrict__ tables, double2* __restrict__ points,
+                                                              double* __restrict__ clustering) {
+    const EdgeJob e = jobs[blockIdx.x];
+    for (int i = threadIdx.x; i < e.n; i += blockDim.x) {
+        const double u = edge_clustering(e, i);
+        double2 p;
+        if (e.curve == 0) {
+            p.x = __dadd_rn(e.line[0], __dmul_rn(u, __dsub_rn(e.line[2], e.line[0])));
+            p.y = __dadd_rn(e.line[1], __dmul_rn(u, __dsub_rn(e.line[3], e.line[1])));
+        } else {
+            p = edge_spline_point(e, tables, u);
+        }
+        clustering[e.out_off + i] = u;
+        points[e.out_off + i] = p;
+    }
+}
+
 }  // namespace tmesh

@@ -2149,6 +2149,80 @@ int tm_dist_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* c
     });
 }
 
+int tm_edges_discretize(const tm_edge_job* jobs, size_t n_jobs, int device) {
+    return guarded([&] {
+        if (n_jobs && !jobs) TM_THROW(TM_ERR_INVALID_ARGUMENT, "jobs is NULL");
+        if (n_jobs == 0) return;
+        require_device(device);
+        std::vector<EdgeJob> dev_jobs(n_jobs);
+        std::vector<double> tables;
+        std::vector<std::pair<const tm_spline*, int64_t>> seen;  // every spline is uploaded once
+        int64_t total = 0;
+        for (size_t k = 0; k < n_jobs; ++k) {
+            const tm_edge_job& j = jobs[k];
+            if (j.n < 2 || j.n > 0x7fffffffull || !j.points || !j.clustering) TM_THROW(TM_ERR_INVALID_ARGUMENT, "edge %zu: needs n >= 2 and output arrays", k);
+            if (j.curve_kind > TM_CURVE_SPLINE || j.clustering_kind > TM_CLUSTERING_SINGLE_HYPERBOLIC) TM_THROW(TM_ERR_INVALID_ARGUMENT, "edge %zu: unknown curve / clustering kind", k);
+            EdgeJob e{};
+            e.out_off = total; e.n = int32_t(j.n); e.curve = int32_t(j.curve_kind); e.clustering = int32_t(j.clustering_kind);
+            e.line[0] = j.line_start[0]; e.line[1] = j.line_start[1]; e.line[2] = j.line_end[0]; e.line[3] = j.line_end[1];
+            e.alpha = j.alpha; e.beta = j.beta;
+            if (j.clustering_kind == TM_CLUSTERING_SINGLE_HYPERBOLIC) {  // Vinokur's inversion of sinh(d)/d = 1/B, clustering.zig:60-81
+                const double y = 1.0 / (double(j.n - 1) * j.delta_s);
+                if (!(y >= 1.0)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "edge %zu: single hyperbolic clustering needs (n-1)*delta_s <= 1 (clustering.zig:68-76)", k);
+                if (y < 2.7829681) {
+                    const double y_bar = y - 1.0;
+                    e.delta = std::sqrt(6.0 * y_bar) * (1.0 + y_bar * (-0.15 + y_bar * (0.057321429 + y_bar * (-0.024907295 + y_bar * (0.0077424461 - 0.0010794123 * y_bar)))));
+                } else {
+                    const double w = 1.0 / y - 0.028527431, v = std::log(y);
+                    e.delta = v + (1.0 + 1.0 / v) * std::log(2.0 * v) - 0.02041793 + w * (0.24902722 + w * (1.9496443 + w * (-2.6294547 + 8.56795911 * w)));
+                }
+            }
+            if (j.curve_kind == TM_CURVE_SPLINE) {
+                const tm_spline* sp = j.spline;
+                if (!sp || sp->n_points < 2 || sp->n_samples < 2 || !sp->params || !sp->points || !sp->second_derivs_x || !sp->second_derivs_y || !sp->sample_arc)
+                    TM_THROW(TM_ERR_INVALID_ARGUMENT, "edge %zu: incomplete spline", k);
+                int64_t off = -1;
+                for (const auto& pr : seen) if (pr.first == sp) off = pr.second;
+                if (off < 0) {
+                    off = int64_t(tables.size());
+                    const size_t m = size_t(sp->n_points);
+                    tables.insert(tables.end(), sp->params, sp->params + m);
+                    tables.insert(tables.end(), sp->points, sp->points + 2 * m);
+                    tables.insert(tables.end(), sp->second_derivs_x, sp->second_derivs_x + m);
+                    tables.insert(tables.end(), sp->second_derivs_y, sp->second_derivs_y + m);
+                    tables.insert(tables.end(), sp->sample_arc, sp->sample_arc + sp->n_samples);
+                    seen.push_back({sp, off});
+                }
+                e.spline_off = off; e.spline_m = int32_t(sp->n_points); e.n_samples = int32_t(sp->n_samples); e.total_length = sp->total_length;
+            }
+            dev_jobs[k] = e;
+            total += int64_t(j.n);
+        }
+        cudaStream_t s = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        try {
+            DevBuf<EdgeJob> d_jobs;
+            DevBuf<double> d_tables, d_cl;
+            DevBuf<double2> d_pts;
+            d_jobs.upload(dev_jobs, s);
+            if (tables.empty()) tables.push_back(0.0);
+            d_tables.upload(tables, s);
+            d_pts.alloc(size_t(total));
+            d_cl.alloc(size_t(total));
+            LAUNCH(edge_discretize_kernel, unsigned(n_jobs), 128, s, (const EdgeJob*)d_jobs.p, (const double*)d_tables.p, d_pts.p, d_cl.p);
+            for (size_t k = 0; k < n_jobs; ++k) {
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].points, d_pts.p + dev_jobs[k].out_off, size_t(jobs[k].n) * sizeof(double2), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].clustering, d_cl.p + dev_jobs[k].out_off, size_t(jobs[k].n) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        cudaStreamDestroy(s);
+    });
+}
+
 int tm_mg_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections, const tm_condition* conditions,
                size_t n_conditions, const double* cell_size, size_t max_levels, uint64_t* n_levels, uint64_t* sizes) {
     return guarded([&] {
