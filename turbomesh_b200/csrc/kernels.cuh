@@ -1125,15 +1125,16 @@ struct RestrictRow {               // rhs_c[dst] = sum_k w[k] * res_f[src[k]]  (
 };
 
 // coarse <- fine for one block: iterate by injection (all nodes, so that copies stay exact copies); residual of the
-// interior rows by full weighting in the coarsened directions, times `scale` (= -(f_i f_j)^2: the undivided Winslow row
-// of a smooth field scales like h_xi^2 h_eta^2, and the restricted quantity is the negative residual).
+// interior rows by full weighting in the coarsened directions, times (f_i f_j)^2 (the undivided Winslow row of a smooth
+// field scales like h_xi^2 h_eta^2).  The result R goes to the coarse level's scratch field; the FAS right-hand side
+// tau_c = row_c(I u_f) - R is then produced by ONE launch of the coarse rows in MODE_REL with R as "rhs".
 constexpr int MGB_ROWS = 1;  // rows per CTA in the block transfer kernels (marching several rows per thread measured slower: less memory-level parallelism)
 __global__ void __launch_bounds__(128) mgb_restrict_kernel(const BlockXfer* __restrict__ blocks /* one per blockIdx.z */, const double2* __restrict__ u_f, const double2* __restrict__ res_f, double2* __restrict__ u_c,
                                                            double2* e_c, double2* __restrict__ rhs_c,
                                                            unsigned long long* __restrict__ change /* may be NULL */,
                                                            const double2* e_prev /* the previous cycle's restricted iterate (may alias e_c) */) {
     const BlockXfer b = blocks[blockIdx.z];
-    const double scale = -(double)(b.fi * b.fj) * (double)(b.fi * b.fj);
+    const double scale = (double)(b.fi * b.fj) * (double)(b.fi * b.fj);  // restricted residual, in coarse row units
     const int J = blockIdx.x * blockDim.x + threadIdx.x;
     const int I_end = min((int)(blockIdx.y + 1) * MGB_ROWS, b.ni_c);
     double dmax = 0.0;
@@ -1197,16 +1198,6 @@ __global__ void mgb_restrict_rows_kernel(const RestrictRow* __restrict__ rows, i
         r.x += row.w[q] * v.x; r.y += row.w[q] * v.y;
     }
     rhs_c[row.dst] = r;
-}
-
-// b += a  (tau_c = row_c(I u_f) + restricted residual; `a` is zero wherever no free row lives)
-__global__ void __launch_bounds__(256) mgb_add_kernel(int64_t n, const double2* __restrict__ a, double2* __restrict__ b) {
-    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
-        const double2 x = a[k];
-        double2 y = b[k];
-        y.x += x.x; y.y += x.y;
-        b[k] = y;
-    }
 }
 
 // fine += bilinear interpolation of the coarse correction (u_c - e_c).  Interior nodes per block; the free rows on

@@ -208,6 +208,8 @@ struct MgLevel {
     DevBuf<double2> U, V, rhs, tmp, E;       // iterate ping-pong, tau term, scratch (row / residual), restricted iterate
     DevBuf<Tile> tiles;
     DevBuf<DevBlock> blk;
+    DevBuf<SmallNode> small;                 // tiny levels: interior node list of winslow_small_level_kernel
+    int n_small = 0;
     // level 1 only: Anderson acceleration history on this level's nodes (see anderson_step)
     std::vector<std::unique_ptr<DevBuf<double2>>> aa_G, aa_F;
     DevBuf<double2> aa_X, aa_D, aa_zero;
@@ -1006,6 +1008,13 @@ void mg_build(tm_mesh* m, RankMesh& r) {
             L->U.alloc(n); L->V.alloc(n); L->rhs.alloc(n); L->E.alloc(n);
             L->U.zero(s); L->V.zero(s); L->rhs.zero(s); L->E.zero(s);
         }
+        if (l > 0 && int64_t(n) <= m->mg_small_nodes) {  // all sweeps of a visit in one single-CTA launch
+            std::vector<SmallNode> nodes;
+            for (int i = 1; i + 1 < ni; ++i)
+                for (int j = 1; j + 1 < nj; ++j) nodes.push_back(SmallNode{int64_t(i) * nj + j, 0, i, j, 0});
+            L->n_small = int(nodes.size());
+            L->small.upload(nodes, s);
+        }
         if (l == 1 && m->mg_aa) {
             for (int k = 0; k < m->mg_aa_window; ++k)
                 for (auto* ring : {&L->aa_G, &L->aa_F}) {
@@ -1039,6 +1048,12 @@ void mg_build(tm_mesh* m, RankMesh& r) {
 // `sweeps` damped-Jacobi sweeps on one level; the fields ping-pong between *pu and *pv
 void mg_smooth(tm_mesh* m, RankMesh& r, MgLevel& L, double2** pu, double2** pv, int level, uint64_t sweeps, double omega, bool stats_on_last) {
     const BndArgs none{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+    if (level > 0 && L.n_small > 0 && !stats_on_last) {
+        LAUNCH(winslow_small_level_kernel, 1, 1024, m->stream, (const SmallNode*)L.small.p, L.n_small, (const DevBlock*)L.blk.p, none, *pu, *pv,
+               (const double2*)L.rhs.p, omega, int(sweeps));
+        if (sweeps & 1) std::swap(*pu, *pv);
+        return;
+    }
     for (uint64_t k = 0; k < sweeps; ++k) {
         const bool st = stats_on_last && k + 1 == sweeps;
         const double2* u = *pu;
@@ -1248,7 +1263,7 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
         TF.walk(cf.ranges[1], f1, a1, n1);
         const int al = along_dir(cc.ranges[0].side);
         const int fa = al == 0 ? F.fi[b0] : F.fj[b0], fn = al == 0 ? F.fj[b0] : F.fi[b0];
-        const double scale = -double(fa * fn) * double(fa * fn);
+        const double scale = double(fa * fn) * double(fa * fn);
         const int64_t nC = Topology::range_len(cc.ranges[0]);
         for (int64_t K = 1; K + 1 < nC; ++K) {
             const int64_t g0c = TC.blocks[b0].off + B0 + K * A0;
@@ -1286,7 +1301,7 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
         if (owner[b] != rank) continue;
         RestrictRow row{};
         row.dst = lc(jr.self);
-        add(row, lf(gf), -double(F.fi[b] * F.fj[b]));
+        add(row, lf(gf), double(F.fi[b] * F.fj[b]));
         rows.push_back(row);
     }
     for (const auto& sr : TC.sliding) {       // update units: a first difference along the inward normal
@@ -1297,7 +1312,7 @@ void mgb_build_transfer(tm_mesh* m, const Topology& TF, const MgbLevel& F, RankM
         const int fn = (inward == 1 || inward == -1) ? F.fj[b] : F.fi[b];
         RestrictRow row{};
         row.dst = lc(sr.self);
-        add(row, lf(gf), -double(fn));
+        add(row, lf(gf), double(fn));
         rows.push_back(row);
     }
     rf.n_rrows = int(rows.size());
@@ -1541,7 +1556,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             if (gather)
                 for (auto& rp : RC) {
                     CUDA_TRY(cudaMemsetAsync(xcur(*rp), 0, size_t(rp->L.n_own) * sizeof(double2), s));
-                    CUDA_TRY(cudaMemsetAsync(rp->mg_rhs.p, 0, size_t(rp->L.n_own) * sizeof(double2), s));
+                    CUDA_TRY(cudaMemsetAsync(rp->mg_tmp.p, 0, size_t(rp->L.n_own) * sizeof(double2), s));
                 }
             for (size_t q = 0; q < RF.size(); ++q) {
                 RankMesh& rf = *RF[q];
@@ -1550,13 +1565,13 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                 if (!rf.xfer_blocks.empty()) {  // all own blocks in one launch (blockIdx.z = block)
                     dim3 g((rf.xf_nj_c + 127) / 128, (rf.xf_ni_c + MGB_ROWS - 1) / MGB_ROWS, unsigned(rf.xfer_blocks.size()));
                     LAUNCH(mgb_restrict_kernel, g, 128, s, (const BlockXfer*)rf.d_xfer_blocks.p, (const double2*)xcur(rf), (const double2*)rf.mg_tmp.p, xcur(rc), rc.E(),
-                           rc.mg_rhs.p, l == 0 ? rf.d_change.p : (unsigned long long*)nullptr, e_prev);
+                           rc.mg_tmp.p, l == 0 ? rf.d_change.p : (unsigned long long*)nullptr, e_prev);
                 }
                 if (rf.n_rrows > 0)
-                    LAUNCH(mgb_restrict_rows_kernel, (rf.n_rrows + 127) / 128, 128, s, (const RestrictRow*)rf.d_rrows.p, rf.n_rrows, (const double2*)rf.mg_tmp.p, rc.mg_rhs.p);
+                    LAUNCH(mgb_restrict_rows_kernel, (rf.n_rrows + 127) / 128, 128, s, (const RestrictRow*)rf.d_rrows.p, rf.n_rrows, (const double2*)rf.mg_tmp.p, rc.mg_tmp.p);
             }
             if (gather) {  // sum of "mine, zero elsewhere" = everybody's blocks (exact: one non-zero contribution per node)
-                for (double2* (*field)(RankMesh&) : {+[](RankMesh& r) { return r.X[r.cur].p; }, +[](RankMesh& r) { return r.mg_rhs.p; }}) {
+                for (double2* (*field)(RankMesh&) : {+[](RankMesh& r) { return r.X[r.cur].p; }, +[](RankMesh& r) { return r.mg_tmp.p; }}) {
                     if (m->emulated) {
                         SumPtrs ptrs{};
                         for (size_t k = 0; k < RC.size(); ++k) ptrs.p[k] = reinterpret_cast<double*>(field(*RC[k]));
@@ -1576,8 +1591,8 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
                     CUDA_TRY(cudaMemcpyAsync(rc.X[1 - rc.cur].p, xcur(rc), size_t(rc.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
                     rc.mg_primed = true;
                 }
-                launch_rows_mg<MODE_REL, 0>(m, rc, xcur(rc), rc.mg_tmp.p, 1.0, (const double2*)rc.mg_zero.p);  // row_c(I u_f) with the level's (HAS_RHS) operator
-                LAUNCH(mgb_add_kernel, rc.vec_grid, 256, s, rc.L.n_own, (const double2*)rc.mg_tmp.p, rc.mg_rhs.p);
+                // tau_c = row_c(I u_f) - R with the level's (HAS_RHS) operator; R is the restricted residual sitting in mg_tmp
+                launch_rows_mg<MODE_REL, 0>(m, rc, xcur(rc), rc.mg_rhs.p, 1.0, (const double2*)rc.mg_tmp.p);
             }
             fine_work += m->mgb[size_t(l) + 1]->work;
         }
