@@ -203,6 +203,14 @@ int tm_mesh_download_control_function(tm_mesh *mesh, size_t block, double *pq);
  * (host memory, ideally pinned). */
 typedef enum tm_field { TM_FIELD_COORDINATES = 0, TM_FIELD_CONTROL_FUNCTION = 1 } tm_field;
 int tm_mesh_download_block_soa(tm_mesh *mesh, size_t block, int field /* tm_field */, double *x, double *y);
+/* Viewer buffers of a (single-GPU) device mesh, built on the device: what createPointBuffer and
+ * createWireframeElementBuffer build on the host (src/gui/lib.zig:227-318).  points receives 2*n_points floats (x,y of
+ * all blocks in block order, f64 -> f32 round to nearest), ranges receives x_min, x_max, y_min, y_max (the maxima start
+ * at the smallest positive normal float, as in the reference), indices receives n_indices 32-bit point indices: per
+ * block first the line segments along j, then those along i.  Any of the three may be NULL; each may be host memory or
+ * device memory (e.g. the mapped pointer of a CUDA-registered OpenGL buffer). */
+int tm_mesh_viewer_sizes(const tm_mesh *mesh, uint64_t *n_points, uint64_t *n_indices);
+int tm_mesh_viewer_buffers(tm_mesh *mesh, float *points, float *ranges /* 4 */, uint32_t *indices);
 /* node kind per block-boundary node in the reference's flat boundary numbering (boundary.zig:248-285);
  * values: 0 fixed, 1 smoothed, 2 connected, 3 laplacian_smoothed, 4 sliding_circ (smooth.zig:1168-1174).
  * `kinds` receives 2*(ni+nj-2) bytes. */

@@ -90,6 +90,12 @@ def lib():
         L.orc_csr_solve.argtypes = [C.c_uint64, ip, ip, dp, dp, dp, C.POINTER(Options), C.POINTER(Stats)]
         L.orc_block_to_soa.argtypes = [C.c_uint64, C.c_uint64, dp, dp, dp]
         L.orc_block_to_soa.restype = None
+        L.orc_viewer_points.argtypes = [C.POINTER(Block), C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.orc_viewer_points.restype = None
+        L.orc_viewer_index_count.argtypes = [C.POINTER(Block), C.c_size_t]
+        L.orc_viewer_index_count.restype = C.c_uint64
+        L.orc_viewer_wireframe.argtypes = [C.POINTER(Block), C.c_size_t, C.POINTER(C.c_uint32)]
+        L.orc_viewer_wireframe.restype = None
         L.orc_clustering.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64, dp]
         L.orc_line_interpolate.argtypes = [dp, dp, dp, C.c_uint64, dp]
         L.orc_line_interpolate.restype = None
@@ -309,3 +315,20 @@ def spline_interpolate(params, points, zx, zy, sample_arc, total_length: float, 
     lib().orc_spline_interpolate(len(arrs[0]), _dp(arrs[0]), _dp(arrs[1]), _dp(arrs[2]), _dp(arrs[3]), len(arrs[4]), _dp(arrs[4]), float(total_length),
                                  _dp(arrs[5]), len(arrs[5]), _dp(out))
     return out
+
+
+def viewer_buffers(blocks_points):
+    """``createPointBuffer`` + ``createWireframeElementBuffer`` (src/gui/lib.zig:227-318) for a list of (ni, nj, 2) blocks:
+    returns (points f32 [2N], range_x f32[2], range_y f32[2], indices u32)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in blocks_points]
+    blocks = (Block * len(arrs))()
+    for k, a in enumerate(arrs):
+        blocks[k].ni, blocks[k].nj, blocks[k].xy = a.shape[0], a.shape[1], _dp(a)
+    n = sum(a.shape[0] * a.shape[1] for a in arrs)
+    pts = np.empty(2 * n, dtype=np.float32)
+    rx, ry = np.empty(2, dtype=np.float32), np.empty(2, dtype=np.float32)
+    fp = C.POINTER(C.c_float)
+    lib().orc_viewer_points(blocks, len(arrs), pts.ctypes.data_as(fp), rx.ctypes.data_as(fp), ry.ctypes.data_as(fp))
+    idx = np.empty(int(lib().orc_viewer_index_count(blocks, len(arrs))), dtype=np.uint32)
+    lib().orc_viewer_wireframe(blocks, len(arrs), idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return pts, rx, ry, idx

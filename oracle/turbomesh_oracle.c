@@ -1442,3 +1442,50 @@ void orc_spline_interpolate(uint64_t m, const double *params, const double *poin
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Viewer buffers (src/gui/lib.zig:227-318): all points of all blocks as f32 pairs with their x / y ranges
+ * (createPointBuffer, :227-265; the maxima start at floatMin(f32), the smallest positive normal, as in the reference) and
+ * the wireframe line indices (createWireframeElementBuffer, :267-318: per block first the segments along j, then along i).
+ * The reference allocates 8x more indices than it writes; n_indices here is what it writes.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include <float.h>
+void orc_viewer_points(const orc_block *blocks, size_t nb, float *points, float range_x[2], float range_y[2])
+{
+    range_x[0] = FLT_MAX; range_x[1] = FLT_MIN; range_y[0] = FLT_MAX; range_y[1] = FLT_MIN;
+    size_t id = 0;
+    for (size_t b = 0; b < nb; ++b)
+        for (uint64_t k = 0; k < blocks[b].ni * blocks[b].nj; ++k) {
+            points[id] = (float)blocks[b].xy[2 * k];
+            if (points[id] < range_x[0]) range_x[0] = points[id];
+            if (points[id] > range_x[1]) range_x[1] = points[id];
+            points[id + 1] = (float)blocks[b].xy[2 * k + 1];
+            if (points[id + 1] < range_y[0]) range_y[0] = points[id + 1];
+            if (points[id + 1] > range_y[1]) range_y[1] = points[id + 1];
+            id += 2;
+        }
+}
+uint64_t orc_viewer_index_count(const orc_block *blocks, size_t nb)
+{
+    uint64_t total = 0;
+    for (size_t b = 0; b < nb; ++b) total += blocks[b].ni * (blocks[b].nj - 1) * 2 + blocks[b].nj * (blocks[b].ni - 1) * 2;
+    return total;
+}
+void orc_viewer_wireframe(const orc_block *blocks, size_t nb, uint32_t *idx)
+{
+    size_t at = 0;
+    uint32_t point_offset = 0;
+    for (size_t b = 0; b < nb; ++b) {
+        const uint64_t ni = blocks[b].ni, nj = blocks[b].nj;
+        uint32_t point_id = 0;
+        for (uint64_t i = 0; i < ni; ++i) {            /* segments along j */
+            for (uint64_t j = 1; j < nj; ++j) { idx[at] = point_offset + point_id; idx[at + 1] = point_offset + point_id + 1; point_id += 1; at += 2; }
+            point_id += 1;
+        }
+        for (uint64_t j = 0; j < nj; ++j) {            /* segments along i */
+            point_id = (uint32_t)j;
+            for (uint64_t i = 1; i < ni; ++i) { idx[at] = point_offset + point_id; idx[at + 1] = point_offset + point_id + (uint32_t)nj; point_id += (uint32_t)nj; at += 2; }
+        }
+        point_offset += (uint32_t)(ni * nj);
+    }
+}

@@ -138,3 +138,16 @@ def test_edge_discretisation_on_the_device(orc, gpu_lib):
             assert np.abs(e.points - ref_p).max() <= 1e-14
         if isinstance(cl, SingleHyperbolicClustering):
             assert e.clustering[0] == 0.0 and e.clustering[-1] == 1.0                  # tfi.zig:135-145 needs exact end points
+
+
+def test_viewer_buffers_on_the_device(orc, gpu_lib):
+    """f32 points + ranges + wireframe indices of the T106 block set, built on the device: bit-exact with the oracle."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    spec, z, meta = load_fixture("t106_laplace")
+    mesh = synthetic.materialize(spec, smoothing.tfi_block)
+    with smoothing.DeviceMesh(mesh) as dm:
+        pts, rng, idx = dm.viewer_buffers()
+    opts, rx, ry, oidx = orc.viewer_buffers([b.points for b in mesh.blocks])
+    assert np.array_equal(pts, opts) and np.array_equal(idx, oidx)
+    assert np.array_equal(rng, np.array([rx[0], rx[1], ry[0], ry[1]], dtype=np.float32))

@@ -223,3 +223,21 @@ def test_edge_discretisation_oracle_matches_the_host_mirror(orc):
     assert np.allclose(pts, np.stack([4.0 * uu, 8.0 * uu], axis=1), atol=1e-9)
     ln = Line((0.1, 0.2), (1.3, -0.4))
     assert np.array_equal(orc.line_interpolate(ln.start, ln.end, uu), ln.interpolate(uu))
+
+
+def test_viewer_buffers_oracle(orc):
+    """gui/lib.zig:227-318: f32 points in block order with ranges, line indices per block (along j, then along i)."""
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=(4, 3, 2)), rng.normal(size=(3, 5, 2)) + 2.0
+    pts, rx, ry, idx = orc.viewer_buffers([a, b])
+    ref = np.concatenate([a.reshape(-1, 2), b.reshape(-1, 2)]).astype(np.float32)
+    assert np.array_equal(pts, ref.ravel())
+    assert rx[0] == ref[:, 0].min() and rx[1] == ref[:, 0].max() and ry[0] == ref[:, 1].min() and ry[1] == ref[:, 1].max()
+    want, off = [], 0
+    for ni, nj in ((4, 3), (3, 5)):
+        want += [v for i in range(ni) for j in range(nj - 1) for v in (off + i * nj + j, off + i * nj + j + 1)]
+        want += [v for j in range(nj) for i in range(ni - 1) for v in (off + i * nj + j, off + (i + 1) * nj + j)]
+        off += ni * nj
+    assert np.array_equal(idx, np.array(want, dtype=np.uint32))
+    neg = orc.viewer_buffers([-np.abs(a) - 1.0])                      # all coordinates negative: the maxima keep their start value
+    assert neg[1][1] == np.float32(1.1754944e-38) and neg[2][1] == np.float32(1.1754944e-38)

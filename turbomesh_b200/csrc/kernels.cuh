@@ -1588,4 +1588,59 @@ __global__ void __launch_bounds__(128) edge_discretize_kernel(const EdgeJob* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Viewer buffers (src/gui/lib.zig:227-318): f32 copies of all points with their x / y ranges
+// (createPointBuffer) and the wireframe line indices (createWireframeElementBuffer: per block first the segments along j,
+// then those along i), produced on the device -- into a mapped GL buffer if the caller hands one in.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) viewer_points_kernel(int64_t n, const double2* __restrict__ x, float2* __restrict__ out, float* __restrict__ partials /* grid x 4 */) {
+    float xmin = 3.402823466e+38f, xmax = 1.175494351e-38f, ymin = 3.402823466e+38f, ymax = 1.175494351e-38f;  // floatMax / floatMin as in the reference
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (int64_t)gridDim.x * 256) {
+        const double2 p = x[k];
+        const float2 f = make_float2(__double2float_rn(p.x), __double2float_rn(p.y));
+        out[k] = f;
+        xmin = fminf(xmin, f.x); xmax = fmaxf(xmax, f.x); ymin = fminf(ymin, f.y); ymax = fmaxf(ymax, f.y);
+    }
+    __shared__ float sh[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][w] = xmin; sh[1][w] = xmax; sh[2][w] = ymin; sh[3][w] = ymax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) { xmin = fminf(xmin, sh[0][q]); xmax = fmaxf(xmax, sh[1][q]); ymin = fminf(ymin, sh[2][q]); ymax = fmaxf(ymax, sh[3][q]); }
+        float* p = partials + (size_t)blockIdx.x * 4;
+        p[0] = xmin; p[1] = xmax; p[2] = ymin; p[3] = ymax;
+    }
+}
+__global__ void viewer_ranges_kernel(const float* __restrict__ partials, int n_part, float* __restrict__ ranges /* xmin xmax ymin ymax */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float r[4] = {3.402823466e+38f, 1.175494351e-38f, 3.402823466e+38f, 1.175494351e-38f};
+    for (int k = 0; k < n_part; ++k) {
+        r[0] = fminf(r[0], partials[4 * k]); r[1] = fmaxf(r[1], partials[4 * k + 1]);
+        r[2] = fminf(r[2], partials[4 * k + 2]); r[3] = fmaxf(r[3], partials[4 * k + 3]);
+    }
+    for (int k = 0; k < 4; ++k) ranges[k] = r[k];
+}
+struct ViewerBlock { int64_t point_off, index_off; int32_t ni, nj; };  // offsets of the block in the point / index buffers
+__global__ void __launch_bounds__(256) viewer_wireframe_kernel(const ViewerBlock* __restrict__ blocks, uint2* __restrict__ lines) {
+    const ViewerBlock b = blocks[blockIdx.y];
+    const int64_t n_j = (int64_t)b.ni * (b.nj - 1), n_i = (int64_t)b.nj * (b.ni - 1);   // segments along j, along i
+    uint2* out = lines + b.index_off / 2;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < n_j + n_i; k += (int64_t)gridDim.x * 256) {
+        unsigned p, q;
+        if (k < n_j) {              // i-th line, j-th segment: (i*nj + j, i*nj + j + 1)
+            const int64_t i = k / (b.nj - 1), j = k - i * (b.nj - 1);
+            p = (unsigned)(b.point_off + i * b.nj + j); q = p + 1u;
+        } else {                    // j-th column, i-th segment: (i*nj + j, (i+1)*nj + j)
+            const int64_t kk = k - n_j, j = kk / (b.ni - 1), i = kk - j * (b.ni - 1);
+            p = (unsigned)(b.point_off + i * b.nj + j); q = p + (unsigned)b.nj;
+        }
+        out[k] = make_uint2(p, q);
+    }
+}
+
 }  // namespace tmesh

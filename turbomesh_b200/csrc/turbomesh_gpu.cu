@@ -2132,6 +2132,59 @@ int tm_mesh_download_block_soa(tm_mesh* m, size_t block, int field, double* x, d
         CUDA_TRY(cudaStreamSynchronize(m->stream));
     });
 }
+int tm_mesh_viewer_sizes(const tm_mesh* m, uint64_t* n_points, uint64_t* n_indices) {
+    return guarded([&] {
+        check_mesh(m);
+        uint64_t np = 0, nx = 0;
+        for (const auto& B : m->topo.blocks) { np += uint64_t(B.ni * B.nj); nx += uint64_t(B.ni * (B.nj - 1) * 2 + B.nj * (B.ni - 1) * 2); }
+        if (n_points) *n_points = np;
+        if (n_indices) *n_indices = nx;
+    });
+}
+int tm_mesh_viewer_buffers(tm_mesh* m, float* points, float* ranges, uint32_t* indices) {
+    return guarded([&] {
+        check_mesh(m);
+        if (m->n_ranks != 1) TM_THROW(TM_ERR_UNSUPPORTED, "viewer buffers are built for single-GPU meshes");
+        if (m->topo.n_nodes >= (int64_t(1) << 32)) TM_THROW(TM_ERR_UNSUPPORTED, "more than 2^32 points: 32-bit line indices (gl.uint, gui/lib.zig:267) cannot address them");
+        CUDA_TRY(cudaSetDevice(m->device));
+        RankMesh& r = *m->ranks[0];
+        cudaStream_t s = m->stream;
+        const int64_t n = r.L.n_own;  // one rank: the local field is all blocks in the reference's order
+        if (points || ranges) {
+            DevBuf<float2> d_pts;
+            DevBuf<float> d_part, d_rng;
+            d_pts.alloc(size_t(n));
+            d_part.alloc(size_t(r.vec_grid) * 4);
+            d_rng.alloc(4);
+            LAUNCH(viewer_points_kernel, r.vec_grid, 256, s, n, (const double2*)r.X[r.cur].p, d_pts.p, d_part.p);
+            LAUNCH(viewer_ranges_kernel, 1, 32, s, (const float*)d_part.p, r.vec_grid, d_rng.p);
+            // cudaMemcpyDefault: the destinations may be host memory or device memory (a mapped GL buffer)
+            if (points) CUDA_TRY(cudaMemcpyAsync(points, d_pts.p, size_t(n) * sizeof(float2), cudaMemcpyDefault, s));
+            if (ranges) CUDA_TRY(cudaMemcpyAsync(ranges, d_rng.p, 4 * sizeof(float), cudaMemcpyDefault, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        if (indices) {
+            std::vector<ViewerBlock> vb;
+            int64_t poff = 0, ioff = 0, most = 0;
+            for (const auto& B : m->topo.blocks) {
+                vb.push_back(ViewerBlock{poff, ioff, int32_t(B.ni), int32_t(B.nj)});
+                const int64_t segs = B.ni * (B.nj - 1) + B.nj * (B.ni - 1);
+                most = std::max(most, segs);
+                poff += B.ni * B.nj;
+                ioff += 2 * segs;
+            }
+            if (vb.size() > 65535) TM_THROW(TM_ERR_UNSUPPORTED, "more than 65535 blocks");
+            DevBuf<ViewerBlock> d_vb;
+            DevBuf<uint2> d_idx;
+            d_vb.upload(vb, s);
+            d_idx.alloc(size_t(ioff / 2));
+            dim3 grid(unsigned(std::max<int64_t>(1, std::min<int64_t>((most + 255) / 256, 4096))), unsigned(vb.size()));
+            LAUNCH(viewer_wireframe_kernel, grid, 256, s, (const ViewerBlock*)d_vb.p, d_idx.p);
+            CUDA_TRY(cudaMemcpyAsync(indices, d_idx.p, size_t(ioff) * sizeof(uint32_t), cudaMemcpyDefault, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+    });
+}
 int tm_mesh_download_boundary_kinds(tm_mesh* m, size_t block, uint8_t* kinds) {
     return guarded([&] {
         check_mesh(m);

@@ -287,6 +287,18 @@ class DeviceMesh:
         check(self._L.tm_mesh_download_block_soa(self._h, block, {"coordinates": 0, "control_function": 1}[field], _dp(x), _dp(y)))
         return x, y
 
+    def viewer_buffers(self):
+        """f32 point buffer, (x_min, x_max, y_min, y_max) and wireframe line indices built on the device
+        (``tm_mesh_viewer_buffers``; gui/lib.zig:227-318)."""
+        n_pts, n_idx = C.c_uint64(), C.c_uint64()
+        check(self._L.tm_mesh_viewer_sizes(self._h, C.byref(n_pts), C.byref(n_idx)))
+        pts = np.empty(2 * n_pts.value, dtype=np.float32)
+        rng = np.empty(4, dtype=np.float32)
+        idx = np.empty(n_idx.value, dtype=np.uint32)
+        fp = C.POINTER(C.c_float)
+        check(self._L.tm_mesh_viewer_buffers(self._h, pts.ctypes.data_as(fp), rng.ctypes.data_as(fp), idx.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return pts, rng, idx
+
     def boundary_kinds(self, block: int) -> np.ndarray:
         ni, nj = C.c_uint64(), C.c_uint64()
         check(self._L.tm_mesh_block_size(self._h, block, C.byref(ni), C.byref(nj)))
