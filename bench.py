@@ -442,7 +442,7 @@ def run_e2e_cascade(args, spec, dm, my_blocks, solver, torch, dist, world, nodes
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="turbomesh_b200", choices=["turbomesh_b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="single-block edge length (N=1)")
