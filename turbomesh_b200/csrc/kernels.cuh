@@ -4,7 +4,8 @@
 //   winslow_interior_kernel StencilData.init + fillBlockInternalPointData       src/core/smoothing/smooth.zig:192-215, 923-992
 //                           fused with the solver's use of the row (relaxation sweep / operator apply / residual),
 //                           so the 9 coefficients live only in registers (matrix-free)
-//   winslow_boundary_kernel fillBlockConnectionData (interface rows), junction rows, sliding rows, connected copies
+//   boundary_rows           fillBlockConnectionData (interface rows), junction rows, sliding rows, connected copies
+//                           (device function: its CTAs ride in the launch of the interior kernels)
 //                                                                               smooth.zig:994-1105, 813-859, 1115-1165
 //   white_*                 White.initControlFunction / White.update            wall_control_function.zig:70-473
 //   vector kernels          BiCGStab.zig:279-370 with x and y advanced in lock-step (double2 per node)
@@ -205,12 +206,36 @@ __device__ __forceinline__ double2 row_result(const Metric& m, double2 rel, doub
 //   stats  per-CTA partials: sum dx^2, sum dy^2, (dot slots), max|d|   (only when STATS)
 // STATS for RELAX: d = out - u.  For APPLY: partial dots with `dotv` (rhat.v, or t.s and t.t) -- see K.
 // ---------------------------------------------------------------------------------------------------
+constexpr int BND_THREADS = 128;
+template <int MODE, bool LAGGED, bool HAS_PQ, int STATS, bool HAS_RHS = false>
+__device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows, int n_j,
+                                              const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
+                                              const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
+                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials,
+                                              const double2* __restrict__ rhs = nullptr, int row_override = -1);
+// The boundary rows ride in the same launch as the interior tiles (the first n_ctas CTAs of the grid): they are few
+// and latency-bound, so they hide behind the interior work instead of costing a launch of their own.
+struct BndArgs {
+    const SmoothedRow* srows;
+    const JunctionRow* jrows;
+    const SlidingRow* lrows;
+    const SlaveRow* slaves;
+    double* partials;
+    int n_s, n_j, n_l, n_ctas;
+};
+
 template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
 __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __restrict__ tiles, const DevBlock* __restrict__ blocks,
                                                                    const double2* __restrict__ u, const double2* __restrict__ xc,
                                                                    const double2* __restrict__ pq, double2* __restrict__ out, double omega,
-                                                                   const double2* __restrict__ dot_a, double* __restrict__ partials) {
-    const Tile t = tiles[blockIdx.x];
+                                                                   const double2* __restrict__ dot_a, double* __restrict__ partials, const BndArgs bnd) {
+    if ((int)blockIdx.x < bnd.n_ctas) {  // the boundary rows ride in the same launch (first n_ctas CTAs), as in the bulk kernel
+        boundary_rows<MODE, LAGGED, HAS_PQ, STATS>(blockIdx.x, bnd.srows, bnd.n_s, bnd.jrows, bnd.n_j, bnd.lrows, bnd.n_l, bnd.slaves, u, xc, pq, out, omega, dot_a,
+                                                   bnd.partials);
+        return;
+    }
+    const int tile_id = (int)blockIdx.x - bnd.n_ctas;
+    const Tile t = tiles[tile_id];
     const DevBlock b = blocks[t.block];
     const int nj = b.nj;
     const int j = t.j0 + threadIdx.x;
@@ -280,7 +305,7 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
     }
     if (STATS != 0) {
         double sums[4] = {s0, s1, s2, s3};
-        block_reduce_store<4, TILE_J>(sums, mx, partials + (size_t)blockIdx.x * 5);
+        block_reduce_store<4, TILE_J>(sums, mx, partials + (size_t)tile_id * 5);
     }
 }
 
@@ -292,24 +317,6 @@ __global__ void __launch_bounds__(TILE_J) winslow_interior_kernel(const Tile* __
 // Consumers read a node and its j-1/j+1 neighbours from shared memory (3 x LDS.128), keep the 3-row window in
 // registers and store results straight from registers (coalesced 16 B per thread).
 // ---------------------------------------------------------------------------------------------------
-constexpr int BND_THREADS = 128;
-template <int MODE, bool LAGGED, bool HAS_PQ, int STATS, bool HAS_RHS = false>
-__device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows, int n_j,
-                                              const SlidingRow* __restrict__ lrows, int n_l, const SlaveRow* __restrict__ slaves,
-                                              const double2* __restrict__ u, const double2* __restrict__ xc, const double2* __restrict__ pq,
-                                              double2* __restrict__ out, double omega, const double2* __restrict__ dot_a, double* __restrict__ partials,
-                                              const double2* __restrict__ rhs = nullptr, int row_override = -1);
-// The boundary rows ride in the same launch as the interior tiles (the first n_ctas CTAs of the grid): they are few
-// and latency-bound, so they hide behind the interior work instead of costing a launch of their own.
-struct BndArgs {
-    const SmoothedRow* srows;
-    const JunctionRow* jrows;
-    const SlidingRow* lrows;
-    const SlaveRow* slaves;
-    double* partials;
-    int n_s, n_j, n_l, n_ctas;
-};
-
 constexpr int BULK_R = 4;    // rows per pipeline stage
 constexpr int BULK_NS = 3;   // stages
 constexpr int BULK_ROW = TILE_J + 2;
@@ -564,16 +571,6 @@ __device__ __forceinline__ void boundary_rows(int cta, const SmoothedRow* __rest
         double sums[4] = {s0, s1, s2, s3};
         block_reduce_store<4, BND_THREADS>(sums, mx, partials + (size_t)cta * 5);
     }
-}
-
-template <int MODE, bool LAGGED, bool HAS_PQ, int STATS>
-__global__ void __launch_bounds__(BND_THREADS) winslow_boundary_kernel(const SmoothedRow* __restrict__ srows, int n_s, const JunctionRow* __restrict__ jrows,
-                                                                       int n_j, const SlidingRow* __restrict__ lrows, int n_l,
-                                                                       const SlaveRow* __restrict__ slaves, const double2* __restrict__ u,
-                                                                       const double2* __restrict__ xc, const double2* __restrict__ pq,
-                                                                       double2* __restrict__ out, double omega, const double2* __restrict__ dot_a,
-                                                                       double* __restrict__ partials) {
-    boundary_rows<MODE, LAGGED, HAS_PQ, STATS>(blockIdx.x, srows, n_s, jrows, n_j, lrows, n_l, slaves, u, xc, pq, out, omega, dot_a, partials);
 }
 
 // mode 0: v[slave] = v[root]; mode 1: v[slave] = v[root] + shift (keeps `connected` copies consistent,

@@ -573,17 +573,13 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
     const double2* pq = r.pq.p;
     cudaStream_t s = part.stream ? part.stream : m->stream;
     const int t_first = part.first, t_count = part.count < 0 ? r.n_tiles : part.count, b_ctas = part.bnd ? r.n_bnd_ctas : 0;
-#define TM_BND(LAG, PQ)                                                                                                                           \
-    if (r.n_bnd_rows > 0)                                                                                                                         \
-        LAUNCH((winslow_boundary_kernel<MODE, LAG, PQ, STATS>), r.n_bnd_ctas, BND_THREADS, s, (const SmoothedRow*)r.d_srows.p,                   \
-               int(r.L.smoothed.size()), (const JunctionRow*)r.d_jrows.p, int(r.L.junction_rows.size()), (const SlidingRow*)r.d_lrows.p,         \
-               int(r.L.sliding.size()), (const SlaveRow*)r.d_slaves.p, u, xc, pq, out, omega, dot_a, r.part_bnd.p)
 #define TM_ROWS(LAG, PQ)                                                                                                                          \
     do {                                                                                                                                          \
-        if (r.n_tiles > 0)                                                                                                                        \
-            LAUNCH((winslow_interior_kernel<MODE, LAG, PQ, STATS>), r.n_tiles, TILE_J, s, (const Tile*)r.d_tiles.p, (const DevBlock*)r.d_blocks.p, \
-                   u, xc, pq, out, omega, dot_a, r.part_int.p);                                                                                   \
-        TM_BND(LAG, PQ);                                                                                                                          \
+        const BndArgs bnd{r.d_srows.p, r.d_jrows.p, r.d_lrows.p, r.d_slaves.p, r.part_bnd.p, int(r.L.smoothed.size()),                            \
+                          int(r.L.junction_rows.size()), int(r.L.sliding.size()), r.n_bnd_ctas};                                                  \
+        if (r.n_tiles + r.n_bnd_ctas > 0)                                                                                                         \
+            LAUNCH((winslow_interior_kernel<MODE, LAG, PQ, STATS>), r.n_tiles + r.n_bnd_ctas, TILE_J, s, (const Tile*)r.d_tiles.p,                \
+                   (const DevBlock*)r.d_blocks.p, u, xc, pq, out, omega, dot_a, r.part_int.p, bnd);                                               \
     } while (0)
 #define TM_ROWS_BULK(PQ)                                                                                                                          \
     do {                                                                                                                                          \
@@ -598,7 +594,6 @@ void launch_rows(tm_mesh* m, RankMesh& r, bool lagged, const double2* u, const d
     else { if (has_pq) TM_ROWS(false, true); else TM_ROWS(false, false); }
 #undef TM_ROWS
 #undef TM_ROWS_BULK
-#undef TM_BND
 }
 
 // multigrid levels: all rows of the rank (interior tiles + boundary CTAs) through the bulk kernel, Laplace control
