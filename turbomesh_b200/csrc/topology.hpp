@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/turbomesh_gpu.h"
@@ -127,10 +128,13 @@ struct Topology {
         }
         if (r.start > r.end) along = -along;
     }
-    size_t block_of(int64_t g) const {
-        size_t b = blocks.size() - 1;
-        while (g < blocks[b].off) --b;
-        return b;
+    size_t block_of(int64_t g) const {  // offsets ascend: binary search (a batch of cuts has thousands of blocks)
+        size_t lo = 0, hi = blocks.size() - 1;
+        while (lo < hi) {
+            const size_t mid = (lo + hi + 1) / 2;
+            if (blocks[mid].off <= g) lo = mid; else hi = mid - 1;
+        }
+        return lo;
     }
     // boundary.zig:248-285; -1 when (block, local) is not on the block boundary
     int64_t bid(size_t block, int64_t local) const {
@@ -205,18 +209,38 @@ struct Topology {
             }
         }
         const size_t ne = ids.size();
+        // The reference scans all pairs a < b with ids[a] == ids[b] in lexicographic order (O(ne^2)) and, per pair, all
+        // junctions found so far.  Same visiting order here, but the candidates come from an index: positions grouped by
+        // id, junctions looked up by the node ids they contain (a batch of cuts has ~1e5 end points).
+        std::vector<size_t> order(ne);
+        for (size_t k = 0; k < ne; ++k) order[k] = k;
+        std::sort(order.begin(), order.end(), [&](size_t x, size_t y) { return ids[x] != ids[y] ? ids[x] < ids[y] : x < y; });
+        std::vector<size_t> rank_of(ne);  // position of k inside `order`
+        for (size_t k = 0; k < ne; ++k) rank_of[order[k]] = k;
+        std::unordered_map<int64_t, std::vector<size_t>> junctions_with;  // node id -> junctions holding it, ascending
+        auto note_copy = [&](size_t j, int64_t g) {  // sorted, unique
+            auto& v = junctions_with[g];
+            const auto it = std::lower_bound(v.begin(), v.end(), j);
+            if (it == v.end() || *it != j) v.insert(it, j);
+        };
         for (size_t a = 0; a + 1 < ne; ++a) {
-            for (size_t b = a + 1; b < ne; ++b) {
-                if (ids[a] != ids[b]) continue;
+            for (size_t q = rank_of[a] + 1; q < ne && ids[order[q]] == ids[a]; ++q) {
+                const size_t b = order[q];  // ascending b > a with the same id
                 bool found = false;
-                for (auto& jn : junctions) {
-                    const size_t n_before = jn.copies.size(); // the reference iterates a slice taken before appending
-                    for (size_t k = 0; k < n_before; ++k) {
-                        if (jn.copies[k].g != ids[a]) continue;
-                        found = true;
-                        const size_t add = (b % 2 == 0) ? b + 1 : b - 1; // smooth.zig:1378
-                        double px, py; periodicity_of(conns[add / 4], px, py);
-                        append_if_unique(jn, ids[add], px, py);
+                const auto hit = junctions_with.find(ids[a]);
+                if (hit != junctions_with.end()) {
+                    const std::vector<size_t> holders = hit->second;  // copy: appending below may touch the map
+                    for (size_t j : holders) {
+                        Junction& jn = junctions[j];
+                        const size_t n_before = jn.copies.size(); // the reference iterates a slice taken before appending
+                        for (size_t k = 0; k < n_before; ++k) {
+                            if (jn.copies[k].g != ids[a]) continue;
+                            found = true;
+                            const size_t add = (b % 2 == 0) ? b + 1 : b - 1; // smooth.zig:1378
+                            double px, py; periodicity_of(conns[add / 4], px, py);
+                            append_if_unique(jn, ids[add], px, py);
+                            note_copy(j, ids[add]);
+                        }
                     }
                 }
                 if (found) continue;
@@ -231,6 +255,7 @@ struct Topology {
                 periodicity_of(conns[p1 / 2], px, py);
                 append_if_unique(jn, ids[2 * p1], px, py);
                 append_if_unique(jn, ids[2 * p1 + 1], px, py);
+                for (const auto& cp : jn.copies) note_copy(junctions.size(), cp.g);
                 junctions.push_back(std::move(jn));
             }
         }
