@@ -210,3 +210,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and "workload" in line["config"]
+
+
+def test_topology_analysis_of_a_batch_of_cuts_is_per_cut_and_fast(gpu_lib):
+    """Independent cuts concatenated into one mesh: every cut contributes exactly the rows of a single cut (the junction
+    discovery visits end-point pairs in the reference's order through an index, not by the O(n^2) scan), in linear time."""
+    import time
+
+    from turbomesh_b200 import smoothing, synthetic
+
+    base, _, _ = __import__("util").load_fixture("t106_white")
+    one = smoothing.dist_plan(base, [0] * len(base.blocks), 0, 1)
+    n = 96
+    batch, groups = synthetic.batch_of_cuts(base, [1.0 + 0.002 * k for k in range(n)])
+    t0 = time.perf_counter()
+    many = smoothing.dist_plan(batch, [0] * len(batch.blocks), 0, 1)
+    assert time.perf_counter() - t0 < 20.0
+    for key in ("n_own", "n_smoothed", "n_junction", "n_sliding", "n_slaves"):
+        assert many[key] == n * one[key], key
+    assert groups[5] == (5 * len(base.blocks), 5 * len(base.blocks) + 1)
