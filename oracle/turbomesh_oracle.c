@@ -2,7 +2,9 @@
  * turbomesh_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
  *
  * A plain-C, single-threaded restatement of the reference's (pascalPost/turbomesh) hot path:
- * boundary-blended linear TFI + the multi-block elliptic smoother with its built-in Krylov solvers.
+ * boundary-blended linear TFI + the multi-block elliptic smoother with its built-in Krylov solvers,
+ * and of the data-parallel steps either side of it (edge discretisation: clustering + line / spline
+ * interpolation; structured SoA output; viewer buffers) at the end of this file.
  * Each function cites the reference file:line it follows (paths relative to the turbomesh repository).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may load
