@@ -16,6 +16,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <limits>
 #include <map>
 #include <vector>
 
@@ -57,34 +58,57 @@ struct ReadSets {
     std::vector<int64_t> synth;              // remote `connected` copies derived locally from their root (sorted, unique)
 };
 
-// remote nodes read by the rows of rank r
-inline ReadSets read_sets(const Topology& T, const std::vector<int32_t>& owner, int r, int n_ranks, const std::map<int64_t, int64_t>& root_of) {
-    ReadSets out;
-    out.recv.assign(size_t(n_ranks), {});
-    auto recv = [&](int64_t g) {
-        const int o = owner_of_node(T, owner, g);
-        if (o != r) out.recv[size_t(o)].push_back(g);
-    };
-    auto need = [&](int64_t g) {
-        if (owner_of_node(T, owner, g) == r) return;
-        const auto it = root_of.find(g);
-        if (it != root_of.end()) { out.synth.push_back(g); recv(it->second); }  // a copy: keep a slot, fetch its root instead
-        else recv(g);
-    };
-    for (const auto& row : T.smoothed)
-        if (owner_of_node(T, owner, row.g0) == r) { need(row.iN); need(row.iNW); need(row.iNE); }
-    for (const auto& row : T.junction_rows)
-        if (owner_of_node(T, owner, row.self) == r)
-            for (int k = 0; k < row.n; ++k) need(row.nbr[k]);
-    for (const auto* list : {&T.slaves, &T.const_slaves})
-        for (const auto& s : *list)
-            if (owner_of_node(T, owner, s.self) == r) need(s.root);
-    for (auto& v : out.recv) {
+// copy -> root for the copies whose root is a free row, sorted by copy id (binary-searched)
+struct RootTable {
+    std::vector<std::pair<int64_t, int64_t>> v;
+    explicit RootTable(const Topology& T) {
+        v.reserve(T.slaves.size());
+        for (const auto& s : T.slaves) v.push_back({s.self, s.root});
         std::sort(v.begin(), v.end());
-        v.erase(std::unique(v.begin(), v.end()), v.end());
     }
-    std::sort(out.synth.begin(), out.synth.end());
-    out.synth.erase(std::unique(out.synth.begin(), out.synth.end()), out.synth.end());
+    bool find(int64_t g, int64_t& root) const {
+        const auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(g, std::numeric_limits<int64_t>::min()));
+        if (it == v.end() || it->first != g) return false;
+        root = it->second;
+        return true;
+    }
+};
+
+// remote nodes read by the rows of EVERY rank, in one pass over the rows (a row is evaluated by the owner of its node)
+inline std::vector<ReadSets> read_sets_all(const Topology& T, const std::vector<int32_t>& owner, int n_ranks, const RootTable& root_of) {
+    std::vector<ReadSets> out;
+    out.resize(size_t(n_ranks));
+    for (auto& rs : out) rs.recv.assign(size_t(n_ranks), {});
+    auto need = [&](int r, int64_t g) {  // rank r reads node g
+        const int o = owner_of_node(T, owner, g);
+        if (o == r) return;
+        int64_t root;
+        if (root_of.find(g, root)) {  // a copy: keep a slot, fetch its root instead
+            out[size_t(r)].synth.push_back(g);
+            const int ro = owner_of_node(T, owner, root);
+            if (ro != r) out[size_t(r)].recv[size_t(ro)].push_back(root);
+        } else {
+            out[size_t(r)].recv[size_t(o)].push_back(g);
+        }
+    };
+    for (const auto& row : T.smoothed) {
+        const int r = owner_of_node(T, owner, row.g0);
+        need(r, row.iN); need(r, row.iNW); need(r, row.iNE);
+    }
+    for (const auto& row : T.junction_rows) {
+        const int r = owner_of_node(T, owner, row.self);
+        for (int k = 0; k < row.n; ++k) need(r, row.nbr[k]);
+    }
+    for (const auto* list : {&T.slaves, &T.const_slaves})
+        for (const auto& s : *list) need(owner_of_node(T, owner, s.self), s.root);
+    for (auto& rs : out) {
+        for (auto& v : rs.recv) {
+            std::sort(v.begin(), v.end());
+            v.erase(std::unique(v.begin(), v.end()), v.end());
+        }
+        std::sort(rs.synth.begin(), rs.synth.end());
+        rs.synth.erase(std::unique(rs.synth.begin(), rs.synth.end()), rs.synth.end());
+    }
     return out;
 }
 
@@ -134,27 +158,23 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
         L.loff[b] = L.n_own;
         L.n_own += T.blocks[b].ni * T.blocks[b].nj;
     }
-    std::map<int64_t, int64_t> root_of;  // copy -> root, for copies whose root is a free row
-    for (const auto& s : T.slaves) root_of[s.self] = s.root;
-    {
-        ReadSets mine_sets = read_sets(T, owner, rank, n_ranks, root_of);
-        L.ghost_ids = std::move(mine_sets.recv);
-        L.synth_ids = std::move(mine_sets.synth);
-    }
+    const RootTable root_of(T);
+    std::vector<ReadSets> all = read_sets_all(T, owner, n_ranks, root_of);
     L.send_ids.assign(size_t(n_ranks), {});
     L.peer_ghost_offset.assign(size_t(n_ranks), 0);
     for (int p = 0; p < n_ranks; ++p) {
         if (p == rank) continue;
-        ReadSets theirs = read_sets(T, owner, p, n_ranks, root_of);
         // p's local field is [own nodes of p | ghosts from rank 0 | from rank 1 | ...]: my segment starts after p's own nodes
         // and the ghosts p receives from the ranks below me
         int64_t off = 0;
         for (size_t b = 0; b < T.blocks.size(); ++b)
             if (owner[b] == p) off += T.blocks[b].ni * T.blocks[b].nj;
-        for (int q = 0; q < rank; ++q) off += int64_t(theirs.recv[size_t(q)].size());
+        for (int q = 0; q < rank; ++q) off += int64_t(all[size_t(p)].recv[size_t(q)].size());
         L.peer_ghost_offset[size_t(p)] = off;
-        L.send_ids[size_t(p)] = std::move(theirs.recv[size_t(rank)]);
+        L.send_ids[size_t(p)] = std::move(all[size_t(p)].recv[size_t(rank)]);
     }
+    L.ghost_ids = std::move(all[size_t(rank)].recv);
+    L.synth_ids = std::move(all[size_t(rank)].synth);
     L.ghost_base.assign(size_t(n_ranks) + 1, 0);
     L.send_base.assign(size_t(n_ranks) + 1, 0);
     for (int p = 0; p < n_ranks; ++p) {
