@@ -229,3 +229,44 @@ def test_topology_analysis_of_a_batch_of_cuts_is_per_cut_and_fast(gpu_lib):
     for key in ("n_own", "n_smoothed", "n_junction", "n_sliding", "n_slaves"):
         assert many[key] == n * one[key], key
     assert groups[5] == (5 * len(base.blocks), 5 * len(base.blocks) + 1)
+
+
+def test_topology_validation_reports_what_the_reference_only_asserts(gpu_lib):
+    """the reference's `std.debug.assert`s vanish in ReleaseFast; the C ABI validates the
+    topology on the host (no GPU needed: tm_dist_plan runs the same analysis as tm_mesh_create) and reports a status code
+    plus a message instead of aborting."""
+    from dataclasses import replace
+
+    from turbomesh_b200 import _lib, smoothing, synthetic
+    from turbomesh_b200.boundary import Side
+
+    def set_range(m, c, s, **kw):
+        cn = m.connections[c]
+        rs = list(cn.ranges)
+        rs[s] = replace(rs[s], **kw)
+        m.connections[c] = replace(cn, ranges=tuple(rs))
+
+    def swap(m):
+        m.connections[0] = replace(m.connections[0], ranges=m.connections[0].ranges[::-1])
+
+    def bad_condition(m):
+        bc = m.boundary_conditions[0]
+        m.boundary_conditions[0] = replace(bc, range=replace(bc.range, block=77))
+
+    cases = [
+        (lambda m: set_range(m, 0, 1, block=9), _lib.TM_ERR_TOPOLOGY, "out of bounds"),
+        (lambda m: set_range(m, 0, 0, end=999), _lib.TM_ERR_TOPOLOGY, "out of bounds"),
+        (lambda m: set_range(m, 0, 1, end=7), _lib.TM_ERR_TOPOLOGY, "differ in length"),
+        (lambda m: (set_range(m, 0, 0, end=3), set_range(m, 0, 1, end=3)), _lib.TM_ERR_UNSUPPORTED, "at least 6 nodes"),  # smooth.zig:631
+        (swap, _lib.TM_ERR_TOPOLOGY, "smooth.zig:627"),
+        (lambda m: set_range(m, 0, 1, block=0, side=Side.j_min), _lib.TM_ERR_TOPOLOGY, ""),  # same-block connections: i_min -> i_max only
+        (bad_condition, _lib.TM_ERR_TOPOLOGY, "condition 0"),
+    ]
+    for mutate, code, text in cases:
+        mesh = synthetic.cascade(2, 2, 12, 9)
+        mutate(mesh)
+        with pytest.raises(_lib.TurbomeshGpuError) as e:
+            smoothing.dist_plan(mesh, [0] * 4, 0, 1)
+        assert e.value.code == code and text in e.value.message, (e.value.code, e.value.message)
+    with pytest.raises(_lib.TurbomeshGpuError, match="owner 5 out of range"):
+        smoothing.dist_plan(synthetic.cascade(2, 2, 12, 9), [0, 0, 0, 5], 0, 2)
