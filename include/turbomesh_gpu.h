@@ -125,7 +125,7 @@ typedef struct tm_smooth_stats {
     double last_inner_residual;    /* max over x,y of the final inner residual norm              */
     double gpu_seconds;            /* device time of the smoothing loop (CUDA events)            */
     int32_t converged;             /* all inner solves reached their tolerance                   */
-    int32_t _pad;
+    int32_t streamed_chunks;       /* tm_smooth_mesh: row chunks the block was streamed in (0 = resident, see tm_smooth_stream_plan) */
 } tm_smooth_stats;
 
 /* -------------------------------------------------------------------------------------------------
@@ -299,6 +299,17 @@ int tm_mg_plan(const tm_block *blocks, size_t n_blocks,
                const tm_connection *connections, size_t n_connections,
                const tm_condition *conditions, size_t n_conditions,
                const double *cell_size, size_t max_levels, uint64_t *n_levels, uint64_t *sizes);
+
+/* Host-only view of how tm_smooth_mesh streams a large single block through the device (needs no GPU).  A block of
+ * ni x nj nodes whose boundary nodes are all fixed (no connections, no inlet / outlet), smoothed by TM_SOLVER_RELAX with
+ * the Laplace control function for a fixed number of `sweeps`, is cut into row chunks: chunk k owns the rows
+ * [owned_first[k], owned_first[k+1]) and travels as the window of `*window_rows` rows starting at window_first[k], which
+ * holds at least `sweeps` extra rows on every side that is not a block boundary -- enough for `sweeps` Jacobi sweeps of
+ * the window to leave the owned rows exactly as sweeps of the whole block would; upload, sweeps and download of
+ * successive chunks overlap.  *n_chunks = 0: the block is smoothed resident (too small, too many sweeps for its
+ * extent, or TM_STREAM=0).  window_first needs 8 entries, owned_first 9. */
+int tm_smooth_stream_plan(uint64_t ni, uint64_t nj, uint64_t sweeps, uint64_t *n_chunks, uint64_t *window_rows,
+                          uint64_t *window_first, uint64_t *owned_first);
 
 /* -------------------------------------------------------------------------------------------------
  * Misc

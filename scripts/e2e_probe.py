@@ -28,7 +28,7 @@ mesh = Mesh([Block2d.__new__(Block2d)], ["block"], [], [])
 mesh.blocks[0].points = host
 def T(f):
     torch.cuda.synchronize(); t0 = time.perf_counter(); r = f(); torch.cuda.synchronize(); return (time.perf_counter() - t0) * 1e3, r
-for it in range(4):
+for it in range(int(os.environ.get('PROBE_ITERS', '4'))):
     t1, _ = T(lambda: smoothing.tfi_block(*edges, out=host))
     t2, _ = T(lambda: smoothing.smooth_mesh(mesh, 1, solver))
     print(f"[{mode}] tfi_block {t1:.1f} ms, smooth_mesh {t2:.1f} ms")

@@ -127,3 +127,34 @@ def test_multigrid_rejects_the_white_control_function(orc, gpu_lib):
     with pytest.raises(_lib.TurbomeshGpuError) as e:
         smoothing.smooth_mesh(mesh, 2, smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=2), smoothing.White(1e-4))
     assert e.value.code == _lib.TM_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("shape,iterations,sweeps", [((700, 160), 2, 12), ((300, 67), 1, 30), ((1500, 40), 3, 5)])
+def test_streamed_host_smoothing_is_bit_identical(gpu_lib, monkeypatch, shape, iterations, sweeps):
+    """tm_smooth_mesh streams a large single block through the device in row chunks, copies overlapped with the sweeps
+    (streamed.inl); every node gets the arithmetic of the resident path, so the meshes are equal bit for bit."""
+    from turbomesh_b200 import smoothing
+    from turbomesh_b200.discrete import Block2d, Mesh
+
+    base = synthetic.materialize(synthetic.single_block(*shape), smoothing.tfi_block).blocks[0].points
+    solver = smoothing.CudaSolver(method="relax", sweeps_per_iteration=sweeps, omega=0.9)
+
+    def run():
+        mesh = Mesh()
+        mesh.add_block("block", Block2d(base.copy()))
+        return mesh.blocks[0].points, smoothing.smooth_mesh(mesh, iterations, solver)
+
+    monkeypatch.setenv("TM_STREAM", "0")
+    resident, st_r = run()
+    monkeypatch.setenv("TM_STREAM", "1")
+    monkeypatch.setenv("TM_STREAM_MIN_NODES", "0")
+    plan = smoothing.stream_plan(shape[0], shape[1], iterations * sweeps)
+    assert plan is not None
+    streamed, st_s = run()
+    assert st_r["streamed_chunks"] == 0 and st_s["streamed_chunks"] == len(plan[1]) >= 2
+    assert np.array_equal(streamed, resident)
+    assert not np.array_equal(streamed, base)
+    assert st_s["last_max_update"] == st_r["last_max_update"]
+    assert st_s["last_sumsq_x"] == pytest.approx(st_r["last_sumsq_x"], rel=1e-12) and st_s["last_sumsq_y"] == pytest.approx(st_r["last_sumsq_y"], rel=1e-12)
+    for key in ("outer_iterations", "inner_iterations", "operator_applications", "nodes", "converged"):
+        assert st_s[key] == st_r[key], key

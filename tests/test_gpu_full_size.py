@@ -139,3 +139,22 @@ def test_uniform_grid_is_a_fixed_point_and_sweeps_are_translation_equivariant_at
     smoothing.smooth_mesh(a, 1, solver)
     smoothing.smooth_mesh(b, 1, solver)
     assert float(np.abs(b.blocks[0].points - shift - a.blocks[0].points).max()) <= 1e-14
+
+
+def test_streamed_and_resident_host_smoothing_agree_bit_for_bit_at_full_size(gpu_lib, full_block, monkeypatch):
+    """The bench's end-to-end step (tm_smooth_mesh on the 8192^2 block, 100 sweeps): 8 row chunks streamed through the
+    device with the copies overlapped give the mesh of the resident path bit for bit."""
+    from turbomesh_b200 import smoothing
+
+    _, before = full_block
+    solver = smoothing.CudaSolver(method="relax", sweeps_per_iteration=100, omega=OMEGA)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TM_STREAM", mode)
+        mesh = Mesh()
+        mesh.add_block("block", Block2d(before.copy()))
+        st = smoothing.smooth_mesh(mesh, 1, solver)
+        out[mode] = (mesh.blocks[0].points, st)
+    assert out["0"][1]["streamed_chunks"] == 0 and out["1"][1]["streamed_chunks"] == 8
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert out["0"][1]["last_max_update"] == out["1"][1]["last_max_update"] > 0.0

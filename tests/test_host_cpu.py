@@ -270,3 +270,37 @@ def test_topology_validation_reports_what_the_reference_only_asserts(gpu_lib):
         assert e.value.code == code and text in e.value.message, (e.value.code, e.value.message)
     with pytest.raises(_lib.TurbomeshGpuError, match="owner 5 out of range"):
         smoothing.dist_plan(synthetic.cascade(2, 2, 12, 9), [0, 0, 0, 5], 0, 2)
+
+
+def test_stream_plan_covers_every_row_once_with_enough_margin(gpu_lib, monkeypatch):
+    """Host-only plan of the streamed tm_smooth_mesh (streamed.inl): the chunks own every row exactly once, every window
+    keeps `sweeps` rows between an artificial edge and the rows it owns, and reads owned rows of its direct neighbours
+    only (the order of uploads and downloads relies on that)."""
+    import random
+
+    from turbomesh_b200 import smoothing
+
+    assert smoothing.stream_plan(512, 512, 10) is None          # below TM_STREAM_MIN_NODES (default 8 Mi nodes): resident
+    w, first, owned = smoothing.stream_plan(8192, 8192, 100)    # the bench's end-to-end step
+    assert len(first) == 8 and w * 8 < 1.2 * 8192
+    monkeypatch.setenv("TM_STREAM_MIN_NODES", "0")
+    rng = random.Random(7)
+    n_plans = 0
+    for _ in range(3000):
+        ni, t = rng.randint(3, 30000), rng.randint(1, 500)
+        plan = smoothing.stream_plan(ni, 64, t)
+        if plan is None:
+            assert ni // (4 * t) < 2 or ni < 9
+            continue
+        n_plans += 1
+        w, first, owned = plan
+        k_n = len(first)
+        assert 2 <= k_n <= 8 and owned[0] == 0 and owned[-1] == ni and first[0] == 0 and first[-1] + w == ni
+        for k in range(k_n):
+            assert owned[k] < owned[k + 1] and first[k] <= owned[k] and owned[k + 1] <= first[k] + w
+            assert first[k] == 0 or owned[k] - first[k] >= t
+            assert first[k] + w == ni or first[k] + w - owned[k + 1] >= t
+            assert k < 2 or first[k] >= owned[k - 1]
+    assert n_plans > 1000
+    monkeypatch.setenv("TM_STREAM", "0")
+    assert smoothing.stream_plan(8192, 8192, 100) is None

@@ -44,7 +44,7 @@ class TmSmoothOptions(C.Structure):
 class TmSmoothStats(C.Structure):
     _fields_ = [("outer_iterations", C.c_uint64), ("inner_iterations", C.c_uint64), ("operator_applications", C.c_uint64), ("nodes", C.c_uint64),
                 ("last_sumsq_x", C.c_double), ("last_sumsq_y", C.c_double), ("last_residual", C.c_double), ("last_max_update", C.c_double),
-                ("last_inner_residual", C.c_double), ("gpu_seconds", C.c_double), ("converged", C.c_int32), ("_pad", C.c_int32)]
+                ("last_inner_residual", C.c_double), ("gpu_seconds", C.c_double), ("converged", C.c_int32), ("streamed_chunks", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
@@ -120,6 +120,7 @@ def load():
     L.tm_mg_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t, dp, C.c_size_t,
                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tm_edges_discretize.argtypes = [C.POINTER(TmEdgeJob), C.c_size_t, C.c_int]
+    L.tm_smooth_stream_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64] + [C.POINTER(C.c_uint64)] * 4
     L.tm_mesh_destroy.argtypes = [vp]
     L.tm_mesh_destroy.restype = None
     L.tm_mesh_upload_block.argtypes = [vp, C.c_size_t, dp]

@@ -9,6 +9,7 @@
 #include <nccl.h>  // types only: NCCL is resolved at run time with dlopen, single-GPU use needs no libnccl
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,16 +68,19 @@ void require_device(int device) {
     if (device >= 0) CUDA_TRY(cudaSetDevice(device));
 }
 
-// Large device allocations are recycled through a small process-wide cache: the one-shot entry points (tm_tfi_block,
+// Device allocations are recycled through a small process-wide cache: the one-shot entry points (tm_tfi_block,
 // tm_smooth_mesh) create and destroy a device mesh per call, and cudaMalloc / cudaFree of GB-sized fields would otherwise
-// cost more than the kernels they bracket.  Exact-size reuse only; at most TM_CACHE_GB (default 8) GiB are kept;
-// tm_release_cached_memory() returns everything to the driver.
+// cost more than the kernels they bracket -- and the ~25 small tables of a mesh matter as well: every cudaFree is a
+// device-wide synchronisation that was measured to take anything from 0.1 to 400 ms on a busy box.  Exact-size reuse
+// only; at most TM_CACHE_GB (default 8) GiB and kMaxEntries buffers are kept; tm_release_cached_memory() returns
+// everything to the driver.
 struct DeviceCache {
     struct Entry { void* p; size_t bytes; int device; };
     std::mutex mu;
     std::vector<Entry> free_list;
     size_t held = 0;
-    static constexpr size_t kMinBytes = size_t(32) << 20;
+    static constexpr size_t kMinBytes = 1;
+    static constexpr size_t kMaxEntries = 1024;
     size_t cap() const {
         static const size_t c = [] { const char* e = std::getenv("TM_CACHE_GB"); return size_t((e ? std::atof(e) : 8.0) * double(size_t(1) << 30)); }();
         return c;
@@ -94,7 +98,7 @@ struct DeviceCache {
     }
     bool give(void* q, size_t bytes, int device) {
         std::lock_guard<std::mutex> lock(mu);
-        if (bytes < kMinBytes || held + bytes > cap()) return false;
+        if (bytes < kMinBytes || held + bytes > cap() || free_list.size() >= kMaxEntries) return false;
         free_list.push_back(Entry{q, bytes, device});
         held += bytes;
         return true;
@@ -997,6 +1001,8 @@ void tfi_validate_host(uint64_t ni, uint64_t nj, const double* x_i_min, const do
         TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: edge corner points are not consistent (tfi.zig:150-162)");
 }
 
+#include "streamed.inl"  // smooth_streamed: tm_smooth_mesh on a large single block, copies overlapped with the sweeps
+
 }  // namespace
 
 // =====================================================================================================
@@ -1008,6 +1014,7 @@ extern "C" {
 const char* tm_last_error(void) { return g_last_error.c_str(); }
 int tm_abi_version(void) { return TM_ABI_VERSION; }
 void tm_release_cached_memory(void) {
+    release_parked_slots();  // the window meshes of the streamed tm_smooth_mesh (streamed.inl)
     g_cache.clear();
     std::lock_guard<std::mutex> lock(g_pinned_mu);
     for (SolveCtl* q : g_pinned_free) cudaFreeHost(q);
@@ -1572,6 +1579,23 @@ int tm_mg_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* con
     });
 }
 
+int tm_smooth_stream_plan(uint64_t ni, uint64_t nj, uint64_t sweeps, uint64_t* n_chunks, uint64_t* window_rows, uint64_t* window_first,
+                          uint64_t* owned_first) {
+    return guarded([&] {
+        if (!n_chunks || !window_rows) TM_THROW(TM_ERR_INVALID_ARGUMENT, "n_chunks / window_rows is NULL");
+        *n_chunks = 0; *window_rows = 0;
+        if (ni < 3 || nj < 3 || ni * nj >= (uint64_t(1) << 31) || sweeps > (uint64_t(1) << 40)) return;
+        StreamPlan P;
+        if (!plan_streaming(int64_t(ni), int64_t(nj), int64_t(sweeps), P)) return;
+        *n_chunks = uint64_t(P.K()); *window_rows = uint64_t(P.W);
+        for (int k = 0; k < P.K(); ++k) {
+            if (window_first) window_first[k] = uint64_t(P.w0[size_t(k)]);
+            if (owned_first) owned_first[k] = uint64_t(P.o0[size_t(k)]);
+        }
+        if (owned_first) owned_first[P.K()] = ni;
+    });
+}
+
 int tm_tfi_block(uint64_t ni, uint64_t nj, const double* x_i_min, const double* x_i_max, const double* x_j_min, const double* x_j_max, const double* s1,
                  const double* s2, const double* t1, const double* t2, double* out_xy) {
     tm_mesh* m = nullptr;
@@ -1580,13 +1604,20 @@ int tm_tfi_block(uint64_t ni, uint64_t nj, const double* x_i_min, const double* 
         if (ni < 3 || nj < 3) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: block smaller than 3x3 nodes");
     });
     if (rc != TM_OK) return rc;
+    const bool trace = std::getenv("TM_STREAM_TRACE") != nullptr;  // host-side phase times on stderr (tuning aid)
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since_start = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     tm_block blk{ni, nj, nullptr};
     rc = tm_mesh_create(&blk, 1, nullptr, 0, nullptr, 0, -1, nullptr, &m);
+    const double t_created = ms_since_start();
     if (rc == TM_OK) rc = tm_mesh_tfi_block(m, 0, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2);
+    const double t_tfi = ms_since_start();
     if (rc == TM_OK) rc = tm_mesh_download_block(m, 0, out_xy);
+    const double t_down = ms_since_start();
     std::string keep = g_last_error;
     tm_mesh_destroy(m);
     g_last_error = keep;
+    if (trace) std::fprintf(stderr, "[tfi] created %.2f ms, tfi queued %.2f ms, downloaded %.2f ms, destroyed %.2f ms\n", t_created, t_tfi, t_down, ms_since_start());
     return rc;
 }
 
@@ -1600,6 +1631,14 @@ int tm_smooth_mesh(tm_block* blocks, size_t n_blocks, const tm_connection* conne
             if (!blocks[b].xy) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %zu has no coordinates", b);
     });
     if (rc != TM_OK) return rc;
+    bool streamed = false;
+    rc = guarded([&] {
+        StreamPlan plan;
+        if (!can_stream(blocks, n_blocks, n_connections, conditions, n_conditions, opts, plan)) return;
+        smooth_streamed(blocks, opts, plan, stats);
+        streamed = true;
+    });
+    if (streamed || rc != TM_OK) return rc;
     rc = tm_mesh_create(blocks, n_blocks, connections, n_connections, conditions, n_conditions, opts->device, nullptr, &m);
     if (rc == TM_OK) rc = tm_mesh_begin_smoothing(m, opts);
     if (rc == TM_OK) rc = tm_mesh_smooth(m, opts, stats);

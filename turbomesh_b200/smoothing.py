@@ -354,6 +354,18 @@ def mg_plan(mesh, cell_size=None, max_levels: int = 32):
     return [[(int(sizes[(l * cm.nb + b) * 2]), int(sizes[(l * cm.nb + b) * 2 + 1])) for b in range(cm.nb)] for l in range(min(int(n.value), max_levels))]
 
 
+def stream_plan(ni: int, nj: int, sweeps: int):
+    """Host-only plan of the streamed ``tm_smooth_mesh`` (``tm_smooth_stream_plan``): ``None`` when the block is smoothed
+    resident, else ``(window_rows, window_first[k], owned_first[k] ... owned_first[K])``."""
+    L = _lib.load()
+    n, w = C.c_uint64(), C.c_uint64()
+    first, owned = (C.c_uint64 * 8)(), (C.c_uint64 * 9)()
+    check(L.tm_smooth_stream_plan(ni, nj, sweeps, C.byref(n), C.byref(w), first, owned))
+    if n.value == 0:
+        return None
+    return int(w.value), [int(v) for v in first[:n.value]], [int(v) for v in owned[:n.value + 1]]
+
+
 def kernel_launch_count() -> int:
     return int(_lib.load().tm_kernel_launch_count())
 

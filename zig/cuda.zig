@@ -46,7 +46,7 @@ pub const tm_smooth_stats = extern struct {
     last_inner_residual: f64,
     gpu_seconds: f64,
     converged: i32,
-    _pad: i32 = 0,
+    streamed_chunks: i32 = 0,
 };
 
 pub extern fn tm_tfi_block(ni: u64, nj: u64, x_i_min: [*]const f64, x_i_max: [*]const f64, x_j_min: [*]const f64, x_j_max: [*]const f64, s1: [*]const f64, s2: [*]const f64, t1: [*]const f64, t2: [*]const f64, out_xy: [*]f64) callconv(.c) c_int;
