@@ -142,7 +142,11 @@ int tm_tfi_block(uint64_t ni, uint64_t nj,
                  const double *s1, const double *s2, const double *t1, const double *t2,
                  double *out_xy);
 
-/* Replaces smoothing.smooth.mesh (src/core/smoothing/smooth.zig:74-166): smooths all blocks in place. */
+/* Replaces smoothing.smooth.mesh (src/core/smoothing/smooth.zig:74-166): smooths all blocks in place.
+ * A large single block whose boundary nodes are all fixed, smoothed by a fixed number of TM_SOLVER_RELAX sweeps, is
+ * streamed through the device in row chunks so that the host<->device copies overlap the sweeps (bit-identical result,
+ * see tm_smooth_stream_plan; stats->streamed_chunks tells); everything else is uploaded, smoothed and downloaded whole.
+ * If a streamed call fails half way the block may be partly smoothed. */
 int tm_smooth_mesh(tm_block *blocks, size_t n_blocks,
                    const tm_connection *connections, size_t n_connections,
                    const tm_condition *conditions, size_t n_conditions,
@@ -315,9 +319,10 @@ int tm_smooth_stream_plan(uint64_t ni, uint64_t nj, uint64_t sweeps, uint64_t *n
  * Misc
  * ------------------------------------------------------------------------------------------------- */
 const char *tm_last_error(void);
-/* Device fields of 32 MiB and more (and the pinned scalar block of a mesh) are recycled through a process-wide cache
- * when a mesh is destroyed, so that the one-shot entry points do not pay cudaMalloc / cudaFree of GB-sized fields per
- * call; at most TM_CACHE_GB GiB (environment, default 8) are kept.  This returns everything to the driver. */
+/* Device buffers (and the pinned scalar block of a mesh) are recycled through a process-wide cache when a mesh is
+ * destroyed, so that the one-shot entry points do not pay cudaMalloc / cudaFree per call; at most TM_CACHE_GB GiB
+ * (environment, default 8) are kept.  The three window meshes of the streamed tm_smooth_mesh are parked between calls
+ * likewise.  This returns everything to the driver (call it before unloading the library). */
 void tm_release_cached_memory(void);
 int tm_abi_version(void);
 /* number of CUDA kernel launches issued by this library since load (bench.py's gpu_launches) */
