@@ -158,3 +158,71 @@ def test_streamed_and_resident_host_smoothing_agree_bit_for_bit_at_full_size(gpu
     assert out["0"][1]["streamed_chunks"] == 0 and out["1"][1]["streamed_chunks"] == 8
     assert np.array_equal(out["0"][0], out["1"][0])
     assert out["0"][1]["last_max_update"] == out["1"][1]["last_max_update"] > 0.0
+
+
+def _interface_row_updates(orc, a, b, side_a, side_b, periodicity=None):
+    """Jacobi updates (b - A x)_r / a_rr of the oracle's `smoothed` rows (smooth.zig:994-1105) of a two-block window mesh
+    whose blocks `a` (side_a) and `b` (side_b) are joined over their whole common side."""
+    from turbomesh_b200.boundary import Connection, Range
+
+    mesh = Mesh()
+    mesh.add_block("a", Block2d(np.ascontiguousarray(a)))
+    mesh.add_block("b", Block2d(np.ascontiguousarray(b)))
+    n, nj = a.shape[0], a.shape[1]
+    mesh.connections.append(Connection((Range(0, side_a, 0, n - 1), Range(1, side_b, 0, n - 1)), periodicity))
+    sys_ = orc.System(mesh, orc.options(control_function="laplace"))
+    sys_.fill(0)
+    p, idx, v, rx, ry = sys_.csr()
+    sys_.close()
+    flat = np.concatenate([a.reshape(-1, 2), b.reshape(-1, 2)])
+    j = 0 if int(side_a) == 0 else nj - 1
+    worst = 0.0
+    for i in range(1, n - 1):
+        r = i * nj + j
+        cols, val = idx[p[r]:p[r + 1]], v[p[r]:p[r + 1]]
+        assert len(cols) == 9
+        diag = val[cols == r][0]
+        worst = max(worst, abs((rx[r] - val @ flat[cols, 0]) / diag), abs((ry[r] - val @ flat[cols, 1]) / diag))
+    return worst
+
+
+def test_config4_block_column_at_full_size_against_the_oracle_rows(orc, gpu_lib):
+    """One GPU's share of config 4 (8 blocks of 4097 x 2049 = 67 M nodes: interfaces, a periodic pair, the plate's walls,
+    sliding inlet / outlet): TFI bit-exact, and on the multigrid-converged mesh the oracle's own interior AND interface
+    rows, assembled on windows cut out of the full-size blocks, are satisfied; copies, walls and sliding nodes hold their
+    defining relations."""
+    from turbomesh_b200 import smoothing
+    from turbomesh_b200.boundary import Side
+
+    ni, nj, height = 4097, 2049, 0.5
+    spec = synthetic.cascade(1, 8, ni, nj, length=1.0 / 8.0, ay=0.015 / 8.0)
+    solver = smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-10)
+    with smoothing.DeviceMesh(spec, upload=False) as dm:
+        for k, b in enumerate(spec.blocks):
+            dm.tfi_block(k, *b.edge_args())
+        tfi = {k: dm.download_block(k) for k in (0, 3)}
+        dm.begin_smoothing(solver)
+        st = dm.smooth(100, solver)
+        got = {k: dm.download_block(k) for k in (0, 1, 3, 4, 7)}
+    for k in tfi:
+        assert np.array_equal(tfi[k], orc.tfi(*spec.blocks[k].edge_args()))
+    assert st["last_max_update"] <= 1e-10 and st["outer_iterations"] < 100, st
+    tol = 2e-10
+    wi, wj = 64, 24
+    for i0 in (1, ni // 2, ni - wi - 1):
+        rows = slice(i0, i0 + wi)
+        # blocks 0 | 1: ordinary interface (side i_max of block 0 = its last j line, side i_min of block 1 = its first)
+        assert _interface_row_updates(orc, got[0][rows, -wj:], got[1][rows, :wj], Side.i_max, Side.i_min) <= tol
+        # blocks 0 | 7: the periodic pair, x0 + p == x7
+        assert _interface_row_updates(orc, got[0][rows, :wj], got[7][rows, -wj:], Side.i_min, Side.i_max, (0.0, height)) <= tol
+        # interior rows
+        win = got[1][rows, 1000:1000 + wi]
+        assert float(np.abs(_oracle_jacobi_update(orc, win, 1.0) - win).max()) <= tol
+    inner = slice(1, ni - 1)
+    assert np.array_equal(got[0][inner, -1], got[1][inner, 0])                                   # connected copies are exact copies
+    assert float(np.abs(got[0][inner, 0] + np.array([0.0, height]) - got[7][inner, -1]).max()) <= 1e-15
+    assert np.array_equal(got[3][inner, -1], tfi[3][inner, -1])                                  # the plate's lower face: fixed wall
+    assert np.array_equal(got[4][inner, 0], orc.tfi(*spec.blocks[4].edge_args())[inner, 0])      # ... and its upper face
+    mid = slice(1, nj - 1)
+    assert np.array_equal(got[1][0, mid, 0], np.zeros(nj - 2))                                   # inlet: x stays, y follows its inner neighbour
+    assert float(np.abs(got[1][0, mid, 1] - got[1][1, mid, 1]).max()) <= tol
