@@ -64,6 +64,13 @@ pub extern fn tm_mesh_download_block(mesh: *tm_mesh, block: usize, xy: [*]f64) c
 /// cgns.zig:69-101 / 110-161 on the device: x[j*ni + i], y[j*ni + i] (field 0 = coordinates, 1 = control function P,Q)
 pub extern fn tm_mesh_download_block_soa(mesh: *tm_mesh, block: usize, field: c_int, x: [*]f64, y: [*]f64) callconv(.c) c_int;
 pub extern fn tm_release_cached_memory() callconv(.c) void;
+/// Host-only: how tm_smooth_mesh would stream a large single block (n_chunks = 0: resident); see the header.
+pub extern fn tm_smooth_stream_plan(ni: u64, nj: u64, sweeps: u64, n_chunks: *u64, window_rows: *u64, window_first: ?[*]u64, owned_first: ?[*]u64) callconv(.c) c_int;
+/// CUDA runtime: page-locks a host range.  tm_smooth_mesh overlaps its host<->device copies with the sweeps only when
+/// the block lives in page-locked memory; a caller that smooths a large block registers `block.points.data` once
+/// (flags = 0) and unregisters it before freeing.  Pageable memory is still correct, just serial.
+pub extern fn cudaHostRegister(ptr: *anyopaque, size: usize, flags: c_uint) callconv(.c) c_int;
+pub extern fn cudaHostUnregister(ptr: *anyopaque) callconv(.c) c_int;
 
 pub const Error = error{ CudaBackendFailed, CudaNoDevice, CudaBadTopology, CudaNotConverged };
 
@@ -80,12 +87,13 @@ fn check(rc: c_int) Error!void {
 
 /// Options of the `"cuda"` variant of `solver.Option` (JSON: `"solver": {"cuda": {"method": "picard_bicgstab"}}`).
 pub const Option = struct {
-    method: enum { picard_bicgstab, relax } = .picard_bicgstab,
+    method: enum { picard_bicgstab, relax, multigrid } = .picard_bicgstab, // = tm_solver (0, 1, 2)
     rtol: f64 = 1e-6, // BiCGStab.zig:20
     atol: f64 = 1e-8, // BiCGStab.zig:21
     max_inner_iterations: u64 = 1000, // BiCGStab.zig:19
     omega: f64 = 1.0,
     sweeps_per_iteration: u64 = 1,
+    stop_max_update: f64 = 0.0, // > 0: stop the outer loop once the mesh moves by less than this (relax / multigrid)
     device: i32 = -1,
 };
 
@@ -157,6 +165,7 @@ pub fn mesh(
     opts.max_inner_iterations = option.max_inner_iterations;
     opts.omega = option.omega;
     opts.sweeps_per_iteration = option.sweeps_per_iteration;
+    opts.stop_max_update = option.stop_max_update;
     opts.device = option.device;
     switch (control_function_algorithm) {
         .laplace => opts.control_function = 0,
