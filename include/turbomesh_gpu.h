@@ -88,10 +88,12 @@ typedef enum tm_control_function { TM_CF_LAPLACE = 0, TM_CF_WHITE = 1 } tm_contr
  *  TM_SOLVER_RELAX  throughput path: `sweeps_per_iteration` damped-Jacobi sweeps of the same 9-point
  *      operator with the coefficients recomputed from the current iterate (32 B/node-update); converges
  *      to the same fixed point as the Picard iteration.
- *  TM_SOLVER_FAS_MULTIGRID  time-to-converged path for a single block whose boundary nodes are all fixed (config 3):
- *      `iterations` V(nu,nu) cycles of a geometric full-approximation-scheme multigrid (nu = sweeps_per_iteration) with
- *      the same damped-Jacobi sweep as smoother on every level, stopped early by stop_max_update (max-norm of the last
- *      fine-level Jacobi update).  Same fixed point as the two other solvers.  Other meshes: TM_ERR_UNSUPPORTED.
+ *  TM_SOLVER_FAS_MULTIGRID  time-to-converged path: `iterations` V(nu,nu) cycles of a geometric full-approximation-scheme
+ *      multigrid (nu = sweeps_per_iteration) with the same damped-Jacobi sweep as smoother on every level, stopped early
+ *      by stop_max_update (max-norm movement of the mesh over one cycle).  A single block with fixed boundary nodes gets a
+ *      non-nested hierarchy (config 3); any multi-block topology -- interfaces, periodic pairs, junctions, sliding inlet /
+ *      outlet, one or several GPUs -- gets nested coarse multi-block meshes with Anderson acceleration (config 4, see
+ *      tm_mg_plan).  Same fixed point as the two other solvers.  White control function: TM_ERR_UNSUPPORTED.
  */
 typedef enum tm_solver { TM_SOLVER_PICARD_BICGSTAB = 0, TM_SOLVER_RELAX = 1, TM_SOLVER_FAS_MULTIGRID = 2 } tm_solver;
 
