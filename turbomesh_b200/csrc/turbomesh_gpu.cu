@@ -1598,27 +1598,47 @@ int tm_smooth_stream_plan(uint64_t ni, uint64_t nj, uint64_t sweeps, uint64_t* n
 
 int tm_tfi_block(uint64_t ni, uint64_t nj, const double* x_i_min, const double* x_i_max, const double* x_j_min, const double* x_j_max, const double* s1,
                  const double* s2, const double* t1, const double* t2, double* out_xy) {
-    tm_mesh* m = nullptr;
     int rc = guarded([&] {
         if (!out_xy) TM_THROW(TM_ERR_INVALID_ARGUMENT, "out_xy is NULL");
         if (ni < 3 || nj < 3) TM_THROW(TM_ERR_INVALID_ARGUMENT, "tfi: block smaller than 3x3 nodes");
     });
     if (rc != TM_OK) return rc;
-    const bool trace = std::getenv("TM_STREAM_TRACE") != nullptr;  // host-side phase times on stderr (tuning aid)
-    const auto t_start = std::chrono::steady_clock::now();
-    auto ms_since_start = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
-    tm_block blk{ni, nj, nullptr};
-    rc = tm_mesh_create(&blk, 1, nullptr, 0, nullptr, 0, -1, nullptr, &m);
-    const double t_created = ms_since_start();
-    if (rc == TM_OK) rc = tm_mesh_tfi_block(m, 0, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2);
-    const double t_tfi = ms_since_start();
-    if (rc == TM_OK) rc = tm_mesh_download_block(m, 0, out_xy);
-    const double t_down = ms_since_start();
-    std::string keep = g_last_error;
-    tm_mesh_destroy(m);
-    g_last_error = keep;
-    if (trace) std::fprintf(stderr, "[tfi] created %.2f ms, tfi queued %.2f ms, downloaded %.2f ms, destroyed %.2f ms\n", t_created, t_tfi, t_down, ms_since_start());
-    return rc;
+    // No device mesh is needed for a single TFI: edges up (one packed buffer), kernel, block down, on a stream of this
+    // call.  Both device buffers come from the allocation cache, so a call costs its copies and little else.
+    return guarded([&] {
+        tfi_validate_host(ni, nj, x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2);
+        if (ni * nj >= (uint64_t(1) << 31)) TM_THROW(TM_ERR_UNSUPPORTED, "tfi: block has 2^31 or more nodes");
+        require_device(-1);
+        const bool trace = std::getenv("TM_STREAM_TRACE") != nullptr;  // host-side phase times on stderr (tuning aid)
+        const auto t_start = std::chrono::steady_clock::now();
+        auto ms_since_start = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+        DevBuf<double> edges;
+        DevBuf<double2> out;
+        struct Stream {  // declared after the buffers: drained and destroyed before they return to the cache
+            cudaStream_t s = nullptr;
+            ~Stream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+        } st;
+        CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+        edges.alloc(size_t(6 * (ni + nj)));
+        out.alloc(size_t(ni * nj));
+        // layout: x_i_min[2ni] x_i_max[2ni] x_j_min[2nj] x_j_max[2nj] s1[ni] s2[ni] t1[nj] t2[nj]  (as in tfi_launch)
+        const double* src[8] = {x_i_min, x_i_max, x_j_min, x_j_max, s1, s2, t1, t2};
+        const size_t cnt[8] = {size_t(2 * ni), size_t(2 * ni), size_t(2 * nj), size_t(2 * nj), size_t(ni), size_t(ni), size_t(nj), size_t(nj)};
+        double* d = edges.p;
+        const double* dev[8];
+        for (int k = 0; k < 8; ++k) {
+            CUDA_TRY(cudaMemcpyAsync(d, src[k], cnt[k] * sizeof(double), cudaMemcpyHostToDevice, st.s));
+            dev[k] = d;
+            d += cnt[k];
+        }
+        dim3 grid(unsigned((nj + TILE_J - 1) / TILE_J), unsigned((ni + TFI_ROWS - 1) / TFI_ROWS));
+        LAUNCH(tfi_kernel, grid, TILE_J, st.s, int(ni), int(nj), (const double2*)dev[0], (const double2*)dev[1], (const double2*)dev[2], (const double2*)dev[3],
+               dev[4], dev[5], dev[6], dev[7], out.p);
+        const double t_queued = ms_since_start();
+        CUDA_TRY(cudaMemcpyAsync(out_xy, out.p, size_t(ni * nj) * sizeof(double2), cudaMemcpyDeviceToHost, st.s));
+        CUDA_TRY(cudaStreamSynchronize(st.s));
+        if (trace) std::fprintf(stderr, "[tfi] queued %.2f ms, downloaded %.2f ms\n", t_queued, ms_since_start());
+    });
 }
 
 int tm_smooth_mesh(tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections, const tm_condition* conditions,
