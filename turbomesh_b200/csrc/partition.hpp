@@ -113,16 +113,19 @@ inline std::vector<ReadSets> read_sets_all(const Topology& T, const std::vector<
 }
 
 // side-0 nodes of interface pairs whose side-1 node belongs to rank r but which live elsewhere (raw coordinates,
-// fetched once when smoothing begins)
-inline std::vector<std::vector<int64_t>> check_sets(const Topology& T, const std::vector<int32_t>& owner, int r, int n_ranks) {
-    std::vector<std::vector<int64_t>> out;
-    out.resize(size_t(n_ranks));
-    for (const auto& p : T.pairs)
-        if (owner_of_node(T, owner, p.g1) == r && owner_of_node(T, owner, p.g0) != r) out[size_t(owner_of_node(T, owner, p.g0))].push_back(p.g0);
-    for (auto& v : out) {
-        std::sort(v.begin(), v.end());
-        v.erase(std::unique(v.begin(), v.end()), v.end());
+// fetched once when smoothing begins): out[r][o] = sorted ids rank r fetches from rank o, for every r in one pass
+inline std::vector<std::vector<std::vector<int64_t>>> check_sets_all(const Topology& T, const std::vector<int32_t>& owner, int n_ranks) {
+    std::vector<std::vector<std::vector<int64_t>>> out;
+    out.assign(size_t(n_ranks), std::vector<std::vector<int64_t>>(size_t(n_ranks)));
+    for (const auto& p : T.pairs) {
+        const int r = owner_of_node(T, owner, p.g1), o = owner_of_node(T, owner, p.g0);
+        if (o != r) out[size_t(r)][size_t(o)].push_back(p.g0);
     }
+    for (auto& per_rank : out)
+        for (auto& v : per_rank) {
+            std::sort(v.begin(), v.end());
+            v.erase(std::unique(v.begin(), v.end()), v.end());
+        }
     return out;
 }
 
@@ -183,10 +186,13 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     }
     L.n_ghost = L.ghost_base[size_t(n_ranks)];
     L.n_synth = int64_t(L.synth_ids.size());
-    L.check_ghost_ids = check_sets(T, owner, rank, n_ranks);
-    L.check_send_ids.assign(size_t(n_ranks), {});
-    for (int p = 0; p < n_ranks; ++p)
-        if (p != rank) L.check_send_ids[size_t(p)] = check_sets(T, owner, p, n_ranks)[size_t(rank)];
+    {
+        auto checks = check_sets_all(T, owner, n_ranks);
+        L.check_send_ids.assign(size_t(n_ranks), {});
+        for (int p = 0; p < n_ranks; ++p)
+            if (p != rank) L.check_send_ids[size_t(p)] = std::move(checks[size_t(p)][size_t(rank)]);
+        L.check_ghost_ids = std::move(checks[size_t(rank)]);
+    }
     L.check_ghost_base.assign(size_t(n_ranks) + 1, 0);
     L.check_send_base.assign(size_t(n_ranks) + 1, 0);
     for (int p = 0; p < n_ranks; ++p) {
@@ -211,22 +217,23 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     };
 
     // slaves owned here: those whose root row is also here are written by the root's thread
-    std::map<int64_t, std::vector<SlaveRow>> by_root;  // keyed by the root's global id
+    struct Rooted { int64_t root; SlaveRow row; };  // keyed by the root's global id; stable order within a root
+    std::vector<Rooted> by_root;
     std::vector<SlaveRow> remote_root;
     for (const auto& s : T.slaves) {
         const bool synth = std::binary_search(L.synth_ids.begin(), L.synth_ids.end(), s.self);
         if (!mine(s.self) && !synth) continue;
         SlaveRow l{lidx(s.self), lidx(s.root), s.sx, s.sy};
-        if (mine(s.root)) by_root[s.root].push_back(l);
+        if (mine(s.root)) by_root.push_back(Rooted{s.root, l});
         else remote_root.push_back(l);
     }
+    std::stable_sort(by_root.begin(), by_root.end(), [](const Rooted& a, const Rooted& b) { return a.root < b.root; });
+    size_t n_attached = 0;
     auto attach = [&](int64_t root_g, int32_t& bgn, int32_t& end) {
         bgn = end = int32_t(L.slaves.size());
-        const auto it = by_root.find(root_g);
-        if (it == by_root.end()) return;
-        for (const auto& s : it->second) L.slaves.push_back(s);
+        auto it = std::lower_bound(by_root.begin(), by_root.end(), root_g, [](const Rooted& a, int64_t g) { return a.root < g; });
+        for (; it != by_root.end() && it->root == root_g; ++it) { L.slaves.push_back(it->row); ++n_attached; }
         end = int32_t(L.slaves.size());
-        by_root.erase(it);
     };
     for (const auto& row : T.smoothed) {
         if (!mine(row.g0)) continue;
@@ -251,7 +258,7 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
         attach(row.self, l.slave_begin, l.slave_end);
         L.sliding.push_back(l);
     }
-    if (!by_root.empty()) TM_THROW(TM_ERR_TOPOLOGY, "internal: %zu slave groups without a root row", by_root.size());
+    if (n_attached != by_root.size()) TM_THROW(TM_ERR_TOPOLOGY, "internal: %zu slaves without a root row", by_root.size() - n_attached);
     L.n_slaves_local_root = int64_t(L.slaves.size());
     for (const auto& s : remote_root) L.slaves.push_back(s);
 
