@@ -98,7 +98,13 @@ struct DeviceCache {
     }
     bool give(void* q, size_t bytes, int device) {
         std::lock_guard<std::mutex> lock(mu);
-        if (bytes < kMinBytes || held + bytes > cap() || free_list.size() >= kMaxEntries) return false;
+        if (bytes < kMinBytes || bytes > cap()) return false;
+        // full: the oldest entries make room (sizes nobody asks for any more must not block the ones in use)
+        while (!free_list.empty() && (held + bytes > cap() || free_list.size() >= kMaxEntries)) {
+            cudaFree(free_list.front().p);
+            held -= free_list.front().bytes;
+            free_list.erase(free_list.begin());
+        }
         free_list.push_back(Entry{q, bytes, device});
         held += bytes;
         return true;
