@@ -35,7 +35,7 @@ inline bool plan_streaming(int64_t ni, int64_t nj, int64_t sweeps, StreamPlan& P
     if (K < 2) return false;
     const int64_t T = sweeps;
     const int64_t W = (ni + (2 * T + 2) * (K - 1) + K - 1) / K;
-    if (W >= ni || W < 3) return false;
+    if (W >= ni || W < 3 || W * nj >= (int64_t(1) << 31)) return false;  // a window is a block of its own: < 2^31 nodes
     P.T = T; P.W = W;
     P.w0.resize(size_t(K)); P.o0.assign(size_t(K) + 1, 0);
     for (int64_t k = 0; k < K; ++k) P.w0[size_t(k)] = (k * (ni - W)) / (K - 1);

@@ -1590,7 +1590,7 @@ int tm_smooth_stream_plan(uint64_t ni, uint64_t nj, uint64_t sweeps, uint64_t* n
     return guarded([&] {
         if (!n_chunks || !window_rows) TM_THROW(TM_ERR_INVALID_ARGUMENT, "n_chunks / window_rows is NULL");
         *n_chunks = 0; *window_rows = 0;
-        if (ni < 3 || nj < 3 || ni * nj >= (uint64_t(1) << 31) || sweeps > (uint64_t(1) << 40)) return;
+        if (ni < 3 || nj < 3 || ni >= (uint64_t(1) << 31) || nj >= (uint64_t(1) << 31) || sweeps > (uint64_t(1) << 40)) return;
         StreamPlan P;
         if (!plan_streaming(int64_t(ni), int64_t(nj), int64_t(sweeps), P)) return;
         *n_chunks = uint64_t(P.K()); *window_rows = uint64_t(P.W);
