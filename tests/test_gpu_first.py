@@ -158,3 +158,44 @@ def test_streamed_host_smoothing_is_bit_identical(gpu_lib, monkeypatch, shape, i
     assert st_s["last_sumsq_x"] == pytest.approx(st_r["last_sumsq_x"], rel=1e-12) and st_s["last_sumsq_y"] == pytest.approx(st_r["last_sumsq_y"], rel=1e-12)
     for key in ("outer_iterations", "inner_iterations", "operator_applications", "nodes", "converged"):
         assert st_s[key] == st_r[key], key
+
+
+@pytest.mark.parametrize("cut", ["i", "j"])
+def test_a_block_split_by_a_connection_smooths_like_the_unsplit_block(orc, gpu_lib, cut):
+    """Interface rows are interior rows written across two blocks (smooth.zig:994-1105): cutting a block in two along a
+    grid line and joining the halves with an ordinary connection must not change the smoothed mesh -- an identity that
+    needs no oracle (tests/test_oracle_cpu.py holds the same test for the oracle)."""
+    from turbomesh_b200 import smoothing
+    from turbomesh_b200.boundary import Connection, Range, Side
+    from turbomesh_b200.discrete import Block2d, Mesh
+
+    base = smoothing.tfi_block(*synthetic.single_block(49, 37).blocks[0].edge_args())
+    whole = Mesh([Block2d(base.copy())], ["b"], [], [])
+    smoothing.smooth_mesh(whole, 4, smoothing.CudaSolver.tight())
+    ref = whole.blocks[0].points
+    assert np.abs(ref - base).max() > 1e-5
+    if cut == "i":
+        a, b = base[:25].copy(), base[24:].copy()
+        conn = Connection((Range(0, Side.j_max, 0, base.shape[1] - 1), Range(1, Side.j_min, 0, base.shape[1] - 1)), None)
+    else:
+        a, b = np.ascontiguousarray(base[:, :19]), np.ascontiguousarray(base[:, 18:])
+        conn = Connection((Range(0, Side.i_max, 0, base.shape[0] - 1), Range(1, Side.i_min, 0, base.shape[0] - 1)), None)
+    halves = Mesh([Block2d(a), Block2d(b)], ["a", "b"], [conn], [])
+    smoothing.smooth_mesh(halves, 4, smoothing.CudaSolver.tight())
+    pa, pb = halves.blocks[0].points, halves.blocks[1].points
+    if cut == "i":
+        got, seam = np.concatenate([pa, pb[1:]], axis=0), np.abs(pa[-1] - pb[0]).max()
+    else:
+        got, seam = np.concatenate([pa, pb[:, 1:]], axis=1), np.abs(pa[:, -1] - pb[:, 0]).max()
+    assert seam == 0.0                       # connected copies are exact copies
+    assert np.abs(got - ref).max() <= 1e-9
+    # the relaxation path: same identity sweep by sweep (to rounding: the halves sum their partial results differently)
+    relax = smoothing.CudaSolver(method="relax", sweeps_per_iteration=25, omega=0.9)
+    whole = Mesh([Block2d(base.copy())], ["b"], [], [])
+    smoothing.smooth_mesh(whole, 1, relax)
+    fresh = (base[:25].copy(), base[24:].copy()) if cut == "i" else (np.ascontiguousarray(base[:, :19]), np.ascontiguousarray(base[:, 18:]))
+    halves = Mesh([Block2d(fresh[0]), Block2d(fresh[1])], ["a", "b"], [conn], [])
+    smoothing.smooth_mesh(halves, 1, relax)
+    pa, pb = halves.blocks[0].points, halves.blocks[1].points
+    got = np.concatenate([pa, pb[1:]], axis=0) if cut == "i" else np.concatenate([pa, pb[:, 1:]], axis=1)
+    assert np.abs(got - whole.blocks[0].points).max() <= 1e-13

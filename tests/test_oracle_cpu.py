@@ -241,3 +241,57 @@ def test_viewer_buffers_oracle(orc):
     assert np.array_equal(idx, np.array(want, dtype=np.uint32))
     neg = orc.viewer_buffers([-np.abs(a) - 1.0])                      # all coordinates negative: the maxima keep their start value
     assert neg[1][1] == np.float32(1.1754944e-38) and neg[2][1] == np.float32(1.1754944e-38)
+
+
+# -------------------------------------------------------------------------------- more identities the operator must obey
+def _smoothed_single_block(orc, points, iterations=3):
+    mesh = Mesh([Block2d(np.array(points, dtype=np.float64, order="C", copy=True))], ["b"], [], [])  # smoothing is in place
+    orc.smooth_mesh(mesh, iterations, orc.tight_options())
+    return mesh.blocks[0].points
+
+
+def test_smoothing_is_scale_rotation_and_reflection_equivariant(orc):
+    """The Winslow operator only sees g11, g22, g12 (smooth.zig:192-215): scaling, rotating or mirroring the mesh commutes
+    with smoothing when no node slides along an axis.  The maps below are exact in binary floating point."""
+    base = orc.tfi(*synthetic.single_block(21, 17).blocks[0].edge_args())
+    ref = _smoothed_single_block(orc, base)
+    assert np.abs(ref - base).max() > 1e-4  # the test smooths something
+    maps = {
+        "scale x4": lambda p: 4.0 * p,
+        "rotate 90": lambda p: np.stack([-p[..., 1], p[..., 0]], axis=-1),
+        "mirror x": lambda p: np.stack([-p[..., 0], p[..., 1]], axis=-1),
+        "swap i and j": None,
+    }
+    for name, f in maps.items():
+        if f is None:  # the same geometry traversed with the index directions exchanged
+            got = _smoothed_single_block(orc, np.ascontiguousarray(base.transpose(1, 0, 2))).transpose(1, 0, 2)
+            want, scale = ref, 1.0
+        else:
+            got, want, scale = _smoothed_single_block(orc, f(base)), f(ref), 4.0 if name.startswith("scale") else 1.0
+        assert np.abs(got - want).max() <= 1e-11 * scale, name
+
+
+@pytest.mark.parametrize("cut", ["i", "j"])
+def test_a_block_split_by_a_connection_smooths_like_the_unsplit_block(orc, cut):
+    """Interface rows (smooth.zig:994-1105) are interior rows written across two blocks: cutting a block in two along a
+    grid line and joining the halves with an ordinary connection must not change the smoothed mesh."""
+    from turbomesh_b200.boundary import Connection, Range, Side
+
+    base = orc.tfi(*synthetic.single_block(25, 19).blocks[0].edge_args())
+    ref = _smoothed_single_block(orc, base, iterations=4)
+    if cut == "i":   # halves share the grid line i = 12: side j_max of the first, j_min of the second (boundary.zig:34-51)
+        a, b = base[:13].copy(), base[12:].copy()
+        conn = Connection((Range(0, Side.j_max, 0, base.shape[1] - 1), Range(1, Side.j_min, 0, base.shape[1] - 1)), None)
+    else:            # halves share the grid line j = 9: side i_max of the first, i_min of the second
+        a, b = np.ascontiguousarray(base[:, :10]), np.ascontiguousarray(base[:, 9:])
+        conn = Connection((Range(0, Side.i_max, 0, base.shape[0] - 1), Range(1, Side.i_min, 0, base.shape[0] - 1)), None)
+    mesh = Mesh([Block2d(a), Block2d(b)], ["a", "b"], [conn], [])
+    orc.smooth_mesh(mesh, 4, orc.tight_options())
+    if cut == "i":
+        got = np.concatenate([mesh.blocks[0].points, mesh.blocks[1].points[1:]], axis=0)
+        seam = np.abs(mesh.blocks[0].points[-1] - mesh.blocks[1].points[0]).max()
+    else:
+        got = np.concatenate([mesh.blocks[0].points, mesh.blocks[1].points[:, 1:]], axis=1)
+        seam = np.abs(mesh.blocks[0].points[:, -1] - mesh.blocks[1].points[:, 0]).max()
+    assert seam <= 1e-14
+    assert np.abs(got - ref).max() <= 1e-11
