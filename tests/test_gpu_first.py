@@ -199,3 +199,38 @@ def test_a_block_split_by_a_connection_smooths_like_the_unsplit_block(orc, gpu_l
     pa, pb = halves.blocks[0].points, halves.blocks[1].points
     got = np.concatenate([pa, pb[1:]], axis=0) if cut == "i" else np.concatenate([pa, pb[:, 1:]], axis=1)
     assert np.abs(got - whole.blocks[0].points).max() <= 1e-13
+
+
+def test_moving_the_seam_of_a_periodic_block_does_not_change_the_mesh(gpu_lib):
+    """A channel periodic across j (same-block connection i_min -> i_max with a periodicity vector): rolling the columns by
+    k and smoothing gives the rolled mesh -- the periodic interface rows with their shifted neighbours are interior rows
+    (tests/test_oracle_cpu.py holds the same identity for the oracle)."""
+    from turbomesh_b200 import smoothing
+    from turbomesh_b200.boundary import Connection, Range, Side
+    from turbomesh_b200.discrete import Block2d, Mesh
+
+    ni, nj, height = 33, 26, 0.5
+    s = np.linspace(0.0, 1.0, ni)[:, None]
+    col = np.arange(nj - 1)[None, :]
+
+    def smoothed(k, solver, iterations):
+        t = (col + k) / (nj - 1.0)
+        x = s + 0.03 * np.sin(2 * np.pi * t) * np.sin(np.pi * s) + 0.02 * np.sin(np.pi * s) * np.cos(4 * np.pi * t)
+        y = height * t + 0.04 * np.sin(2 * np.pi * s) + 0.015 * np.sin(np.pi * s) * np.sin(2 * np.pi * t)
+        pts = np.stack([x, y], axis=-1)
+        pts = np.concatenate([pts, pts[:, :1] + np.array([0.0, height])], axis=1)
+        conn = Connection((Range(0, Side.i_min, 0, ni - 1), Range(0, Side.i_max, 0, ni - 1)), (0.0, height))
+        mesh = Mesh([Block2d(pts.copy())], ["ring"], [conn], [])
+        smoothing.smooth_mesh(mesh, iterations, solver)
+        out = mesh.blocks[0].points
+        assert np.abs(out[1:-1, -1] - (out[1:-1, 0] + np.array([0.0, height]))).max() == 0.0   # copies are exact copies
+        return out[:, :-1], pts[:, :-1]
+
+    for solver, iterations, tol in ((smoothing.CudaSolver.tight(), 4, 1e-9), (smoothing.CudaSolver(method="relax", sweeps_per_iteration=30, omega=0.9), 1, 1e-13)):
+        ref, start = smoothed(0, solver, iterations)
+        assert np.abs(ref - start).max() > 1e-4
+        for k in (1, 9, nj - 2):
+            got, _ = smoothed(k, solver, iterations)
+            want = np.roll(ref, -k, axis=1).copy()
+            want[:, (nj - 1) - k:, 1] += height
+            assert np.abs(got - want).max() <= tol, (solver.method, k)

@@ -295,3 +295,41 @@ def test_a_block_split_by_a_connection_smooths_like_the_unsplit_block(orc, cut):
         seam = np.abs(mesh.blocks[0].points[:, -1] - mesh.blocks[1].points[:, 0]).max()
     assert seam <= 1e-14
     assert np.abs(got - ref).max() <= 1e-11
+
+
+def test_moving_the_seam_of_a_periodic_block_does_not_change_the_mesh(orc):
+    """A channel that is periodic across j (same-block connection i_min -> i_max with a periodicity vector, the only
+    same-block form the reference supports, smooth.zig:522-559): where the seam lies is arbitrary, so rolling the columns
+    by k and smoothing must give the rolled mesh -- the periodic interface rows with their shifted neighbours and
+    right-hand sides (smooth.zig:1029-1061) are just interior rows."""
+    from turbomesh_b200.boundary import Connection, Range, Side
+
+    ni, nj, height = 17, 14, 0.5  # nj - 1 distinct columns
+    s = np.linspace(0.0, 1.0, ni)[:, None]
+    col = np.arange(nj - 1)[None, :]
+
+    def channel(columns):
+        t = columns / (nj - 1.0)
+        x = s + 0.03 * np.sin(2 * np.pi * t) * np.sin(np.pi * s) + 0.02 * np.sin(np.pi * s) * np.cos(4 * np.pi * t)
+        y = height * t + 0.04 * np.sin(2 * np.pi * s) + 0.015 * np.sin(np.pi * s) * np.sin(2 * np.pi * t)
+        return np.stack([x + 0 * t, y], axis=-1)
+
+    def smoothed(k):
+        """Columns k, k+1, ..., k+nj-2 and, as last column, the periodic image of the first."""
+        pts = channel(col + k)
+        pts = np.concatenate([pts, pts[:, :1] + np.array([0.0, height])], axis=1)
+        conn = Connection((Range(0, Side.i_min, 0, ni - 1), Range(0, Side.i_max, 0, ni - 1)), (0.0, height))
+        mesh = Mesh([Block2d(pts.copy())], ["ring"], [conn], [])  # smoothing is in place
+        orc.smooth_mesh(mesh, 4, orc.tight_options())
+        out = mesh.blocks[0].points
+        assert np.abs(out[:, -1] - out[:, 0] - np.array([0.0, height])).max() <= 1e-14
+        return out[:, :-1], pts[:, :-1]
+
+    ref, start = smoothed(0)
+    assert np.abs(ref - start).max() > 1e-4
+    for k in (1, 5, nj - 2):
+        got, _ = smoothed(k)
+        # column c of the rolled mesh is column (c + k) of the reference, lifted by one period where it wrapped around
+        want = np.roll(ref, -k, axis=1).copy()
+        want[:, (nj - 1) - k:, 1] += height
+        assert np.abs(got - want).max() <= 1e-11, k
