@@ -304,3 +304,16 @@ def test_stream_plan_covers_every_row_once_with_enough_margin(gpu_lib, monkeypat
     assert n_plans > 1000
     monkeypatch.setenv("TM_STREAM", "0")
     assert smoothing.stream_plan(8192, 8192, 100) is None
+
+
+def test_spline_t106a_surface_length_known_answer():
+    """spline.zig:306-514 ("T106 blade coordinate integration"): the spline through the published T106A contour (184 points
+    over chord, chord 198 mm) is 264.7 mm + 230.0 mm long within 1e-2.  Table and expected value: tests/golden/
+    t106a_blade_table.npz (written by tests/golden/make_spline_fixture.py from the reference's test)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "t106a_blade_table.npz"))
+    spline = FittingSpline(z["points_over_chord"] * float(z["chord"]))
+    assert abs(spline.integrate() - float(z["surface_length"])) <= float(z["tolerance"])
+    # the length is the sum over the 200-sample arc table (spline.zig:74-110), slightly below the contour's polyline
+    pts = z["points_over_chord"] * float(z["chord"])
+    polyline = float(np.sqrt((np.diff(pts, axis=0) ** 2).sum(axis=1)).sum())
+    assert 0.99 * polyline < spline.integrate() < polyline
