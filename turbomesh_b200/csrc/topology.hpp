@@ -438,6 +438,7 @@ struct Topology {
             }
         }
         // eliminate connected rows: x_self = x_master - rhs_self, chains followed to the root
+        std::vector<int32_t> copies(nbn, 0);  // per flat boundary id of a free root: copies hanging off it
         for (size_t b = 0; b < blocks.size(); ++b) {
             const int64_t nbb = 2 * (blocks[b].ni + blocks[b].nj - 2);
             for (int64_t q = 0; q < nbb; ++q) {
@@ -458,18 +459,11 @@ struct Topology {
                     if (kind[cur] != K_CONNECTED) break;
                 }
                 if (kind[cur] == K_FIXED) const_slaves.push_back({self, root, sx, sy});
-                else slaves.push_back({self, root, sx, sy});
+                else { slaves.push_back({self, root, sx, sy}); copies[cur] += 1; }  // cur = the root's boundary id
             }
         }
         // per root: how many copies hang off it anywhere in the mesh
-        std::vector<std::pair<int64_t, int32_t>> cnt;
-        for (const auto& sl : slaves) cnt.push_back({sl.root, 1});
-        std::sort(cnt.begin(), cnt.end());
-        auto copies_of = [&](int64_t g) {
-            const auto lo = std::lower_bound(cnt.begin(), cnt.end(), std::make_pair(g, int32_t(0)));
-            const auto hi = std::upper_bound(cnt.begin(), cnt.end(), std::make_pair(g, int32_t(2)));
-            return int32_t(hi - lo);
-        };
+        auto copies_of = [&](int64_t g) { return copies[size_t(bid_of_global(g))]; };
         for (auto& r : smoothed) { r.slave_begin = r.slave_end = 0; r.n_copies = copies_of(r.g0); }
         for (auto& r : junction_rows) { r.slave_begin = r.slave_end = 0; r.n_copies = copies_of(r.self); }
         for (auto& r : sliding) { r.slave_begin = r.slave_end = 0; r.n_copies = copies_of(r.self); r._pad = 0; }
