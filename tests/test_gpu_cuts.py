@@ -43,5 +43,5 @@ def test_batch_of_cuts_matches_per_cut_oracle(gpu_lib, orc, control):
         orc.smooth_mesh(cpu, iterations, orc.tight_options(max_iters=100000, **kw))
         err = max(float(np.abs(got[c * nb + k] - cpu.blocks[k].points).max()) for k in range(nb))
         chord = 0.0799 * sc
-        tol = max(1e-9 * chord, 2.0 * meta["oracle_spread"]) if control == "white" else 1e-9 * chord
+        tol = 1e-9 * chord   # 3 outer iterations: the mesh is still regular, fp64 reproduces the exact sequence (tests/golden/t106_white_truth.npz)
         assert err <= tol, (c, err, tol)

@@ -86,7 +86,10 @@ def test_emulated_ranks_t106_white(gpu_lib):
     spec, z, meta = load_fixture("t106_white")
     mesh0 = synthetic.materialize(spec, smoothing.tfi_block)
     cf = smoothing.White(meta["ds_target"], meta["theta_target"])
-    many, st = _run(mesh0, [0, 0, 0, 1, 1, 1, 0, 1], 2, smoothing.CudaSolver.tight(), meta["iterations"], cf)
-    err = max(float(np.abs(b.points - z[f"smooth_b{k}"]).max()) for k, b in enumerate(many.blocks))
+    # 8 outer iterations against the extended-precision truth (beyond that fp64 cannot resolve config 1 to 1e-9 chord, see
+    # tests/test_gpu_rows.py::test_t106_white_against_the_extended_precision_truth)
+    tz = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "t106_white_truth.npz"))
+    many, st = _run(mesh0, [0, 0, 0, 1, 1, 1, 0, 1], 2, smoothing.CudaSolver.tight(), 8, cf)
+    err = max(float(np.abs(b.points - tz[f"truth8_b{k}"]).max()) for k, b in enumerate(many.blocks))
     assert st["converged"] == 1
-    assert err <= max(1e-9 * chord_of(many), 2.0 * meta["oracle_spread"])
+    assert err <= 1e-9 * chord_of(many)
