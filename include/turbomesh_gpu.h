@@ -194,6 +194,25 @@ int tm_mesh_smooth(tm_mesh *mesh, const tm_smooth_options *opts, tm_smooth_stats
 /* Blocks until all work queued on the mesh's stream has finished. */
 int tm_mesh_synchronize(tm_mesh *mesh);
 
+/* Independent systems.  Blocks that no connection joins never exchange a value: every connected component of the block
+ * graph -- every 2D cut of a batch -- is a linear system of its own.  TM_SOLVER_PICARD_BICGSTAB solves each component for
+ * x and y with its own Krylov scalars, its own ||b||, tolerance max(atol, rtol ||b||) (GMRES.zig:305-306 /
+ * BiCGStab.zig:291), iteration count and stopping test, exactly as the reference does when it meshes the cuts one after the
+ * other (smooth.zig:104-154 per mesh).  Components are numbered in the order of their lowest block.  The per-component
+ * record describes the LAST outer iteration of the last tm_mesh_smooth call (single-process meshes; index 0 = x solve,
+ * 1 = y solve; status 1 converged, 2 breakdown, 3 iteration cap). */
+typedef struct tm_component_stats {
+    uint64_t nodes;
+    uint64_t iterations[2];
+    double tolerance[2], norm_b[2], norm_r[2];
+    int32_t status[2];
+    uint64_t operator_applications;   /* applications of the 9-point operator to this component (both solves advance together) */
+    uint64_t restarts;                /* true-residual restarts (1 = none) */
+} tm_component_stats;
+uint64_t tm_mesh_component_count(const tm_mesh *mesh);
+int tm_mesh_component_of_block(const tm_mesh *mesh, size_t block, uint64_t *component);
+int tm_mesh_component_stats(const tm_mesh *mesh, size_t component, tm_component_stats *out);
+
 /* Accessors (mirror the WASM surface, src/wasm/lib.zig:97-124) */
 uint64_t tm_mesh_block_count(const tm_mesh *mesh);
 uint64_t tm_mesh_node_count(const tm_mesh *mesh);

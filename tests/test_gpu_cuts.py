@@ -45,3 +45,58 @@ def test_batch_of_cuts_matches_per_cut_oracle(gpu_lib, orc, control):
         chord = 0.0799 * sc
         tol = 1e-9 * chord   # 3 outer iterations: the mesh is still regular, fp64 reproduces the exact sequence (tests/golden/t106_white_truth.npz)
         assert err <= tol, (c, err, tol)
+
+
+def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc):
+    """The reference meshes the cuts one after the other: each has its own ||b||, tolerance max(atol, rtol ||b||)
+    (GMRES.zig:305-306 / BiCGStab.zig:291), iteration count and stopping test.  At the reference's default tolerances
+    (rtol 1e-6) a batch must therefore behave cut by cut like separate runs -- round 1 tested one norm over the batch."""
+    from turbomesh_b200 import smoothing
+
+    base, z, meta = load_fixture("t106_white")
+    scales = [1.0, 1.5, 0.25, 3.0]     # very different ||b|| per cut: a batch-wide tolerance would be dominated by the largest
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    sol = smoothing.CudaSolver(method="picard_bicgstab", rtol=1e-6, atol=1e-8, max_inner_iterations=1000)
+    nb = len(base.blocks)
+
+    def run(sc, iterations):
+        batch, groups = synthetic.batch_of_cuts(base, sc)
+        with smoothing.DeviceMesh(batch, upload=False) as dm:
+            for k, b in enumerate(batch.blocks):
+                dm.tfi_block(k, *b.edge_args())
+            dm.set_white_groups(groups)
+            dm.begin_smoothing(sol, cf)
+            st = dm.smooth(iterations, sol, cf)
+            assert dm.component_count == len(sc)
+            assert [dm.component_of_block(k) for k in range(len(batch.blocks))] == [k // nb for k in range(len(batch.blocks))]
+            comps = [dm.component_stats(c) for c in range(len(sc))]
+            return [dm.download_block(k) for k in range(len(batch.blocks))], st, comps
+
+    got, st, comps = run(scales, 2)
+    assert st["converged"] == 1
+    for c, sc in enumerate(scales):
+        rec = comps[c]
+        assert rec["nodes"] == 25118 and rec["status"] == (1, 1)
+        for xy in range(2):
+            assert rec["tolerance"][xy] == max(1e-8, 1e-6 * rec["norm_b"][xy])
+            assert rec["norm_r"][xy] <= rec["tolerance"][xy]            # every cut meets ITS tolerance
+            assert rec["norm_b"][xy] == pytest.approx(comps[0]["norm_b"][xy] * sc / scales[0], rel=1e-9)
+        alone, st1, (rec1,) = run([sc], 2)
+        # the same cut on its own: same iteration counts (to the rounding of differently ordered sums), same mesh within the tolerance
+        for xy in range(2):
+            assert abs(rec["iterations"][xy] - rec1["iterations"][xy]) <= 3, (c, rec, rec1)
+            assert rec["norm_b"][xy] == pytest.approx(rec1["norm_b"][xy], rel=1e-12)
+        err = max(float(np.abs(got[c * nb + k] - alone[k]).max()) for k in range(nb))
+        assert err <= 20 * max(rec["tolerance"]), (c, err)
+    assert st["inner_iterations"] == sum(sum(r["iterations"]) for r in comps)
+    # ||b|| is the norm of the reference's right-hand side (fixed rows carry their coordinates, ...): oracle's assembled rhs of cut 0
+    single, _ = synthetic.batch_of_cuts(base, [scales[0]])
+    cpu = synthetic.materialize(single, orc.tfi)
+    O = orc.System(cpu, orc.options(control_function="white", ds_target=meta["ds_target"], theta_target=meta["theta_target"]))
+    O.iterate(0)
+    O.fill(1)
+    for xy, y_mode in enumerate((False, True)):
+        O.fill_specific(y_mode)
+        rhs = O.csr()[3 + xy]
+        assert comps[0]["norm_b"][xy] == pytest.approx(float(np.linalg.norm(rhs)), rel=1e-5)
+    O.close()

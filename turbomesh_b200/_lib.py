@@ -74,6 +74,16 @@ class TmEdgeJob(C.Structure):
                 ("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double))]
 
 
+class TmComponentStats(C.Structure):
+    _fields_ = [("nodes", C.c_uint64), ("iterations", C.c_uint64 * 2), ("tolerance", C.c_double * 2), ("norm_b", C.c_double * 2),
+                ("norm_r", C.c_double * 2), ("status", C.c_int32 * 2), ("operator_applications", C.c_uint64), ("restarts", C.c_uint64)]
+
+    def as_dict(self):
+        return {"nodes": int(self.nodes), "iterations": tuple(self.iterations), "tolerance": tuple(self.tolerance), "norm_b": tuple(self.norm_b),
+                "norm_r": tuple(self.norm_r), "status": tuple(self.status), "operator_applications": int(self.operator_applications),
+                "restarts": int(self.restarts)}
+
+
 class TurbomeshGpuError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"turbomesh_gpu error {code}: {message}")
@@ -131,6 +141,10 @@ def load():
     L.tm_mesh_begin_smoothing.argtypes = [vp, C.POINTER(TmSmoothOptions)]
     L.tm_mesh_smooth.argtypes = [vp, C.POINTER(TmSmoothOptions), C.POINTER(TmSmoothStats)]
     L.tm_mesh_synchronize.argtypes = [vp]
+    L.tm_mesh_component_count.argtypes = [vp]
+    L.tm_mesh_component_count.restype = C.c_uint64
+    L.tm_mesh_component_of_block.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.tm_mesh_component_stats.argtypes = [vp, C.c_size_t, C.POINTER(TmComponentStats)]
     L.tm_mesh_block_count.argtypes = [vp]
     L.tm_mesh_block_count.restype = C.c_uint64
     L.tm_mesh_node_count.argtypes = [vp]

@@ -273,7 +273,7 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     std::vector<uint8_t> over(size_t(T.n_boundary), 0);
     for (const auto& f : T.fixed_overrides) {
         over[size_t(T.bid_of_global(f.self))] = 1;
-        if (mine(f.self)) L.rhs_terms.push_back(RhsTerm{0, f.x, f.y, 0, 0});
+        if (mine(f.self)) L.rhs_terms.push_back(RhsTerm{lidx(f.self), f.x, f.y, 0, 0});
     }
     for (int32_t b : L.own_blocks) {
         const auto& B = T.blocks[size_t(b)];
@@ -288,9 +288,9 @@ inline LocalTables localize(const Topology& T, const std::vector<int32_t>& owner
     for (const auto& s : T.sliding)
         if (mine(s.self)) L.rhs_terms.push_back(RhsTerm{lidx(s.self), s.rhs_x, s.rhs_y, s.rhs_x_from_initial, 0});
     for (const auto& j : T.junction_rows)
-        if (mine(j.self)) L.rhs_terms.push_back(RhsTerm{0, j.rhs_x, j.rhs_y, 0, 0});
+        if (mine(j.self)) L.rhs_terms.push_back(RhsTerm{lidx(j.self), j.rhs_x, j.rhs_y, 0, 0});
     for (const auto& c : T.connected_rhs)
-        if (mine(c.self)) L.rhs_terms.push_back(RhsTerm{0, c.x, c.y, 0, 0});  // smooth.zig:904-915
+        if (mine(c.self)) L.rhs_terms.push_back(RhsTerm{lidx(c.self), c.x, c.y, 0, 0});  // smooth.zig:904-915
 
     L.owns_white = T.blocks.size() >= 2 && owner[0] == rank && owner[1] == rank;
     return L;

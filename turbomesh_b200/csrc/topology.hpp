@@ -77,7 +77,7 @@ struct FixedOverride {      // a fixed node whose rhs was overwritten by the per
     double x, y;
 };
 struct RhsTerm {            // a row of the reference system with a non-zero right-hand side (for ||b||, BiCGStab.zig:289-291)
-    int64_t g;              // node whose coordinate is the rhs (from_x / from_y), else unused
+    int64_t g;              // the row's node; its coordinate is the rhs where from_x / from_y is set
     double cx, cy;          // constant rhs
     int32_t from_x, from_y;
 };
@@ -113,6 +113,10 @@ struct Topology {
     bool white_ok = false;
     std::string white_why;
     std::vector<tm_connection> conns_copy;  // kept for set_white_groups
+    // connected components of the block graph (blocks joined by connections): independent linear systems -- the cuts of a
+    // batch --, numbered in the order of their lowest block
+    std::vector<int32_t> comp_of_block;
+    int32_t n_comp = 0;
     int64_t min_conn_nodes = 6;             // smooth.zig:631 (lenInternal() > 3); coarse multigrid levels relax this to 3
 
     // ---- helpers -------------------------------------------------------------------------------
@@ -173,6 +177,7 @@ struct Topology {
         for (size_t c = 0; c < nbc; ++c) {
             if (!range_ok(bcs[c].range) || bcs[c].kind > TM_BC_OUTLET) TM_THROW(TM_ERR_TOPOLOGY, "condition %zu: invalid range or kind", c);
         }
+        find_components(conns, nc);
         find_junctions(conns, nc);
         classify(conns, nc, bcs, nbc);
         build_rows(conns, nc, bcs, nbc);
@@ -181,6 +186,23 @@ struct Topology {
     }
 
   private:
+    void find_components(const tm_connection* conns, size_t nc) {
+        std::vector<int32_t> parent(blocks.size());
+        for (size_t b = 0; b < parent.size(); ++b) parent[b] = int32_t(b);
+        auto find = [&](int32_t k) { while (parent[size_t(k)] != k) { parent[size_t(k)] = parent[size_t(parent[size_t(k)])]; k = parent[size_t(k)]; } return k; };
+        for (size_t c = 0; c < nc; ++c) {
+            const int32_t a = find(int32_t(conns[c].ranges[0].block)), b = find(int32_t(conns[c].ranges[1].block));
+            if (a != b) parent[size_t(std::max(a, b))] = std::min(a, b);   // the root is the lowest block of the component
+        }
+        comp_of_block.assign(blocks.size(), -1);
+        n_comp = 0;
+        for (size_t b = 0; b < blocks.size(); ++b) {
+            const int32_t root = find(int32_t(b));
+            if (comp_of_block[size_t(root)] < 0) comp_of_block[size_t(root)] = n_comp++;   // roots are met first (root <= b)
+            comp_of_block[b] = comp_of_block[size_t(root)];
+        }
+    }
+
     static void periodicity_of(const tm_connection& c, double& px, double& py) {
         px = c.has_periodicity ? c.periodicity[0] : 0.0;
         py = c.has_periodicity ? c.periodicity[1] : 0.0;

@@ -22,6 +22,7 @@
 
 #include "../../include/turbomesh_gpu.h"
 #include "kernels.cuh"
+#include "krylov_kernels.cuh"
 #include "io_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "mg_plan.hpp"
@@ -230,6 +231,22 @@ struct MgLevel {
     bool aa_have_x = false;
 };
 
+// plan of the persistent Krylov kernel (krylov.inl): components, warp tiles, CTA groups
+struct KrylovPlan {
+    DevBuf<WTile> wtiles;
+    DevBuf<KComp> comps;
+    DevBuf<int32_t> group_comps, cta_group;
+    DevBuf<KGroup> groups;
+    DevBuf<KCtl> ctl;
+    DevBuf<KBarrier> bars;
+    DevBuf<double> partials;
+    std::vector<KComp> h_comps;
+    std::vector<KCtl> h_ctl;
+    int n_groups = 0, n_ctas = 0, group_ctas = 0;
+    bool built_pq = false;
+};
+
+
 // Everything one rank keeps on its GPU.  A distributed mesh holds exactly one; the in-process emulation of several
 // ranks on one GPU (tests of the multi-rank logic) holds all of them.
 struct RankMesh {
@@ -254,6 +271,7 @@ struct RankMesh {
     DevBuf<SolveCtl> d_ctl;
     DevBuf<double2> kr, krhat, kp, kv, ks, kt, kd;
     bool krylov_ready = false;
+    std::unique_ptr<KrylovPlan> kplan;       // single-rank meshes: built on the first Picard solve
     std::vector<EdgeCache> edges;        // indexed by position in L.own_blocks
     std::vector<uint8_t> have_coords;
     int n_tiles = 0, n_rim_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
@@ -387,6 +405,36 @@ void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank, const s
     cudaStream_t s = m->stream;
     r.L = localize(topo, owner_override ? *owner_override : m->owner, rank, m->n_ranks);
     r.N = r.L.n_local;
+    {   // boundary rows and rhs terms grouped by component (independent systems): the persistent Krylov kernel walks them per component
+        auto comp_of_local = [&](int64_t l) {
+            size_t lo = 0, hi = r.L.own_blocks.size() - 1;  // own blocks ascend in the local field
+            while (lo < hi) {
+                const size_t mid = (lo + hi + 1) / 2;
+                if (r.L.loff[size_t(r.L.own_blocks[mid])] <= l) lo = mid; else hi = mid - 1;
+            }
+            return topo.comp_of_block[size_t(r.L.own_blocks[lo])];
+        };
+        auto group_by_component = [&](auto& rows, auto node_of) {
+            std::vector<int32_t> key(rows.size());
+            bool sorted = true;
+            for (size_t k = 0; k < rows.size(); ++k) {
+                key[k] = comp_of_local(node_of(rows[k]));
+                sorted = sorted && (k == 0 || key[k - 1] <= key[k]);
+            }
+            if (sorted) return;  // the usual case: a batch is concatenated cut by cut
+            std::vector<size_t> perm(rows.size());
+            for (size_t k = 0; k < perm.size(); ++k) perm[k] = k;
+            std::stable_sort(perm.begin(), perm.end(), [&](size_t x, size_t y) { return key[x] < key[y]; });
+            auto copy = rows;
+            for (size_t k = 0; k < perm.size(); ++k) rows[k] = copy[perm[k]];
+        };
+        if (!r.L.own_blocks.empty() && topo.n_comp > 1) {
+            group_by_component(r.L.smoothed, [](const SmoothedRow& x) { return x.g0; });
+            group_by_component(r.L.junction_rows, [](const JunctionRow& x) { return x.self; });
+            group_by_component(r.L.sliding, [](const SlidingRow& x) { return x.self; });
+            group_by_component(r.L.rhs_terms, [](const RhsTerm& x) { return x.g; });
+        }
+    }
     r.X[0].alloc(size_t(std::max<int64_t>(r.N, 1)));
     r.X[1].alloc(size_t(std::max<int64_t>(r.N, 1)));
     r.X[0].zero(s);
@@ -831,6 +879,8 @@ void bicgstab_cycle(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* st)
     if (exec) cudaGraphExecDestroy(exec);
 }
 
+#include "krylov.inl"  // krylov_solve_persistent: all inner solves of an outer iteration in one cooperative launch
+
 // One outer (Picard) iteration = the reference's fill + solve(x) + solve(y) (smooth.zig:104-154), with the two
 // solves advanced in lock-step by a matrix-free BiCGStab on the row-scaled system.  One extension over BiCGStab.zig
 // that only matters when the tolerance is tighter than the reference's: whenever the solver reports convergence or
@@ -854,7 +904,9 @@ void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats
             RankMesh& r = *rp;
             CUDA_TRY(cudaMemcpyAsync(r.X[1 - r.cur].p, r.X[r.cur].p, size_t(r.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
         }
-        for (int cycle = 0;; ++cycle) {
+        const bool persistent = krylov_persistent_possible(m);
+        if (persistent) krylov_solve_persistent(m, *m->ranks[0], o, st);
+        for (int cycle = 0; !persistent; ++cycle) {
             if (cycle > 0) refresh_x();
             for (auto& rp : m->ranks) {
                 RankMesh& r = *rp;
@@ -877,10 +929,12 @@ void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats
                 LAUNCH(add_correction_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, xnew(r), r.kd.p);
             }
         }
-        refresh_x();
-        st->inner_iterations += uint64_t(m->h_ctl->iters[0]) + uint64_t(m->h_ctl->iters[1]);
-        st->last_inner_residual = std::fmax(m->h_ctl->norm_r[0], m->h_ctl->norm_r[1]);
-        if (m->h_ctl->done[0] != 1 || m->h_ctl->done[1] != 1) st->converged = 0;  // log.warn "did not converge", BiCGStab.zig:368-369
+        if (!persistent) {
+            refresh_x();
+            st->inner_iterations += uint64_t(m->h_ctl->iters[0]) + uint64_t(m->h_ctl->iters[1]);
+            st->last_inner_residual = std::fmax(m->h_ctl->norm_r[0], m->h_ctl->norm_r[1]);
+            if (m->h_ctl->done[0] != 1 || m->h_ctl->done[1] != 1) st->converged = 0;  // log.warn "did not converge", BiCGStab.zig:368-369
+        }
         for (auto& rp : m->ranks) {
             RankMesh& r = *rp;
             LAUNCH(diff_stats_kernel, r.vec_grid, VEC_THREADS, s, r.L.n_own, (const double2*)r.X[r.cur].p, (const double2*)r.X[1 - r.cur].p, r.part_vec.p);
@@ -1343,6 +1397,31 @@ int tm_mesh_set_white_groups(tm_mesh* m, const uint64_t* block_pairs, size_t n_g
     });
 }
 
+uint64_t tm_mesh_component_count(const tm_mesh* m) { return m ? uint64_t(m->topo.n_comp) : 0; }
+int tm_mesh_component_of_block(const tm_mesh* m, size_t block, uint64_t* component) {
+    return guarded([&] {
+        check_mesh(m);
+        if (block >= m->topo.blocks.size() || !component) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block index out of range / component is NULL");
+        *component = uint64_t(m->topo.comp_of_block[block]);
+    });
+}
+int tm_mesh_component_stats(const tm_mesh* m, size_t component, tm_component_stats* out) {
+    return guarded([&] {
+        check_mesh(m);
+        if (!out || component >= size_t(m->topo.n_comp)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "component index out of range / out is NULL");
+        if (m->ranks.size() != 1 || !m->ranks[0]->kplan) TM_THROW(TM_ERR_UNSUPPORTED, "per-component records exist after a TM_SOLVER_PICARD_BICGSTAB solve of a single-process mesh");
+        const KrylovPlan& P = *m->ranks[0]->kplan;
+        const KCtl& k = P.h_ctl[component];
+        std::memset(out, 0, sizeof *out);
+        out->nodes = uint64_t(P.h_comps[component].nodes);
+        for (int c = 0; c < 2; ++c) {
+            out->iterations[c] = uint64_t(k.iters[c]); out->tolerance[c] = k.tol[c]; out->norm_b[c] = k.norm_b[c]; out->norm_r[c] = k.norm_r[c];
+            out->status[c] = k.done[c];
+        }
+        out->operator_applications = uint64_t(k.applications);
+        out->restarts = uint64_t(k.cycles);
+    });
+}
 uint64_t tm_mesh_block_count(const tm_mesh* m) { return m ? m->topo.blocks.size() : 0; }
 uint64_t tm_mesh_node_count(const tm_mesh* m) { return m ? uint64_t(m->topo.n_nodes) : 0; }
 int tm_mesh_halo_path(const tm_mesh* m) {

@@ -306,6 +306,22 @@ class DeviceMesh:
         check(self._L.tm_mesh_download_boundary_kinds(self._h, block, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
 
+    @property
+    def component_count(self) -> int:
+        """Independent systems of the mesh: connected components of the block graph (the cuts of a batch)."""
+        return int(self._L.tm_mesh_component_count(self._h))
+
+    def component_of_block(self, block: int) -> int:
+        c = C.c_uint64()
+        check(self._L.tm_mesh_component_of_block(self._h, block, C.byref(c)))
+        return int(c.value)
+
+    def component_stats(self, component: int) -> dict:
+        """Record of the inner solves of ``component`` in the last outer iteration (``tm_mesh_component_stats``)."""
+        st = _lib.TmComponentStats()
+        check(self._L.tm_mesh_component_stats(self._h, component, C.byref(st)))
+        return st.as_dict()
+
     def block_device_ptr(self, block: int) -> int:
         return int(self._L.tm_mesh_block_device_ptr(self._h, block) or 0)
 
