@@ -6,9 +6,12 @@
 
 A *step* is one pass of the hot path over one synthetic mesh: TFI of every block from its (device-resident) edges,
 then `--sweeps` smoothing sweeps of the whole mesh (interior rows, interface/junction/sliding rows, residual
-reduction).  node-updates = nodes x sweeps.  Workload: N=1 -> BASELINE.json config 3 (single block 8192 x 8192, the
-largest single-GPU configuration); N>1 -> config 4 in tiling form, 8 blocks of 4097 x 2049 per GPU (64 blocks / 512 Mi
-nodes at N=8), weak scaling.  Both also report the time to a converged mesh (TFI + FAS multigrid).  Prints ONE JSON line on rank 0.
+reduction).  node-updates = nodes x sweeps.  Workload at EVERY N (so that the driver's scaling efficiency compares like
+with like): BASELINE.json config 4, one block column of 8 blocks of 4097 x 2049 per GPU (64 blocks / 512 Mi nodes at
+N = 8), weak scaling; `--workload single` is config 3 (one 8192^2 block), `--workload cuts` config 5.  After the timed
+region every rank checks its blocks against the oracle's assembled rows (`parity_check`), the N = 1 line also carries the
+reference's own configurations (`configs`: T106, LS89 x4, 128 cuts, the 8192^2 block) with the CPU port timed on the same
+mesh in the same run.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -28,9 +31,18 @@ import numpy as np  # noqa: E402
 METRIC = "node-updates/s"
 UNIT = "node-updates/s"
 BYTES_PER_NODE_UPDATE = 32.0  # read own x,y (16 B) + write new x,y (16 B), Laplace control function
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of winslow_interior_kernel on the 8192^2 block, from the
-# committed ncu capture (profiles/); None until measured.
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 2.150e9  # profiles/r1_ncu_winslow_interior_bulk_8192.txt: 1.1287 GB read + 1.0214 GB written
+BYTES_PER_NODE_UPDATE_PQ = 48.0  # ... + 16 B of P,Q when the White control function is resident
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    summaries (profiles/ncu_traffic.json names the file each number was read from); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f).get(key)
+        return (float(rec["dram_bytes_per_launch"]), rec["source"]) if rec else (None, None)
+    except Exception:
+        return None, None
 
 
 def measured_peak():
@@ -98,58 +110,418 @@ def dist_env():
 
 
 # --------------------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port of the reference algorithm).  Only this function and run_reference() touch oracle/.
+# Workloads
 # --------------------------------------------------------------------------------------------------------------
-def cpu_baseline_sample(n: int = 512):
-    """Reference algorithm on one host core, bounded sample of the single-block workload: TFI + one outer iteration with
-    the reference's default solver (gmres + ilu0, rtol 1e-6; examples/T106/T106.json:29-33)."""
+CASCADE_SAMPLE_BLOCK = {1: (257, 129), 2: (193, 97), 4: (129, 65), 8: (97, 49)}   # bounded CPU samples: ~3e5 nodes at every N
+
+
+def cascade_spec(world, args, block=None):
+    """Config 4 in tiling form: one block column (8 blocks) per GPU; the passage grows with N (length = N/8) so that the cells
+    stay square, its waviness scales alike."""
+    from turbomesh_b200 import synthetic
+
+    ni, nj = block or (args.block_ni, args.block_nj)
+    n_bj = args.blocks_per_gpu
+    spec = synthetic.cascade(world, n_bj, ni, nj, length=world / 8.0, ay=0.015 * world / 8.0)
+    owner = [bi for bi in range(world) for _ in range(n_bj)]
+    return spec, owner
+
+
+def workload_name(kind, world, args):
+    if kind == "single":
+        return f"single_block_{args.size}x{args.size} (config 3: synthetic single-block fp64 grid, TFI + elliptic smoothing)"
+    return (f"cascade_{world}x{args.blocks_per_gpu}_blocks_of_{args.block_ni}x{args.block_nj} (config 4: synthetic multi-block cascade passage, "
+            f"{args.blocks_per_gpu} blocks per GPU, interface halo exchange once per sweep)")
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm).  Only the functions of this section touch oracle/ as the thing timed.
+# --------------------------------------------------------------------------------------------------------------
+def cpu_sample(kind, world, args):
+    """Reference algorithm on one host core on a bounded sample of the arm's workload (same topology, smaller blocks): TFI + one
+    outer iteration with the reference's default solver (gmres + ilu0, rtol 1e-6; examples/T106/T106.json:29-33)."""
     from oracle import oracle as orc
     from turbomesh_b200 import synthetic
 
-    spec = synthetic.single_block(n, n)
+    if kind == "single":
+        n = args.ref_size
+        spec, what = synthetic.single_block(n, n), f"single block {n}x{n} (same analytic edges as the GPU workload)"
+    else:
+        blk = CASCADE_SAMPLE_BLOCK.get(world, (97, 49))
+        spec, _ = cascade_spec(world, args, blk)
+        what = f"cascade of {world}x{args.blocks_per_gpu} blocks of {blk[0]}x{blk[1]} (the GPU workload's topology at reduced block size)"
+    nodes = sum(b.size[0] * b.size[1] for b in spec.blocks)
     t0 = time.perf_counter()
     mesh = synthetic.materialize(spec, orc.tfi)
     t_tfi = time.perf_counter() - t0
     t0 = time.perf_counter()
     st = orc.smooth_mesh(mesh, 1, orc.options())
     t_smooth = time.perf_counter() - t0
-    updates = float(n) * n * st["matvecs"]  # one node-update = one application of the 9-point operator to one node
+    updates = float(nodes) * st["matvecs"]  # one node-update = one application of the 9-point operator to one node
     return {"value": updates / (t_tfi + t_smooth), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"single block {n}x{n} (same analytic edges as the GPU workload): TFI + 1 outer iteration gmres/ilu0 rtol 1e-6, "
-                      f"{st['matvecs']} operator applications, {t_tfi + t_smooth:.2f} s; the reference is single-threaded",
+            "sample": f"{what}, {nodes} nodes: TFI + 1 outer iteration gmres/ilu0 rtol 1e-6, {st['matvecs']} operator applications, "
+                      f"{t_tfi + t_smooth:.2f} s; the reference is single-threaded",
             "seconds": t_tfi + t_smooth, "tfi_seconds": t_tfi, "krylov_iterations": st["krylov_iterations"]}
+
+
+def _fixture(name):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import load_fixture
+
+    return load_fixture(name)
+
+
+def cpu_reference_config(name, iterations=None):
+    """The reference's own configuration `name` (tests/golden fixture: the block edges the O4H template produced from the
+    reference's example files) through the oracle port with the reference's settings: TFI + `iterations` outer iterations,
+    White control function, gmres + ilu0, rtol 1e-6 / atol 1e-8 / 1000 inner iterations, one host core."""
+    from oracle import oracle as orc
+    from turbomesh_b200 import synthetic
+
+    spec, z, meta = _fixture(name)
+    its = iterations or meta["iterations"]
+    t0 = time.perf_counter()
+    mesh = synthetic.materialize(spec, orc.tfi)
+    t_tfi = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    st = orc.smooth_mesh(mesh, its, orc.options(control_function="white", ds_target=meta["ds_target"], theta_target=meta["theta_target"]))
+    t_smooth = time.perf_counter() - t0
+    nodes = mesh.num_nodes()
+    return {"seconds": t_tfi + t_smooth, "tfi_seconds": t_tfi, "outer_iterations": its, "krylov_iterations": st["krylov_iterations"],
+            "operator_applications": st["matvecs"], "node_updates_per_s": nodes * st["matvecs"] / (t_tfi + t_smooth), "not_converged_solves": st["not_converged"],
+            "cores": 1, "kind": "port", "solver": "gmres+ilu0 rtol 1e-6 atol 1e-8 max 1000 (reference defaults)"}, mesh
+
+
+def reference_configs_cpu(args):
+    """CPU legs of the `configs` block: config 1 in full, config 2 for `--ref-ls89-iterations` of its 10 outer iterations
+    (95 s in full), config 5 as one cut (the reference meshes cuts one after the other: per-cut time x cuts)."""
+    out = {}
+    out["config1_t106"], _ = cpu_reference_config("t106_white")
+    out["config2_ls89_x4"], _ = cpu_reference_config("ls89x4_white", args.ref_ls89_iterations)
+    out["config5_cut"] = dict(out["config1_t106"], note="one T106 cut; a batch of n cuts costs n times this on the reference (sequential, single-threaded)")
+    return out
 
 
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return  # the reference is a single-process CPU program; other ranks exit without work
-    n = args.ref_size
+    kind = args.workload or "cascade"
     vals = []
     for k in range(args.warmup + args.steps):
-        s = cpu_baseline_sample(n)
+        smp = cpu_sample(kind, world, args)
         if k >= args.warmup:
-            vals.append(s)
+            vals.append(smp)
     secs = float(np.mean([v["seconds"] for v in vals]))
     value = float(np.mean([v["value"] for v in vals]))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"single_block_{n}x{n} (bounded CPU sample of config 3: synthetic single-block fp64 grid, TFI + elliptic smoothing)",
+            "config": {"workload": workload_name(kind, world, args), "sample": vals[-1]["sample"],
                        "solver": "gmres+ilu0 rtol 1e-6 (reference defaults), 1 outer iteration per step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": vals[-1]["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_configs and world == 1:
+        line["configs"] = reference_configs_cpu(args)
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Parity inside the bench (the oracle as checker): after the timed region one more sweep is taken apart on windows
+# --------------------------------------------------------------------------------------------------------------
+def parity_check(dm, spec, owner, rank, world, args, dist, kind):
+    """One extra damped-Jacobi sweep of the timed mesh, checked against the oracle's assembled rows on windows cut out of the
+    full-size blocks: interior rows, an ordinary interface, the periodic pair and (N > 1) an interface whose two sides live
+    on different GPUs; `connected` copies must be exact copies, on the same GPU and across GPUs.  Every rank checks its own
+    blocks; rank 0 reports the worst case.  Raises if anything is off: a fast wrong answer is not a bench value."""
+    from oracle import rowcheck
+    from turbomesh_b200 import smoothing
+
+    one = smoothing.CudaSolver(method="relax", sweeps_per_iteration=1, omega=args.omega, device=int(os.environ.get("LOCAL_RANK", "0")))
+    n_bj = args.blocks_per_gpu if kind != "single" else 1
+    mine = [b for b in range(len(spec.blocks)) if owner[b] == rank]
+    need = sorted(set(mine[:3] + mine[-1:]))
+    before = {b: dm.download_block(b) for b in need}
+    st = dm.smooth(1, one)
+    after = {b: dm.download_block(b) for b in need}
+    wi, wj = 64, 24
+    worst, windows, copies_exact, periodic_dev = 0.0, 0, True, 0.0
+    b0 = mine[0]
+    ni, nj = before[b0].shape[:2]
+    for i0 in sorted({1, ni // 2, ni - wi - 1}):
+        rows = slice(i0, i0 + wi)
+        jm = max(1, min(nj - wi - 1, nj // 2))
+        win = before[b0][rows, jm:jm + wi]
+        want = rowcheck.interior_update(win, args.omega)
+        worst = max(worst, float(np.abs(after[b0][rows, jm:jm + wi][1:-1, 1:-1] - want[1:-1, 1:-1]).max())); windows += 1
+        if kind == "single":
+            continue
+        b1, bl = mine[1], mine[-1]
+        # blocks (bi, 0) | (bi, 1): side i_max of the first = its last j line, side i_min of the second = its first
+        want = rowcheck.interface_update(before[b0][rows, -wj:], before[b1][rows, :wj], 1, 0, args.omega)
+        worst = max(worst, float(np.abs(after[b0][rows, -1][1:-1] - want).max())); windows += 1
+        copies_exact = copies_exact and bool(np.array_equal(after[b0][rows, -1], after[b1][rows, 0]))
+        # the periodic pair (bi, 0) | (bi, n_bj - 1): x0 + p == x_last
+        height = 0.5
+        want = rowcheck.interface_update(before[b0][rows, :wj], before[bl][rows, -wj:], 0, 1, args.omega, (0.0, height))
+        worst = max(worst, float(np.abs(after[b0][rows, 0][1:-1] - want).max())); windows += 1
+        periodic_dev = max(periodic_dev, float(np.abs(after[b0][rows, 0] + np.array([0.0, height]) - after[bl][rows, -1]).max()))
+    cross = None
+    if world > 1 and kind != "single":
+        # block (r, 2) j_max | block (r + 1, 2) j_min: the two sides live on different GPUs
+        bm = mine[2]
+        cols = slice(nj // 2, nj // 2 + wi)
+        payload = {"first_b": before[bm][:wj, cols].copy(), "first_a": after[bm][0, cols].copy()}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload)
+        if rank + 1 < world:
+            nb = gathered[rank + 1]
+            want = rowcheck.interface_update(before[bm][-wj:, cols], nb["first_b"], 3, 2, args.omega)
+            cross = float(np.abs(after[bm][-1, cols][1:-1] - want).max())
+            worst = max(worst, cross); windows += 1
+            copies_exact = copies_exact and bool(np.array_equal(after[bm][-1, cols], nb["first_a"]))
+    rec = {"max_row_update_mismatch": worst, "windows": windows, "copies_exact": copies_exact, "periodic_copy_max_deviation": periodic_dev,
+           "cross_gpu_interface_mismatch": cross, "sweep_max_update": st["last_max_update"]}
+    if world > 1:
+        allrec = [None] * world
+        dist.all_gather_object(allrec, rec)
+        rec = {"max_row_update_mismatch": max(r["max_row_update_mismatch"] for r in allrec), "windows": sum(r["windows"] for r in allrec),
+               "copies_exact": all(r["copies_exact"] for r in allrec), "periodic_copy_max_deviation": max(r["periodic_copy_max_deviation"] for r in allrec),
+               "cross_gpu_interface_mismatch": max([r["cross_gpu_interface_mismatch"] for r in allrec if r["cross_gpu_interface_mismatch"] is not None] or [None]),
+               "sweep_max_update": st["last_max_update"], "ranks_checked": world}
+    rec["tolerance"] = 5e-14
+    rec["what"] = ("one extra sweep after the timed region vs the damped-Jacobi update computed from the oracle's assembled CSR rows (interior, interface, "
+                   "periodic and cross-GPU interface windows of the full-size blocks); copies compared bit for bit")
+    ok = rec["max_row_update_mismatch"] <= rec["tolerance"] and rec["copies_exact"] and rec["periodic_copy_max_deviation"] <= 1e-15
+    rec["ok"] = bool(ok)
+    return rec
 
 
 # --------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------
+def time_to_converged(dm, my_blocks, stream, torch, dist, world, local, nodes_total, repeats):
+    """TFI + FAS multigrid V(3,3) until the mesh changes by <= 1e-10 (chord / passage height are O(1)) per cycle."""
+    from turbomesh_b200 import smoothing
+
+    mg = smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-10, device=local)
+    best, cold = None, None
+    for _ in range(repeats):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        evs[0].record(stream)
+        for b in my_blocks:
+            dm.tfi_block_resident(b)
+        dm.begin_smoothing(mg)
+        st_mg = dm.smooth(100, mg)
+        evs[1].record(stream)
+        dm.synchronize()
+        tt = torch.tensor([evs[0].elapsed_time(evs[1]) * 1e-3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_all = float(tt.item())
+        if cold is None:
+            cold = t_all   # the first run also builds the multigrid hierarchy (one-off per topology)
+        if best is None or t_all < best[0]:
+            best = (t_all, st_mg)
+    ops = best[1]["operator_applications"]
+    return {"seconds": best[0], "solver_seconds": best[1]["gpu_seconds"], "cycles": best[1]["outer_iterations"],
+            "criterion": "max-norm change of the mesh over one V(3,3) cycle <= 1e-10 (chord / passage height are O(1))", "last_max_update": best[1]["last_max_update"],
+            "fine_grid_operator_applications": ops, "cold_seconds_incl_hierarchy_setup": cold,
+            "solver": "TFI + geometric FAS multigrid over the whole block topology, damped-Jacobi smoother (omega 0.8), Anderson(3) on level-1 samples",
+            "equivalent_node_updates_per_s": nodes_total * ops / best[1]["gpu_seconds"],
+            "hbm_fraction_of_equivalent_sweeps": nodes_total * ops / best[1]["gpu_seconds"] * BYTES_PER_NODE_UPDATE / 1e9 / (measured_peak()[0] * world),
+            "note": "best of %d; includes TFI and begin_smoothing; max over ranks" % repeats}
+
+
+def measure_sweeps(args, kind, torch, dist, rank, world, local, barrier, steps, warmup, with_ttc, with_e2e, with_parity):
+    """The timed region of one workload: K steps of (TFI of every block + begin_smoothing + `sweeps` sweeps)."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    sweeps = args.sweeps
+    solver = smoothing.CudaSolver(method="relax", sweeps_per_iteration=sweeps, omega=args.omega, device=local)
+    stream = torch.cuda.Stream()                         # the library launches on this stream, so torch events see its kernels
+    if kind == "single":
+        spec = synthetic.single_block(args.size, args.size)
+        owner = [0]
+        dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False)
+    else:
+        spec, owner = cascade_spec(world, args)
+        uid = [smoothing.dist_unique_id() if (rank == 0 and world > 1) else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0)
+        dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False, owner=owner, rank=rank, n_ranks=world, unique_id=uid[0])
+    my_blocks = [b for b in range(len(spec.blocks)) if owner[b] == rank]
+    nodes_local = sum(spec.blocks[b].size[0] * spec.blocks[b].size[1] for b in my_blocks)
+    nodes_total = sum(b.size[0] * b.size[1] for b in spec.blocks)
+    for b in my_blocks:  # upload the edges once: afterwards the TFI inputs are resident in HBM
+        dm.tfi_block(b, *spec.blocks[b].edge_args())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step():
+        for b in my_blocks:
+            dm.tfi_block_resident(b)
+        dm.begin_smoothing(solver)
+        return dm.smooth(1, solver)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = smoothing.kernel_launch_count()
+    sweep_seconds, sweep_launches = 0.0, 0
+    t0 = time.perf_counter()
+    stats = None
+    ev0.record(stream)
+    for _ in range(steps):
+        stats = step()
+        sweep_seconds += stats["gpu_seconds"]          # CUDA events on the library's stream around the sweep loop only
+        sweep_launches += sweeps
+    ev1.record(stream)
+    dm.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    elapsed = ev0.elapsed_time(ev1) * 1e-3              # device time of exactly K steps on the launching stream
+    launches = smoothing.kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")   # max over ranks
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    value = nodes_total * sweeps * steps / elapsed
+    parity = parity_check(dm, spec, owner, rank, world, args, dist, kind) if with_parity else None
+    ttc = time_to_converged(dm, my_blocks, stream, torch, dist, world, local, nodes_total, 3 if kind == "single" else 2) if with_ttc else None
+    e2e = None
+    if with_e2e and kind == "single":
+        e2e = run_e2e(args, spec, solver, torch)
+    elif with_e2e:
+        e2e = run_e2e_cascade(args, spec, dm, my_blocks, solver, torch, dist, world, nodes_total, barrier)
+    peak, peak_src = measured_peak()
+    per_launch = sweep_seconds / max(sweep_launches, 1)
+    achieved = BYTES_PER_NODE_UPDATE * nodes_local / per_launch / 1e9
+    traffic, traffic_src = ncu_traffic("single_block_8192x8192" if (kind == "single" and args.size == 8192) else
+                                       f"cascade_column_{args.blocks_per_gpu}x{args.block_ni}x{args.block_nj}")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "winslow_interior_bulk_kernel<RELAX>", "algorithmic_bytes_per_launch": BYTES_PER_NODE_UPDATE * nodes_local,
+                "avg_launch_ms": per_launch * 1e3, "peak_source": peak_src + ", sustained copy figure"}
+    out = {"value": value, "ms_per_step": elapsed / steps * 1e3, "nodes_total": nodes_total, "nodes_local": nodes_local, "roofline": roofline, "clocks": clocks,
+           "gpu_launches": launches, "wall_ms_per_step": wall / steps * 1e3, "last_max_update": stats["last_max_update"] if stats else None,
+           "halo_exchange": dm.halo_path, "parity_check": parity, "time_to_converged": ttc, "e2e": e2e}
+    dm.close()
+    return out
+
+
+def gpu_reference_config(name, torch, local, iterations=None, repeats=3):
+    """Configs 1 / 2 through the CUDA path with the reference's settings (White, rtol 1e-6 / atol 1e-8 / 1000, 10 outer
+    iterations): device-resident (TFI from resident edges + smoothing, CUDA events) and end to end through tm_tfi_block +
+    tm_smooth_mesh with host buffers (wall clock)."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    spec, z, meta = _fixture(name)
+    its = iterations or meta["iterations"]
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    sol = smoothing.CudaSolver(method="picard_bicgstab", rtol=1e-6, atol=1e-8, max_inner_iterations=1000, device=local)
+    stream = torch.cuda.Stream()
+    best = None
+    with smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False) as dm:
+        for k, b in enumerate(spec.blocks):
+            dm.tfi_block(k, *b.edge_args())
+        for _ in range(repeats + 1):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record(stream)
+            for k in range(len(spec.blocks)):
+                dm.tfi_block_resident(k)
+            dm.begin_smoothing(sol, cf)
+            st = dm.smooth(its, sol, cf)
+            ev[1].record(stream)
+            dm.synchronize()
+            sec = ev[0].elapsed_time(ev[1]) * 1e-3
+            if best is None or sec < best[0]:
+                best = (sec, st)
+    sec, st = best
+    nodes = st["nodes"]
+    e2e_best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        mesh = synthetic.materialize(spec, smoothing.tfi_block)      # Block2d.init per block: edges H2D, TFI, block D2H
+        smoothing.smooth_mesh(mesh, its, sol, cf)                    # smooth.mesh: blocks H2D, solve, blocks D2H
+        dt = time.perf_counter() - t0
+        e2e_best = dt if e2e_best is None else min(e2e_best, dt)
+    peak = measured_peak()[0]
+    rate = nodes * st["operator_applications"] / st["gpu_seconds"]
+    return {"nodes": nodes, "outer_iterations": its, "seconds": sec, "solver_seconds": st["gpu_seconds"], "e2e_seconds_host_buffers": e2e_best,
+            "krylov_iterations": st["inner_iterations"], "operator_applications": st["operator_applications"], "converged": st["converged"],
+            "node_updates_per_s": rate, "roofline_frac_48B": rate * BYTES_PER_NODE_UPDATE_PQ / 1e9 / peak,
+            "solver": "matrix-free BiCGStab on the row-scaled system, one persistent cooperative kernel per outer iteration; rtol 1e-6 atol 1e-8 max 1000"}
+
+
+def gpu_cuts(args, torch, local, n_cuts, repeats=2):
+    """Config 5 on one GPU: a batch of independent T106 cuts (replicas only), each solved as its own system."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    base, z, meta = _fixture("t106_white")
+    scales = [1.0 + 0.2 * k / max(n_cuts - 1, 1) for k in range(n_cuts)]
+    batch, groups = synthetic.batch_of_cuts(base, scales)
+    stream = torch.cuda.Stream()
+    t0 = time.perf_counter()
+    dm = smoothing.DeviceMesh(batch, device=local, stream=stream.cuda_stream, upload=False)
+    t_create = time.perf_counter() - t0
+    for k, b in enumerate(batch.blocks):
+        dm.tfi_block(k, *b.edge_args())
+    dm.set_white_groups(groups)
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    sol = smoothing.CudaSolver(method="picard_bicgstab", rtol=1e-6, atol=1e-8, max_inner_iterations=1000, device=local)
+    best = None
+    for _ in range(repeats + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(stream)
+        for k in range(len(batch.blocks)):
+            dm.tfi_block_resident(k)
+        dm.begin_smoothing(sol, cf)
+        st = dm.smooth(meta["iterations"], sol, cf)
+        ev[1].record(stream)
+        dm.synchronize()
+        sec = ev[0].elapsed_time(ev[1]) * 1e-3
+        if best is None or sec < best[0]:
+            best = (sec, st)
+    sec, st = best
+    worst = max(max(dm.component_stats(c)["norm_r"][xy] / dm.component_stats(c)["tolerance"][xy] for xy in range(2)) for c in range(0, n_cuts, max(1, n_cuts // 16)))
+    dm.close()
+    peak = measured_peak()[0]
+    rate = st["nodes"] * st["operator_applications"] / st["gpu_seconds"]
+    return {"cuts": n_cuts, "nodes": st["nodes"], "seconds": sec, "solver_seconds": st["gpu_seconds"], "create_seconds": t_create, "cuts_per_second": n_cuts / sec,
+            "krylov_iterations": st["inner_iterations"], "operator_applications": st["operator_applications"], "converged": st["converged"],
+            "worst_sampled_residual_over_own_tolerance": worst, "node_updates_per_s": rate, "roofline_frac_48B": rate * BYTES_PER_NODE_UPDATE_PQ / 1e9 / peak,
+            "note": "every cut is its own linear system (own ||b||, tolerance, iteration count); the solves of ~20 cuts at a time stay L2-resident, "
+                    "so the 48 B/node-update HBM roofline is not a bound for this configuration"}
+
+
+def configs_block(args, torch, local):
+    """The reference's own configurations in the driver-run line (N = 1): GPU seconds next to the CPU port on the same mesh in
+    the same run."""
+    cpu = {} if args.no_cpu_baseline else reference_configs_cpu(args)
+    out = {}
+    g1 = gpu_reference_config("t106_white", torch, local)
+    out["config1_t106"] = {"gpu": g1, "cpu": cpu.get("config1_t106"), "same_config": True}
+    g2 = gpu_reference_config("ls89x4_white", torch, local)
+    g2s = gpu_reference_config("ls89x4_white", torch, local, iterations=args.ref_ls89_iterations, repeats=1)
+    out["config2_ls89_x4"] = {"gpu": g2, "gpu_same_iterations_as_cpu": g2s, "cpu": cpu.get("config2_ls89_x4"), "same_config": True,
+                              "note": f"the CPU port runs {args.ref_ls89_iterations} of the 10 outer iterations (95 s in full); the ratio uses the GPU run of the same iterations"}
+    g5 = gpu_cuts(args, torch, local, args.cuts_per_gpu)
+    out["config5_cuts"] = {"gpu": g5, "cpu_one_cut": cpu.get("config5_cut"), "same_config": True,
+                           "note": "CPU time of the batch = cuts x one cut (independent meshes, sequential single-threaded reference)"}
+    for key, g, c, scale in (("config1_t106", g1, cpu.get("config1_t106"), 1.0), ("config2_ls89_x4", g2s, cpu.get("config2_ls89_x4"), 1.0),
+                             ("config5_cuts", g5, cpu.get("config5_cut"), float(args.cuts_per_gpu))):
+        if c:
+            out[key]["cpu_over_gpu_seconds"] = c["seconds"] * scale / g["seconds"]
+            if "e2e_seconds_host_buffers" in g:
+                out[key]["cpu_over_gpu_seconds_e2e"] = c["seconds"] * scale / g["e2e_seconds_host_buffers"]
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-
-    from turbomesh_b200 import smoothing, synthetic
 
     rank, world, local = dist_env()
     if world != args.gpus:
@@ -166,137 +538,42 @@ def run_gpu(args):
 
     if args.workload == "cuts":
         return run_cuts(args, torch, dist, rank, world, local, barrier)
-    sweeps = args.sweeps
-    solver = smoothing.CudaSolver(method="relax", sweeps_per_iteration=sweeps, omega=args.omega, device=local)
-    stream = torch.cuda.Stream()                         # the library launches on this stream, so torch events see its kernels
-    kind = args.workload or ("single" if world == 1 else "cascade")
-    if kind == "single":
-        if world != 1:
-            raise SystemExit("the single-block workload does not shard; use --workload cascade for N > 1")
-        ni = nj = args.size
-        spec = synthetic.single_block(ni, nj)
-        workload = f"single_block_{ni}x{nj} (config 3: synthetic single-block fp64 grid, TFI + elliptic smoothing)"
-        dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False)
-        my_blocks = list(range(len(spec.blocks)))
-    else:
-        # config 4 in tiling form: one block column (8 blocks of block_ni x block_nj) per GPU; 8 x 8 blocks / 512 Mi nodes at N = 8
-        n_bj = args.blocks_per_gpu
-        # the passage grows with N (length = N/8) so that the cells stay square: 8 x 8 blocks on a 1 x 0.5 passage at N = 8
-        # (the waviness scales with it, so the grid lines have the same inclination at every N)
-        spec = synthetic.cascade(world, n_bj, args.block_ni, args.block_nj, length=world / 8.0, ay=0.015 * world / 8.0)
-        owner = [bi for bi in range(world) for _ in range(n_bj)]
-        workload = (f"cascade_{world}x{n_bj}_blocks_of_{args.block_ni}x{args.block_nj} (config 4: synthetic multi-block cascade passage, "
-                    f"{n_bj} blocks per GPU, interface halo exchange once per sweep)")
-        uid = [smoothing.dist_unique_id() if (rank == 0 and world > 1) else None]
-        if world > 1:
-            dist.broadcast_object_list(uid, src=0)
-        dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False, owner=owner, rank=rank, n_ranks=world, unique_id=uid[0])
-        my_blocks = [b for b in range(len(spec.blocks)) if owner[b] == rank]
-    nodes_local = sum(spec.blocks[b].size[0] * spec.blocks[b].size[1] for b in my_blocks)
-    nodes_total = sum(b.size[0] * b.size[1] for b in spec.blocks)
-
-    for b in my_blocks:  # upload the edges once: afterwards the TFI inputs are resident in HBM
-        dm.tfi_block(b, *spec.blocks[b].edge_args())
-
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def step():
-        for b in my_blocks:
-            dm.tfi_block_resident(b)
-        dm.begin_smoothing(solver)
-        return dm.smooth(1, solver)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = smoothing.kernel_launch_count()
-    sweep_seconds, sweep_launches = 0.0, 0
-    t0 = time.perf_counter()
-    stats = None
-    ev0.record(stream)
-    for _ in range(args.steps):
-        stats = step()
-        sweep_seconds += stats["gpu_seconds"]          # CUDA events on the library's stream around the sweep loop only
-        sweep_launches += sweeps
-    ev1.record(stream)
-    dm.synchronize()
-    barrier()
-    wall = time.perf_counter() - t0
-    elapsed = ev0.elapsed_time(ev1) * 1e-3              # device time of exactly K steps on the launching stream
-    launches = smoothing.kernel_launch_count() - launches0
-    clocks = sampler.stop()
-    t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")   # max over ranks
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed = float(t.item())
-    value = nodes_total * sweeps * args.steps / elapsed
-
-    # ---- time to converged mesh (single block): TFI + FAS multigrid V(3,3) until the mesh changes by <= 1e-10 chord per cycle ----
-    ttc = None
-    if not args.no_ttc:
-        mg = smoothing.CudaSolver(method="multigrid", sweeps_per_iteration=3, omega=0.8, stop_max_update=1e-10, device=local)
-        best, cold = None, None
-        for _ in range(3 if kind == "single" else 2):
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            evs[0].record(stream)
-            for b in my_blocks:
-                dm.tfi_block_resident(b)
-            dm.begin_smoothing(mg)
-            st_mg = dm.smooth(100, mg)
-            evs[1].record(stream)
-            dm.synchronize()
-            tt = torch.tensor([evs[0].elapsed_time(evs[1]) * 1e-3], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_all = float(tt.item())
-            if cold is None:
-                cold = t_all   # the first run also builds the multigrid hierarchy (one-off per topology)
-            if best is None or t_all < best[0]:
-                best = (t_all, st_mg)
-        ops = best[1]["operator_applications"]
-        ttc = {"seconds": best[0], "solver_seconds": best[1]["gpu_seconds"], "cycles": best[1]["outer_iterations"],
-               "criterion": "max-norm change of the mesh over one V(3,3) cycle <= 1e-10 (chord / passage height are O(1))", "last_max_update": best[1]["last_max_update"],
-               "fine_grid_operator_applications": ops, "cold_seconds_incl_hierarchy_setup": cold,
-               "solver": "TFI + geometric FAS multigrid over the whole block topology, damped-Jacobi smoother (omega 0.8), Anderson(3) on level-1 samples",
-               "equivalent_node_updates_per_s": nodes_total * ops / best[1]["gpu_seconds"],
-               "hbm_fraction_of_equivalent_sweeps": nodes_total * ops / best[1]["gpu_seconds"] * BYTES_PER_NODE_UPDATE / 1e9 / (measured_peak()[0] * world),
-               "note": "best of %d; includes TFI and begin_smoothing; max over ranks" % (3 if kind == "single" else 2)}
-
-    # ---- end to end through the reference-facing calls with HOST buffers (Block2d.init -> smooth.mesh) ----
-    e2e = None
-    if kind == "single" and not args.no_e2e:
-        e2e = run_e2e(args, spec, solver, torch)
-    elif not args.no_e2e:
-        e2e = run_e2e_cascade(args, spec, dm, my_blocks, solver, torch, dist, world, nodes_total, barrier)
-
-    peak, peak_src = measured_peak()
-    per_launch = sweep_seconds / max(sweep_launches, 1)
-    achieved = BYTES_PER_NODE_UPDATE * nodes_local / per_launch / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (kind == "single" and args.size == 8192) else None, "kernel": "winslow_interior_bulk_kernel<RELAX>",
-                "algorithmic_bytes_per_launch": BYTES_PER_NODE_UPDATE * nodes_local, "avg_launch_ms": per_launch * 1e3,
-                "peak_source": peak_src + ", sustained copy figure"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    kind = args.workload or "cascade"
+    if kind == "single" and world != 1:
+        raise SystemExit("the single-block workload does not shard; use --workload cascade for N > 1")
+    m = measure_sweeps(args, kind, torch, dist, rank, world, local, barrier, args.steps, args.warmup, not args.no_ttc, not args.no_e2e, not args.no_parity)
+    line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "nodes": nodes_total, "sweeps_per_step": sweeps, "omega": args.omega,
+            "config": {"workload": workload_name(kind, world, args), "nodes": m["nodes_total"], "sweeps_per_step": args.sweeps, "omega": args.omega,
                        "step": "TFI of all blocks from device-resident edges + begin_smoothing + sweeps (damped Jacobi, coefficients from the current iterate)",
-                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2", "nodes_per_gpu": nodes_local,
-                       "halo_exchange": dm.halo_path},
-            "roofline": roofline, "clocks": clocks, "gpu_launches": launches, "wall_ms_per_step": wall / args.steps * 1e3,
-            "last_max_update": stats["last_max_update"] if stats else None}
-    if e2e:
-        line["e2e"] = e2e
-    line["time_to_converged"] = ttc if ttc else {"seconds": None, "note": "skipped (--no-ttc)"}
+                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2", "nodes_per_gpu": m["nodes_local"],
+                       "halo_exchange": m["halo_exchange"]},
+            "roofline": m["roofline"], "clocks": m["clocks"], "gpu_launches": m["gpu_launches"], "wall_ms_per_step": m["wall_ms_per_step"],
+            "last_max_update": m["last_max_update"]}
+    if m["e2e"]:
+        line["e2e"] = m["e2e"]
+    if m["parity_check"]:
+        line["parity_check"] = m["parity_check"]
+    line["time_to_converged"] = m["time_to_converged"] or {"seconds": None, "note": "skipped (--no-ttc)"}
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_sample(kind, world, args).items() if k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_configs:
+            cfg = configs_block(args, torch, local)
+            if kind != "single":   # config 3, the 8192^2 block, next to the headline workload
+                s3 = measure_sweeps(args, "single", torch, dist, rank, world, local, barrier, max(3, min(args.steps, 5)), 3, not args.no_ttc, not args.no_e2e, not args.no_parity)
+                cfg["config3_single_block"] = {"workload": workload_name("single", 1, args), **{k: s3[k] for k in ("value", "ms_per_step", "roofline", "time_to_converged", "e2e", "parity_check")}}
+            line["configs"] = cfg
+    ok = True
+    for pc in [m["parity_check"]] + ([line["configs"]["config3_single_block"]["parity_check"]] if "configs" in line and "config3_single_block" in line["configs"] else []):
+        ok = ok and (pc is None or pc["ok"])
     if rank == 0:
-        if not args.no_cpu_baseline and world == 1 and kind == "single":
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline_sample(args.ref_size).items() if k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
-    dm.close()
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("parity_check failed: the timed mesh does not satisfy the oracle's rows")
 
 
 def run_cuts(args, torch, dist, rank, world, local, barrier):
@@ -448,7 +725,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="turbomesh_b200", choices=["turbomesh_b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="single-block edge length (N=1)")
-    ap.add_argument("--workload", default=None, choices=["single", "cascade", "cuts"], help="default: single for N=1, cascade for N>1")
+    ap.add_argument("--workload", default=None, choices=["single", "cascade", "cuts"], help="default: cascade (config 4, one block column per GPU) at every N")
     ap.add_argument("--cuts-per-gpu", type=int, default=128, help="--workload cuts: T106 cuts per GPU (1024 cuts on 8 GPUs)")
     ap.add_argument("--block-ni", type=int, default=4097, help="cascade: nodes per block along i (2^k + 1 keeps every multigrid level nested)")
     ap.add_argument("--block-nj", type=int, default=2049)
@@ -459,6 +736,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ttc", action="store_true", help="skip the time-to-converged (multigrid) measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle-row check of the timed mesh")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (configs 1, 2, 3, 5 next to the headline workload; N = 1 only)")
+    ap.add_argument("--ref-ls89-iterations", type=int, default=2, help="outer iterations of config 2 the CPU port runs (10 take ~95 s)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

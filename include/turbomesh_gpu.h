@@ -113,7 +113,10 @@ typedef struct tm_smooth_options {
     uint64_t sweeps_per_iteration; /* TM_SOLVER_RELAX: sweeps per outer iteration                */
     double stop_max_update;        /* > 0: stop the outer loop early once max|x_new-x_old| <= this */
     int32_t device;                /* CUDA device ordinal, -1 = current                          */
-    int32_t _pad;
+    int32_t inner_refinement_cycles; /* TM_SOLVER_PICARD_BICGSTAB: after an inner solve has met its tolerance, this many further
+                                      cycles each ask for a 10x smaller TRUE residual (iterative refinement).  0 = the reference's
+                                      behaviour.  For "exact Picard step" parity runs: the 2-norm of the row-scaled residual bounds the
+                                      smooth part of the error only loosely. */
 } tm_smooth_options;
 
 typedef struct tm_smooth_stats {

@@ -71,4 +71,4 @@ if __name__ == "__main__":
     if "t106_white" in which:
         make("t106_white", {8, 10})
     if "ls89x4_white" in which:
-        make("ls89x4_white", {10})
+        make("ls89x4_white", {5, 10})

@@ -43,6 +43,32 @@ def main():
         mine = [b for b in range(len(owner)) if owner[b] == rank]
         out[name] = {"max_diff": max(float(np.abs(one.blocks[b].points - many.blocks[b].points).max()) for b in mine),
                      "update_1": st1["last_max_update"], "update_n": stn["last_max_update"]}
+    # The overlapped schedule (rim tiles + exchange on a second stream next to the bulk of the sweep, relax_sweep in
+    # csrc/turbomesh_gpu.cu) is only taken when the rim is a small part of the tiles: blocks large enough for that, compared
+    # bit for bit with the serial schedule (TM_OVERLAP=0) and, to rounding, with a single process.
+    big = (world, 2, 1025, 513)
+    spec = synthetic.cascade(*big)
+    owner = [bi for bi in range(big[0]) for _ in range(big[1])]
+    mine = [b for b in range(len(owner)) if owner[b] == rank]
+    sol = smoothing.CudaSolver(method="relax", sweeps_per_iteration=25, omega=0.9, device=local)
+    res = {}
+    for mode in ("1", "0", "single"):
+        os.environ["TM_OVERLAP"] = "1" if mode == "single" else mode
+        kw = {}
+        if mode != "single":
+            uid = [smoothing.dist_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            kw = dict(owner=owner, rank=rank, n_ranks=world, unique_id=uid[0])
+        with smoothing.DeviceMesh(spec, device=local, upload=False, **kw) as dm:
+            for b in (mine if mode != "single" else range(len(owner))):
+                dm.tfi_block(b, *spec.blocks[b].edge_args())
+            dm.begin_smoothing(sol)
+            st = dm.smooth(2, sol)
+            res[mode] = ([dm.download_block(b) for b in mine], st["last_max_update"])
+    os.environ.pop("TM_OVERLAP", None)
+    out["overlap"] = {"bit_identical_to_serial_schedule": all(np.array_equal(a, b) for a, b in zip(res["1"][0], res["0"][0])),
+                      "max_diff_to_single_process": max(float(np.abs(a - b).max()) for a, b in zip(res["1"][0], res["single"][0])),
+                      "update": res["1"][1], "update_single": res["single"][1]}
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:

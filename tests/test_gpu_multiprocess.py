@@ -33,3 +33,6 @@ def test_two_processes_match_a_single_process(gpu_lib, p2p):
     for r in json.loads(line[0][len("DIST_RESULT "):]):
         assert r["halo_path"].startswith("nvlink peer memory" if p2p == "1" else "nccl"), r
         assert r["relax"]["max_diff"] <= 1e-14 and r["multigrid"]["max_diff"] <= 1e-13 and r["picard"]["max_diff"] <= 1e-10, r
+        # the overlapped rim / bulk schedule on blocks large enough to take it (1025 x 513)
+        assert r["overlap"]["bit_identical_to_serial_schedule"] and r["overlap"]["max_diff_to_single_process"] <= 1e-14, r
+        assert r["overlap"]["update"] > 0

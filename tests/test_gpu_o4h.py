@@ -24,17 +24,19 @@ def _smooth_and_compare(name, gpu_lib):
     err = max(float(np.abs(b.points - z[f"smooth_b{k}"]).max()) for k, b in enumerate(mesh.blocks))
     moved = max(float(np.abs(b.points - z[f"tfi_b{k}"]).max()) for k, b in enumerate(mesh.blocks)) if "tfi_b0" in z else None
     print(f"{name}: chord {chord:.4f}, max|dx| vs golden {err:.3e} ({err / chord:.3e} chord), moved {moved}, stats {st}")
-    assert st["converged"] == 1
-    # North-star tolerance: max |dx| <= 1e-9 * chord, asserted as such.  One documented exception: T106 + White after the
-    # reference's 10 iterations, where fp64 itself is 1.5e-8 chord away from exact arithmetic (`fp64_direct_vs_truth` of
-    # tests/golden/t106_white_truth.npz: the White leading-edge update collapses a cell to ~2e-13 m) and BOTH sides of this
-    # comparison are fp64 results: the bound is that measured floor, once for each side, with a factor 3.  The strict
-    # 1e-9 chord check of that configuration runs against the extended-precision truth in tests/test_gpu_rows.py.
+    assert st["last_inner_residual"] <= 1e-13
+    # North-star tolerance: max |dx| <= 1e-9 * chord, asserted as such.  One documented exception: the White configurations
+    # after the reference's full 10 iterations, where fp64 itself is 1.5e-8 chord (T106) / 4.8e-10 chord (LS89 x4) away from
+    # exact arithmetic (`fp64_direct_vs_truth` of tests/golden/*_truth.npz: the White leading-edge update collapses a cell to
+    # 2e-13 m / 5e-19 m) and BOTH sides of this comparison are fp64 results: the bound is that measured floor, once for each
+    # side, with a factor 3.  The strict 1e-9 chord checks of these configurations (8 / 5 outer iterations, while the mesh is
+    # regular) run against the extended-precision truth in tests/test_gpu_rows.py.
     tol = 1e-9 * chord
-    if name == "t106_white":
+    truth = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + "_truth.npz")
+    if os.path.exists(truth):   # White configurations: the measured fp64 floor of the full 10 iterations, once for each side, factor 3
         import json
-        floor = json.loads(str(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "t106_white_truth.npz"))["meta"]))["per_iteration"][9]["fp64_direct_vs_truth"]
-        tol = 6.0 * floor
+        floor = json.loads(str(np.load(truth)["meta"]))["per_iteration"][meta["iterations"] - 1]["fp64_direct_vs_truth"]
+        tol = max(tol, 6.0 * floor)
     print(f"  tolerance {tol:.3e} (1e-9 chord = {1e-9 * chord:.3e})")
     assert err <= tol
     return mesh, st

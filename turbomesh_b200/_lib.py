@@ -38,7 +38,7 @@ class TmSmoothOptions(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("solver", C.c_uint32), ("iterations", C.c_uint64), ("control_function", C.c_uint32),
                 ("fail_on_no_convergence", C.c_uint32), ("white_ds_target", C.c_double), ("white_theta_target", C.c_double),
                 ("rtol", C.c_double), ("atol", C.c_double), ("max_inner_iterations", C.c_uint64), ("omega", C.c_double),
-                ("sweeps_per_iteration", C.c_uint64), ("stop_max_update", C.c_double), ("device", C.c_int32), ("_pad", C.c_int32)]
+                ("sweeps_per_iteration", C.c_uint64), ("stop_max_update", C.c_double), ("device", C.c_int32), ("inner_refinement_cycles", C.c_int32)]
 
 
 class TmSmoothStats(C.Structure):

@@ -156,7 +156,7 @@ struct Topology {
     bool range_ok(const tm_range& r) const {
         if (r.block >= blocks.size() || r.side > 3) return false;
         const int64_t ext = (r.side == TM_SIDE_I_MIN || r.side == TM_SIDE_I_MAX) ? blocks[r.block].ni : blocks[r.block].nj;
-        return int64_t(r.start) < ext && int64_t(r.end) < ext;
+        return r.start < uint64_t(ext) && r.end < uint64_t(ext);  // unsigned: values >= 2^63 must not pass as negative numbers
     }
 
     // ---- construction --------------------------------------------------------------------------

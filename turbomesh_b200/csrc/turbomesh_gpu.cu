@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: NCCL is resolved at run time with dlopen, single-GPU use needs no libnccl
 
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -23,6 +24,7 @@
 #include "../../include/turbomesh_gpu.h"
 #include "kernels.cuh"
 #include "krylov_kernels.cuh"
+#include "krylov_phased.cuh"
 #include "io_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "mg_plan.hpp"
@@ -247,6 +249,22 @@ struct KrylovPlan {
 };
 
 
+// plan of the phased Krylov path (krylov.inl / krylov_phased.cuh): warp tiles and boundary chunks per component
+struct PhasedPlan {
+    DevBuf<WTile> wtiles;
+    DevBuf<int32_t> wt_comp;
+    DevBuf<BChunk> chunks;
+    DevBuf<KPComp> comps;
+    DevBuf<KState> state;
+    DevBuf<double> partials;
+    DevBuf<int> count;
+    int* h_count = nullptr;   // pinned
+    std::vector<KPComp> h_comps;
+    std::vector<KState> h_state;
+    int n_comp = 0, n_wtiles = 0, n_chunks = 0;
+    ~PhasedPlan() { if (h_count) cudaFreeHost(h_count); }
+};
+
 // Everything one rank keeps on its GPU.  A distributed mesh holds exactly one; the in-process emulation of several
 // ranks on one GPU (tests of the multi-rank logic) holds all of them.
 struct RankMesh {
@@ -269,9 +287,10 @@ struct RankMesh {
     DevBuf<double> part_int, part_bnd, part_vec, bconst, red;
     DevBuf<unsigned long long> d_worst;
     DevBuf<SolveCtl> d_ctl;
-    DevBuf<double2> kr, krhat, kp, kv, ks, kt, kd;
+    DevBuf<double2> kr, krhat, kp, kv, ks, kt, kd, kp2, kv2;
     bool krylov_ready = false;
     std::unique_ptr<KrylovPlan> kplan;       // single-rank meshes: built on the first Picard solve
+    std::unique_ptr<PhasedPlan> pplan;
     std::vector<EdgeCache> edges;        // indexed by position in L.own_blocks
     std::vector<uint8_t> have_coords;
     int n_tiles = 0, n_rim_tiles = 0, n_bnd_rows = 0, n_bnd_ctas = 0, vec_grid = 1;
@@ -521,11 +540,13 @@ void build_rank(tm_mesh* m, const Topology& topo, RankMesh& r, int rank, const s
 
 #include "exchange.inl"  // p2p_setup / p2p_add_tmp / p2p_check: CUDA IPC plumbing of the peer-memory halo exchange
 
+bool krylov_persistent_possible(const tm_mesh* m);
 void ensure_krylov(tm_mesh* m) {
     for (auto& rp : m->ranks) {
         RankMesh& r = *rp;
         if (r.krylov_ready) continue;
-        for (DevBuf<double2>* v : {&r.kr, &r.krhat, &r.kp, &r.kv, &r.ks, &r.kt, &r.kd}) {
+        for (DevBuf<double2>* v : {&r.kr, &r.krhat, &r.kp, &r.kv, &r.ks, &r.kt, &r.kd, &r.kp2, &r.kv2}) {
+            if ((v == &r.kp2 || v == &r.kv2) && !krylov_persistent_possible(m)) continue;  // ping-pong partners of the persistent kernel
             v->alloc(size_t(std::max<int64_t>(r.N, 1)));
             v->zero(m->stream);
         }
@@ -905,7 +926,14 @@ void run_picard_bicgstab(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats
             CUDA_TRY(cudaMemcpyAsync(r.X[1 - r.cur].p, r.X[r.cur].p, size_t(r.N) * sizeof(double2), cudaMemcpyDeviceToDevice, s));
         }
         const bool persistent = krylov_persistent_possible(m);
-        if (persistent) krylov_solve_persistent(m, *m->ranks[0], o, st);
+        if (persistent) {
+            // One or a few systems: the persistent kernel (a group of CTAs per system, everything L2-resident, barriers instead
+            // of launches).  A batch of many systems: one launch per phase over all of them (HBM-bound, high occupancy).
+            const char* e = std::getenv("TM_KRYLOV");
+            const bool batch = e ? std::strcmp(e, "phased") == 0 : m->topo.n_comp > 8;
+            if (batch) krylov_solve_phased(m, *m->ranks[0], o, st);
+            else krylov_solve_persistent(m, *m->ranks[0], o, st);
+        }
         for (int cycle = 0; !persistent; ++cycle) {
             if (cycle > 0) refresh_x();
             for (auto& rp : m->ranks) {
@@ -1276,7 +1304,20 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
                 bad_conn = p.conn; bad_point = p.point;
             }
         }
+        // every rank must fail together: a rank that threw alone would leave its peers waiting in the next exchange
+        bool elsewhere = false;
+        if (m->n_ranks > 1 && !m->emulated) {
+            RankMesh& r0 = *m->ranks[0];
+            const double mine_bad = bad_conn >= 0 ? 1.0 : 0.0;
+            double any_bad = 0.0;
+            CUDA_TRY(cudaMemcpyAsync(r0.red.p, &mine_bad, sizeof(double), cudaMemcpyHostToDevice, s));
+            NCCL_TRY(g_nccl.AllReduce(r0.red.p, r0.red.p, 1, ncclDouble, ncclMax, m->comm, s));
+            CUDA_TRY(cudaMemcpyAsync(&any_bad, r0.red.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            elsewhere = any_bad > 0.0 && bad_conn < 0;
+        }
         if (bad_conn >= 0) TM_THROW(TM_ERR_TOPOLOGY, "non matching points for connection %d point %d (tolerance 1e-15 abs, smooth.zig:220-275)", bad_conn, bad_point);
+        if (elsewhere) TM_THROW(TM_ERR_TOPOLOGY, "non matching interface points were found by another rank (connectionDataCheck, smooth.zig:220-275)");
         // rhs of fixed / sliding rows is captured from the initial mesh (smooth.zig:790-796, 853-858); then every copy of
         // a node is made exactly consistent with its root (x_copy = x_root + shift), constants included
         for (auto& rp : m->ranks) {
@@ -1409,10 +1450,23 @@ int tm_mesh_component_stats(const tm_mesh* m, size_t component, tm_component_sta
     return guarded([&] {
         check_mesh(m);
         if (!out || component >= size_t(m->topo.n_comp)) TM_THROW(TM_ERR_INVALID_ARGUMENT, "component index out of range / out is NULL");
-        if (m->ranks.size() != 1 || !m->ranks[0]->kplan) TM_THROW(TM_ERR_UNSUPPORTED, "per-component records exist after a TM_SOLVER_PICARD_BICGSTAB solve of a single-process mesh");
+        if (m->ranks.size() != 1 || (!m->ranks[0]->kplan && !m->ranks[0]->pplan))
+            TM_THROW(TM_ERR_UNSUPPORTED, "per-component records exist after a TM_SOLVER_PICARD_BICGSTAB solve of a single-process mesh");
+        std::memset(out, 0, sizeof *out);
+        if (m->ranks[0]->pplan) {
+            const PhasedPlan& P = *m->ranks[0]->pplan;
+            const KState& k = P.h_state[component];
+            out->nodes = uint64_t(P.h_comps[component].nodes);
+            for (int c = 0; c < 2; ++c) {
+                out->iterations[c] = uint64_t(k.iters[c]); out->tolerance[c] = k.tol[c]; out->norm_b[c] = k.norm_b[c]; out->norm_r[c] = k.norm_r[c];
+                out->status[c] = k.done[c];
+            }
+            out->operator_applications = uint64_t(k.applications);
+            out->restarts = uint64_t(k.cycles);
+            return;
+        }
         const KrylovPlan& P = *m->ranks[0]->kplan;
         const KCtl& k = P.h_ctl[component];
-        std::memset(out, 0, sizeof *out);
         out->nodes = uint64_t(P.h_comps[component].nodes);
         for (int c = 0; c < 2; ++c) {
             out->iterations[c] = uint64_t(k.iters[c]); out->tolerance[c] = k.tol[c]; out->norm_b[c] = k.norm_b[c]; out->norm_r[c] = k.norm_r[c];

@@ -50,6 +50,7 @@ class CudaSolver:
     omega: float = 1.0
     sweeps_per_iteration: int = 1
     stop_max_update: float = 0.0
+    inner_refinement_cycles: int = 0
     fail_on_no_convergence: bool = False
     device: int = -1
 
@@ -63,6 +64,7 @@ class CudaSolver:
         kw.setdefault("rtol", 0.0)
         kw.setdefault("atol", 1e-13)
         kw.setdefault("max_inner_iterations", 200000)
+        kw.setdefault("inner_refinement_cycles", 2)
         return CudaSolver(**kw)
 
 
@@ -76,6 +78,7 @@ def make_options(iterations: int, solver: Optional[CudaSolver] = None, control_f
     o.iterations = int(iterations)
     o.rtol, o.atol, o.max_inner_iterations = solver.rtol, solver.atol, int(solver.max_inner_iterations)
     o.omega, o.sweeps_per_iteration, o.stop_max_update = solver.omega, int(solver.sweeps_per_iteration), solver.stop_max_update
+    o.inner_refinement_cycles = int(solver.inner_refinement_cycles)
     o.fail_on_no_convergence = 1 if solver.fail_on_no_convergence else 0
     o.device = solver.device
     if isinstance(control_function, White):

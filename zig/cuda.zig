@@ -32,7 +32,7 @@ pub const tm_smooth_options = extern struct {
     sweeps_per_iteration: u64,
     stop_max_update: f64,
     device: i32,
-    _pad: i32 = 0,
+    inner_refinement_cycles: i32 = 0,
 };
 pub const tm_smooth_stats = extern struct {
     outer_iterations: u64,
