@@ -127,7 +127,23 @@ def cascade_spec(world, args, block=None):
     return spec, owner
 
 
+def passages_spec(world, args, factor=None):
+    """Config 4 as named: `world` pitch-wise O4H passages around the T106 profile (the blade edges of the committed T106 fixture,
+    moved to x >= 0), one passage per GPU, cell counts = T106.json's times `--passage-factor`."""
+    from turbomesh_b200 import synthetic
+
+    spec0, z, meta = _fixture("t106_white")
+    up, down = z["b0_x_i_min"].copy(), z["b1_x_i_min"].copy()
+    x0 = min(up[:, 0].min(), down[:, 0].min())
+    up[:, 0] -= x0
+    down[:, 0] -= x0
+    return synthetic.o4h_passages(up, down, meta["pitch"], n_passages=world, factor=factor or args.passage_factor)
+
+
 def workload_name(kind, world, args):
+    if kind == "passages":
+        return (f"o4h_passages_{world}x8_blocks_factor_{args.passage_factor} (config 4: synthetic multi-block T106-topology cascade, {world} pitch-wise O4H "
+                f"passages of 8 blocks, cell counts of examples/T106 x {args.passage_factor}, one passage per GPU, interface halo exchange once per sweep)")
     if kind == "single":
         return f"single_block_{args.size}x{args.size} (config 3: synthetic single-block fp64 grid, TFI + elliptic smoothing)"
     return (f"cascade_{world}x{args.blocks_per_gpu}_blocks_of_{args.block_ni}x{args.block_nj} (config 4: synthetic multi-block cascade passage, "
@@ -146,6 +162,10 @@ def cpu_sample(kind, world, args):
     if kind == "single":
         n = args.ref_size
         spec, what = synthetic.single_block(n, n), f"single block {n}x{n} (same analytic edges as the GPU workload)"
+    elif kind == "passages":
+        f = {1: 2}.get(world, 1)
+        spec, _ = passages_spec(world, args, f)
+        what = f"{world} O4H passages at cell-count factor {f} (the GPU workload's topology at reduced block size)"
     else:
         blk = CASCADE_SAMPLE_BLOCK.get(world, (97, 49))
         spec, _ = cascade_spec(world, args, blk)
@@ -206,7 +226,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return  # the reference is a single-process CPU program; other ranks exit without work
-    kind = args.workload or "cascade"
+    kind = {"tiling": "cascade", None: "passages"}.get(args.workload, args.workload)
     vals = []
     for k in range(args.warmup + args.steps):
         smp = cpu_sample(kind, world, args)
@@ -231,63 +251,100 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------------------
 def parity_check(dm, spec, owner, rank, world, args, dist, kind):
     """One extra damped-Jacobi sweep of the timed mesh, checked against the oracle's assembled rows on windows cut out of the
-    full-size blocks: interior rows, an ordinary interface, the periodic pair and (N > 1) an interface whose two sides live
-    on different GPUs; `connected` copies must be exact copies, on the same GPU and across GPUs.  Every rank checks its own
-    blocks; rank 0 reports the worst case.  Raises if anything is off: a fast wrong answer is not a bench value."""
+    full-size blocks: interior rows, up to three ordinary connections (sub-ranges and reversed traversal as they come), a
+    periodic pair and (N > 1) a connection whose two sides live on different GPUs; `connected` copies must be exact copies
+    (periodic ones: equal up to the shift), on the same GPU and across GPUs.  Every rank checks its own blocks; rank 0 reports
+    the worst case.  The run fails if anything is off: a fast wrong answer is not a bench value."""
     from oracle import rowcheck
     from turbomesh_b200 import smoothing
 
     one = smoothing.CudaSolver(method="relax", sweeps_per_iteration=1, omega=args.omega, device=int(os.environ.get("LOCAL_RANK", "0")))
-    n_bj = args.blocks_per_gpu if kind != "single" else 1
+    sizes = [b.size for b in spec.blocks]
+    n, depth = 64, 24
+
+    def usable(c):
+        return all(min(sizes[r.block]) >= depth + 2 for r in c.ranges) and abs(c.ranges[0].end - c.ranges[0].start) + 1 >= n + 6
+
+    conns = [c for c in spec.connections if usable(c)]
+    local = [c for c in conns if owner[c.ranges[0].block] == rank and owner[c.ranges[1].block] == rank]
+    plain = [c for c in local if c.periodicity is None]
+    chosen = [plain[k] for k in sorted({0, len(plain) // 2, len(plain) - 1})] if plain else []
+    chosen += [c for c in local if c.periodicity is not None][:1]
+    cross = {}   # rank -> its first connection whose side 1 lives on another rank (every rank computes the same table)
+    for c in conns:
+        r0 = owner[c.ranges[0].block]
+        if owner[c.ranges[1].block] != r0 and r0 not in cross:
+            cross[r0] = c
     mine = [b for b in range(len(spec.blocks)) if owner[b] == rank]
-    need = sorted(set(mine[:3] + mine[-1:]))
-    before = {b: dm.download_block(b) for b in need}
+    need = {max(mine, key=lambda b: sizes[b][0] * sizes[b][1])}
+    for c in chosen:
+        need |= {c.ranges[0].block, c.ranges[1].block}
+    for r, c in cross.items():
+        if r == rank:
+            need.add(c.ranges[0].block)
+        if owner[c.ranges[1].block] == rank:
+            need.add(c.ranges[1].block)
+    before = {b: dm.download_block(b) for b in sorted(need)}
     st = dm.smooth(1, one)
-    after = {b: dm.download_block(b) for b in need}
-    wi, wj = 64, 24
+    after = {b: dm.download_block(b) for b in sorted(need)}
     worst, windows, copies_exact, periodic_dev = 0.0, 0, True, 0.0
-    b0 = mine[0]
-    ni, nj = before[b0].shape[:2]
-    for i0 in sorted({1, ni // 2, ni - wi - 1}):
-        rows = slice(i0, i0 + wi)
-        jm = max(1, min(nj - wi - 1, nj // 2))
-        win = before[b0][rows, jm:jm + wi]
+    big = max(mine, key=lambda b: sizes[b][0] * sizes[b][1])
+    ni, nj = sizes[big]
+    for i0 in sorted({1, ni // 2, ni - n - 1}):
+        j0 = max(1, min(nj - n - 1, nj // 2))
+        win = before[big][i0:i0 + n, j0:j0 + n]
         want = rowcheck.interior_update(win, args.omega)
-        worst = max(worst, float(np.abs(after[b0][rows, jm:jm + wi][1:-1, 1:-1] - want[1:-1, 1:-1]).max())); windows += 1
-        if kind == "single":
-            continue
-        b1, bl = mine[1], mine[-1]
-        # blocks (bi, 0) | (bi, 1): side i_max of the first = its last j line, side i_min of the second = its first
-        want = rowcheck.interface_update(before[b0][rows, -wj:], before[b1][rows, :wj], 1, 0, args.omega)
-        worst = max(worst, float(np.abs(after[b0][rows, -1][1:-1] - want).max())); windows += 1
-        copies_exact = copies_exact and bool(np.array_equal(after[b0][rows, -1], after[b1][rows, 0]))
-        # the periodic pair (bi, 0) | (bi, n_bj - 1): x0 + p == x_last
-        height = 0.5
-        want = rowcheck.interface_update(before[b0][rows, :wj], before[bl][rows, -wj:], 0, 1, args.omega, (0.0, height))
-        worst = max(worst, float(np.abs(after[b0][rows, 0][1:-1] - want).max())); windows += 1
-        periodic_dev = max(periodic_dev, float(np.abs(after[b0][rows, 0] + np.array([0.0, height]) - after[bl][rows, -1]).max()))
-    cross = None
-    if world > 1 and kind != "single":
-        # block (r, 2) j_max | block (r + 1, 2) j_min: the two sides live on different GPUs
-        bm = mine[2]
-        cols = slice(nj // 2, nj // 2 + wi)
-        payload = {"first_b": before[bm][:wj, cols].copy(), "first_a": after[bm][0, cols].copy()}
+        worst = max(worst, float(np.abs(after[big][i0:i0 + n, j0:j0 + n][1:-1, 1:-1] - want[1:-1, 1:-1]).max())); windows += 1
+
+    def window(c, side):
+        r = c.ranges[side]
+        k0 = (abs(r.end - r.start) + 1 - n) // 2
+        return k0
+
+    def check(c, win_b, mini_b, line_b_after):
+        """side-0 rows of connection c against the oracle; copies on side 1 against side 0"""
+        nonlocal worst, windows, copies_exact, periodic_dev
+        r0, r1 = c.ranges
+        k0 = window(c, 0)
+        wa, ma, ia = rowcheck.cut_window(before[r0.block], r0, k0, n, depth)
+        want = rowcheck.connection_update(wa, r0.side, ma, win_b, r1.side, mini_b, args.omega, c.periodicity)
+        got = np.array([after[r0.block][ia(k)] for k in range(n)])
+        worst = max(worst, float(np.abs(got[1:-1] - want).max())); windows += 1
+        if c.periodicity is None:
+            copies_exact = copies_exact and bool(np.array_equal(got[1:-1], line_b_after[1:-1]))
+        else:
+            periodic_dev = max(periodic_dev, float(np.abs(got[1:-1] + np.array(c.periodicity) - line_b_after[1:-1]).max()))
+
+    def side1(c, blocks_before, blocks_after):
+        r1 = c.ranges[1]
+        k0 = window(c, 0)
+        wb, mb, ib = rowcheck.cut_window(blocks_before[r1.block], r1, k0, n, depth)
+        return wb, mb, np.array([blocks_after[r1.block][ib(k)] for k in range(n)])
+
+    for c in chosen:
+        check(c, *side1(c, before, after))
+    cross_mismatch = None
+    if world > 1:
+        payload = {r: side1(c, before, after) for r, c in cross.items() if owner[c.ranges[1].block] == rank}
         gathered = [None] * world
         dist.all_gather_object(gathered, payload)
-        if rank + 1 < world:
-            nb = gathered[rank + 1]
-            want = rowcheck.interface_update(before[bm][-wj:, cols], nb["first_b"], 3, 2, args.omega)
-            cross = float(np.abs(after[bm][-1, cols][1:-1] - want).max())
-            worst = max(worst, cross); windows += 1
-            copies_exact = copies_exact and bool(np.array_equal(after[bm][-1, cols], nb["first_a"]))
+        if rank in cross:
+            c = cross[rank]
+            src = gathered[owner[c.ranges[1].block]][rank]
+            w0 = worst
+            worst = 0.0
+            check(c, *src)
+            cross_mismatch = worst
+            worst = max(worst, w0)
     rec = {"max_row_update_mismatch": worst, "windows": windows, "copies_exact": copies_exact, "periodic_copy_max_deviation": periodic_dev,
-           "cross_gpu_interface_mismatch": cross, "sweep_max_update": st["last_max_update"]}
+           "cross_gpu_interface_mismatch": cross_mismatch, "sweep_max_update": st["last_max_update"]}
     if world > 1:
         allrec = [None] * world
         dist.all_gather_object(allrec, rec)
+        cm = [r["cross_gpu_interface_mismatch"] for r in allrec if r["cross_gpu_interface_mismatch"] is not None]
         rec = {"max_row_update_mismatch": max(r["max_row_update_mismatch"] for r in allrec), "windows": sum(r["windows"] for r in allrec),
                "copies_exact": all(r["copies_exact"] for r in allrec), "periodic_copy_max_deviation": max(r["periodic_copy_max_deviation"] for r in allrec),
-               "cross_gpu_interface_mismatch": max([r["cross_gpu_interface_mismatch"] for r in allrec if r["cross_gpu_interface_mismatch"] is not None] or [None]),
+               "cross_gpu_interface_mismatch": max(cm) if cm else None, "cross_gpu_connections_checked": len(cm),
                "sweep_max_update": st["last_max_update"], "ranks_checked": world}
     rec["tolerance"] = 5e-14
     rec["what"] = ("one extra sweep after the timed region vs the damped-Jacobi update computed from the oracle's assembled CSR rows (interior, interface, "
@@ -345,7 +402,7 @@ def measure_sweeps(args, kind, torch, dist, rank, world, local, barrier, steps, 
         owner = [0]
         dm = smoothing.DeviceMesh(spec, device=local, stream=stream.cuda_stream, upload=False)
     else:
-        spec, owner = cascade_spec(world, args)
+        spec, owner = passages_spec(world, args) if kind == "passages" else cascade_spec(world, args)
         uid = [smoothing.dist_unique_id() if (rank == 0 and world > 1) else None]
         if world > 1:
             dist.broadcast_object_list(uid, src=0)
@@ -400,7 +457,7 @@ def measure_sweeps(args, kind, torch, dist, rank, world, local, barrier, steps, 
     per_launch = sweep_seconds / max(sweep_launches, 1)
     achieved = BYTES_PER_NODE_UPDATE * nodes_local / per_launch / 1e9
     traffic, traffic_src = ncu_traffic("single_block_8192x8192" if (kind == "single" and args.size == 8192) else
-                                       f"cascade_column_{args.blocks_per_gpu}x{args.block_ni}x{args.block_nj}")
+                                       (f"o4h_passage_factor_{args.passage_factor}" if kind == "passages" else f"cascade_column_{args.blocks_per_gpu}x{args.block_ni}x{args.block_nj}"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "winslow_interior_bulk_kernel<RELAX>", "algorithmic_bytes_per_launch": BYTES_PER_NODE_UPDATE * nodes_local,
                 "avg_launch_ms": per_launch * 1e3, "peak_source": peak_src + ", sustained copy figure"}
@@ -538,7 +595,7 @@ def run_gpu(args):
 
     if args.workload == "cuts":
         return run_cuts(args, torch, dist, rank, world, local, barrier)
-    kind = args.workload or "cascade"
+    kind = {"tiling": "cascade", None: "passages"}.get(args.workload, args.workload)
     if kind == "single" and world != 1:
         raise SystemExit("the single-block workload does not shard; use --workload cascade for N > 1")
     m = measure_sweeps(args, kind, torch, dist, rank, world, local, barrier, args.steps, args.warmup, not args.no_ttc, not args.no_e2e, not args.no_parity)
@@ -547,7 +604,7 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(kind, world, args), "nodes": m["nodes_total"], "sweeps_per_step": args.sweeps, "omega": args.omega,
                        "step": "TFI of all blocks from device-resident edges + begin_smoothing + sweeps (damped Jacobi, coefficients from the current iterate)",
-                       "cache": "inputs (2 x 1.07 GB ping-pong fields per GPU) are larger than the 126 MB L2", "nodes_per_gpu": m["nodes_local"],
+                       "cache": "inputs (2 ping-pong fields of 16 B x nodes_per_gpu) are far larger than the 126 MB L2", "nodes_per_gpu": m["nodes_local"],
                        "halo_exchange": m["halo_exchange"]},
             "roofline": m["roofline"], "clocks": m["clocks"], "gpu_launches": m["gpu_launches"], "wall_ms_per_step": m["wall_ms_per_step"],
             "last_max_update": m["last_max_update"]}
@@ -725,7 +782,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="turbomesh_b200", choices=["turbomesh_b200", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="single-block edge length (N=1)")
-    ap.add_argument("--workload", default=None, choices=["single", "cascade", "cuts"], help="default: cascade (config 4, one block column per GPU) at every N")
+    ap.add_argument("--workload", default=None, choices=["passages", "tiling", "cascade", "single", "cuts"],
+                    help="default: passages (config 4 as named: one O4H passage per GPU) at every N; tiling / cascade = config 4 as a Cartesian tiling")
+    ap.add_argument("--passage-factor", type=int, default=48, help="passages: cell counts of examples/T106 times this (48 -> 55 M nodes per passage)")
     ap.add_argument("--cuts-per-gpu", type=int, default=128, help="--workload cuts: T106 cuts per GPU (1024 cuts on 8 GPUs)")
     ap.add_argument("--block-ni", type=int, default=4097, help="cascade: nodes per block along i (2^k + 1 keeps every multigrid level nested)")
     ap.add_argument("--block-nj", type=int, default=2049)

@@ -82,3 +82,49 @@ def interface_update(a: np.ndarray, b: np.ndarray, side_a: int, side_b: int, ome
     else:
         rows = (ni - 1) * nj + np.arange(1, nj - 1)
     return _rows_update(p, idx, v, rx, ry, flat, rows, omega)
+
+
+# ---- general form: any connection (sub-ranges, reversed traversal, periodic), windows cut around nodes k0 .. k0 + n - 1 ----
+def cut_window(points: np.ndarray, rng, k0: int, n: int, depth: int):
+    """Window of `depth` lines inward from the side of `rng` that holds nodes k0 .. k0 + n - 1 of the range (in traversal
+    order).  Returns (window, (mini_start, mini_end), index) where `index(k)` is the (i, j) of range node k0 + k in the block."""
+    ni, nj = points.shape[:2]
+    side, s, e = int(rng.side), int(rng.start), int(rng.end)
+    sign = 1 if e >= s else -1
+    a, b = s + sign * k0, s + sign * (k0 + n - 1)
+    lo, hi = min(a, b), max(a, b)
+    if side == 0:
+        win, index = points[lo:hi + 1, 0:depth], (lambda k: (a + sign * k, 0))
+    elif side == 1:
+        win, index = points[lo:hi + 1, nj - depth:nj], (lambda k: (a + sign * k, nj - 1))
+    elif side == 2:
+        win, index = points[0:depth, lo:hi + 1], (lambda k: (0, a + sign * k))
+    else:
+        win, index = points[ni - depth:ni, lo:hi + 1], (lambda k: (ni - 1, a + sign * k))
+    mini = (0, n - 1) if sign > 0 else (n - 1, 0)
+    return np.ascontiguousarray(win), mini, index
+
+
+def connection_update(win_a, side_a, mini_a, win_b, side_b, mini_b, omega: float, periodicity=None) -> np.ndarray:
+    """Damped-Jacobi update of the interior nodes (k = 1 .. n - 2, traversal order of side a) of the `smoothed` side-0 rows of
+    the connection between the two windows, from the oracle's interface rows (smooth.zig:994-1105)."""
+    conn = _Connection(_Range(0, side_a, mini_a[0], mini_a[1]), _Range(1, side_b, mini_b[0], mini_b[1]), periodicity)
+    sys_ = orc.System(_Mesh([win_a, win_b], [conn]), orc.options(control_function="laplace"))
+    sys_.fill(0)
+    p, idx, v, rx, ry = sys_.csr()
+    sys_.close()
+    flat = np.concatenate([np.ascontiguousarray(win_a, dtype=np.float64).reshape(-1, 2), np.ascontiguousarray(win_b, dtype=np.float64).reshape(-1, 2)])
+    ni, nj = win_a.shape[:2]
+    n = abs(mini_a[1] - mini_a[0]) + 1
+    sign = 1 if mini_a[1] >= mini_a[0] else -1
+    pos = [mini_a[0] + sign * k for k in range(1, n - 1)]
+    side_a = int(side_a)
+    if side_a == 0:
+        rows = [q * nj for q in pos]
+    elif side_a == 1:
+        rows = [q * nj + nj - 1 for q in pos]
+    elif side_a == 2:
+        rows = list(pos)
+    else:
+        rows = [(ni - 1) * nj + q for q in pos]
+    return _rows_update(p, idx, v, rx, ry, flat, np.array(rows), omega)

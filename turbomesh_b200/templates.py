@@ -105,7 +105,7 @@ class O4H:
 
         # Block BLADE_UP (0) -- O4H.zig:115-148
         blade_up_i_min, blade_up_i_max = up_edge, up_outer_edge
-        o_cluster = cluster.SingleHyperbolicClustering(delta_s=0.01)
+        o_cluster = cluster.SingleHyperbolicClustering(delta_s=getattr(self, "o_grid_delta_s", 0.01))  # O4H.zig:129 hard-codes 0.01; refined synthetic passages scale it
         blade_up_j_min = Edge.init(nc.o_grid + 1, Line(pt(blade_up_i_min.points[0]), pt(blade_up_i_max.points[0])), o_cluster)
         blade_up_j_max = Edge.init(nc.o_grid + 1, Line(pt(blade_up_i_min.points[-1]), pt(blade_up_i_max.points[-1])), o_cluster)
         blade_up_id = mesh.add_block("blade_up", Block2d.init(blade_up_i_min, blade_up_i_max, blade_up_j_min, blade_up_j_max, tfi))
