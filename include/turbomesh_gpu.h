@@ -231,6 +231,14 @@ int tm_mesh_download_control_function(tm_mesh *mesh, size_t block, double *pq);
  * (host memory, ideally pinned). */
 typedef enum tm_field { TM_FIELD_COORDINATES = 0, TM_FIELD_CONTROL_FUNCTION = 1 } tm_field;
 int tm_mesh_download_block_soa(tm_mesh *mesh, size_t block, int field /* tm_field */, double *x, double *y);
+/* Structured writer fed by the same device-side transposition: all blocks held by this process as a multi-block 2D PLOT3D
+ * grid file (binary, C stream layout, fp64, no IBLANK: int32 nblocks; nblocks x (int32 ni, int32 nj); per block all x with i
+ * fastest, then all y) -- the wire format of structured multi-block grids, and block for block the arrays the reference hands
+ * to cg_coord_write (src/core/cgns.zig:26-168; CGNS itself needs libcgns / HDF5, which the reference links as system
+ * libraries).  function_path (may be NULL) receives the control function as a PLOT3D function file with two variables
+ * (P, Q), the fields cgns.zig:110-161 writes as a FlowSolution.  Blocks of other ranks are not written. */
+int tm_mesh_write_plot3d(tm_mesh *mesh, const char *grid_path, const char *function_path);
+
 /* Viewer buffers of a (single-GPU) device mesh, built on the device: what createPointBuffer and
  * createWireframeElementBuffer build on the host (src/gui/lib.zig:227-318).  points receives 2*n_points floats (x,y of
  * all blocks in block order, f64 -> f32 round to nearest), ranges receives x_min, x_max, y_min, y_max (the maxima start

@@ -3,7 +3,7 @@
     python tests/golden/make_fixtures.py
 
 Inputs come from the reference's shipped examples (examples/T106/T106.json + T106_ps.dat / T106_ss.dat,
-examples/LS89/LS89.json); the O4H template (host mirror in turbomesh_b200/templates.py) turns them into block edges,
+examples/LS89/LS89.json); the O4H template (host restatement in tests/inputgen/templates.py) turns them into block edges,
 the CPU oracle (oracle/turbomesh_oracle.c) produces TFI and smoothed meshes.  The reference itself cannot run here
 (Zig is not installed), so these are ORACLE outputs: parity stays "unpinned" with respect to the Zig binary.
 
@@ -22,10 +22,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import oracle as orc  # noqa: E402
 from turbomesh_b200.discrete import Block2d, Edge  # noqa: E402
-from turbomesh_b200.input import Input  # noqa: E402
+from inputgen.input import Input  # noqa: E402
 
 REF = "/root/reference"
 

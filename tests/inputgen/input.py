@@ -8,7 +8,8 @@ from typing import Optional
 
 import numpy as np
 
-from . import clustering as cluster
+from turbomesh_b200 import clustering as cluster
+
 from .geometry import Geometry, Profile
 from .templates import O4H, NumCells
 

@@ -1,4 +1,4 @@
-"""Automated blocking templates -- host-side mirror of ``src/core/templates/O4H.zig``.
+"""Automated blocking templates -- host-side restatement of ``src/core/templates/O4H.zig`` (INPUT-GEN, not product code).
 
 The O4H template builds the 8-block cascade topology (two O-grid halves + in/out/down/up/upstream/
 downstream), calls ``Block2d.init`` (the TFI hot path) once per block and declares the 21 connections
@@ -13,9 +13,11 @@ from typing import Optional
 
 import numpy as np
 
-from . import clustering as cluster
-from .boundary import Condition, ConditionTag, Connection, Range, Side
-from .discrete import Block2d, Edge, EdgeView, Mesh
+from turbomesh_b200 import clustering as cluster
+from turbomesh_b200.boundary import Condition, ConditionTag, Connection, Range, Side
+from turbomesh_b200.discrete import Block2d, Edge, Mesh
+
+from .edges import EdgeView, combine
 from .geometry import Geometry, Line
 
 
@@ -115,7 +117,7 @@ class O4H:
         blade_down_id = mesh.add_block("blade_down", Block2d.init(blade_down_i_min, blade_down_i_max, blade_up_j_min, blade_up_j_max, tfi))
 
         # Block IN (2) -- O4H.zig:168-212
-        in_j_min = Edge.combine([EdgeView(blade_up_i_max, nc.in_up_j, 0), EdgeView(blade_down_i_max, 0, nc.in_down_j)])
+        in_j_min = combine([EdgeView(blade_up_i_max, nc.in_up_j, 0), EdgeView(blade_down_i_max, 0, nc.in_down_j)])
         assert len(in_j_min.points) == nc.in_up_j + nc.in_down_j + 1
         in_x_00, in_x_01 = pt(in_j_min.points[0]), pt(in_j_min.points[-1])
         in_x_start = le[0] - inlet_distance * 0.5
@@ -127,7 +129,7 @@ class O4H:
         in_id = mesh.add_block("in", Block2d.init(in_i_min, in_i_max, in_j_min, in_j_max, tfi))
 
         # Block OUT (3) -- O4H.zig:214-248
-        out_j_min = Edge.combine([
+        out_j_min = combine([
             EdgeView(blade_down_i_max, nc.in_down_j + nc.middle_i, len(blade_down_i_max.points) - 1),
             EdgeView(blade_up_i_max, len(blade_up_i_max.points) - 1, nc.in_up_j + nc.bulge + nc.middle_i + nc.out_i),
         ])
@@ -142,7 +144,7 @@ class O4H:
         out_id = mesh.add_block("out", Block2d.init(out_i_min, out_i_max, out_j_min, out_j_max, tfi))
 
         # Block DOWN (4) -- O4H.zig:250-290
-        down_i_min = Edge.combine([
+        down_i_min = combine([
             EdgeView(in_i_max, nc.in_i, 0),
             EdgeView(blade_down_i_max, nc.in_down_j, nc.in_down_j + nc.middle_i),
             EdgeView(out_i_min, 0, nc.out_i),
@@ -158,7 +160,7 @@ class O4H:
 
         # Block UP (5) -- O4H.zig:292-346
         up_j_min = out_i_max
-        up_i_min = Edge.combine([
+        up_i_min = combine([
             EdgeView(blade_up_i_max, nc.in_up_j + nc.middle_i + nc.bulge + nc.out_i, nc.in_up_j),
             EdgeView(in_i_min, 0, nc.in_i),
         ])
@@ -168,12 +170,12 @@ class O4H:
         up_x_10 = in_x_10
         up_i_max_0 = Edge.init(nc.bulge + 1, Line(up_x_01, up_x_i_max_middle), uniform)
         up_i_max_1 = Edge.init(len(up_i_min.points) - nc.bulge, Line(up_x_i_max_middle, up_x_11), uniform)
-        up_i_max = Edge.combine([EdgeView(up_i_max_0, 0, nc.bulge), EdgeView(up_i_max_1, 0, len(up_i_max_1.points) - 1)])
+        up_i_max = combine([EdgeView(up_i_max_0, 0, nc.bulge), EdgeView(up_i_max_1, 0, len(up_i_max_1.points) - 1)])
         up_j_max = Edge.init(nc.out_i + 1, Line(up_x_10, up_x_11), uniform)
         up_id = mesh.add_block("up", Block2d.init(up_i_min, up_i_max, up_j_min, up_j_max, tfi))
 
         # Block UPSTREAM (6) -- O4H.zig:348-384
-        upstream_j_max = Edge.combine([
+        upstream_j_max = combine([
             EdgeView(down_j_min, nc.down_j, 0),
             EdgeView(in_j_max, len(in_j_max.points) - 1, 0),
             EdgeView(up_j_max, 0, len(up_j_max.points) - 1),
@@ -187,7 +189,7 @@ class O4H:
         upstream_id = mesh.add_block("upstream", Block2d.init(upstream_i_min, upstream_i_max, upstream_j_min, upstream_j_max, tfi))
 
         # Block DOWNSTREAM (7) -- O4H.zig:386-420
-        downstream_j_min = Edge.combine([
+        downstream_j_min = combine([
             EdgeView(down_j_max, len(down_j_max.points) - 1, 0),
             EdgeView(out_j_max, 0, len(out_j_max.points) - 1),
             EdgeView(up_i_max_0, 0, len(up_i_max_0.points) - 1),

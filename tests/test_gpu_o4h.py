@@ -120,8 +120,8 @@ def test_edge_discretisation_on_the_device(orc, gpu_lib):
     clustering), a few ulp through CUDA's pow / tanh for the Roberts and hyperbolic clusterings."""
     from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform
     from turbomesh_b200.discrete import Edge
-    from turbomesh_b200.geometry import Line
-    from turbomesh_b200.spline import FittingSpline
+    from inputgen.geometry import Line
+    from inputgen.spline import FittingSpline
 
     t = np.linspace(0.0, 1.0, 215)
     blade = FittingSpline(np.stack([0.08 * t, 0.03 * np.sin(np.pi * t) + 0.01 * t ** 2], axis=1))   # a T106-sized suction side
@@ -159,3 +159,37 @@ def test_viewer_buffers_on_the_device(orc, gpu_lib):
     opts, rx, ry, oidx = orc.viewer_buffers([b.points for b in mesh.blocks])
     assert np.array_equal(pts, opts) and np.array_equal(idx, oidx)
     assert np.array_equal(rng, np.array([rx[0], rx[1], ry[0], ry[1]], dtype=np.float32))
+
+
+def test_plot3d_writer_round_trip(gpu_lib, orc, tmp_path):
+    """f2: the in-tree structured writer (multi-block PLOT3D, fed by the device-side AoS -> SoA transposition): the file holds,
+    block for block, exactly the CoordinateX / CoordinateY arrays the oracle's restatement of cgns.zig:69-101 produces, and the
+    function file the P / Q fields of cgns.zig:110-161."""
+    from turbomesh_b200 import smoothing
+
+    spec, z, meta = load_fixture("t106_white")
+    mesh = synthetic.materialize(spec, smoothing.tfi_block)
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    grid, fun = str(tmp_path / "t106.xyz"), str(tmp_path / "t106.f")
+    with smoothing.DeviceMesh(mesh) as dm:
+        sol = smoothing.CudaSolver(method="picard_bicgstab")
+        dm.begin_smoothing(sol, cf)
+        dm.smooth(2, sol, cf)
+        dm.write_plot3d(grid, fun)
+        blocks = [dm.download_block(k) for k in range(len(mesh.blocks))]
+        pq = [dm.control_function(k) for k in range(len(mesh.blocks))]
+    raw = np.fromfile(grid, dtype=np.int32, count=1 + 2 * len(blocks))
+    assert raw[0] == len(blocks) and [tuple(raw[1 + 2 * k:3 + 2 * k]) for k in range(len(blocks))] == [b.shape[:2] for b in blocks]
+    body = np.fromfile(grid, dtype=np.float64, offset=4 * (1 + 2 * len(blocks)))
+    pos = 0
+    for b in blocks:   # x with i fastest, then y: the oracle's CoordinateX / CoordinateY buffers
+        ox, oy = orc.block_to_soa(b)
+        n = ox.size
+        assert np.array_equal(body[pos:pos + n], ox) and np.array_equal(body[pos + n:pos + 2 * n], oy)
+        pos += 2 * n
+    assert pos == body.size
+    for got, want in zip(smoothing.read_plot3d(grid), blocks):
+        assert np.array_equal(got, want)
+    for got, want in zip(smoothing.read_plot3d(fun, n_vars=2), pq):
+        assert np.array_equal(got, want)
+    assert np.abs(pq[0]).max() > 0 and not pq[4].any()

@@ -12,9 +12,10 @@ import pytest
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform
-from turbomesh_b200.discrete import Edge, EdgeView
-from turbomesh_b200.geometry import Line
-from turbomesh_b200.spline import FittingSpline
+from inputgen.edges import EdgeView, combine
+from turbomesh_b200.discrete import Edge
+from inputgen.geometry import Line
+from inputgen.spline import FittingSpline
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
@@ -29,13 +30,13 @@ def _two_edges():
 def test_edge_combine_known_answers():
     """The four cases of the reference's `combining edges` test (discrete.zig:219-290), exact equality."""
     e1, e2 = _two_edges()
-    e = Edge.combine([EdgeView(e1, 0, 2), EdgeView(e2, 0, 2)])
+    e = combine([EdgeView(e1, 0, 2), EdgeView(e2, 0, 2)])
     assert np.array_equal(e.points, [[0, 0], [1, 0], [2, 0], [3, 0], [4, 0]]) and np.array_equal(e.clustering, [0, 0.25, 0.5, 0.75, 1.0])
-    e = Edge.combine([EdgeView(e1, 1, 2), EdgeView(e2, 0, 1)])
+    e = combine([EdgeView(e1, 1, 2), EdgeView(e2, 0, 1)])
     assert np.array_equal(e.points, [[1, 0], [2, 0], [3, 0]]) and np.array_equal(e.clustering, [0, 0.5, 1.0])
-    e = Edge.combine([EdgeView(e2, 2, 0), EdgeView(e1, 2, 0)])
+    e = combine([EdgeView(e2, 2, 0), EdgeView(e1, 2, 0)])
     assert np.array_equal(e.points, [[4, 0], [3, 0], [2, 0], [1, 0], [0, 0]]) and np.array_equal(e.clustering, [0, 0.25, 0.5, 0.75, 1.0])
-    e = Edge.combine([EdgeView(e2, 1, 0), EdgeView(e1, 2, 1)])
+    e = combine([EdgeView(e2, 1, 0), EdgeView(e1, 2, 1)])
     assert np.array_equal(e.points, [[3, 0], [2, 0], [1, 0]]) and np.array_equal(e.clustering, [0, 0.5, 1.0])
 
 
@@ -72,7 +73,7 @@ def test_clusterings_hit_end_points_exactly():
 def test_csv_and_t106_profile_known_answers():
     """csv.zig:59-67 (first / last row) and spline.zig:306-514 (T106 surface length 0.4947 +- 1e-2, here the CSV profile
     is in metres with chord ~0.1 m, so only the CSV rows and the profile consistency are pinned)."""
-    from turbomesh_b200.input import Input, parse_csv_into_vec2d
+    from inputgen.input import Input, parse_csv_into_vec2d
 
     d = parse_csv_into_vec2d(f"{REF}/examples/T106/T106_ps.dat")
     assert tuple(d[0]) == (1.127030384, -0.047185256) and tuple(d[-1]) == (1.047805900, 0.000076595)
@@ -86,7 +87,7 @@ def test_csv_and_t106_profile_known_answers():
 def test_o4h_template_reproduces_committed_fixture_inputs(orc):
     """The committed T106 fixture inputs are what the O4H mirror produces from the reference's example files."""
     from util import load_fixture
-    from turbomesh_b200.input import Input
+    from inputgen.input import Input
 
     inp = Input.from_json(open(f"{REF}/examples/T106/T106.json").read())
     calls = []
@@ -153,6 +154,40 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "turbomesh_oracle" not in text, f
+                assert "inputgen" not in text, f    # the INPUT-GEN restatements (tests/inputgen) are not product code either
+
+
+def test_o4h_passages_rewire_the_pitchwise_periodic_connections(orc):
+    """Config 4 as named (tests/inputgen/passages.py): k pitch-wise O4H passages; the template's three periodic connections
+    become ordinary connections between neighbouring passages and stay periodic (k * pitch) between the last and the first.
+    The oracle accepts the mesh (connectionDataCheck, topology rules) and classifies it like k copies of one passage."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from inputgen import passages
+    from util import load_fixture
+
+    from turbomesh_b200 import smoothing, synthetic
+
+    spec, z, meta = load_fixture("t106_white")
+    one = orc.System(synthetic.materialize(spec, orc.tfi))
+    base_kinds = np.bincount(one.kinds(), minlength=5)
+    n_junctions = len(one.junctions())
+    one.close()
+    for k in (1, 3):
+        mesh, owner = passages.o4h_passages(z["b0_x_i_min"], z["b1_x_i_min"], meta["pitch"], n_passages=k, factor=1, o_grid_delta_s=0.01)
+        assert len(mesh.blocks) == 8 * k and len(mesh.connections) == 21 * k and owner == [p for p in range(k) for _ in range(8)]
+        per = [c for c in mesh.connections if c.periodicity is not None]
+        assert len(per) == 3 and all(c.periodicity == (0.0, k * meta["pitch"]) for c in per)
+        assert all(c.ranges[0].block <= c.ranges[1].block for c in mesh.connections)
+        m = synthetic.materialize(mesh, orc.tfi)
+        S = orc.System(m)
+        assert np.array_equal(np.bincount(S.kinds(), minlength=5), k * base_kinds) and len(S.junctions()) == k * n_junctions
+        S.close()
+        if k == 1:   # one passage is the T106 example mesh (up to the re-fit of the profile splines through the fixture's edge nodes)
+            for a, b in zip(m.blocks, synthetic.materialize(spec, orc.tfi).blocks):
+                assert a.points.shape == b.points.shape and np.abs(a.points - b.points).max() < 1e-5
+    # the multigrid hierarchy of the refined passage: cell counts x 8 halve three times (and once more, like T106 itself)
+    mesh, _ = passages.o4h_passages(z["b0_x_i_min"], z["b1_x_i_min"], meta["pitch"], n_passages=2, factor=8)
+    assert len(smoothing.mg_plan(mesh)) >= 4
 
 
 # ---- host-only planning of the multi-block multigrid hierarchy (tm_mg_plan) -----------------------------------------

@@ -203,8 +203,8 @@ def test_edge_discretisation_oracle_matches_the_host_mirror(orc):
     """clustering.create + Curve.interpolate (discrete.zig:17-31): the C restatement and the host-side mirror agree bit for
     bit (same libm), incl. the reference's straight-line known answer for the spline (spline.zig:235-304)."""
     from turbomesh_b200.clustering import Roberts, SingleHyperbolicClustering, Uniform
-    from turbomesh_b200.geometry import Line
-    from turbomesh_b200.spline import FittingSpline
+    from inputgen.geometry import Line
+    from inputgen.spline import FittingSpline
 
     for n in (2, 5, 41, 200):
         assert np.array_equal(orc.clustering("uniform", n), Uniform().compute(n))

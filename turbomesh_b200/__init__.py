@@ -1,9 +1,9 @@
 """turbomesh_b200 -- B200 (sm_100a) back-end for turbomesh's hot path: 2D TFI + multi-block elliptic smoothing.
 
-Host-side mirror of the reference's ``src/core`` block/mesh API (``discrete``, ``boundary``, ``clustering``,
-``spline``, ``geometry``, ``templates``, ``input``, ``smoothing``) whose two hot calls -- ``Block2d.init`` (TFI) and
-``smoothing.mesh`` -- go through the C ABI of ``include/turbomesh_gpu.h`` to hand-written CUDA kernels.
+Host-side mirror of the part of the reference's ``src/core`` block/mesh API the path sits behind (``discrete``, ``boundary``,
+``clustering``, ``smoothing``) whose two hot calls -- ``Block2d.init`` (TFI) and ``smoothing.mesh`` -- go through the C ABI of
+``include/turbomesh_gpu.h`` to hand-written CUDA kernels; ``synthetic`` holds the workloads of the named shapes.
 """
-from . import boundary, clustering, discrete, geometry, spline  # noqa: F401
+from . import boundary, clustering, discrete  # noqa: F401
 
-__all__ = ["boundary", "clustering", "discrete", "geometry", "spline", "templates", "input", "smoothing", "synthetic"]
+__all__ = ["boundary", "clustering", "discrete", "smoothing", "synthetic"]

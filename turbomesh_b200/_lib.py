@@ -155,6 +155,7 @@ def load():
     L.tm_mesh_download_control_function.argtypes = [vp, C.c_size_t, dp]
     L.tm_mesh_download_boundary_kinds.argtypes = [vp, C.c_size_t, C.POINTER(C.c_uint8)]
     L.tm_mesh_download_block_soa.argtypes = [vp, C.c_size_t, C.c_int, dp, dp]
+    L.tm_mesh_write_plot3d.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.tm_mesh_viewer_sizes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tm_mesh_viewer_buffers.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     _lib = L

@@ -1536,6 +1536,52 @@ int tm_mesh_download_block_soa(tm_mesh* m, size_t block, int field, double* x, d
         CUDA_TRY(cudaStreamSynchronize(m->stream));
     });
 }
+int tm_mesh_write_plot3d(tm_mesh* m, const char* grid_path, const char* function_path) {
+    return guarded([&] {
+        check_mesh(m);
+        if (!grid_path) TM_THROW(TM_ERR_INVALID_ARGUMENT, "grid_path is NULL");
+        CUDA_TRY(cudaSetDevice(m->device));
+        struct File {
+            FILE* f = nullptr;
+            ~File() { if (f) std::fclose(f); }
+        };
+        std::vector<std::pair<RankMesh*, int32_t>> own;   // blocks held by this process, in global block order
+        for (size_t b = 0; b < m->topo.blocks.size(); ++b)
+            for (auto& rp : m->ranks)
+                if (rp->L.rank == m->owner[b]) own.push_back({rp.get(), int32_t(b)});
+        std::vector<double> host;
+        for (int pass = 0; pass < (function_path ? 2 : 1); ++pass) {
+            File out;
+            out.f = std::fopen(pass == 0 ? grid_path : function_path, "wb");
+            if (!out.f) TM_THROW(TM_ERR_INVALID_ARGUMENT, "cannot open %s for writing", pass == 0 ? grid_path : function_path);
+            auto put = [&](const void* p, size_t bytes) { if (std::fwrite(p, 1, bytes, out.f) != bytes) TM_THROW(TM_ERR_INVALID_ARGUMENT, "short write (disk full?)"); };
+            const int32_t nb = int32_t(own.size());
+            put(&nb, sizeof nb);
+            for (const auto& ob : own) {
+                const auto& B = m->topo.blocks[size_t(ob.second)];
+                const int32_t dims[3] = {int32_t(B.ni), int32_t(B.nj), 2};
+                put(dims, (pass == 0 ? 2 : 3) * sizeof(int32_t));
+            }
+            for (const auto& ob : own) {
+                RankMesh& r = *ob.first;
+                const auto& B = m->topo.blocks[size_t(ob.second)];
+                const size_t n = size_t(B.ni * B.nj);
+                host.resize(2 * n);
+                if (pass == 1 && (!r.has_pq || !r.pq.p)) {   // laplace: all zero (wall_control_function.zig:29-33)
+                    std::fill(host.begin(), host.end(), 0.0);
+                } else {
+                    const double2* src = (pass == 0 ? r.X[r.cur].p : r.pq.p) + r.L.loff[size_t(ob.second)];
+                    if (r.soa_stage.n < 2 * n) r.soa_stage.alloc(2 * n);
+                    dim3 grid(unsigned((B.nj + 31) / 32), unsigned((B.ni + 31) / 32));
+                    LAUNCH(aos_to_soa_kernel, grid, 256, m->stream, int(B.ni), int(B.nj), src, r.soa_stage.p, r.soa_stage.p + n);
+                    CUDA_TRY(cudaMemcpyAsync(host.data(), r.soa_stage.p, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+                    CUDA_TRY(cudaStreamSynchronize(m->stream));
+                }
+                put(host.data(), 2 * n * sizeof(double));
+            }
+        }
+    });
+}
 int tm_mesh_viewer_sizes(const tm_mesh* m, uint64_t* n_points, uint64_t* n_indices) {
     return guarded([&] {
         check_mesh(m);

@@ -1,6 +1,6 @@
 """Discrete mesh model -- host-side mirror of ``src/core/discrete.zig``.
 
-``Block2d.init`` is one of the two call sites of the accelerated path: it allocates the block and runs
+``Edge`` / ``Block2d`` / ``Mesh`` keep the reference's field names.  ``Block2d.init`` is one of the two call sites of the accelerated path: it allocates the block and runs
 the boundary-blended TFI (``discrete.zig:142-159`` -> ``tfi.zig:112-208``) -- here through the C ABI
 (``tm_tfi_block``) on the GPU.  There is no CPU fallback; a ``tfi=`` callable can be injected (the test
 suite injects the CPU oracle as the checker).
@@ -14,8 +14,6 @@ import numpy as np
 
 from . import clustering as cluster
 from .boundary import Condition, Connection
-from .geometry import Line
-from .spline import FittingSpline
 
 
 class Edge:
@@ -30,10 +28,9 @@ class Edge:
     def init(n: int, curve, clustering) -> "Edge":
         """``Edge.init``, ``discrete.zig:17-31``."""
         u = cluster.create(clustering, n)
-        if isinstance(curve, (Line, FittingSpline)):
-            data = curve.interpolate(u)
-        else:
-            raise TypeError("curve must be a Line or a FittingSpline")
+        if not hasattr(curve, "interpolate"):
+            raise TypeError("curve must offer interpolate(u) (geometry.zig:18-40 Line, spline.zig:24-222 FittingSpline)")
+        data = curve.interpolate(u)
         return Edge(data, u)
 
     @staticmethod
@@ -62,10 +59,10 @@ class Edge:
                 j.clustering_kind, j.delta_s = 2, clustering.delta_s
             else:
                 raise TypeError("unknown clustering function")
-            if isinstance(curve, Line):
+            if hasattr(curve, "start") and hasattr(curve, "end"):       # a line (geometry.zig:18-40)
                 j.curve_kind = 0
                 j.line_start[0], j.line_start[1], j.line_end[0], j.line_end[1] = curve.start[0], curve.start[1], curve.end[0], curve.end[1]
-            elif isinstance(curve, FittingSpline):
+            elif hasattr(curve, "second_derivs"):                        # an already fitted spline (spline.zig:24-40): its tables are borrowed
                 j.curve_kind = 1
                 if id(curve) not in splines:
                     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (curve.params, curve.points, curve.second_derivs[0], curve.second_derivs[1], curve.sample_arc)]
@@ -76,70 +73,12 @@ class Edge:
                     splines[id(curve)] = sp
                 j.spline = C.pointer(splines[id(curve)])
             else:
-                raise TypeError("curve must be a Line or a FittingSpline")
+                raise TypeError("curve must be a line (start, end) or a fitted spline (params, points, second_derivs, sample_arc, total_length)")
         _lib.check(_lib.load().tm_edges_discretize(jobs, len(specs), device))
         return [Edge(p, c) for p, c in out]
 
     def copy(self) -> "Edge":
         return Edge(self.points.copy(), self.clustering.copy())
-
-    @staticmethod
-    def combine(edges: Sequence["EdgeView"]) -> "Edge":
-        """``Edge.combine``, ``discrete.zig:38-91``: concatenates views, dropping the duplicated joints."""
-        assert len(edges) > 1
-        tol = 1e-10
-        for k in range(len(edges) - 1):
-            a = edges[k].edge.points[edges[k].end]
-            b = edges[k + 1].edge.points[edges[k + 1].start]
-            if not (abs(a[0] - b[0]) <= tol and abs(a[1] - b[1]) <= tol):
-                raise ValueError(f"edges {k + 1} and {k + 2} cannot be combined as end points do not match: {a} and {b}")
-        n = sum(e.len() for e in edges) - (len(edges) - 1)
-        u = np.empty(n, dtype=np.float64)
-        points = np.empty((n, 2), dtype=np.float64)
-        start = 0
-        for e in edges:
-            start += e.clone_points(points[start:]) - 1
-        start = 0
-        last_value = 0.0
-        for e in edges:
-            start += e.clone_clustering(u[start:], last_value) - 1
-            last_value = float(u[start])
-        for k in range(n):
-            u[k] = u[k] / last_value
-        return Edge(points, u)
-
-
-@dataclass
-class EdgeView:
-    """``discrete.zig:94-136``."""
-
-    edge: Edge
-    start: int
-    end: int
-
-    def len(self) -> int:
-        return abs(self.start - self.end) + 1
-
-    def clone_points(self, buffer: np.ndarray) -> int:
-        n = self.len()
-        if self.start > self.end:
-            buffer[:n] = self.edge.points[self.end : self.start + 1][::-1]
-        else:
-            buffer[:n] = self.edge.points[self.start : self.end + 1]
-        return n
-
-    def clone_clustering(self, buffer: np.ndarray, initial_value: float) -> int:
-        # NOTE (reference behaviour): for reversed views the deltas are still accumulated from
-        # min(start, end) upwards, i.e. the clustering is not reversed (discrete.zig:119-135).
-        buffer[0] = initial_value
-        first, last = min(self.start, self.end), max(self.start, self.end)
-        last_value = float(self.edge.clustering[first])
-        i_buf = 1
-        for i in range(first + 1, last + 1):
-            delta = float(self.edge.clustering[i]) - last_value
-            buffer[i_buf] = initial_value + delta
-            i_buf += 1
-        return i_buf
 
 
 TfiFn = Callable[..., np.ndarray]

@@ -9,6 +9,7 @@ Everything here needs the CUDA library and a GPU; nothing falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from dataclasses import dataclass, field
 from typing import Optional
@@ -290,6 +291,11 @@ class DeviceMesh:
         check(self._L.tm_mesh_download_block_soa(self._h, block, {"coordinates": 0, "control_function": 1}[field], _dp(x), _dp(y)))
         return x, y
 
+    def write_plot3d(self, grid_path: str, function_path: Optional[str] = None):
+        """Multi-block PLOT3D grid file (and, optionally, the control function as a function file) of the blocks this
+        process holds -- the structured output step right after the path (``cgns.write``, cgns.zig:26-168)."""
+        check(self._L.tm_mesh_write_plot3d(self._h, os.fsencode(grid_path), os.fsencode(function_path) if function_path else None))
+
     def viewer_buffers(self):
         """f32 point buffer, (x_min, x_max, y_min, y_max) and wireframe line indices built on the device
         (``tm_mesh_viewer_buffers``; gui/lib.zig:227-318)."""
@@ -394,3 +400,18 @@ def device_info(device: int = -1) -> dict:
     sms, mem = C.c_int(), C.c_uint64()
     check(_lib.load().tm_device_info(device, name, 256, C.byref(sms), C.byref(mem)))
     return {"name": name.value.decode(), "sm_count": sms.value, "global_mem_bytes": mem.value}
+
+
+def read_plot3d(path: str, n_vars: Optional[int] = None):
+    """Reads a file written by :meth:`DeviceMesh.write_plot3d`: a list of (ni, nj, 2) arrays (x, y of a grid file, or P, Q
+    of a function file when ``n_vars`` is given)."""
+    with open(path, "rb") as f:
+        nb = int(np.fromfile(f, dtype=np.int32, count=1)[0])
+        width = 2 if n_vars is None else 3
+        dims = np.fromfile(f, dtype=np.int32, count=width * nb).reshape(nb, width)
+        out = []
+        for ni, nj in dims[:, :2]:
+            a = np.fromfile(f, dtype=np.float64, count=2 * int(ni) * int(nj)).reshape(2, int(nj), int(ni))
+            out.append(np.ascontiguousarray(a.transpose(2, 1, 0)))
+        assert f.read(1) == b""
+    return out
