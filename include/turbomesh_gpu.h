@@ -326,6 +326,32 @@ typedef struct tm_edge_job {
  * pow / tanh inside the Roberts and hyperbolic clusterings are CUDA's (a few ulp from any host libm). */
 int tm_edges_discretize(const tm_edge_job *jobs, size_t n_jobs, int device);
 
+/* The two other edge operations of the automated blocking, batched on the device (one CTA per job, bit-exact with the
+ * reference's operation order):
+ *   Edge.combine (src/core/discrete.zig:38-91 over the views of :94-136): the views' points back to back without the
+ *   duplicated joints (which must agree within 1e-10, else TM_ERR_INVALID_ARGUMENT); clustering re-accumulated and normalised.
+ *   projectNormal (src/core/templates/O4H.zig:531-574): every point moved by `distance` along the normal of the edge. */
+typedef struct tm_edge_view {
+    const double *points;         /* source Edge.points, interleaved x,y                               */
+    const double *clustering;     /* source Edge.clustering                                            */
+    uint64_t n;                   /* points of the source edge                                         */
+    uint64_t start, end;          /* EdgeView.start / .end (start > end: traversed backwards)          */
+} tm_edge_view;
+typedef struct tm_combine_job {
+    const tm_edge_view *views;    /* at least 2, at most 16                                            */
+    uint64_t n_views;
+    double *points;               /* out: 2 * n doubles with n = sum(len) - (n_views - 1), host memory */
+    double *clustering;           /* out: n doubles                                                    */
+} tm_combine_job;
+int tm_edges_combine(const tm_combine_job *jobs, size_t n_jobs, int device);
+typedef struct tm_project_job {
+    const double *points;         /* Edge.points, 2 * n doubles                                        */
+    uint64_t n;                   /* >= 2                                                              */
+    double distance;
+    double *out;                  /* 2 * n doubles, host memory                                        */
+} tm_project_job;
+int tm_edges_project_normal(const tm_project_job *jobs, size_t n_jobs, int device);
+
 /* Host-only view of the multigrid hierarchy TM_SOLVER_FAS_MULTIGRID builds for a multi-block mesh (needs no GPU): nested
  * coarsening of block sizes and connection / condition ranges, directions tied into classes by the connections.
  * cell_size (may be NULL = all equal) holds the mean cell size per (block, direction), 2*n_blocks entries -- the solver

@@ -1,1 +1,5 @@
-for k in persistent phased; do TM_KRYLOV=$k timeout 250 python scripts/ls89_tight.py 2>&1 | tail -4; TM_KRYLOV=$k timeout 250 python scripts/ls89_tight.py t106_white 2>&1 | tail -4; done
+echo "== o=8 thick 0.004"; OGRID=8 THICK=0.004 timeout 120 python scripts/mg_passages.py 8 2>&1 | tail -3
+echo "== o=8 thick 0.004 AA off"; TM_MG_AA=0 OGRID=8 THICK=0.004 timeout 120 python scripts/mg_passages.py 8 2>&1 | tail -2
+echo "== o=4 thick 0.002"; OGRID=4 THICK=0.002 timeout 120 python scripts/mg_passages.py 8 2>&1 | tail -2
+echo "== o=8 thick 0.004 factor 16"; OGRID=8 THICK=0.004 timeout 120 python scripts/mg_passages.py 16 2>&1 | tail -2
+echo "== o=8 thick 0.004 nu 5"; NU=5 OGRID=8 THICK=0.004 timeout 120 python scripts/mg_passages.py 8 2>&1 | tail -2

@@ -15,7 +15,7 @@ from .templates import O4H, NumCells
 
 
 def o4h_passages(profile_up: np.ndarray, profile_down: np.ndarray, pitch: float, n_passages: int = 8, factor: int = 48,
-                 num_cells=None, o_grid_delta_s: Optional[float] = None) -> Tuple[Mesh, List[int]]:
+                 num_cells=None, o_grid_delta_s: Optional[float] = None, o_grid_thickness: Optional[float] = None) -> Tuple[Mesh, List[int]]:
     """Config 4 as BASELINE.json names it: `n_passages` pitch-wise copies of the 8-block O4H topology (O4H.zig:423-521) around a
     blade profile, passage k shifted by k * pitch; the three pitch-wise periodic connections of the template (#18 upstream,
     #19 down <-> up, #20 downstream; O4H.zig:503-514) are rewired passage k <-> k + 1 as ordinary connections and stay
@@ -39,6 +39,8 @@ def o4h_passages(profile_up: np.ndarray, profile_down: np.ndarray, pitch: float,
 
     tmpl = O4H(blade_clustering=Roberts(0.5, 1.03), num_cells=nc)
     tmpl.o_grid_delta_s = o_grid_delta_s if o_grid_delta_s is not None else 0.5 / nc.o_grid
+    if o_grid_thickness is not None:
+        tmpl.o_grid_thickness = o_grid_thickness
     one = tmpl.run(geom, tfi=record)
     nb = len(calls)
     assert nb == 8

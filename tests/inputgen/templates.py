@@ -91,7 +91,7 @@ class O4H:
         inlet_distance = self.inlet_distance if self.inlet_distance is not None else default_spacing * float(nc.upstream_i)
         outlet_distance = self.outlet_distance if self.outlet_distance is not None else default_spacing * float(nc.downstream_i)
 
-        d = 0.001  # O4H.zig:102 (hard-coded O-grid offset)
+        d = getattr(self, "o_grid_thickness", 0.001)  # O4H.zig:102 hard-codes the O-grid offset 0.001; synthetic passages may widen it
         down_outer_edge = Edge(project_normal(down_edge.points, d), down_edge.clustering.copy())
         up_outer_edge = Edge(project_normal(up_edge.points, -d), up_edge.clustering.copy())
         up_outer_edge.points[0] = down_outer_edge.points[0]

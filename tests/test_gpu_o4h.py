@@ -193,3 +193,43 @@ def test_plot3d_writer_round_trip(gpu_lib, orc, tmp_path):
     for got, want in zip(smoothing.read_plot3d(fun, n_vars=2), pq):
         assert np.array_equal(got, want)
     assert np.abs(pq[0]).max() > 0 and not pq[4].any()
+
+
+def test_edge_combine_and_project_normal_on_the_device(gpu_lib):
+    """Edge.combine and projectNormal batched on the GPU (tm_edges_combine, tm_edges_project_normal): the reference's own
+    known-answer vectors (discrete.zig:219-290) and bit-exact agreement with the host restatements on the edges the O4H
+    blocking of T106 combines / offsets (reversed views, three-view joins, the O-grid offset d = +-0.001)."""
+    from inputgen.edges import EdgeView, combine
+    from inputgen.geometry import Line
+    from inputgen.templates import project_normal
+    from turbomesh_b200.clustering import Uniform
+    from turbomesh_b200.discrete import Edge
+
+    e1 = Edge.init(3, Line((0.0, 0.0), (2.0, 0.0)), Uniform())
+    e2 = Edge.init(3, Line((2.0, 0.0), (4.0, 0.0)), Uniform())
+    got = Edge.combine_batch([[(e1, 0, 2), (e2, 0, 2)], [(e1, 1, 2), (e2, 0, 1)], [(e2, 2, 0), (e1, 2, 0)], [(e2, 1, 0), (e1, 2, 1)]])
+    assert np.array_equal(got[0].points, [[0, 0], [1, 0], [2, 0], [3, 0], [4, 0]]) and np.array_equal(got[0].clustering, [0, 0.25, 0.5, 0.75, 1.0])
+    assert np.array_equal(got[1].points, [[1, 0], [2, 0], [3, 0]]) and np.array_equal(got[1].clustering, [0, 0.5, 1.0])
+    assert np.array_equal(got[2].points, [[4, 0], [3, 0], [2, 0], [1, 0], [0, 0]]) and np.array_equal(got[2].clustering, [0, 0.25, 0.5, 0.75, 1.0])
+    assert np.array_equal(got[3].points, [[3, 0], [2, 0], [1, 0]]) and np.array_equal(got[3].clustering, [0, 0.5, 1.0])
+    # the T106 blocking: edges of the committed fixture (Roberts-clustered blade edges, hyperbolic O-grid lines, uniform lines)
+    spec, z, meta = load_fixture("t106_white")
+    b = spec.blocks
+    up_outer, down_outer = b[0].i_max, b[1].i_max            # the O-grid's outer line (projectNormal of the blade edges)
+    in_i_max, out_i_min, in_i_min = b[2].i_max, b[3].i_min, b[2].i_min
+    jobs = [[(up_outer, 30, 0), (down_outer, 0, 10)],                                              # in.j_min    (O4H.zig:168-178)
+            [(in_i_max, 10, 0), (down_outer, 10, 110), (out_i_min, 0, 10)],                        # down.i_min  (:250-258)
+            [(up_outer, 180, 30), (in_i_min, 0, 10)]]                                              # up.i_min    (:297-303)
+    dev = Edge.combine_batch(jobs)
+    for job, d in zip(jobs, dev):
+        h = combine([EdgeView(*v) for v in job])
+        assert np.array_equal(d.points, h.points) and np.array_equal(d.clustering, h.clustering)
+    assert np.array_equal(dev[0].points, b[2].j_min.points) and np.array_equal(dev[1].points, b[4].i_min.points) and np.array_equal(dev[2].points, b[5].i_min.points)
+    assert np.array_equal(dev[1].clustering, b[4].i_min.clustering)
+    with pytest.raises(Exception):   # joints that do not match (discrete.zig:43-56)
+        Edge.combine_batch([[(up_outer, 30, 0), (down_outer, 5, 10)]])
+    blade_up, blade_down = b[0].i_min.points, b[1].i_min.points
+    outs = Edge.project_normal_batch([(blade_up, -0.001), (blade_down, 0.001), (blade_up[:2], 0.25)])
+    for (pts, d), o in zip(((blade_up, -0.001), (blade_down, 0.001), (blade_up[:2], 0.25)), outs):
+        assert np.array_equal(o, project_normal(pts, d))
+    assert np.array_equal(outs[1][1:-1], down_outer.points[1:-1])    # what the fixture's O-grid line was made of (its ends are overwritten, O4H.zig:109-110)

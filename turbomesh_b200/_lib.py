@@ -84,6 +84,18 @@ class TmComponentStats(C.Structure):
                 "restarts": int(self.restarts)}
 
 
+class TmEdgeView(C.Structure):
+    _fields_ = [("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double)), ("n", C.c_uint64), ("start", C.c_uint64), ("end", C.c_uint64)]
+
+
+class TmCombineJob(C.Structure):
+    _fields_ = [("views", C.POINTER(TmEdgeView)), ("n_views", C.c_uint64), ("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double))]
+
+
+class TmProjectJob(C.Structure):
+    _fields_ = [("points", C.POINTER(C.c_double)), ("n", C.c_uint64), ("distance", C.c_double), ("out", C.POINTER(C.c_double))]
+
+
 class TurbomeshGpuError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"turbomesh_gpu error {code}: {message}")
@@ -130,6 +142,8 @@ def load():
     L.tm_mg_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t, dp, C.c_size_t,
                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tm_edges_discretize.argtypes = [C.POINTER(TmEdgeJob), C.c_size_t, C.c_int]
+    L.tm_edges_combine.argtypes = [C.POINTER(TmCombineJob), C.c_size_t, C.c_int]
+    L.tm_edges_project_normal.argtypes = [C.POINTER(TmProjectJob), C.c_size_t, C.c_int]
     L.tm_smooth_stream_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64] + [C.POINTER(C.c_uint64)] * 4
     L.tm_mesh_destroy.argtypes = [vp]
     L.tm_mesh_destroy.restype = None

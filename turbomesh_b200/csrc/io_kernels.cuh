@@ -30,6 +30,68 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(int ni, int nj, const d
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Edge.combine and projectNormal, the two other edge operations of the O4H blocking, batched: one
+// CTA per job.
+//   combine         discrete.zig:38-91 with the views of :94-136: the views' points back to back without the duplicated
+//                   joints; clustering = offset of the view + (c[i] - c[first]) -- for a reversed view the differences
+//                   still run from min(start, end) upwards (reference behaviour, :119-135) -- normalised by the last value
+//   projectNormal   templates/O4H.zig:531-574: x_i + d n, n = (t_y, -t_x) / |t|, t central (one-sided at the two ends)
+// Round-to-nearest intrinsics in the reference's operation order: bit-exact.
+// ---------------------------------------------------------------------------------------------------
+struct CombineView { int64_t src_off; int32_t start, end; };     // src_off: first point of the source edge in the input arrays
+struct CombineJob { int64_t out_off; int32_t view_begin, n_views, n, _pad; };
+__global__ void __launch_bounds__(128) edge_combine_kernel(const CombineJob* __restrict__ jobs, const CombineView* __restrict__ views,
+                                                            const double2* __restrict__ src_pts, const double* __restrict__ src_cl,
+                                                            double2* __restrict__ out_pts, double* __restrict__ out_cl) {
+    const CombineJob job = jobs[blockIdx.x];
+    __shared__ double s_init[16];   // clustering value at the first node of every view
+    __shared__ int s_first[17];     // first output index of every view
+    __shared__ double s_last;
+    if (threadIdx.x == 0) {
+        double value = 0.0;
+        int pos = 0;
+        for (int v = 0; v < job.n_views; ++v) {
+            const CombineView w = views[job.view_begin + v];
+            const int first = min(w.start, w.end), last = max(w.start, w.end);
+            s_init[v] = value;
+            s_first[v] = pos;
+            value = __dadd_rn(value, __dsub_rn(src_cl[w.src_off + last], src_cl[w.src_off + first]));
+            pos += last - first;       // the joint is shared with the next view
+        }
+        s_first[job.n_views] = pos;
+        s_last = value;
+    }
+    __syncthreads();
+    for (int v = 0; v < job.n_views; ++v) {
+        const CombineView w = views[job.view_begin + v];
+        const int first = min(w.start, w.end), len = abs(w.start - w.end) + 1;
+        const int step = w.start > w.end ? -1 : 1;
+        const double c_first = src_cl[w.src_off + first];
+        for (int k = threadIdx.x; k < len; k += blockDim.x) {
+            if (k == len - 1 && v + 1 < job.n_views) continue;  // the joint is written by the NEXT view (discrete.zig:66-70 overwrites it)
+            out_pts[job.out_off + s_first[v] + k] = src_pts[w.src_off + w.start + step * k];
+            const double u = k == 0 ? s_init[v] : __dadd_rn(s_init[v], __dsub_rn(src_cl[w.src_off + first + k], c_first));
+            out_cl[job.out_off + s_first[v] + k] = __ddiv_rn(u, s_last);
+        }
+    }
+}
+
+struct ProjectJob { int64_t off; int32_t n, _pad; double distance; };
+__global__ void __launch_bounds__(128) project_normal_kernel(const ProjectJob* __restrict__ jobs, const double2* __restrict__ in, double2* __restrict__ out) {
+    const ProjectJob job = jobs[blockIdx.x];
+    const double2* e = in + job.off;
+    for (int i = threadIdx.x; i < job.n; i += blockDim.x) {
+        double tx, ty;
+        if (i == 0) { tx = __dsub_rn(e[1].x, e[0].x); ty = __dsub_rn(e[1].y, e[0].y); }
+        else if (i == job.n - 1) { tx = __dsub_rn(e[i].x, e[i - 1].x); ty = __dsub_rn(e[i].y, e[i - 1].y); }
+        else { tx = __dmul_rn(0.5, __dsub_rn(e[i + 1].x, e[i - 1].x)); ty = __dmul_rn(0.5, __dsub_rn(e[i + 1].y, e[i - 1].y)); }
+        const double inv = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty))));
+        const double nx = __dmul_rn(inv, ty), ny = __dmul_rn(inv, -tx);
+        out[job.off + i] = make_double2(__dadd_rn(e[i].x, __dmul_rn(job.distance, nx)), __dadd_rn(e[i].y, __dmul_rn(job.distance, ny)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Edge discretisation, the step right before the path: discrete.Edge.init =
 // clustering.create + Curve.interpolate (src/core/discrete.zig:17-31), batched -- one CTA per edge, one thread per point.
 //   clustering   clustering.zig:9-17 (uniform), :24-42 (Roberts), :56-95 (Vinokur tanh; delta comes from the host)

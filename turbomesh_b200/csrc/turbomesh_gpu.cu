@@ -1741,6 +1741,105 @@ int tm_edges_discretize(const tm_edge_job* jobs, size_t n_jobs, int device) {
     });
 }
 
+int tm_edges_combine(const tm_combine_job* jobs, size_t n_jobs, int device) {
+    return guarded([&] {
+        if (n_jobs && !jobs) TM_THROW(TM_ERR_INVALID_ARGUMENT, "jobs is NULL");
+        if (n_jobs == 0) return;
+        std::vector<CombineJob> dj(n_jobs);
+        std::vector<CombineView> dv;
+        std::vector<double> src_pts, src_cl;
+        std::vector<std::pair<const double*, int64_t>> seen;  // every source edge is uploaded once
+        int64_t total = 0;
+        for (size_t k = 0; k < n_jobs; ++k) {
+            const tm_combine_job& j = jobs[k];
+            if (!j.views || j.n_views < 2 || j.n_views > 16 || !j.points || !j.clustering) TM_THROW(TM_ERR_INVALID_ARGUMENT, "combine %zu: needs 2..16 views and output arrays", k);
+            CombineJob c{};
+            c.out_off = total; c.view_begin = int32_t(dv.size()); c.n_views = int32_t(j.n_views);
+            int64_t n = 0;
+            for (size_t v = 0; v < j.n_views; ++v) {
+                const tm_edge_view& w = j.views[v];
+                if (!w.points || !w.clustering || w.start >= w.n || w.end >= w.n || w.n > 0x7fffffffull) TM_THROW(TM_ERR_INVALID_ARGUMENT, "combine %zu: view %zu out of range", k, v);
+                if (v > 0) {  // discrete.zig:43-56: end point of the previous view == start point of this one within 1e-10
+                    const tm_edge_view& q = j.views[v - 1];
+                    for (int d = 0; d < 2; ++d)
+                        if (!(std::fabs(q.points[2 * q.end + d] - w.points[2 * w.start + d]) <= 1e-10))
+                            TM_THROW(TM_ERR_INVALID_ARGUMENT, "combine %zu: edges %zu and %zu cannot be combined as end points do not match (discrete.zig:43-56)", k, v, v + 1);
+                }
+                int64_t off = -1;
+                for (const auto& pr : seen) if (pr.first == w.points) off = pr.second;
+                if (off < 0) {
+                    off = int64_t(src_cl.size());
+                    src_pts.insert(src_pts.end(), w.points, w.points + 2 * w.n);
+                    src_cl.insert(src_cl.end(), w.clustering, w.clustering + w.n);
+                    seen.push_back({w.points, off});
+                }
+                dv.push_back(CombineView{off, int32_t(w.start), int32_t(w.end)});
+                n += int64_t(w.start > w.end ? w.start - w.end : w.end - w.start) + 1;
+            }
+            c.n = int32_t(n - int64_t(j.n_views - 1));
+            total += c.n;
+            dj[k] = c;
+        }
+        require_device(device);
+        cudaStream_t s = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        try {
+            DevBuf<CombineJob> d_jobs;
+            DevBuf<CombineView> d_views;
+            DevBuf<double> d_src_pts, d_src_cl, d_cl;
+            DevBuf<double2> d_pts;
+            d_jobs.upload(dj, s); d_views.upload(dv, s); d_src_pts.upload(src_pts, s); d_src_cl.upload(src_cl, s);
+            d_pts.alloc(size_t(total)); d_cl.alloc(size_t(total));
+            LAUNCH(edge_combine_kernel, unsigned(n_jobs), 128, s, (const CombineJob*)d_jobs.p, (const CombineView*)d_views.p, (const double2*)d_src_pts.p,
+                   (const double*)d_src_cl.p, d_pts.p, d_cl.p);
+            for (size_t k = 0; k < n_jobs; ++k) {
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].points, d_pts.p + dj[k].out_off, size_t(dj[k].n) * sizeof(double2), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].clustering, d_cl.p + dj[k].out_off, size_t(dj[k].n) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        cudaStreamDestroy(s);
+    });
+}
+
+int tm_edges_project_normal(const tm_project_job* jobs, size_t n_jobs, int device) {
+    return guarded([&] {
+        if (n_jobs && !jobs) TM_THROW(TM_ERR_INVALID_ARGUMENT, "jobs is NULL");
+        if (n_jobs == 0) return;
+        std::vector<ProjectJob> dj(n_jobs);
+        std::vector<double> in;
+        int64_t total = 0;
+        for (size_t k = 0; k < n_jobs; ++k) {
+            const tm_project_job& j = jobs[k];
+            if (!j.points || !j.out || j.n < 2 || j.n > 0x7fffffffull) TM_THROW(TM_ERR_INVALID_ARGUMENT, "projectNormal %zu: needs n >= 2 and input / output arrays", k);
+            dj[k] = ProjectJob{total, int32_t(j.n), 0, j.distance};
+            in.insert(in.end(), j.points, j.points + 2 * j.n);
+            total += int64_t(j.n);
+        }
+        require_device(device);
+        cudaStream_t s = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        try {
+            DevBuf<ProjectJob> d_jobs;
+            DevBuf<double> d_in;
+            DevBuf<double2> d_out;
+            d_jobs.upload(dj, s); d_in.upload(in, s);
+            d_out.alloc(size_t(total));
+            LAUNCH(project_normal_kernel, unsigned(n_jobs), 128, s, (const ProjectJob*)d_jobs.p, (const double2*)d_in.p, d_out.p);
+            for (size_t k = 0; k < n_jobs; ++k)
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].out, d_out.p + dj[k].off, size_t(dj[k].n) * sizeof(double2), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        cudaStreamDestroy(s);
+    });
+}
+
 int tm_mg_plan(const tm_block* blocks, size_t n_blocks, const tm_connection* connections, size_t n_connections, const tm_condition* conditions,
                size_t n_conditions, const double* cell_size, size_t max_levels, uint64_t* n_levels, uint64_t* sizes) {
     return guarded([&] {

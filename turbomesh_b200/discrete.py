@@ -80,6 +80,51 @@ class Edge:
     def copy(self) -> "Edge":
         return Edge(self.points.copy(), self.clustering.copy())
 
+    @staticmethod
+    def combine_batch(jobs, device: int = -1) -> List["Edge"]:
+        """``Edge.combine`` (``discrete.zig:38-91``) for many edges at once on the GPU (``tm_edges_combine``): ``jobs`` = one list
+        of views ``(edge, start, end)`` per combined edge (``EdgeView``, ``discrete.zig:94-136``)."""
+        import ctypes as C
+
+        from . import _lib
+
+        dp = C.POINTER(C.c_double)
+        cj = (_lib.TmCombineJob * max(len(jobs), 1))()
+        keep, out = [], []
+        for k, views in enumerate(jobs):
+            cv = (_lib.TmEdgeView * len(views))()
+            n = 0
+            for v, (edge, start, end) in enumerate(views):
+                cv[v].points, cv[v].clustering = edge.points.ctypes.data_as(dp), edge.clustering.ctypes.data_as(dp)
+                cv[v].n, cv[v].start, cv[v].end = len(edge.clustering), int(start), int(end)
+                n += abs(int(start) - int(end)) + 1
+            n -= len(views) - 1
+            pts, cl = np.empty((n, 2), dtype=np.float64), np.empty(n, dtype=np.float64)
+            cj[k].views, cj[k].n_views, cj[k].points, cj[k].clustering = cv, len(views), pts.ctypes.data_as(dp), cl.ctypes.data_as(dp)
+            keep.append(cv)
+            out.append((pts, cl))
+        _lib.check(_lib.load().tm_edges_combine(cj, len(jobs), device))
+        return [Edge(p, c) for p, c in out]
+
+    @staticmethod
+    def project_normal_batch(jobs, device: int = -1) -> List[np.ndarray]:
+        """``projectNormal`` (``templates/O4H.zig:531-574``) for many edges at once on the GPU: ``jobs`` = [(points (n, 2), distance)]."""
+        import ctypes as C
+
+        from . import _lib
+
+        dp = C.POINTER(C.c_double)
+        cj = (_lib.TmProjectJob * max(len(jobs), 1))()
+        keep, out = [], []
+        for k, (points, distance) in enumerate(jobs):
+            src = np.ascontiguousarray(points, dtype=np.float64)
+            dst = np.empty_like(src)
+            cj[k].points, cj[k].n, cj[k].distance, cj[k].out = src.ctypes.data_as(dp), len(src), float(distance), dst.ctypes.data_as(dp)
+            keep.append(src)
+            out.append(dst)
+        _lib.check(_lib.load().tm_edges_project_normal(cj, len(jobs), device))
+        return out
+
 
 TfiFn = Callable[..., np.ndarray]
 
