@@ -413,9 +413,11 @@ def passages_multigrid_status(dm, my_blocks, torch, dist, world, local, cycles=2
         st = dm.smooth(cycles - 1, mg)
     finally:
         os.environ.pop("TM_MG_AA", None)
-    sums = st["last_sumsq_x"] + st["last_sumsq_y"]
+    finite = bool(np.isfinite(dm.download_block(my_blocks[0])).all())
+    probe = smoothing.CudaSolver(method="relax", sweeps_per_iteration=1, omega=1.0, device=local)
+    resid = dm.smooth(1, probe)["last_max_update"] if finite else None
     return {"seconds": None, "status": "not converged", "cycles_run": cycles, "mesh_change_first_cycle": first, "mesh_change_last_cycle": st["last_max_update"],
-            "finite": bool(sums == sums), "solver_seconds": st["gpu_seconds"],
+            "finite": finite, "jacobi_update_after_the_cycles": resid, "solver_seconds": st["gpu_seconds"],
             "note": "geometric FAS multigrid V(3,3) on the O4H passage topology stalls (mesh change per cycle ~1e-4 after 20 cycles; with the Anderson "
                     "step it can diverge): time-to-converged of config 4 is reported on the tiling form (time_to_converged)"}
 

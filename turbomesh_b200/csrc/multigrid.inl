@@ -172,7 +172,7 @@ void run_fas_multigrid(tm_mesh* m, const tm_smooth_options* o, tm_smooth_stats* 
             MgLevel& C = *r.mg[size_t(l) + 1];
             const double w = double(F.ni) * F.nj / (double(r.mg[0]->ni) * r.mg[0]->nj);
             mg_smooth(m, r, F, &U[size_t(l)], &V[size_t(l)], l, nu, o->omega, false);
-            if (l == 0 && !C.aa_G.empty()) anderson_step_single(m, r, F, C, U[0]);
+            if (l == 0 && m->mg_aa && !C.aa_G.empty()) anderson_step_single(m, r, F, C, U[0]);
             mg_residual(m, r, F, U[size_t(l)], l);
             fine_work += w * double(nu + 1);
             dim3 gc((C.nj + 127) / 128, C.ni);
@@ -582,7 +582,7 @@ void run_fas_multigrid_blocks(tm_mesh* m, const tm_smooth_options* o, tm_smooth_
             RankList& RF = ranks_of(l);
             RankList& RC = ranks_of(l + 1);
             smooth(l, nu);
-            if (l == 0 && !RC.empty() && !RC[0]->aa_G.empty()) anderson_step(m, RF, RC);
+            if (l == 0 && m->mg_aa && !RC.empty() && !RC[0]->aa_G.empty()) anderson_step(m, RF, RC);
             for (auto& rp : RF) launch_rows_mg<MODE_REL, 0>(m, *rp, xcur(*rp), rp->mg_tmp.p, 1.0, l > 0 ? (const double2*)rp->mg_rhs.p : nullptr);
             exchange_on(m, RF, tmp_of);
             fine_work += m->mgb[size_t(l)]->work;

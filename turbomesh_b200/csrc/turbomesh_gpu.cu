@@ -1282,6 +1282,8 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
         validate_options(o);
         CUDA_TRY(cudaSetDevice(m->device));
         cudaStream_t s = m->stream;
+        if (const char* e = std::getenv("TM_MG_AA")) m->mg_aa = std::atoi(e) != 0;   // (may be switched per smoothing run; the buffers exist if it was on at creation)
+        else m->mg_aa = true;
         for (auto& rp : m->ranks)
             for (size_t k = 0; k < rp->have_coords.size(); ++k)
                 if (!rp->have_coords[k]) TM_THROW(TM_ERR_INVALID_ARGUMENT, "block %d has no coordinates yet", int(rp->L.own_blocks[k]));
