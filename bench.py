@@ -416,10 +416,11 @@ def passages_multigrid_status(dm, my_blocks, torch, dist, world, local, cycles=2
     finite = bool(np.isfinite(dm.download_block(my_blocks[0])).all())
     probe = smoothing.CudaSolver(method="relax", sweeps_per_iteration=1, omega=1.0, device=local)
     resid = dm.smooth(1, probe)["last_max_update"] if finite else None
-    return {"seconds": None, "status": "not converged", "cycles_run": cycles, "mesh_change_first_cycle": first, "mesh_change_last_cycle": st["last_max_update"],
+    return {"seconds": None, "status": "not converged (stalls)" if finite else "not converged (diverges)", "cycles_run": cycles, "mesh_change_first_cycle": first, "mesh_change_last_cycle": st["last_max_update"],
             "finite": finite, "jacobi_update_after_the_cycles": resid, "solver_seconds": st["gpu_seconds"],
-            "note": "geometric FAS multigrid V(3,3) on the O4H passage topology stalls (mesh change per cycle ~1e-4 after 20 cycles; with the Anderson "
-                    "step it can diverge): time-to-converged of config 4 is reported on the tiling form (time_to_converged)"}
+            "note": "the geometric FAS multigrid does not converge on the O4H passage topology yet (it stalls at a mesh change of ~1e-4 per cycle on "
+                    "passages of <= 1.5 M nodes and diverges on finer ones, DESIGN.md section 4): the time to a converged mesh of config 4 is reported "
+                    "on the tiling form (time_to_converged)"}
 
 
 def measure_sweeps(args, kind, torch, dist, rank, world, local, barrier, steps, warmup, with_ttc, with_e2e, with_parity):

@@ -47,7 +47,7 @@ def test_batch_of_cuts_matches_per_cut_oracle(gpu_lib, orc, control):
         assert err <= tol, (c, err, tol)
 
 
-def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc):
+def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc, monkeypatch):
     """The reference meshes the cuts one after the other: each has its own ||b||, tolerance max(atol, rtol ||b||)
     (GMRES.zig:305-306 / BiCGStab.zig:291), iteration count and stopping test.  At the reference's default tolerances
     (rtol 1e-6) a batch must therefore behave cut by cut like separate runs -- round 1 tested one norm over the batch."""
@@ -89,8 +89,16 @@ def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc):
             assert rec["tolerance"][xy] == pytest.approx(rec1["tolerance"][xy], rel=1e-12)
             assert rec["norm_b"][xy] == pytest.approx(rec1["norm_b"][xy], rel=1e-12)
         err = max(float(np.abs(got[c * nb + k] - alone[k]).max()) for k in range(nb))
-        assert err <= 20 * max(rec["tolerance"]), (c, err)
+        assert err <= 2e-3 * sc, (c, err)    # two solves that both stop at rtol 1e-6 (the exact Picard step is 7e-4 chord away from either)
     assert st["inner_iterations"] == sum(sum(r["iterations"]) for r in comps)
+    # independence, bit for bit: in the phased form (one launch per phase over all systems, the path batches take) a cut's solve
+    # does not depend on which other cuts share the launches
+    monkeypatch.setenv("TM_KRYLOV", "phased")
+    a, _, ca = run(scales, 2)
+    b, _, cb = run([scales[0], scales[3]], 2)
+    for k in range(nb):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[3 * nb + k], b[nb + k])
+    assert ca[0] == cb[0] and ca[3] == cb[1]
     # ||b|| is the norm of the reference's right-hand side (fixed rows carry their coordinates, ...): oracle's assembled rhs of cut 0
     single, _ = synthetic.batch_of_cuts(base, [scales[0]])
     cpu = synthetic.materialize(single, orc.tfi)
