@@ -815,9 +815,28 @@ def run_e2e_cascade(args, spec, dm, my_blocks, solver, torch, dist, world, nodes
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+    # what the host link allows: the blocks come down AFTER the sweeps (every block is coupled to its neighbours until the last
+    # sweep), so a step cannot be shorter than the sweeps plus the read-back at the link rate measured here with all ranks copying
+    dev = torch.empty(int(d2h), dtype=torch.uint8, device="cuda")
+    pin = torch.empty(int(d2h), dtype=torch.uint8, pin_memory=True)
+    pin.copy_(dev, non_blocking=True); torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter(); pin.copy_(dev, non_blocking=True); torch.cuda.synchronize()
+    link = d2h / (time.perf_counter() - t0) / 1e9
+    lt = torch.tensor([link], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt, op=dist.ReduceOp.MIN)
+    link = float(lt.item())
+    del dev, pin
+    compute_ms = st["gpu_seconds"] * 1e3
+    ceiling_ms = compute_ms + d2h / (link * 1e9) * 1e3
     return {"value": nodes_total * solver.sweeps_per_iteration / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": dt * 1e3, "api": "tm_mesh_tfi_block (host edges) + tm_mesh_begin_smoothing + tm_mesh_smooth + tm_mesh_download_block (pinned host blocks), per rank",
-            "steps": steps, "last_max_update": st["last_max_update"], "note": "bytes per rank"}
+            "steps": steps, "last_max_update": st["last_max_update"], "note": "bytes per rank",
+            "host_link": {"d2h_gbs_per_rank_all_ranks_copying": link, "sweeps_ms": compute_ms, "read_back_ms_at_link_rate": d2h / (link * 1e9) * 1e3,
+                          "step_floor_ms_without_overlap": ceiling_ms, "e2e_ceiling": nodes_total * solver.sweeps_per_iteration / (ceiling_ms * 1e-3),
+                          "note": "serial floor = sweeps + read-back of the smoothed blocks at the measured link rate; only streaming the blocks out "
+                                  "while others are still swept (ghost zones per interface row) could beat it"}}
 
 
 def main():

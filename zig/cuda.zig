@@ -64,6 +64,17 @@ pub extern fn tm_mesh_download_block(mesh: *tm_mesh, block: usize, xy: [*]f64) c
 /// cgns.zig:69-101 / 110-161 on the device: x[j*ni + i], y[j*ni + i] (field 0 = coordinates, 1 = control function P,Q)
 pub extern fn tm_mesh_download_block_soa(mesh: *tm_mesh, block: usize, field: c_int, x: [*]f64, y: [*]f64) callconv(.c) c_int;
 pub extern fn tm_release_cached_memory() callconv(.c) void;
+// independent systems (one per cut of a batch), structured writer, the edge operations of the blocking
+pub const tm_component_stats = extern struct { nodes: u64, iterations: [2]u64, tolerance: [2]f64, norm_b: [2]f64, norm_r: [2]f64, status: [2]i32, operator_applications: u64, restarts: u64 };
+pub extern fn tm_mesh_component_count(mesh: *const tm_mesh) callconv(.c) u64;
+pub extern fn tm_mesh_component_of_block(mesh: *const tm_mesh, block: usize, component: *u64) callconv(.c) c_int;
+pub extern fn tm_mesh_component_stats(mesh: *const tm_mesh, component: usize, out: *tm_component_stats) callconv(.c) c_int;
+pub extern fn tm_mesh_write_plot3d(mesh: *tm_mesh, grid_path: [*:0]const u8, function_path: ?[*:0]const u8) callconv(.c) c_int;
+pub const tm_edge_view = extern struct { points: [*]const f64, clustering: [*]const f64, n: u64, start: u64, end: u64 };
+pub const tm_combine_job = extern struct { views: [*]const tm_edge_view, n_views: u64, points: [*]f64, clustering: [*]f64 };
+pub const tm_project_job = extern struct { points: [*]const f64, n: u64, distance: f64, out: [*]f64 };
+pub extern fn tm_edges_combine(jobs: [*]const tm_combine_job, n_jobs: usize, device: c_int) callconv(.c) c_int;
+pub extern fn tm_edges_project_normal(jobs: [*]const tm_project_job, n_jobs: usize, device: c_int) callconv(.c) c_int;
 /// Host-only: how tm_smooth_mesh would stream a large single block (n_chunks = 0: resident); see the header.
 pub extern fn tm_smooth_stream_plan(ni: u64, nj: u64, sweeps: u64, n_chunks: *u64, window_rows: *u64, window_first: ?[*]u64, owned_first: ?[*]u64) callconv(.c) c_int;
 /// CUDA runtime: page-locks a host range.  tm_smooth_mesh overlaps its host<->device copies with the sweeps only when
