@@ -244,9 +244,14 @@ void phased_plan_build(tm_mesh* m, RankMesh& r) {
 template <int PHASE>
 void phased_launch(tm_mesh* m, RankMesh& r, const KPArgs& a) {
     const PhasedPlan& P = *r.pplan;
-    const unsigned grid = unsigned((P.n_wtiles + KP_WARPS - 1) / KP_WARPS + P.n_chunks);
-    if (r.has_pq) LAUNCH((krylov_phase_kernel<PHASE, true>), grid, KP_THREADS, m->stream, a);
-    else LAUNCH((krylov_phase_kernel<PHASE, false>), grid, KP_THREADS, m->stream, a);
+    const unsigned g_tiles = unsigned((P.n_wtiles + KP_WARPS - 1) / KP_WARPS), g_chunks = unsigned(P.n_chunks);
+    if (r.has_pq) {
+        if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, true, true>), g_tiles, KP_THREADS, m->stream, a);
+        if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, true, false>), g_chunks, KP_THREADS, m->stream, a);
+    } else {
+        if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, false, true>), g_tiles, KP_THREADS, m->stream, a);
+        if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, false, false>), g_chunks, KP_THREADS, m->stream, a);
+    }
     if (PHASE != KP_ADD) LAUNCH((krylov_finalize_kernel<PHASE>), unsigned((P.n_comp + 3) / 4), 128, m->stream, a);
 }
 

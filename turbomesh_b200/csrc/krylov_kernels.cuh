@@ -48,7 +48,7 @@ struct KCtl {    // per component; index 0 = x solve, 1 = y solve
     int32_t applications, cycles;
 };
 struct KGroup { int32_t comp_begin, comp_end, cta_begin, n_ctas; };   // components [comp_begin, comp_end) of group_comps
-struct alignas(128) KBarrier { unsigned int count, gen; unsigned int _pad[30]; };
+struct alignas(128) KBarrier { unsigned int count; unsigned int _pad0[31]; unsigned int gen; unsigned int _pad1[31]; };   // arrivals and the polled generation on separate lines
 
 struct KArgs {
     const WTile* wtiles;
@@ -198,7 +198,7 @@ __device__ __forceinline__ void k_interior_march(const WTile& t, const DevBlock&
     double2 lf = u(b.off + l - 1), rt = u(b.off + l + 1);
     double2 C0 = u(b.off + l), D0 = rt - lf, R0 = (rt - C0) + (lf - C0);
     double2 cC0 = ldg2(cb + l), cD0 = ldg2(cb + l + 1) - ldg2(cb + l - 1);
-#pragma unroll 2
+#pragma unroll 1
     for (int i = t.i0; i < i_end; ++i) {
         const int64_t lp = l + nj;
         const double2 lfp = u(b.off + lp - 1), rtp = u(b.off + lp + 1);

@@ -52,11 +52,13 @@ struct KPArgs {
 
 enum KPhase : int { KP_R0 = 0, KP_A = 1, KP_B = 2, KP_C = 3, KP_ADD = 4 };
 
-template <int PHASE, bool HAS_PQ>
+// TILES = true: the interior warp tiles (grid = ceil(n_wtiles / 4)); false: the boundary chunks (grid = n_chunks).  Two kernels
+// rather than one so that the register count of the tile path (the bandwidth path) is not set by the gather-heavy row path.
+template <int PHASE, bool HAS_PQ, bool TILES>
 __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_tile_ctas = (a.n_wtiles + KP_WARPS - 1) / KP_WARPS;
-    const bool is_tile = (int)blockIdx.x < n_tile_ctas;
+    const int n_tile_ctas = TILES ? 0x7fffffff : 0;
+    const bool is_tile = TILES;
     int comp, slot;
     WTile t{};
     BChunk ch{};
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
                     },
                     [&](const JunctionRow& row) { init(row.self, k_junction<MODE_RESID>(row, xval).res, row.slave_begin, row.slave_end); },
                     [&](const SlidingRow& row) { init(row.self, k_sliding<MODE_RESID>(row, xval).res, row.slave_begin, row.slave_end); });
-            if (a.cycle == 0 && (int)blockIdx.x - n_tile_ctas == a.comps[comp].ch_begin) {  // the component's first chunk also sums the constant part of ||b||^2
+            if (a.cycle == 0 && (int)blockIdx.x == a.comps[comp].ch_begin) {  // the component's first chunk also sums the constant part of ||b||^2
                 const KPComp K = a.comps[comp];
                 for (int q = K.rt_begin + tid; q < K.rt_end; q += KP_THREADS) {
                     const RhsTerm rt = a.rterms[q];
