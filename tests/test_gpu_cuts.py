@@ -90,7 +90,7 @@ def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc, monkeypa
             assert rec["norm_b"][xy] == pytest.approx(rec1["norm_b"][xy], rel=1e-12)
         err = max(float(np.abs(got[c * nb + k] - alone[k]).max()) for k in range(nb))
         assert err <= 2e-3 * sc, (c, err)    # two solves that both stop at rtol 1e-6 (the exact Picard step is 7e-4 chord away from either)
-    assert st["inner_iterations"] == sum(sum(r["iterations"]) for r in comps)
+    assert st["inner_iterations"] >= sum(sum(r["iterations"]) for r in comps) > 0    # the stats sum over both outer iterations, the records hold the last
     # independence, bit for bit: in the phased form (one launch per phase over all systems, the path batches take) a cut's solve
     # does not depend on which other cuts share the launches
     monkeypatch.setenv("TM_KRYLOV", "phased")
