@@ -367,7 +367,9 @@ void mgb_build(tm_mesh* m) {
     cudaStream_t s = m->stream;
     const size_t nb = m->h_blocks.size();
     // the hierarchy is planned on the host (mg_plan.hpp); here its levels get their device meshes and transfer tables
-    std::vector<MgPlanLevel> plan = plan_multigrid(m->h_blocks, m->h_conns, m->h_bcs, block_cell_sizes(m));
+    int max_levels = 20;
+    if (const char* e = std::getenv("TM_MG_MAX_LEVELS")) max_levels = std::max(1, std::atoi(e));   // tuning / diagnostics
+    std::vector<MgPlanLevel> plan = plan_multigrid(m->h_blocks, m->h_conns, m->h_bcs, block_cell_sizes(m), max_levels);
     {
         std::unique_ptr<MgbLevel> L0(new MgbLevel());
         L0->blocks = plan[0].blocks; L0->conns = plan[0].conns; L0->bcs = plan[0].bcs;
