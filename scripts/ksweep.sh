@@ -1,7 +1,7 @@
 export TM_MG_AA=0
-timeout 120 python scripts/mg_passages_diag.py 4 relax 2>&1 | tail -1
-TM_MG_MAX_LEVELS=2 TM_MG_COARSEST_SWEEPS=3000 timeout 120 python scripts/mg_passages_diag.py 4 mg 2>&1 | tail -1
-TM_MG_MAX_LEVELS=2 timeout 120 python scripts/mg_passages_diag.py 4 mg 2>&1 | tail -1
-timeout 120 python scripts/mg_passages_diag.py 4 mg 2>&1 | tail -1
-PICARD=6 timeout 200 python scripts/mg_passages_diag.py 4 mg 2>&1 | tail -2
-PICARD=6 TM_MG_MAX_LEVELS=2 TM_MG_COARSEST_SWEEPS=3000 timeout 200 python scripts/mg_passages_diag.py 4 mg 2>&1 | tail -1
+timeout 100 python scripts/mg_features.py 4 2>&1 | tail -2
+OMEGA=0.6 timeout 100 python scripts/mg_features.py 4 2>&1 | tail -1
+NU=6 timeout 100 python scripts/mg_features.py 4 2>&1 | tail -1
+TM_MG_COARSEST_SWEEPS=3000 timeout 100 python scripts/mg_features.py 4 2>&1 | tail -1
+TM_MG_MAX_LEVELS=5 TM_MG_COARSEST_SWEEPS=3000 timeout 100 python scripts/mg_features.py 4 2>&1 | tail -1
+WHICH=outer timeout 100 python scripts/mg_features.py 4 2>&1 | tail -2
