@@ -326,6 +326,20 @@ typedef struct tm_edge_job {
  * pow / tanh inside the Roberts and hyperbolic clusterings are CUDA's (a few ulp from any host libm). */
 int tm_edges_discretize(const tm_edge_job *jobs, size_t n_jobs, int device);
 
+/* Spline fit, batched on the device (one CTA per spline): spline.FittingSpline.init (src/core/spline.zig:24-110, 141-200) --
+ * chord-length parameters, natural-cubic second derivatives, the arc-length table of n_samples entries (201 in the
+ * reference) and the total length.  The outputs are exactly the slices a tm_spline views; bit-exact with the reference's
+ * operation order.  Coincident consecutive points (CoincidentParameters, spline.zig:176-178): TM_ERR_INVALID_ARGUMENT. */
+typedef struct tm_spline_fit_job {
+    uint64_t n_points;            /* >= 2                                                              */
+    const double *points;         /* interleaved x,y, 2*n_points                                       */
+    uint64_t n_samples;           /* >= 2                                                              */
+    double *params, *second_derivs_x, *second_derivs_y;   /* out: n_points each, host memory           */
+    double *sample_arc;           /* out: n_samples                                                    */
+    double *total_length;         /* out: 1                                                            */
+} tm_spline_fit_job;
+int tm_splines_fit(const tm_spline_fit_job *jobs, size_t n_jobs, int device);
+
 /* The two other edge operations of the automated blocking, batched on the device (one CTA per job, bit-exact with the
  * reference's operation order):
  *   Edge.combine (src/core/discrete.zig:38-91 over the views of :94-136): the views' points back to back without the

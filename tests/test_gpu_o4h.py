@@ -233,3 +233,28 @@ def test_edge_combine_and_project_normal_on_the_device(gpu_lib):
     for (pts, d), o in zip(((blade_up, -0.001), (blade_down, 0.001), (blade_up[:2], 0.25)), outs):
         assert np.array_equal(o, project_normal(pts, d))
     assert np.array_equal(outs[1][1:-1], down_outer.points[1:-1])    # what the fixture's O-grid line was made of (its ends are overwritten, O4H.zig:109-110)
+
+
+def test_spline_fit_on_the_device(gpu_lib):
+    """spline.FittingSpline.init batched on the GPU (tm_splines_fit): chord parameters, second derivatives, the 201-entry
+    arc-length table and the total length, bit-exact against the host restatement of spline.zig:24-200 -- on the T106 blade
+    sides of the committed fixture, the reference's straight-line known answer (spline.zig:235-264) and a two-point spline; the
+    fitted tables then feed the device edge discretisation."""
+    from inputgen.spline import FittingSpline
+    from turbomesh_b200.clustering import Uniform
+    from turbomesh_b200.discrete import Edge, FittedSpline
+
+    spec, z, meta = load_fixture("t106_white")
+    sets = [z["b0_x_i_min"], z["b1_x_i_min"], np.array([(0.0, 0.0), (0.5, 0.5), (1.0, 1.0), (2.0, 2.0), (3.0, 3.0), (4.0, 4.0)]), np.array([(0.0, 0.0), (0.0, 3.0)])]
+    got = FittedSpline.fit_batch(sets)
+    for pts, g in zip(sets, got):
+        h = FittingSpline(pts)
+        assert np.array_equal(g.params, h.params)
+        assert np.array_equal(g.second_derivs[0], h.second_derivs[0]) and np.array_equal(g.second_derivs[1], h.second_derivs[1])
+        assert np.array_equal(g.sample_arc, h.sample_arc) and g.total_length == h.total_length
+    assert abs(got[2].total_length - np.sqrt(2.0) * 4.0) < 1e-9 and abs(got[3].total_length - 3.0) < 1e-9     # spline.zig:235-304
+    e_dev = Edge.init_batch([(221, got[0], Uniform())])[0]
+    e_host = Edge.init(221, FittingSpline(sets[0]), Uniform())
+    assert np.array_equal(e_dev.points, e_host.points)
+    with pytest.raises(Exception):
+        FittedSpline.fit_batch([np.array([(0.0, 0.0), (1.0, 1.0), (1.0, 1.0), (2.0, 0.0)])])     # CoincidentParameters

@@ -84,6 +84,12 @@ class TmComponentStats(C.Structure):
                 "restarts": int(self.restarts)}
 
 
+class TmSplineFitJob(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("points", C.POINTER(C.c_double)), ("n_samples", C.c_uint64), ("params", C.POINTER(C.c_double)),
+                ("second_derivs_x", C.POINTER(C.c_double)), ("second_derivs_y", C.POINTER(C.c_double)), ("sample_arc", C.POINTER(C.c_double)),
+                ("total_length", C.POINTER(C.c_double))]
+
+
 class TmEdgeView(C.Structure):
     _fields_ = [("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double)), ("n", C.c_uint64), ("start", C.c_uint64), ("end", C.c_uint64)]
 
@@ -142,6 +148,7 @@ def load():
     L.tm_mg_plan.argtypes = [C.POINTER(TmBlock), C.c_size_t, C.POINTER(TmConnection), C.c_size_t, C.POINTER(TmCondition), C.c_size_t, dp, C.c_size_t,
                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.tm_edges_discretize.argtypes = [C.POINTER(TmEdgeJob), C.c_size_t, C.c_int]
+    L.tm_splines_fit.argtypes = [C.POINTER(TmSplineFitJob), C.c_size_t, C.c_int]
     L.tm_edges_combine.argtypes = [C.POINTER(TmCombineJob), C.c_size_t, C.c_int]
     L.tm_edges_project_normal.argtypes = [C.POINTER(TmProjectJob), C.c_size_t, C.c_int]
     L.tm_smooth_stream_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64] + [C.POINTER(C.c_uint64)] * 4

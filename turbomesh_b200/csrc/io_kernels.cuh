@@ -120,6 +120,27 @@ __device__ __forceinline__ double edge_clustering(const EdgeJob& e, int i) {
         return __dadd_rn(1.0, __ddiv_rn(tanh(__dmul_rn(__dmul_rn(0.5, e.delta), __dsub_rn(u, 1.0))), tanh(__dmul_rn(0.5, e.delta))));
     return u;
 }
+// FittingSpline.eval (spline.zig:202-222) on the tables of a fitted spline, reference operation order
+__device__ __forceinline__ double2 spline_eval_param(const double* params, const double* points, const double* zx, const double* zy, int m, double param) {
+    const double uu = param < 0.0 ? 0.0 : (param > 1.0 ? 1.0 : param);
+    // idx = number of knots params[1..] below uu (the reference scans linearly), at most m-2
+    int lo = 0, hi = m - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (params[mid + 1] < uu) lo = mid + 1; else hi = mid;
+    }
+    const int idx = lo >= m - 1 ? m - 2 : lo;
+    const double h = __dsub_rn(params[idx + 1], params[idx]);
+    const double a = __ddiv_rn(__dsub_rn(params[idx + 1], uu), h), b = __ddiv_rn(__dsub_rn(uu, params[idx]), h);
+    const double a3 = __dsub_rn(__dmul_rn(__dmul_rn(a, a), a), a), b3 = __dsub_rn(__dmul_rn(__dmul_rn(b, b), b), b);
+    const double hh = __dmul_rn(h, h);
+    auto comp = [&](double y0, double y1, double z0, double z1) {
+        const double lin = __dadd_rn(__dmul_rn(a, y0), __dmul_rn(b, y1));
+        const double cub = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(a3, z0), __dmul_rn(b3, z1)), hh), 6.0);
+        return __dadd_rn(lin, cub);
+    };
+    return make_double2(comp(points[2 * idx], points[2 * idx + 2], zx[idx], zx[idx + 1]), comp(points[2 * idx + 1], points[2 * idx + 3], zy[idx], zy[idx + 1]));
+}
 __device__ __forceinline__ double2 edge_spline_point(const EdgeJob& e, const double* __restrict__ tables, double u) {
     const int m = e.spline_m;
     const double* params = tables + e.spline_off;
@@ -143,24 +164,7 @@ __device__ __forceinline__ double2 edge_spline_point(const EdgeJob& e, const dou
             param = __dadd_rn(p0, __dmul_rn(t, __dsub_rn(p1, p0)));
         }
     }
-    const double uu = param < 0.0 ? 0.0 : (param > 1.0 ? 1.0 : param);
-    // idx = number of knots params[1..] below uu (the reference scans linearly), at most m-2
-    int lo = 0, hi = m - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi) / 2;
-        if (params[mid + 1] < uu) lo = mid + 1; else hi = mid;
-    }
-    const int idx = lo >= m - 1 ? m - 2 : lo;
-    const double h = __dsub_rn(params[idx + 1], params[idx]);
-    const double a = __ddiv_rn(__dsub_rn(params[idx + 1], uu), h), b = __ddiv_rn(__dsub_rn(uu, params[idx]), h);
-    const double a3 = __dsub_rn(__dmul_rn(__dmul_rn(a, a), a), a), b3 = __dsub_rn(__dmul_rn(__dmul_rn(b, b), b), b);
-    const double hh = __dmul_rn(h, h);
-    auto comp = [&](double y0, double y1, double z0, double z1) {
-        const double lin = __dadd_rn(__dmul_rn(a, y0), __dmul_rn(b, y1));
-        const double cub = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(a3, z0), __dmul_rn(b3, z1)), hh), 6.0);
-        return __dadd_rn(lin, cub);
-    };
-    return make_double2(comp(points[2 * idx], points[2 * idx + 2], zx[idx], zx[idx + 1]), comp(points[2 * idx + 1], points[2 * idx + 3], zy[idx], zy[idx + 1]));
+    return spline_eval_param(params, points, zx, zy, m, param);
 }
 __global__ void __launch_bounds__(128) edge_discretize_kernel(const EdgeJob* __restrict__ jobs, const double* __restrict__ tables, double2* __restrict__ points,
                                                               double* __restrict__ clustering) {
@@ -176,6 +180,66 @@ __global__ void __launch_bounds__(128) edge_discretize_kernel(const EdgeJob* __r
         }
         clustering[e.out_off + i] = u;
         points[e.out_off + i] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Spline fit, the first step of the blocking (spline.FittingSpline.init, src/core/spline.zig:24-110,
+// 141-200): chord-length parameters, natural-cubic second derivatives by the tridiagonal recurrence, the 201-entry arc-length
+// table.  One CTA per spline: the recurrences are serial (lanes 0 / 1 take x / y), the table's samples are evaluated by all
+// threads and summed by one in the reference's left-to-right order -- bit-exact.
+// ---------------------------------------------------------------------------------------------------
+struct SplineFitJob { int64_t pt_off, arc_off; int32_t n, n_samples; };
+__global__ void __launch_bounds__(128) spline_fit_kernel(const SplineFitJob* jobs, const double2* pts_all, double* params_all, double* zx_all, double* zy_all,
+                                                          double* tmp_all /* 2 per point */, double* arc_all, double2* sample_all, double* total_length, int* err) {
+    const SplineFitJob job = jobs[blockIdx.x];
+    const double2* pts = pts_all + job.pt_off;
+    double* params = params_all + job.pt_off;
+    double* z[2] = {zx_all + job.pt_off, zy_all + job.pt_off};
+    double* arc = arc_all + job.arc_off;
+    double2* samples = sample_all + job.arc_off;
+    const int n = job.n, m = job.n_samples;
+    auto dist = [](double2 a, double2 b) {
+        const double dx = __dsub_rn(b.x, a.x), dy = __dsub_rn(b.y, a.y);
+        return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+    };
+    if (threadIdx.x == 0) {  // computeChordParams, spline.zig:141-155
+        double total = 0.0;
+        params[0] = 0.0;
+        for (int i = 1; i < n; ++i) { total = __dadd_rn(total, dist(pts[i - 1], pts[i])); params[i] = total; }
+        for (int i = 0; i < n; ++i) params[i] = total == 0.0 ? __ddiv_rn((double)i, (double)(n - 1)) : __ddiv_rn(params[i], total);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {  // computeSecondDerivs, spline.zig:157-200
+        const int c = threadIdx.x;
+        double* zc = z[c];
+        double* tmp = tmp_all + 2 * job.pt_off + (size_t)c * n;
+        auto y = [&](int i) { return c == 0 ? pts[i].x : pts[i].y; };
+        for (int i = 0; i < n; ++i) { zc[i] = 0.0; tmp[i] = 0.0; }
+        if (n > 2) {
+            for (int i = 1; i < n - 1; ++i) {
+                const double h_im1 = __dsub_rn(params[i], params[i - 1]), h_i = __dsub_rn(params[i + 1], params[i]);
+                if (h_im1 == 0.0 || h_i == 0.0) { *err = 1; break; }   // CoincidentParameters
+                const double alpha = __dsub_rn(__ddiv_rn(__dsub_rn(y(i + 1), y(i)), h_i), __ddiv_rn(__dsub_rn(y(i), y(i - 1)), h_im1));
+                const double denom = __dsub_rn(__dmul_rn(2.0, __dsub_rn(params[i + 1], params[i - 1])), __dmul_rn(h_im1, tmp[i - 1]));
+                tmp[i] = __ddiv_rn(h_i, denom);
+                zc[i] = __ddiv_rn(__dsub_rn(__dmul_rn(6.0, alpha), __dmul_rn(h_im1, zc[i - 1])), denom);
+            }
+            zc[n - 1] = 0.0;
+            for (int k = n - 2; k >= 0; --k) zc[k] = __dsub_rn(zc[k], __dmul_rn(tmp[k], zc[k + 1]));
+        }
+    }
+    __syncthreads();
+    const double* flat = reinterpret_cast<const double*>(pts);
+    for (int k = threadIdx.x; k < m; k += blockDim.x)  // the samples of the arc-length table, spline.zig:87-110
+        samples[k] = spline_eval_param(params, flat, z[0], z[1], n, __ddiv_rn((double)k, (double)(m - 1)));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double length = 0.0;
+        arc[0] = 0.0;
+        for (int k = 1; k < m; ++k) { length = __dadd_rn(length, dist(samples[k - 1], samples[k])); arc[k] = length; }
+        total_length[blockIdx.x] = length;
+        for (int k = 0; k < m; ++k) arc[k] = length == 0.0 ? 0.0 : __ddiv_rn(arc[k], length);
     }
 }
 

@@ -1743,6 +1743,57 @@ int tm_edges_discretize(const tm_edge_job* jobs, size_t n_jobs, int device) {
     });
 }
 
+int tm_splines_fit(const tm_spline_fit_job* jobs, size_t n_jobs, int device) {
+    return guarded([&] {
+        if (n_jobs && !jobs) TM_THROW(TM_ERR_INVALID_ARGUMENT, "jobs is NULL");
+        if (n_jobs == 0) return;
+        std::vector<SplineFitJob> dj(n_jobs);
+        std::vector<double> pts;
+        int64_t n_pts = 0, n_arc = 0;
+        for (size_t k = 0; k < n_jobs; ++k) {
+            const tm_spline_fit_job& j = jobs[k];
+            if (j.n_points < 2 || j.n_points > 0x7fffffffull || j.n_samples < 2 || j.n_samples > 0x7fffffffull || !j.points || !j.params || !j.second_derivs_x ||
+                !j.second_derivs_y || !j.sample_arc || !j.total_length)
+                TM_THROW(TM_ERR_INVALID_ARGUMENT, "spline %zu: needs >= 2 points, >= 2 samples and all output arrays (spline.zig:41-45)", k);
+            dj[k] = SplineFitJob{n_pts, n_arc, int32_t(j.n_points), int32_t(j.n_samples)};
+            pts.insert(pts.end(), j.points, j.points + 2 * j.n_points);
+            n_pts += int64_t(j.n_points);
+            n_arc += int64_t(j.n_samples);
+        }
+        require_device(device);
+        cudaStream_t s = nullptr;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        try {
+            DevBuf<SplineFitJob> d_jobs;
+            DevBuf<double> d_pts, d_params, d_zx, d_zy, d_tmp, d_arc, d_len;
+            DevBuf<double2> d_samples;
+            DevBuf<int> d_err;
+            d_jobs.upload(dj, s); d_pts.upload(pts, s);
+            d_params.alloc(size_t(n_pts)); d_zx.alloc(size_t(n_pts)); d_zy.alloc(size_t(n_pts)); d_tmp.alloc(size_t(2 * n_pts));
+            d_arc.alloc(size_t(n_arc)); d_samples.alloc(size_t(n_arc)); d_len.alloc(n_jobs);
+            d_err.alloc(1); d_err.zero(s);
+            LAUNCH(spline_fit_kernel, unsigned(n_jobs), 128, s, (const SplineFitJob*)d_jobs.p, (const double2*)d_pts.p, d_params.p, d_zx.p, d_zy.p, d_tmp.p, d_arc.p,
+                   d_samples.p, d_len.p, d_err.p);
+            int err = 0;
+            CUDA_TRY(cudaMemcpyAsync(&err, d_err.p, sizeof err, cudaMemcpyDeviceToHost, s));
+            for (size_t k = 0; k < n_jobs; ++k) {
+                const size_t n = size_t(dj[k].n);
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].params, d_params.p + dj[k].pt_off, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].second_derivs_x, d_zx.p + dj[k].pt_off, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].second_derivs_y, d_zy.p + dj[k].pt_off, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].sample_arc, d_arc.p + dj[k].arc_off, size_t(dj[k].n_samples) * sizeof(double), cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(jobs[k].total_length, d_len.p + k, sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (err) TM_THROW(TM_ERR_INVALID_ARGUMENT, "spline fit: coincident consecutive points (CoincidentParameters, spline.zig:176-178)");
+        } catch (...) {
+            cudaStreamDestroy(s);
+            throw;
+        }
+        cudaStreamDestroy(s);
+    });
+}
+
 int tm_edges_combine(const tm_combine_job* jobs, size_t n_jobs, int device) {
     return guarded([&] {
         if (n_jobs && !jobs) TM_THROW(TM_ERR_INVALID_ARGUMENT, "jobs is NULL");

@@ -126,6 +126,35 @@ class Edge:
         return out
 
 
+class FittedSpline:
+    """Tables of a fitted ``spline.FittingSpline(2)`` (``spline.zig:24-40``) produced on the GPU by ``tm_splines_fit``; usable as the
+    curve of :meth:`Edge.init_batch`."""
+
+    def __init__(self, points, params, zx, zy, sample_arc, total_length):
+        self.points, self.params, self.second_derivs, self.sample_arc, self.total_length = points, params, [zx, zy], sample_arc, total_length
+
+    @staticmethod
+    def fit_batch(point_sets, n_samples: int = 201, device: int = -1) -> List["FittedSpline"]:
+        import ctypes as C
+
+        from . import _lib
+
+        dp = C.POINTER(C.c_double)
+        jobs = (_lib.TmSplineFitJob * max(len(point_sets), 1))()
+        keep, out = [], []
+        for k, pts in enumerate(point_sets):
+            src = np.ascontiguousarray(pts, dtype=np.float64)
+            n = len(src)
+            arrs = [np.empty(n), np.empty(n), np.empty(n), np.empty(n_samples), np.empty(1)]
+            j = jobs[k]
+            j.n_points, j.points, j.n_samples = n, src.ctypes.data_as(dp), n_samples
+            j.params, j.second_derivs_x, j.second_derivs_y, j.sample_arc, j.total_length = [a.ctypes.data_as(dp) for a in arrs]
+            keep.append(src)
+            out.append((src, arrs))
+        _lib.check(_lib.load().tm_splines_fit(jobs, len(point_sets), device))
+        return [FittedSpline(src, a[0], a[1], a[2], a[3], float(a[4][0])) for src, a in out]
+
+
 TfiFn = Callable[..., np.ndarray]
 
 

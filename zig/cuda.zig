@@ -70,6 +70,8 @@ pub extern fn tm_mesh_component_count(mesh: *const tm_mesh) callconv(.c) u64;
 pub extern fn tm_mesh_component_of_block(mesh: *const tm_mesh, block: usize, component: *u64) callconv(.c) c_int;
 pub extern fn tm_mesh_component_stats(mesh: *const tm_mesh, component: usize, out: *tm_component_stats) callconv(.c) c_int;
 pub extern fn tm_mesh_write_plot3d(mesh: *tm_mesh, grid_path: [*:0]const u8, function_path: ?[*:0]const u8) callconv(.c) c_int;
+pub const tm_spline_fit_job = extern struct { n_points: u64, points: [*]const f64, n_samples: u64, params: [*]f64, second_derivs_x: [*]f64, second_derivs_y: [*]f64, sample_arc: [*]f64, total_length: *f64 };
+pub extern fn tm_splines_fit(jobs: [*]const tm_spline_fit_job, n_jobs: usize, device: c_int) callconv(.c) c_int;
 pub const tm_edge_view = extern struct { points: [*]const f64, clustering: [*]const f64, n: u64, start: u64, end: u64 };
 pub const tm_combine_job = extern struct { views: [*]const tm_edge_view, n_views: u64, points: [*]f64, clustering: [*]f64 };
 pub const tm_project_job = extern struct { points: [*]const f64, n: u64, distance: f64, out: [*]f64 };
