@@ -205,3 +205,28 @@ def test_ls89_x4_white_against_the_extended_precision_truth(gpu_lib):
     print(f"LS89 x4 + White vs truth: GPU {errs[5] / chord:.2e} chord after 5 iterations, {errs[10] / chord:.2e} chord after 10; fp64 direct-LU floor {floor / chord:.2e} chord")
     assert errs[5] <= 1e-9 * chord
     assert errs[10] <= 6.0 * floor
+
+
+def test_two_level_preconditioner_is_a_drop_in(gpu_lib, monkeypatch):
+    """Opt-in coarse space of the persistent Krylov kernel (krylov_coarse.cuh, TM_KRYLOV_COARSE=1): the same exact Picard
+    sequence on T106 + White (8 iterations against the extended-precision truth, the bound of the default path) with
+    markedly fewer Krylov iterations than point-Jacobi."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    spec, z, meta = load_fixture("t106_white")
+    tz = np.load(os.path.join(GOLDEN, "t106_white_truth.npz"))
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    sol = smoothing.CudaSolver.tight()
+    its = {}
+    for coarse in ("0", "1"):
+        monkeypatch.setenv("TM_KRYLOV_COARSE", coarse)
+        mesh = synthetic.materialize(spec, smoothing.tfi_block)
+        with smoothing.DeviceMesh(mesh) as dm:
+            dm.begin_smoothing(sol, cf)
+            st = dm.smooth(8, sol, cf)
+            blocks = [dm.download_block(k) for k in range(len(mesh.blocks))]
+        assert st["converged"] == 1 and st["last_inner_residual"] <= 1e-13
+        err = max(float(np.abs(b - tz[f"truth8_b{k}"]).max()) for k, b in enumerate(blocks))
+        assert err <= 1e-9 * chord_of(mesh), (coarse, err / chord_of(mesh))
+        its[coarse] = st["inner_iterations"]
+    assert its["1"] < 0.7 * its["0"], its

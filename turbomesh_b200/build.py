@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "turbomesh_gpu.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "krylov_kernels.cuh"), os.path.join(HERE, "csrc", "krylov.inl"), os.path.join(HERE, "csrc", "krylov_phased.cuh"), os.path.join(HERE, "csrc", "mg_kernels.cuh"), os.path.join(HERE, "csrc", "io_kernels.cuh"), os.path.join(HERE, "csrc", "topology.hpp"), os.path.join(HERE, "csrc", "partition.hpp"), os.path.join(HERE, "csrc", "mg_plan.hpp"), os.path.join(HERE, "csrc", "multigrid.inl"), os.path.join(HERE, "csrc", "exchange.inl"), os.path.join(HERE, "csrc", "streamed.inl"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "krylov_kernels.cuh"), os.path.join(HERE, "csrc", "krylov.inl"), os.path.join(HERE, "csrc", "krylov_coarse.cuh"), os.path.join(HERE, "csrc", "krylov_phased.cuh"), os.path.join(HERE, "csrc", "mg_kernels.cuh"), os.path.join(HERE, "csrc", "io_kernels.cuh"), os.path.join(HERE, "csrc", "topology.hpp"), os.path.join(HERE, "csrc", "partition.hpp"), os.path.join(HERE, "csrc", "mg_plan.hpp"), os.path.join(HERE, "csrc", "multigrid.inl"), os.path.join(HERE, "csrc", "exchange.inl"), os.path.join(HERE, "csrc", "streamed.inl"),
         os.path.join(HERE, "..", "include", "turbomesh_gpu.h")]
 OUT = os.path.join(HERE, "libturbomesh_gpu.so")
 

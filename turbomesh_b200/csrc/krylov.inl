@@ -11,6 +11,238 @@ bool krylov_persistent_possible(const tm_mesh* m) {
     return true;
 }
 
+// ---- two-level preconditioner (krylov_coarse.cuh): aggregates, contribution lists, needed lists, assembly work items ----
+int coarse_max_aggregates() {
+    int cap = 256;
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE_MAX")) cap = std::max(8, std::min(1024, std::atoi(e)));
+    return cap;
+}
+size_t coarse_smem_bytes(int nc_max, int need_max = 0, int src_max = 0) {
+    return size_t(4) * size_t(nc_max) * sizeof(double2) + size_t(need_max) * size_t(nc_max) * sizeof(double) + (size_t(need_max) + size_t(nc_max) + 1 + size_t(src_max)) * sizeof(int32_t) + size_t(src_max) * sizeof(double2);
+}
+bool coarse_enabled() {
+    // opt-in: halves the iteration count on the reference's meshes but costs more per iteration than it saves at these sizes, and
+    // on meshes with a collapsed cell (LS89 + White after a few outer iterations) its corrections along the nearly singular
+    // direction are invisible to the residual test
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE")) return std::atoi(e) != 0;
+    return false;
+}
+
+void coarse_plan_build(tm_mesh* m, RankMesh& r, KrylovPlan& P, const std::vector<KComp>& comps, const std::vector<WTile>& wtiles) {
+    P.n_items = 0;
+    const Topology& T = m->topo;
+    if (!coarse_enabled() || T.n_nodes >= (int64_t(1) << 30)) return;
+    cudaStream_t s = m->stream;
+    const int n_comp = T.n_comp;
+    const int cap = coarse_max_aggregates();
+    std::vector<std::vector<size_t>> blocks_of((size_t)n_comp);
+    for (size_t b = 0; b < T.blocks.size(); ++b) blocks_of[size_t(T.comp_of_block[b])].push_back(b);
+    // patch sizes: the finest of the list that keeps a component within `cap` aggregates (rows even, columns a multiple of 8:
+    // a warp tile's two rows and each of its 8-lane segments then lie inside one aggregate)
+    static const int cand[][2] = {{8, 8}, {16, 8}, {16, 16}, {32, 16}, {32, 32}, {64, 32}, {64, 64}, {128, 64}, {128, 128}, {256, 128}, {256, 256}};
+    int fixed_ai = 0, fixed_aj = 0;
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE_PATCH")) {
+        if (std::sscanf(e, "%dx%d", &fixed_ai, &fixed_aj) != 2 || fixed_ai < 2 || fixed_ai % 2 || fixed_aj < 8 || fixed_aj % 8) fixed_ai = fixed_aj = 0;
+    }
+    std::vector<int32_t> agg(size_t(T.n_nodes), -1);
+    std::vector<KCoarse> coarse((size_t)n_comp, KCoarse{});
+    std::vector<int32_t> agg_block;                       // per aggregate (mesh-wide numbering)
+    struct Patch { int ai, aj, gi, gj, base; };
+    std::vector<Patch> patch(T.blocks.size(), Patch{0, 0, 0, 0, 0});
+    auto counts = [&](const BlockInfo& B, int ai, int aj, int& gi, int& gj) {
+        gi = int(std::max<int64_t>(1, (B.ni - 2 + ai / 2) / ai));
+        gj = int(std::max<int64_t>(1, (B.nj - 2 + aj / 2) / aj));
+    };
+    int64_t g_size = 0;
+    int nc_max = 0;
+    for (int c = 0; c < n_comp; ++c) {
+        bool ok = true;
+        for (size_t b : blocks_of[size_t(c)]) if (T.blocks[b].ni < 3 || T.blocks[b].nj < 3) ok = false;
+        if (!ok) continue;
+        int ai = 0, aj = 0;
+        for (const auto& cd : cand) {
+            int64_t n = 0;
+            for (size_t b : blocks_of[size_t(c)]) { int gi, gj; counts(T.blocks[b], cd[0], cd[1], gi, gj); n += int64_t(gi) * gj; }
+            if (n <= cap) { ai = cd[0]; aj = cd[1]; break; }
+        }
+        if (fixed_ai) { ai = fixed_ai; aj = fixed_aj; }
+        if (!ai) continue;
+        int nc = 0;
+        for (size_t b : blocks_of[size_t(c)]) {
+            int gi, gj; counts(T.blocks[b], ai, aj, gi, gj);
+            patch[b] = Patch{ai, aj, gi, gj, nc};
+            nc += gi * gj;
+        }
+        if (nc > 1024 || nc < 2) { for (size_t b : blocks_of[size_t(c)]) patch[b] = Patch{0, 0, 0, 0, 0}; continue; }
+        KCoarse& C = coarse[size_t(c)];
+        C.nc = nc;
+        C.agg_base = int32_t(agg_block.size());
+        C.g_off = g_size;
+        g_size += int64_t(nc) * nc;
+        nc_max = std::max(nc_max, nc);
+        for (size_t b : blocks_of[size_t(c)]) for (int k = 0; k < patch[b].gi * patch[b].gj; ++k) agg_block.push_back(int32_t(b));
+    }
+    if (nc_max == 0) return;
+    // aggregate of the interior node nearest to (i, j) of block b
+    auto patch_of = [&](size_t b, int64_t i, int64_t j) -> int32_t {
+        const Patch& p = patch[b];
+        if (!p.ai) return -1;
+        const auto& B = T.blocks[b];
+        const int64_t ic = std::min(std::max<int64_t>(i, 1), B.ni - 2) - 1, jc = std::min(std::max<int64_t>(j, 1), B.nj - 2) - 1;
+        return int32_t(p.base + std::min<int64_t>(ic / p.ai, p.gi - 1) * p.gj + std::min<int64_t>(jc / p.aj, p.gj - 1));
+    };
+    auto patch_of_node = [&](int64_t g) -> int32_t {
+        const size_t b = T.block_of(g);
+        const int64_t l = g - T.blocks[b].off;
+        return patch_of(b, l / T.blocks[b].nj, l % T.blocks[b].nj);
+    };
+    for (size_t b = 0; b < T.blocks.size(); ++b) {
+        if (!patch[b].ai) continue;
+        const auto& B = T.blocks[b];
+        for (int64_t i = 1; i <= B.ni - 2; ++i)
+            for (int64_t j = 1; j <= B.nj - 2; ++j) agg[size_t(B.off + i * B.nj + j)] = patch_of(b, i, j);
+    }
+    for (const SmoothedRow& row : r.L.smoothed) agg[size_t(row.g0)] = patch_of_node(row.g0);
+    for (const JunctionRow& row : r.L.junction_rows) agg[size_t(row.self)] = patch_of_node(row.self);
+    for (const SlaveRow& sl : r.L.slaves) agg[size_t(sl.self)] = agg[size_t(sl.root)];
+    // members (the rows of an aggregate), contribution slots, neighbour aggregates
+    const int32_t n_agg = int32_t(agg_block.size());
+    std::vector<std::vector<int32_t>> members((size_t)n_agg), slots((size_t)n_agg), nbrs((size_t)n_agg);
+    auto add_unique = [](std::vector<int32_t>& v, int32_t x) { if (x >= 0 && std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    auto srow_nodes = [](const SmoothedRow& row, int64_t (&out)[9]) {
+        out[0] = row.g0; out[1] = row.g0 - row.d0; out[2] = row.g0 + row.d0; out[3] = row.g0 + row.n0; out[4] = row.g0 - row.d0 + row.n0;
+        out[5] = row.g0 + row.d0 + row.n0; out[6] = row.iN; out[7] = row.iNW; out[8] = row.iNE;
+    };
+    int64_t n_slots = 0;
+    std::vector<int32_t> need_ptr(1, 0), need;
+    const int gwarps = P.group_ctas * K_WARPS;
+    for (int c = 0; c < n_comp; ++c) {
+        KCoarse& C = coarse[size_t(c)];
+        const KComp& K = comps[size_t(c)];
+        C.slot_base = int32_t(n_slots);
+        C.need_base = int32_t(need_ptr.size() - 1);
+        const int n_tiles = K.wt_end - K.wt_begin;
+        const int n_s = K.s_end - K.s_begin, n_j = K.j_end - K.j_begin, n_l = K.l_end - K.l_begin;
+        n_slots += int64_t(4) * n_tiles + n_s + n_j + n_l;
+        if (n_slots >= 0x7fffffff) TM_THROW(TM_ERR_UNSUPPORTED, "internal: too many contribution slots");
+        if (C.nc == 0) { for (int k = 0; k < P.group_ctas; ++k) need_ptr.push_back(int32_t(need.size())); continue; }
+        std::vector<std::vector<int32_t>> need_of((size_t)P.group_ctas);
+        const int32_t ab = C.agg_base;
+        for (int w = K.wt_begin; w < K.wt_end; ++w) {
+            const WTile& t = wtiles[size_t(w)];
+            const auto& B = T.blocks[size_t(t.block)];
+            const int crank = ((w - K.wt_begin) % gwarps) / K_WARPS;
+            for (int seg = 0; seg < 4; ++seg) {
+                const int64_t j = t.j0 + 8 * seg;
+                if (j > B.nj - 2) break;
+                slots[size_t(ab + patch_of(size_t(t.block), t.i0, j))].push_back(int32_t(C.slot_base + 4 * (w - K.wt_begin) + seg));
+            }
+            for (int64_t i = t.i0 - 1; i <= std::min<int64_t>(t.i0 + t.rows, B.ni - 1); ++i)
+                for (int64_t j = t.j0 - 1; j <= std::min<int64_t>(t.j0 + 32, B.nj - 1); ++j) {
+                    const int32_t a0 = agg[size_t(B.off + i * B.nj + j)];
+                    add_unique(need_of[size_t(crank)], a0);
+                    if (i >= t.i0 && i < t.i0 + t.rows && j >= t.j0 && j < t.j0 + 32 && j <= B.nj - 2) {   // a row of the tile: its 3 x 3 neighbourhood
+                        const int32_t I = agg[size_t(B.off + i * B.nj + j)];
+                        members[size_t(ab + I)].push_back(int32_t(B.off + i * B.nj + j));
+                        for (int di = -1; di <= 1; ++di)
+                            for (int dj = -1; dj <= 1; ++dj) add_unique(nbrs[size_t(ab + I)], agg[size_t(B.off + (i + di) * B.nj + j + dj)]);
+                    }
+                }
+        }
+        const int w_idle = k_bnd_warps(gwarps, n_tiles);
+        auto bnd_crank = [&](int q) { return (gwarps - 1 - (q % w_idle)) / K_WARPS; };   // the kernel's for_bnd
+        for (int q = 0; q < n_s; ++q) {
+            const SmoothedRow& row = r.L.smoothed[size_t(K.s_begin + q)];
+            const int32_t I = agg[size_t(row.g0)];
+            slots[size_t(ab + I)].push_back(int32_t(C.slot_base + 4 * n_tiles + q));
+            members[size_t(ab + I)].push_back(int32_t((1u << 30) | uint32_t(K.s_begin + q)));
+            int64_t nodes[9];
+            srow_nodes(row, nodes);
+            for (int64_t g : nodes) { add_unique(need_of[size_t(bnd_crank(q))], agg[size_t(g)]); add_unique(nbrs[size_t(ab + I)], agg[size_t(g)]); }
+        }
+        for (int q = 0; q < n_j; ++q) {
+            const JunctionRow& row = r.L.junction_rows[size_t(K.j_begin + q)];
+            const int32_t I = agg[size_t(row.self)];
+            slots[size_t(ab + I)].push_back(int32_t(C.slot_base + 4 * n_tiles + n_s + q));
+            members[size_t(ab + I)].push_back(int32_t((2u << 30) | uint32_t(K.j_begin + q)));
+            const int cr = bnd_crank(n_s + q);
+            add_unique(need_of[size_t(cr)], I); add_unique(nbrs[size_t(ab + I)], I);
+            for (int k = 0; k < row.n; ++k) { add_unique(need_of[size_t(cr)], agg[size_t(row.nbr[k])]); add_unique(nbrs[size_t(ab + I)], agg[size_t(row.nbr[k])]); }
+        }
+        for (int q = 0; q < n_l; ++q) {
+            const SlidingRow& row = r.L.sliding[size_t(K.l_begin + q)];
+            add_unique(need_of[size_t(bnd_crank(n_s + n_j + q))], agg[size_t(row.inner)]);
+        }
+        for (int k = 0; k < P.group_ctas; ++k) {
+            std::sort(need_of[size_t(k)].begin(), need_of[size_t(k)].end());
+            need.insert(need.end(), need_of[size_t(k)].begin(), need_of[size_t(k)].end());
+            need_ptr.push_back(int32_t(need.size()));
+        }
+    }
+    std::vector<int32_t> contrib_ptr(1, 0), contrib_src, mem_ptr(1, 0), mem_code;
+    std::vector<CoarseItem> items;
+    for (int c = 0; c < n_comp; ++c) {
+        const KCoarse& C = coarse[size_t(c)];
+        for (int I = 0; I < C.nc; ++I) {
+            const size_t g = size_t(C.agg_base + I);
+            contrib_src.insert(contrib_src.end(), slots[g].begin(), slots[g].end());
+            contrib_ptr.push_back(int32_t(contrib_src.size()));
+            mem_code.insert(mem_code.end(), members[g].begin(), members[g].end());
+            mem_ptr.push_back(int32_t(mem_code.size()));
+            std::sort(nbrs[g].begin(), nbrs[g].end());
+            for (int32_t J : nbrs[g]) items.push_back(CoarseItem{c, I, J});
+        }
+    }
+    P.n_items = int(items.size());
+    P.nc_max = nc_max;
+    P.n_slots = n_slots;
+    P.g_size = g_size;
+    // shared-memory caches of the static tables, as far as they fit (the rows of G first)
+    int need_max = 0, src_max = 0;
+    for (size_t k = 0; k + 1 < need_ptr.size(); ++k) need_max = std::max(need_max, need_ptr[k + 1] - need_ptr[k]);
+    for (int c = 0; c < n_comp; ++c)
+        if (coarse[size_t(c)].nc) src_max = std::max(src_max, contrib_ptr[size_t(coarse[size_t(c)].agg_base + coarse[size_t(c)].nc)] - contrib_ptr[size_t(coarse[size_t(c)].agg_base)]);
+    const size_t smem_cap = 190 * 1024;
+    if (std::getenv("TM_KRYLOV_COARSE_NOCACHE")) need_max = src_max = 0;
+    if (coarse_smem_bytes(nc_max, need_max, 0) > smem_cap) need_max = 0;
+    if (coarse_smem_bytes(nc_max, need_max, src_max) > smem_cap) src_max = 0;
+    P.need_max = need_max; P.src_max = src_max;
+    P.smem = coarse_smem_bytes(nc_max, need_max, src_max);
+    P.coarse_every = 1;
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE_EVERY")) P.coarse_every = std::max(1, std::atoi(e));
+    P.coarse.upload(coarse, s);
+    P.agg.upload(agg, s);
+    P.agg_block.upload(agg_block, s);
+    P.contrib_ptr.upload(contrib_ptr, s); P.contrib_src.upload(contrib_src, s);
+    P.need_ptr.upload(need_ptr, s); P.need.upload(need, s);
+    P.mem_ptr.upload(mem_ptr, s); P.mem_code.upload(mem_code, s);
+    P.items.upload(items, s);
+    P.G.alloc(size_t(g_size)); P.G.zero(s);
+    P.contrib.alloc(size_t(2) * size_t(n_slots)); P.contrib.zero(s);
+    P.coarse_ok.alloc(size_t(n_comp)); P.coarse_ok.zero(s);
+    P.h_coarse_ok.assign(size_t(n_comp), 0);
+    P.coarse_age = -1;
+    CUDA_TRY(cudaFuncSetAttribute(coarse_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * 1024 * sizeof(double))));
+}
+
+// G = (P^T A P)^-1 with the lagged coefficients of this outer iteration (X[cur], pq)
+void coarse_refresh(tm_mesh* m, RankMesh& r, KrylovPlan& P) {
+    cudaStream_t s = m->stream;
+    CUDA_TRY(cudaMemsetAsync(P.G.p, 0, size_t(P.g_size) * sizeof(double), s));
+    const unsigned grid = unsigned((int64_t(P.n_items) * 32 + 255) / 256);
+    if (r.has_pq)
+        LAUNCH(coarse_assemble_kernel<true>, grid, 256, s, (const CoarseItem*)P.items.p, P.n_items, (const KCoarse*)P.coarse.p, (const int32_t*)P.mem_ptr.p, (const int32_t*)P.mem_code.p,
+               (const int32_t*)P.agg_block.p, (const int32_t*)P.agg.p, (const DevBlock*)r.d_blocks.p, (const SmoothedRow*)r.d_srows.p, (const JunctionRow*)r.d_jrows.p,
+               (const double2*)r.X[r.cur].p, (const double2*)r.pq.p, P.G.p);
+    else
+        LAUNCH(coarse_assemble_kernel<false>, grid, 256, s, (const CoarseItem*)P.items.p, P.n_items, (const KCoarse*)P.coarse.p, (const int32_t*)P.mem_ptr.p, (const int32_t*)P.mem_code.p,
+               (const int32_t*)P.agg_block.p, (const int32_t*)P.agg.p, (const DevBlock*)r.d_blocks.p, (const SmoothedRow*)r.d_srows.p, (const JunctionRow*)r.d_jrows.p,
+               (const double2*)r.X[r.cur].p, (const double2*)r.pq.p, P.G.p);
+    coarse_invert_kernel<<<unsigned(m->topo.n_comp), COARSE_INV_THREADS, 2 * size_t(P.nc_max) * sizeof(double), s>>>((const KCoarse*)P.coarse.p, P.G.p, P.coarse_ok.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
 void krylov_plan_build(tm_mesh* m, RankMesh& r) {
     if (r.kplan && r.kplan->built_pq == r.has_pq) return;
     r.kplan.reset(new KrylovPlan());
@@ -21,8 +253,12 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
     const int n_comp = T.n_comp;
     // how many CTAs can be co-resident (cooperative launch)
     int per_sm = 0;
-    if (r.has_pq) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bicgstab_persistent_kernel<true>, K_THREADS, 0));
-    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bicgstab_persistent_kernel<false>, K_THREADS, 0));
+    if (coarse_enabled()) {
+        if (r.has_pq) { CUDA_TRY(cudaFuncSetAttribute(bicgstab_persistent_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(200 * 1024))); }
+        else { CUDA_TRY(cudaFuncSetAttribute(bicgstab_persistent_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(200 * 1024))); }
+    }
+    if (r.has_pq) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bicgstab_persistent_kernel<true, true>, K_THREADS, coarse_enabled() ? size_t(190 * 1024) : size_t(0)));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bicgstab_persistent_kernel<false, true>, K_THREADS, coarse_enabled() ? size_t(190 * 1024) : size_t(0)));
     if (per_sm < 1) TM_THROW(TM_ERR_CUDA, "the persistent Krylov kernel does not fit on an SM");
     if (const char* e = std::getenv("TM_KRYLOV_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));
     const int max_ctas = per_sm * m->sm_count;
@@ -45,8 +281,8 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
         const int rounds = (n_comp + n_groups - 1) / n_groups;
         n_groups = (n_comp + rounds - 1) / rounds;
     }
-    int group_ctas = std::max(1, std::min(want_ctas, max_ctas / n_groups));
-    if (const char* e = std::getenv("TM_KRYLOV_GROUP_CTAS")) group_ctas = std::max(1, std::min(max_ctas / n_groups, std::atoi(e)));
+    int group_ctas = std::max(1, std::min(std::min(want_ctas, K_MAX_GROUP), max_ctas / n_groups));
+    if (const char* e = std::getenv("TM_KRYLOV_GROUP_CTAS")) group_ctas = std::max(1, std::min(std::min(max_ctas / n_groups, K_MAX_GROUP), std::atoi(e)));
     P.n_groups = n_groups; P.group_ctas = group_ctas; P.n_ctas = n_groups * group_ctas;
     // components to groups: largest first onto the least loaded group
     std::vector<int32_t> order((size_t)n_comp), group_of((size_t)n_comp, 0);
@@ -114,6 +350,7 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
     P.ctl.alloc(size_t(n_comp)); P.ctl.zero(s);
     P.bars.alloc(size_t(n_groups)); P.bars.zero(s);
     P.partials.alloc(size_t(2) * size_t(P.n_ctas) * K_NACC); P.partials.zero(s);
+    coarse_plan_build(m, r, P, comps, wtiles);
     CUDA_TRY(cudaStreamSynchronize(s));
 }
 
@@ -127,7 +364,7 @@ void krylov_solve_persistent(tm_mesh* m, RankMesh& r, const tm_smooth_options* o
     a.wtiles = P.wtiles.p; a.blocks = r.d_blocks.p;
     a.srows = r.d_srows.p; a.jrows = r.d_jrows.p; a.lrows = r.d_lrows.p; a.slaves = r.d_slaves.p; a.rterms = r.d_rhs_terms.p;
     a.comps = P.comps.p; a.group_comps = P.group_comps.p; a.groups = P.groups.p; a.cta_group = P.cta_group.p;
-    a.ctl = P.ctl.p; a.bars = P.bars.p; a.partials = P.partials.p;
+    a.ctl = P.ctl.p; a.bars = P.bars.p; a.partials = P.partials.p; a.epoch = ++P.epoch;
     a.xc = r.X[r.cur].p; a.pq = r.pq.p; a.xnew = r.X[1 - r.cur].p;
     a.r = r.kr.p; a.rhat = r.krhat.p; a.p[0] = r.kp.p; a.p[1] = r.kp2.p; a.v[0] = r.kv.p; a.v[1] = r.kv2.p; a.s = r.ks.p; a.t = r.kt.p; a.d = r.kd.p;
     a.rtol = o->rtol; a.atol = o->atol;
@@ -135,12 +372,41 @@ void krylov_solve_persistent(tm_mesh* m, RankMesh& r, const tm_smooth_options* o
     a.max_restarts = 60;
     a.n_ctas_total = P.n_ctas;
     a.polish = std::max(0, int(o->inner_refinement_cycles));
+    const bool coarse = P.n_items > 0;
+    if (coarse) {
+        if (P.coarse_age < 0 || P.coarse_age >= P.coarse_every) { coarse_refresh(m, r, P); P.coarse_age = 0; }
+        P.coarse_age += 1;
+        a.coarse = P.coarse.p; a.coarse_ok = P.coarse_ok.p; a.agg = P.agg.p; a.contrib_ptr = P.contrib_ptr.p; a.contrib_src = P.contrib_src.p;
+        a.need_ptr = P.need_ptr.p; a.need = P.need.p; a.G = P.G.p; a.contrib = P.contrib.p; a.n_slots = P.n_slots; a.nc_max = P.nc_max; a.need_max = P.need_max; a.src_max = P.src_max;
+    }
+    const bool timing = std::getenv("TM_KRYLOV_TIMING") != nullptr;
+    if (timing) {
+        if (!P.timing.p) P.timing.alloc(size_t(P.n_ctas) * 8);
+        P.timing.zero(s);
+        a.timing = P.timing.p;
+    }
     void* params[] = {&a};
-    const void* fn = r.has_pq ? (const void*)bicgstab_persistent_kernel<true> : (const void*)bicgstab_persistent_kernel<false>;
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(unsigned(P.n_ctas)), dim3(K_THREADS), params, 0, s));
+    const void* fn = coarse ? (r.has_pq ? (const void*)bicgstab_persistent_kernel<true, true> : (const void*)bicgstab_persistent_kernel<false, true>)
+                            : (r.has_pq ? (const void*)bicgstab_persistent_kernel<true, false> : (const void*)bicgstab_persistent_kernel<false, false>);
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(unsigned(P.n_ctas)), dim3(K_THREADS), params, coarse ? P.smem : 0, s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CUDA_TRY(cudaMemcpyAsync(P.h_ctl.data(), P.ctl.p, P.h_ctl.size() * sizeof(KCtl), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    if (timing) {
+        std::vector<long long> t(size_t(P.n_ctas) * 8);
+        CUDA_TRY(cudaMemcpy(t.data(), P.timing.p, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < P.n_ctas; ++c) for (int k = 0; k < 8; ++k) sum[k] += double(t[size_t(c) * 8 + size_t(k)]) / P.n_ctas;
+        for (int k : {1, 4}) {
+            long long mn = t[size_t(k)], mx = mn; int imx = 0, imn = 0;
+            for (int c = 0; c < P.n_ctas; ++c) { const long long v = t[size_t(c) * 8 + size_t(k)]; if (v > mx) { mx = v; imx = c; } if (v < mn) { mn = v; imn = c; } }
+            std::fprintf(stderr, "  slot %d: min %lld (CTA %d) max %lld (CTA %d);", k, mn, imn, mx, imx);
+            for (int c = 0; c < P.n_ctas; c += std::max(1, P.n_ctas / 12)) std::fprintf(stderr, " %lld", t[size_t(c) * 8 + size_t(k)]);
+            std::fprintf(stderr, "\n");
+        }
+        std::fprintf(stderr, "krylov timing (mean cycles per CTA): R0 %.0f  A %.0f  B %.0f  C %.0f  barrier+sums %.0f  coarse %.0f  rest %.0f  (%d CTAs; coarse: %d aggregates, needed lists <= %d, slot lists <= %d, %zu B shared)\n", sum[0], sum[1], sum[2], sum[3], sum[4],
+                     sum[5], sum[6], P.n_ctas, P.nc_max, P.need_max, P.src_max, P.smem);
+    }
     double weighted_apps = 0.0, worst = 0.0;
     for (size_t c = 0; c < P.h_ctl.size(); ++c) {
         const KCtl& k = P.h_ctl[c];

@@ -23,7 +23,7 @@
 
 #include "../../include/turbomesh_gpu.h"
 #include "kernels.cuh"
-#include "krylov_kernels.cuh"
+#include "krylov_coarse.cuh"
 #include "krylov_phased.cuh"
 #include "io_kernels.cuh"
 #include "mg_kernels.cuh"
@@ -241,11 +241,23 @@ struct KrylovPlan {
     DevBuf<KGroup> groups;
     DevBuf<KCtl> ctl;
     DevBuf<KBarrier> bars;
-    DevBuf<double> partials;
+    DevBuf<double2> partials;
+    unsigned long long epoch = 0;
     std::vector<KComp> h_comps;
     std::vector<KCtl> h_ctl;
     int n_groups = 0, n_ctas = 0, group_ctas = 0;
     bool built_pq = false;
+    // two-level preconditioner (krylov_coarse.cuh); n_items == 0: not in use
+    DevBuf<KCoarse> coarse;
+    DevBuf<int32_t> coarse_ok, agg, contrib_ptr, contrib_src, need_ptr, need, mem_ptr, mem_code, agg_block;
+    DevBuf<CoarseItem> items;
+    DevBuf<double> G;
+    DevBuf<double2> contrib;
+    int64_t n_slots = 0, g_size = 0;
+    int n_items = 0, nc_max = 0, need_max = 0, src_max = 0, coarse_age = -1, coarse_every = 1;
+    size_t smem = 0;
+    std::vector<int32_t> h_coarse_ok;
+    DevBuf<long long> timing;   // TM_KRYLOV_TIMING
 };
 
 
@@ -1384,6 +1396,7 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
                 rp->mg_E.zero(s);
                 rp->aa_head = -1; rp->aa_count = 0; rp->aa_have_x = false;
             }
+        for (auto& rp : m->ranks) if (rp->kplan) rp->kplan->coarse_age = -1;   // the coarse operator is rebuilt from the new mesh
         m->outer_done = 0;
         m->begun = true;
         CUDA_TRY(cudaStreamSynchronize(s));
