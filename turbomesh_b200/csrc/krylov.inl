@@ -150,7 +150,8 @@ void coarse_plan_build(tm_mesh* m, RankMesh& r, KrylovPlan& P, const std::vector
                 }
         }
         const int w_idle = k_bnd_warps(gwarps, n_tiles);
-        auto bnd_crank = [&](int q) { return (gwarps - 1 - (q % w_idle)) / K_WARPS; };   // the kernel's for_bnd
+        const int gthreads = gwarps * 32;
+        auto bnd_crank = [&](int q) { return w_idle > 0 ? (gwarps - 1 - (q % w_idle)) / K_WARPS : (gthreads - 1 - (q % gthreads)) / K_THREADS; };   // the kernel's for_bnd
         for (int q = 0; q < n_s; ++q) {
             const SmoothedRow& row = r.L.smoothed[size_t(K.s_begin + q)];
             const int32_t I = agg[size_t(row.g0)];

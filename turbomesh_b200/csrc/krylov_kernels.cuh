@@ -38,6 +38,7 @@
 //
 // The arithmetic of a row is the one of kernels.cuh (difference form, row-scaled system D^-1 A x = D^-1 b).
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace tmesh {
@@ -292,8 +293,8 @@ __device__ __forceinline__ void k_interior_nodes(const WTile& t, const DevBlock&
         if (q < t.rows) store(b.off + (int64_t)(t.i0 + q) * b.nj + j, tmp[q]);
 }
 
-// warps that take boundary rows: those without a tile in the first round (at least one CTA's worth), else all
-__host__ __device__ inline int k_bnd_warps(int gwarps, int n_tiles) { return gwarps - n_tiles >= K_WARPS ? gwarps - n_tiles : gwarps; }
+// warps without a tile in the first round that share the boundary rows (0: fewer than a CTA's worth -- thread-linear assignment)
+__host__ __device__ inline int k_bnd_warps(int gwarps, int n_tiles) { return gwarps - n_tiles >= K_WARPS ? gwarps - n_tiles : 0; }
 
 struct KScal {   // solver scalars of one component, identical in every thread of the group
     double rho_old[2], rho_new[2], alpha[2], omega[2], beta[2], tol[2], tol_eff[2], norm_b[2], norm_r[2];
@@ -334,17 +335,18 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
     // every CTA has arrived AND the sums are here -- no arrival counter, no second round trip for the data.  Two buffers: a
     // CTA can be at most one reduction ahead of the slowest.
     unsigned long long stamp = a.epoch << 32;
-    auto reduce = [&](double (&acc)[K_NACC]) {
+    auto reduce = [&](double (&acc)[K_NACC], auto n_tag) {
+        constexpr int N = decltype(n_tag)::value;                    // sums in use: acc[0 .. N)
 #pragma unroll
-        for (int k = 0; k < K_NACC; ++k) acc[k] = warp_sum(acc[k]);
+        for (int k = 0; k < N; ++k) acc[k] = warp_sum(acc[k]);
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < K_NACC; ++k) sh_part[warp][k] = acc[k];
+            for (int k = 0; k < N; ++k) sh_part[warp][k] = acc[k];
         }
         __syncthreads();
         stamp += 1;
         double2* const mine = a.partials + ((size_t)parity * a.n_ctas_total + blockIdx.x) * K_NACC;
-        if (tid < K_NACC) {
+        if (tid < N) {
             double s = 0.0;
             for (int w = 0; w < K_WARPS; ++w) s += sh_part[w][tid];
             st_release_stamped(mine + tid, s, stamp);
@@ -352,39 +354,42 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
         {
             const double2* base = a.partials + ((size_t)parity * a.n_ctas_total + G.cta_begin) * K_NACC;
             for (int c = tid; c < G.n_ctas; c += K_THREADS) {
-                double v[K_NACC];
+                double v[N];
                 bool ok;
                 do {
                     ok = true;
 #pragma unroll
-                    for (int k = 0; k < K_NACC; ++k) ok &= ld_relaxed_stamped(base + (size_t)c * K_NACC + k, stamp, v[k]);
+                    for (int k = 0; k < N; ++k) ok &= ld_relaxed_stamped(base + (size_t)c * K_NACC + k, stamp, v[k]);
                 } while (!ok);
 #pragma unroll
-                for (int k = 0; k < K_NACC; ++k) sh_all[c][k] = v[k];
+                for (int k = 0; k < N; ++k) sh_all[c][k] = v[k];
             }
             __threadfence();   // acquire side of the release stores
         }
         __syncthreads();
         if (warp == 0) {
-            double s[K_NACC];
+            double s[N];
 #pragma unroll
-            for (int k = 0; k < K_NACC; ++k) s[k] = 0.0;
+            for (int k = 0; k < N; ++k) s[k] = 0.0;
             for (int c = lane; c < G.n_ctas; c += 32) {
 #pragma unroll
-                for (int k = 0; k < K_NACC; ++k) s[k] += sh_all[c][k];
+                for (int k = 0; k < N; ++k) s[k] += sh_all[c][k];
             }
 #pragma unroll
-            for (int k = 0; k < K_NACC; ++k) s[k] = warp_sum(s[k]);
+            for (int k = 0; k < N; ++k) s[k] = warp_sum(s[k]);
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < K_NACC; ++k) sh_red[k] = s[k];
+                for (int k = 0; k < N; ++k) sh_red[k] = s[k];
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < K_NACC; ++k) acc[k] = sh_red[k];
+        for (int k = 0; k < N; ++k) acc[k] = sh_red[k];
         parity ^= 1;
     };
+    using N2 = std::integral_constant<int, 2>;
+    using N4 = std::integral_constant<int, 4>;
+    using N10 = std::integral_constant<int, 10>;
 
     for (int gc = G.comp_begin; gc < G.comp_end; ++gc) {
         const int comp = a.group_comps[gc];
@@ -530,13 +535,18 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                 fn(w, t, a.blocks[t.block]);
             }
         };
-        // boundary rows: spread over the warps that have no tile in the first round (all warps if there is none), one row per
-        // lane and round, consecutive rows on consecutive warps -- k_bnd_first / k_bnd_stride are mirrored by the host (krylov.inl)
+        // Boundary rows.  With warps to spare (a single system on many CTAs) they are spread over the warps that have no tile,
+        // consecutive rows on consecutive warps: a few rows per warp, no CTA is a straggler.  Otherwise consecutive rows go to
+        // consecutive threads, from the end of the group (coalesced along the interface lines).  Mirrored by the host (krylov.inl).
         const int w_idle = k_bnd_warps(gwarps, n_tiles);
         auto for_bnd = [&](auto&& fs, auto&& fj, auto&& fl) {
             const int back = gwarps - 1 - gwarp;
-            if (back >= w_idle) return;
-            for (int q = back + lane * w_idle; q < n_bnd; q += 32 * w_idle) {
+            int q0 = gthreads - 1 - gthread, dq = gthreads;
+            if (w_idle > 0) {
+                if (back >= w_idle) return;
+                q0 = back + lane * w_idle; dq = 32 * w_idle;
+            }
+            for (int q = q0; q < n_bnd; q += dq) {
                 if (q < n_s) fs(q, a.srows[K.s_begin + q]);
                 else if (q < n_s + n_j) fj(q, a.jrows[K.j_begin + q - n_s]);
                 else fl(q, a.lrows[K.l_begin + q - n_s - n_j]);
@@ -585,7 +595,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                 }
             }
             tick(0);
-            reduce(acc);
+            reduce(acc, N4{});
             tick(4);
             applications += 1;
             coarse_post(cpar0, e_r);
@@ -676,7 +686,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                             [&](int, const SlidingRow& row) { put(row.self, k_sliding<MODE_APPLY>(row, pval), row.slave_begin, row.slave_end); });
                 }
                 tick(1);
-                reduce(accA);
+                reduce(accA, N2{});
                 tick(4);
                 pb ^= 1; vb ^= 1;
                 applications += 1;
@@ -741,7 +751,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                             [&](int, const SlidingRow& row) { put(row.self, k_sliding<MODE_APPLY>(row, sval), row.slave_begin, row.slave_end); });
                 }
                 tick(2);
-                reduce(accB);
+                reduce(accB, N10{});
                 tick(4);
                 applications += 1;
                 coarse_post(cparB, e_t);
