@@ -350,7 +350,7 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
     P.cta_group.upload(cta_group, s);
     P.ctl.alloc(size_t(n_comp)); P.ctl.zero(s);
     P.bars.alloc(size_t(n_groups)); P.bars.zero(s);
-    P.partials.alloc(size_t(2) * size_t(P.n_ctas) * K_NACC); P.partials.zero(s);
+    P.partials.alloc(size_t(2) * size_t(P.n_ctas) * K_REC); P.partials.zero(s);
     coarse_plan_build(m, r, P, comps, wtiles);
     CUDA_TRY(cudaStreamSynchronize(s));
 }

@@ -48,6 +48,7 @@ constexpr int K_WARPS = K_THREADS / 32;
 constexpr int K_NACC = 10;       // sums a phase reduces
 constexpr int K_TILE_ROWS = 2;   // rows of a warp tile
 constexpr int K_MAX_GROUP = 160; // CTAs of a group (one per SM)
+constexpr int K_REC = 16;        // doubles of a CTA's record in the exchange (128 bytes): K_NACC sums, the stamp in the last one
 
 struct WTile { int32_t block, i0, j0, rows; };   // 32 columns starting at interior column j0, `rows` rows starting at interior row i0
 
@@ -87,7 +88,7 @@ struct KArgs {
     const int32_t* cta_group;
     KCtl* ctl;
     KBarrier* bars;
-    double2* partials;           // 2 x n_ctas x K_NACC stamped values {sum, stamp}: see reduce()
+    double* partials;            // 2 x n_ctas records of K_REC doubles {sums ..., stamp}: see reduce()
     unsigned long long epoch;    // launch counter (> 0): the high half of the stamps
     const double2* xc;           // lagged coordinates (the mesh before this outer iteration)
     const double2* pq;           // control function (HAS_PQ)
@@ -115,16 +116,13 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// a value and its stamp travel in ONE 16-byte store / load: the value is valid when the stamp is the expected one
-__device__ __forceinline__ void st_release_stamped(double2* p, double v, unsigned long long stamp) {
-    asm volatile("st.release.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(stamp) : "memory");
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ bool ld_relaxed_stamped(const double2* p, unsigned long long stamp, double& v) {
-    long long bits;
-    unsigned long long got;
-    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(got) : "l"(p) : "memory");
-    v = __longlong_as_double(bits);
-    return got == stamp;
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -330,10 +328,12 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
     auto tick = [&](int slot) { if (a.timing) { const long long now = clock64(); tacc[slot] += now - tlast; tlast = now; } };
 
     // Barrier + combination of the group's partial sums in one exchange (fixed order: bit-identical in every CTA).  A CTA
-    // publishes its K_NACC sums as stamped 16-byte values with release stores (cumulative over what its threads wrote before the
-    // __syncthreads) and polls the stamped values of all CTAs of the group: when the last one carries this reduction's stamp,
-    // every CTA has arrived AND the sums are here -- no arrival counter, no second round trip for the data.  Two buffers: a
-    // CTA can be at most one reduction ahead of the slowest.
+    // writes its sums into a 128-byte record and publishes the record's STAMP with a release store (cumulative over what
+    // its threads wrote before the __syncthreads); thread c of every CTA polls the stamp of CTA c with acquire loads and,
+    // once it carries this exchange's number, reads that record: when all are in, every CTA has arrived AND the sums are
+    // here -- no arrival counter, and only one polled word per pair of CTAs (polling stamped VALUES costs n^2 N loads per round:
+    // 12.7k cycles per exchange for 99 CTAs and 10 sums against 6.9k this way, scripts/micro/exchange_bench.cu).  Two buffers:
+    // a CTA can be at most one exchange ahead of the slowest.
     unsigned long long stamp = a.epoch << 32;
     auto reduce = [&](double (&acc)[K_NACC], auto n_tag) {
         constexpr int N = decltype(n_tag)::value;                    // sums in use: acc[0 .. N)
@@ -345,26 +345,26 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
         }
         __syncthreads();
         stamp += 1;
-        double2* const mine = a.partials + ((size_t)parity * a.n_ctas_total + blockIdx.x) * K_NACC;
+        double* const mine = a.partials + ((size_t)parity * a.n_ctas_total + blockIdx.x) * K_REC;
         if (tid < N) {
             double s = 0.0;
             for (int w = 0; w < K_WARPS; ++w) s += sh_part[w][tid];
-            st_release_stamped(mine + tid, s, stamp);
+            __stcg(mine + tid, s);
         }
+        __syncthreads();
+        if (tid == 0) st_release_u64(reinterpret_cast<unsigned long long*>(mine + K_REC - 1), stamp);
         {
-            const double2* base = a.partials + ((size_t)parity * a.n_ctas_total + G.cta_begin) * K_NACC;
+            const double* base = a.partials + ((size_t)parity * a.n_ctas_total + G.cta_begin) * K_REC;
             for (int c = tid; c < G.n_ctas; c += K_THREADS) {
-                double v[N];
-                bool ok;
-                do {
-                    ok = true;
+                const double* rec = base + (size_t)c * K_REC;
+                while (ld_acquire_u64(reinterpret_cast<const unsigned long long*>(rec + K_REC - 1)) != stamp) {}
 #pragma unroll
-                    for (int k = 0; k < N; ++k) ok &= ld_relaxed_stamped(base + (size_t)c * K_NACC + k, stamp, v[k]);
-                } while (!ok);
-#pragma unroll
-                for (int k = 0; k < N; ++k) sh_all[c][k] = v[k];
+                for (int k = 0; k < N; k += 2) {
+                    const double2 v = __ldcg(reinterpret_cast<const double2*>(rec + k));
+                    sh_all[c][k] = v.x;
+                    if (k + 1 < N) sh_all[c][k + 1] = v.y;
+                }
             }
-            __threadfence();   // acquire side of the release stores
         }
         __syncthreads();
         if (warp == 0) {

@@ -241,7 +241,7 @@ struct KrylovPlan {
     DevBuf<KGroup> groups;
     DevBuf<KCtl> ctl;
     DevBuf<KBarrier> bars;
-    DevBuf<double2> partials;
+    DevBuf<double> partials;
     unsigned long long epoch = 0;
     std::vector<KComp> h_comps;
     std::vector<KCtl> h_ctl;
