@@ -131,7 +131,7 @@ void coarse_plan_build(tm_mesh* m, RankMesh& r, KrylovPlan& P, const std::vector
         for (int w = K.wt_begin; w < K.wt_end; ++w) {
             const WTile& t = wtiles[size_t(w)];
             const auto& B = T.blocks[size_t(t.block)];
-            const int crank = ((w - K.wt_begin) % gwarps) / K_WARPS;
+            const int crank = ((w - K.wt_begin) % (gwarps - K.bnd_warps)) / K_WARPS;
             for (int seg = 0; seg < 4; ++seg) {
                 const int64_t j = t.j0 + 8 * seg;
                 if (j > B.nj - 2) break;
@@ -149,9 +149,7 @@ void coarse_plan_build(tm_mesh* m, RankMesh& r, KrylovPlan& P, const std::vector
                     }
                 }
         }
-        const int w_idle = k_bnd_warps(gwarps, n_tiles);
-        const int gthreads = gwarps * 32;
-        auto bnd_crank = [&](int q) { return w_idle > 0 ? (gwarps - 1 - (q % w_idle)) / K_WARPS : (gthreads - 1 - (q % gthreads)) / K_THREADS; };   // the kernel's for_bnd
+        auto bnd_crank = [&](int q) { return (gwarps - 1 - (q % std::max(K.bnd_warps, 1))) / K_WARPS; };   // the kernel's for_bnd
         for (int q = 0; q < n_s; ++q) {
             const SmoothedRow& row = r.L.smoothed[size_t(K.s_begin + q)];
             const int32_t I = agg[size_t(row.g0)];
@@ -305,29 +303,8 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
         groups[size_t(g)].n_ctas = group_ctas;
         for (int k = 0; k < group_ctas; ++k) cta_group[size_t(g * group_ctas + k)] = g;
     }
-    // warp tiles per component: rows chosen so that every warp of the group gets about two tiles per phase
-    std::vector<KComp> comps((size_t)n_comp);
-    std::vector<WTile> wtiles;
-    const int group_warps = group_ctas * K_WARPS;
-    for (int c = 0; c < n_comp; ++c) {
-        KComp& K = comps[size_t(c)];
-        K = KComp{};
-        K.nodes = int32_t(std::min<int64_t>(nodes[size_t(c)], 0x7fffffff));
-        int rows = int(std::max<int64_t>(1, std::min<int64_t>(K_TILE_ROWS, nodes[size_t(c)] / (32 * int64_t(group_warps)))));
-        if (const char* e = std::getenv("TM_KRYLOV_TILE_ROWS")) rows = std::max(1, std::min(K_TILE_ROWS, std::atoi(e)));
-        K.wt_begin = int32_t(wtiles.size());
-        for (size_t b = 0; b < T.blocks.size(); ++b) {
-            if (T.comp_of_block[b] != c) continue;
-            const auto& B = T.blocks[b];
-            const int64_t interior_i = B.ni - 2;
-            const int64_t n_i = std::max<int64_t>(1, (interior_i + rows - 1) / rows);
-            const int64_t rr = (interior_i + n_i - 1) / n_i;
-            for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += rr)
-                for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += 32) wtiles.push_back(WTile{int32_t(b), int32_t(i0), int32_t(j0), int32_t(std::min<int64_t>(rr, B.ni - 1 - i0))});
-        }
-        K.wt_end = int32_t(wtiles.size());
-    }
     // boundary rows / rhs terms are grouped by component already (build_rank): find the ranges
+    std::vector<KComp> comps((size_t)n_comp, KComp{});
     auto ranges = [&](auto& rows, auto node_of, auto set) {
         size_t k = 0;
         for (int c = 0; c < n_comp; ++c) {
@@ -341,6 +318,46 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
     ranges(r.L.junction_rows, [](const JunctionRow& x) { return x.self; }, [](KComp& K, int32_t b, int32_t e) { K.j_begin = b; K.j_end = e; });
     ranges(r.L.sliding, [](const SlidingRow& x) { return x.self; }, [](KComp& K, int32_t b, int32_t e) { K.l_begin = b; K.l_end = e; });
     ranges(r.L.rhs_terms, [](const RhsTerm& x) { return x.g; }, [](KComp& K, int32_t b, int32_t e) { K.rt_begin = b; K.rt_end = e; });
+    // Warp tiles per component.  One row per tile gives the most parallelism, two rows halve the number of tiles: two when the
+    // tiles of a phase and the boundary rows (a warp per 32 of them) then fit the group's warps in ONE round -- every warp has
+    // one task, the warps left over share the boundary rows (k_bnd_warps) -- or when there are several rounds anyway.
+    std::vector<WTile> wtiles;
+    const int group_warps = group_ctas * K_WARPS;
+    for (int c = 0; c < n_comp; ++c) {
+        KComp& K = comps[size_t(c)];
+        K.nodes = int32_t(std::min<int64_t>(nodes[size_t(c)], 0x7fffffff));
+        auto tiles_with = [&](int64_t rows) {
+            int64_t n = 0;
+            for (size_t b = 0; b < T.blocks.size(); ++b) {
+                if (T.comp_of_block[b] != c) continue;
+                const auto& B = T.blocks[b];
+                n += ((B.ni - 2 + rows - 1) / rows) * ((B.nj - 2 + 31) / 32);
+            }
+            return n;
+        };
+        const int64_t bnd_chunks = (int64_t(K.s_end - K.s_begin) + (K.j_end - K.j_begin) + (K.l_end - K.l_begin) + 31) / 32;
+        int rows = 1;
+        if (tiles_with(1) + bnd_chunks > group_warps) rows = K_TILE_ROWS;
+        if (const char* e = std::getenv("TM_KRYLOV_TILE_ROWS")) rows = std::max(1, std::min(K_TILE_ROWS, std::atoi(e)));
+        // warps set aside for the boundary rows: all that are left in a single round, else a share by work (32 boundary rows
+        // cost about two tiles: three kinds of rows, gathers across blocks)
+        const int64_t nt = tiles_with(rows);
+        if (bnd_chunks == 0) K.bnd_warps = 0;
+        else if (nt + bnd_chunks <= group_warps) K.bnd_warps = int32_t(group_warps - nt);
+        else K.bnd_warps = int32_t(std::max<int64_t>(1, std::min<int64_t>(group_warps / 2, (2 * bnd_chunks * group_warps + (nt + 2 * bnd_chunks) / 2) / (nt + 2 * bnd_chunks))));
+        if (const char* e = std::getenv("TM_KRYLOV_BND_WARPS")) K.bnd_warps = std::max(bnd_chunks ? 1 : 0, std::min(group_warps - 1, std::atoi(e)));
+        K.wt_begin = int32_t(wtiles.size());
+        for (size_t b = 0; b < T.blocks.size(); ++b) {
+            if (T.comp_of_block[b] != c) continue;
+            const auto& B = T.blocks[b];
+            const int64_t interior_i = B.ni - 2;
+            const int64_t n_i = std::max<int64_t>(1, (interior_i + rows - 1) / rows);
+            const int64_t rr = (interior_i + n_i - 1) / n_i;
+            for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += rr)
+                for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += 32) wtiles.push_back(WTile{int32_t(b), int32_t(i0), int32_t(j0), int32_t(std::min<int64_t>(rr, B.ni - 1 - i0))});
+        }
+        K.wt_end = int32_t(wtiles.size());
+    }
     P.h_comps = comps;
     P.h_ctl.assign(size_t(n_comp), KCtl{});
     P.wtiles.upload(wtiles, s);
@@ -402,7 +419,7 @@ void krylov_solve_persistent(tm_mesh* m, RankMesh& r, const tm_smooth_options* o
             long long mn = t[size_t(k)], mx = mn; int imx = 0, imn = 0;
             for (int c = 0; c < P.n_ctas; ++c) { const long long v = t[size_t(c) * 8 + size_t(k)]; if (v > mx) { mx = v; imx = c; } if (v < mn) { mn = v; imn = c; } }
             std::fprintf(stderr, "  slot %d: min %lld (CTA %d) max %lld (CTA %d);", k, mn, imn, mx, imx);
-            for (int c = 0; c < P.n_ctas; c += std::max(1, P.n_ctas / 12)) std::fprintf(stderr, " %lld", t[size_t(c) * 8 + size_t(k)]);
+            for (int c = 0; c < P.n_ctas; c += (std::getenv("TM_KRYLOV_TIMING_ALL") ? 1 : std::max(1, P.n_ctas / 12))) std::fprintf(stderr, " %lld", t[size_t(c) * 8 + size_t(k)] / 1000);
             std::fprintf(stderr, "\n");
         }
         std::fprintf(stderr, "krylov timing (mean cycles per CTA): R0 %.0f  A %.0f  B %.0f  C %.0f  barrier+sums %.0f  coarse %.0f  rest %.0f  (%d CTAs; coarse: %d aggregates, needed lists <= %d, slot lists <= %d, %zu B shared)\n", sum[0], sum[1], sum[2], sum[3], sum[4],

@@ -56,7 +56,8 @@ struct KComp {   // one independent system: ranges into the component-sorted tab
     int32_t wt_begin, wt_end;
     int32_t s_begin, s_end, j_begin, j_end, l_begin, l_end;
     int32_t rt_begin, rt_end;
-    int32_t nodes, _pad;
+    int32_t nodes;
+    int32_t bnd_warps;   // warps of the group (from its end) that take the boundary rows and no tiles
 };
 struct KCtl {    // per component; index 0 = x solve, 1 = y solve
     double tol[2], norm_b[2], norm_r[2];
@@ -291,9 +292,6 @@ __device__ __forceinline__ void k_interior_nodes(const WTile& t, const DevBlock&
         if (q < t.rows) store(b.off + (int64_t)(t.i0 + q) * b.nj + j, tmp[q]);
 }
 
-// warps without a tile in the first round that share the boundary rows (0: fewer than a CTA's worth -- thread-linear assignment)
-__host__ __device__ inline int k_bnd_warps(int gwarps, int n_tiles) { return gwarps - n_tiles >= K_WARPS ? gwarps - n_tiles : 0; }
-
 struct KScal {   // solver scalars of one component, identical in every thread of the group
     double rho_old[2], rho_new[2], alpha[2], omega[2], beta[2], tol[2], tol_eff[2], norm_b[2], norm_r[2];
     double pend[2];   // omega of the last iteration whose d += omega s^ is still to be taken (by the next phase A or the final update)
@@ -404,6 +402,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
         }
         const int nc = CS.nc;                                        // uniform over the group
         const int n_tiles = K.wt_end - K.wt_begin;
+        const int tile_warps = gwarps - K.bnd_warps;
         const double2 z2 = make_double2(0.0, 0.0);
         int n_need = 0, n_src = 0;
         const int32_t* need = nullptr;
@@ -526,26 +525,33 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
 
         // Row-owner loops.  Interior nodes: warp tiles.  Boundary rows: one thread per row, taken from the END of the group's
         // threads (the warps without a tile).  `mirror` hands a value to the `connected` copies of a row's node.
-        auto mirror = [&](double2* f, int sb, int se, double2 val) {
-            for (int k = sb; k < se; ++k) f[a.slaves[k].self] = val;
+auto mirror = [&](int sb, int se, auto&& put_copy) {   // put_copy(node of the copy) stores every field of the phase
+            // the indices of up to four copies are fetched before anything is stored: a store may alias the table as far as the
+            // compiler knows, so index loads behind stores would cost an L2 round trip each (a junction node has up to four copies)
+            for (int k0 = sb; k0 < se; k0 += 4) {
+                int64_t id[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) id[u] = k0 + u < se ? a.slaves[k0 + u].self : (int64_t)-1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (id[u] >= 0) put_copy(id[u]);
+            }
         };
         auto for_tiles = [&](auto&& fn) {
-            for (int w = K.wt_begin + gwarp; w < K.wt_end; w += gwarps) {
+            if (gwarp >= tile_warps) return;
+            for (int w = K.wt_begin + gwarp; w < K.wt_end; w += tile_warps) {
                 const WTile t = a.wtiles[w];
                 fn(w, t, a.blocks[t.block]);
             }
         };
-        // Boundary rows.  With warps to spare (a single system on many CTAs) they are spread over the warps that have no tile,
-        // consecutive rows on consecutive warps: a few rows per warp, no CTA is a straggler.  Otherwise consecutive rows go to
-        // consecutive threads, from the end of the group (coalesced along the interface lines).  Mirrored by the host (krylov.inl).
-        const int w_idle = k_bnd_warps(gwarps, n_tiles);
+        // Boundary rows: spread over the K.bnd_warps last warps of the group, which have no tiles (krylov.inl sizes them so
+        // that every warp has about the same work) -- consecutive rows on consecutive warps, so a warp holds few rows of
+        // each kind and no CTA is a straggler.  Mirrored by the host (coarse_plan_build).
+        const int w_bnd = K.bnd_warps;
         auto for_bnd = [&](auto&& fs, auto&& fj, auto&& fl) {
             const int back = gwarps - 1 - gwarp;
-            int q0 = gthreads - 1 - gthread, dq = gthreads;
-            if (w_idle > 0) {
-                if (back >= w_idle) return;
-                q0 = back + lane * w_idle; dq = 32 * w_idle;
-            }
+            if (back >= w_bnd) return;
+            const int q0 = back + lane * w_bnd, dq = 32 * w_bnd;
             for (int q = q0; q < n_bnd; q += dq) {
                 if (q < n_s) fs(q, a.srows[K.s_begin + q]);
                 else if (q < n_s + n_j) fj(q, a.jrows[K.j_begin + q - n_s]);
@@ -564,7 +570,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                 auto xval = [&](int64_t k) { return a.xnew[k]; };
                 auto init = [&](int64_t k, double2 res, int sb, int se) {   // phase A forms r = s - omega t: s = r, t = 0
                     a.s[k] = res; a.t[k] = z; a.rhat[k] = res; P0[k] = z; V0[k] = z; a.d[k] = z;
-                    mirror(a.s, sb, se, res); mirror(a.t, sb, se, z); mirror(P0, sb, se, z); mirror(V0, sb, se, z);
+                    mirror(sb, se, [&](int64_t c) { a.s[c] = res; a.t[c] = z; P0[c] = z; V0[c] = z; });
                     acc[0] += res.x * res.x; acc[1] += res.y * res.y;
                 };
                 for_tiles([&](int w, const WTile& t, const DevBlock& b) {
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                             a.d[k] = dd;
                         }
                         a.r[k] = rr; Pnew[k] = o.centre; Vnew[k] = o.res;
-                        mirror(a.r, sb, se, rr); mirror(Pnew, sb, se, o.centre); mirror(Vnew, sb, se, o.res);
+                        mirror(sb, se, [&](int64_t c) { a.r[c] = rr; Pnew[c] = o.centre; Vnew[c] = o.res; });
                         const double2 h = a.rhat[k];
                         accA[0] += h.x * o.res.x; accA[1] += h.y * o.res.y;
                     };
@@ -724,7 +730,7 @@ __global__ void __launch_bounds__(K_THREADS) bicgstab_persistent_kernel(const KA
                             ss = make_double2(mx ? 0.0 : rr.x - ax * vv.x, my ? 0.0 : rr.y - ay * vv.y);
                         }
                         a.s[k] = ss; a.t[k] = o.res; a.d[k] = dd;
-                        mirror(a.s, sb, se, ss); mirror(a.t, sb, se, o.res);
+                        mirror(sb, se, [&](int64_t c) { a.s[c] = ss; a.t[c] = o.res; });
                         const double2 h = a.rhat[k];
                         accB[0] += ss.x * ss.x; accB[1] += ss.y * ss.y;
                         accB[2] += ss.x * o.res.x; accB[3] += ss.y * o.res.y;
