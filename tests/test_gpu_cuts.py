@@ -110,3 +110,41 @@ def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc, monkeypa
         rhs = O.csr()[3 + xy]
         assert comps[0]["norm_b"][xy] == pytest.approx(float(np.linalg.norm(rhs)), rel=1e-5)
     O.close()
+
+
+def test_two_level_preconditioner_in_the_batch_path(gpu_lib, monkeypatch):
+    """The coarse space of the phased launches (krylov_phased.cuh, on by default for batches with tall tiles): the cuts of a
+    batch reach the same exact Picard sequence -- cut 0 (the unscaled T106) against the extended-precision truth, the others
+    against the point-Jacobi run -- with well under 60 % of the Krylov iterations."""
+    from turbomesh_b200 import smoothing
+    from util import GOLDEN, chord_of
+
+    base, z, meta = load_fixture("t106_white")
+    tz = np.load(os.path.join(GOLDEN, "t106_white_truth.npz"))
+    scales = [1.0, 1.2, 0.6]
+    nb = len(base.blocks)
+    cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+    sol = smoothing.CudaSolver.tight()
+    monkeypatch.setenv("TM_KRYLOV", "phased")
+    monkeypatch.setenv("TM_KRYLOV_TILE_ROWS", "8")     # tall tiles: what a large batch gets (a small one has 2-row tiles and no coarse space)
+    res, its = {}, {}
+    for coarse in ("0", "1"):
+        monkeypatch.setenv("TM_KRYLOV_COARSE", coarse)
+        batch, groups = synthetic.batch_of_cuts(base, scales)
+        with smoothing.DeviceMesh(batch, upload=False) as dm:
+            for k, b in enumerate(batch.blocks):
+                dm.tfi_block(k, *b.edge_args())
+            dm.set_white_groups(groups)
+            dm.begin_smoothing(sol, cf)
+            st = dm.smooth(8, sol, cf)
+            res[coarse] = [dm.download_block(k) for k in range(len(batch.blocks))]
+        assert st["converged"] == 1 and st["last_inner_residual"] <= 1e-13
+        its[coarse] = st["inner_iterations"]
+    chord = float(np.ptp(res["0"][0][:, 0, 0]))
+    for coarse in ("0", "1"):
+        err = max(float(np.abs(res[coarse][k] - tz[f"truth8_b{k}"]).max()) for k in range(nb))
+        assert err <= 1e-9 * chord, (coarse, err / chord)
+    for c, sc in enumerate(scales):
+        d = max(float(np.abs(res["0"][c * nb + k] - res["1"][c * nb + k]).max()) for k in range(nb))
+        assert d <= 1e-9 * chord * sc, (c, d / (chord * sc))
+    assert its["1"] < 0.6 * its["0"], its

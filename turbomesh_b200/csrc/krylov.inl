@@ -225,18 +225,19 @@ void coarse_plan_build(tm_mesh* m, RankMesh& r, KrylovPlan& P, const std::vector
 }
 
 // G = (P^T A P)^-1 with the lagged coefficients of this outer iteration (X[cur], pq)
-void coarse_refresh(tm_mesh* m, RankMesh& r, KrylovPlan& P) {
+template <class Plan>
+void coarse_refresh(tm_mesh* m, RankMesh& r, Plan& P) {
     cudaStream_t s = m->stream;
     CUDA_TRY(cudaMemsetAsync(P.G.p, 0, size_t(P.g_size) * sizeof(double), s));
     const unsigned grid = unsigned((int64_t(P.n_items) * 32 + 255) / 256);
     if (r.has_pq)
         LAUNCH(coarse_assemble_kernel<true>, grid, 256, s, (const CoarseItem*)P.items.p, P.n_items, (const KCoarse*)P.coarse.p, (const int32_t*)P.mem_ptr.p, (const int32_t*)P.mem_code.p,
                (const int32_t*)P.agg_block.p, (const int32_t*)P.agg.p, (const DevBlock*)r.d_blocks.p, (const SmoothedRow*)r.d_srows.p, (const JunctionRow*)r.d_jrows.p,
-               (const double2*)r.X[r.cur].p, (const double2*)r.pq.p, P.G.p);
+               (const double2*)r.X[r.cur].p, (const double2*)r.pq.p, P.G.p, int(std::is_same<Plan, PhasedPlan>::value));
     else
         LAUNCH(coarse_assemble_kernel<false>, grid, 256, s, (const CoarseItem*)P.items.p, P.n_items, (const KCoarse*)P.coarse.p, (const int32_t*)P.mem_ptr.p, (const int32_t*)P.mem_code.p,
                (const int32_t*)P.agg_block.p, (const int32_t*)P.agg.p, (const DevBlock*)r.d_blocks.p, (const SmoothedRow*)r.d_srows.p, (const JunctionRow*)r.d_jrows.p,
-               (const double2*)r.X[r.cur].p, (const double2*)r.pq.p, P.G.p);
+               (const double2*)r.X[r.cur].p, (const double2*)r.pq.p, P.G.p, int(std::is_same<Plan, PhasedPlan>::value));
     coarse_invert_kernel<<<unsigned(m->topo.n_comp), COARSE_INV_THREADS, 2 * size_t(P.nc_max) * sizeof(double), s>>>((const KCoarse*)P.coarse.p, P.G.p, P.coarse_ok.p);
     CUDA_TRY(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -441,6 +442,161 @@ void krylov_solve_persistent(tm_mesh* m, RankMesh& r, const tm_smooth_options* o
 // ---------------------------------------------------------------------------------------------------------------
 // Phased form (krylov_phased.cuh): one launch per phase over all components, scalars per component; the default.
 // ---------------------------------------------------------------------------------------------------------------
+// Coarse space of the phased path: an aggregate is a segment group of a warp tile (the tile's rows x 8, 16 or 32 columns), so
+// that a tile's restriction is its segment sums; boundary rows as in coarse_plan_build.  Slots: 4 per warp tile, then one
+// per smoothed row, then one per junction row (table order).
+bool coarse_enabled_batch() {
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE")) return std::atoi(e) != 0;
+    return true;
+}
+void phased_coarse_build(tm_mesh* m, RankMesh& r, PhasedPlan& P, const std::vector<KPComp>& comps, const std::vector<WTile>& wtiles, int tile_rows) {
+    P.n_items = 0;
+    const Topology& T = m->topo;
+    if (!coarse_enabled_batch() || tile_rows < 8 || tile_rows % 2 || T.n_nodes >= (int64_t(1) << 30)) return;
+    cudaStream_t s = m->stream;
+    const int n_comp = T.n_comp;
+    int cap = 512;
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE_MAX")) cap = std::max(8, std::min(1024, std::atoi(e)));
+    std::vector<std::vector<size_t>> blocks_of((size_t)n_comp);
+    for (size_t b = 0; b < T.blocks.size(); ++b) blocks_of[size_t(T.comp_of_block[b])].push_back(b);
+    struct Patch { int ai, aj, gi, gj, base; };
+    std::vector<Patch> patch(T.blocks.size(), Patch{0, 0, 0, 0, 0});
+    auto rows_of = [&](const BlockInfo& B) {   // the tile height phased_plan_build gives the block
+        const int64_t interior_i = B.ni - 2;
+        const int64_t n_i = std::max<int64_t>(1, (interior_i + tile_rows - 1) / tile_rows);
+        return int((interior_i + n_i - 1) / n_i);
+    };
+    std::vector<KCoarse> coarse((size_t)n_comp, KCoarse{});
+    std::vector<int32_t> agg_block;
+    int64_t g_size = 0;
+    int nc_max = 0;
+    for (int c = 0; c < n_comp; ++c) {
+        bool ok = true;
+        for (size_t b : blocks_of[size_t(c)]) if (T.blocks[b].ni < 3 || T.blocks[b].nj < 3) ok = false;
+        if (!ok) continue;
+        int aj = 0, nc = 0;
+        for (int cand : {8, 16, 32}) {
+            int64_t n = 0;
+            for (size_t b : blocks_of[size_t(c)]) {
+                const auto& B = T.blocks[b];
+                const int ai = rows_of(B);
+                n += ((B.ni - 2 + ai - 1) / ai) * std::max<int64_t>(1, (B.nj - 2 + cand / 2) / cand);
+            }
+            if (n <= cap) { aj = cand; nc = int(n); break; }
+        }
+        if (!aj || nc < 2) continue;
+        int base = 0;
+        for (size_t b : blocks_of[size_t(c)]) {
+            const auto& B = T.blocks[b];
+            const int ai = rows_of(B);
+            const int gi = int((B.ni - 2 + ai - 1) / ai), gj = int(std::max<int64_t>(1, (B.nj - 2 + aj / 2) / aj));
+            patch[b] = Patch{ai, aj, gi, gj, base};
+            base += gi * gj;
+        }
+        KCoarse& C = coarse[size_t(c)];
+        C.nc = nc; C.agg_base = int32_t(agg_block.size()); C.g_off = g_size;
+        g_size += int64_t(nc) * nc;
+        nc_max = std::max(nc_max, nc);
+        for (size_t b : blocks_of[size_t(c)]) for (int k = 0; k < patch[b].gi * patch[b].gj; ++k) agg_block.push_back(int32_t(b));
+    }
+    if (nc_max == 0) return;
+    auto patch_of = [&](size_t b, int64_t i, int64_t j) -> int32_t {
+        const Patch& p = patch[b];
+        if (!p.ai) return -1;
+        const auto& B = T.blocks[b];
+        const int64_t ic = std::min(std::max<int64_t>(i, 1), B.ni - 2) - 1, jc = std::min(std::max<int64_t>(j, 1), B.nj - 2) - 1;
+        return int32_t(p.base + std::min<int64_t>(ic / p.ai, p.gi - 1) * p.gj + std::min<int64_t>(jc / p.aj, p.gj - 1));
+    };
+    auto patch_of_node = [&](int64_t g) -> int32_t {
+        const size_t b = T.block_of(g);
+        const int64_t l = g - T.blocks[b].off;
+        return patch_of(b, l / T.blocks[b].nj, l % T.blocks[b].nj);
+    };
+    std::vector<int32_t> agg(size_t(T.n_nodes), -1);
+    for (size_t b = 0; b < T.blocks.size(); ++b) {
+        if (!patch[b].ai) continue;
+        const auto& B = T.blocks[b];
+        for (int64_t i = 1; i <= B.ni - 2; ++i)
+            for (int64_t j = 1; j <= B.nj - 2; ++j) agg[size_t(B.off + i * B.nj + j)] = patch_of(b, i, j);
+    }
+    for (const SmoothedRow& row : r.L.smoothed) agg[size_t(row.g0)] = patch_of_node(row.g0);
+    for (const JunctionRow& row : r.L.junction_rows) agg[size_t(row.self)] = patch_of_node(row.self);
+    for (const SlaveRow& sl : r.L.slaves) agg[size_t(sl.self)] = agg[size_t(sl.root)];
+    const int32_t n_agg = int32_t(agg_block.size());
+    std::vector<std::vector<int32_t>> members((size_t)n_agg), slots((size_t)n_agg), nbrs((size_t)n_agg);
+    auto add_unique = [](std::vector<int32_t>& v, int32_t x) { if (x >= 0 && std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    const int64_t sslot0 = int64_t(4) * int64_t(wtiles.size()), jslot0 = sslot0 + int64_t(r.L.smoothed.size());
+    const int64_t n_slots = jslot0 + int64_t(r.L.junction_rows.size());
+    if (n_slots >= 0x7fffffff) return;
+    for (size_t w = 0; w < wtiles.size(); ++w) {
+        const WTile& t = wtiles[w];
+        if (!patch[size_t(t.block)].ai) continue;
+        const auto& B = T.blocks[size_t(t.block)];
+        const int32_t ab = coarse[size_t(T.comp_of_block[size_t(t.block)])].agg_base;
+        for (int seg = 0; seg < 4; ++seg) {
+            const int64_t j = t.j0 + 8 * seg;
+            if (j > B.nj - 2) break;
+            slots[size_t(ab + patch_of(size_t(t.block), t.i0, j))].push_back(int32_t(4 * w + size_t(seg)));
+        }
+        for (int64_t i = t.i0; i < t.i0 + t.rows; ++i)
+            for (int64_t j = t.j0; j < t.j0 + 32 && j <= B.nj - 2; ++j) {
+                const int32_t I = agg[size_t(B.off + i * B.nj + j)];
+                members[size_t(ab + I)].push_back(int32_t(B.off + i * B.nj + j));
+                for (int di = -1; di <= 1; ++di)
+                    for (int dj = -1; dj <= 1; ++dj) add_unique(nbrs[size_t(ab + I)], agg[size_t(B.off + (i + di) * B.nj + j + dj)]);
+            }
+    }
+    for (size_t q = 0; q < r.L.smoothed.size(); ++q) {
+        const SmoothedRow& row = r.L.smoothed[q];
+        const int32_t I = agg[size_t(row.g0)];
+        if (I < 0) continue;
+        const int32_t ab = coarse[size_t(T.comp_of_block[T.block_of(row.g0)])].agg_base;
+        slots[size_t(ab + I)].push_back(int32_t(sslot0 + int64_t(q)));
+        members[size_t(ab + I)].push_back(int32_t((1u << 30) | uint32_t(q)));
+        const int64_t nodes[9] = {row.g0, row.g0 - row.d0, row.g0 + row.d0, row.g0 + row.n0, row.g0 - row.d0 + row.n0, row.g0 + row.d0 + row.n0, row.iN, row.iNW, row.iNE};
+        for (int64_t g : nodes) add_unique(nbrs[size_t(ab + I)], agg[size_t(g)]);
+    }
+    for (size_t q = 0; q < r.L.junction_rows.size(); ++q) {
+        const JunctionRow& row = r.L.junction_rows[q];
+        const int32_t I = agg[size_t(row.self)];
+        if (I < 0) continue;
+        const int32_t ab = coarse[size_t(T.comp_of_block[T.block_of(row.self)])].agg_base;
+        slots[size_t(ab + I)].push_back(int32_t(jslot0 + int64_t(q)));
+        members[size_t(ab + I)].push_back(int32_t((2u << 30) | uint32_t(q)));
+        add_unique(nbrs[size_t(ab + I)], I);
+        for (int k = 0; k < row.n; ++k) add_unique(nbrs[size_t(ab + I)], agg[size_t(row.nbr[k])]);
+    }
+    std::vector<int32_t> contrib_ptr(1, 0), contrib_src, mem_ptr(1, 0), mem_code;
+    std::vector<CoarseItem> items;
+    for (int c = 0; c < n_comp; ++c) {
+        const KCoarse& C = coarse[size_t(c)];
+        for (int I = 0; I < C.nc; ++I) {
+            const size_t g = size_t(C.agg_base + I);
+            contrib_src.insert(contrib_src.end(), slots[g].begin(), slots[g].end());
+            contrib_ptr.push_back(int32_t(contrib_src.size()));
+            mem_code.insert(mem_code.end(), members[g].begin(), members[g].end());
+            mem_ptr.push_back(int32_t(mem_code.size()));
+            std::sort(nbrs[g].begin(), nbrs[g].end());
+            for (int32_t J : nbrs[g]) items.push_back(CoarseItem{c, I, J});
+        }
+    }
+    (void)comps;
+    P.n_items = int(items.size());
+    P.nc_max = nc_max; P.g_size = g_size; P.sslot0 = int(sslot0); P.jslot0 = int(jslot0);
+    P.coarse_every = 1;
+    if (const char* e = std::getenv("TM_KRYLOV_COARSE_EVERY")) P.coarse_every = std::max(1, std::atoi(e));
+    P.coarse.upload(coarse, s); P.agg.upload(agg, s); P.agg_block.upload(agg_block, s);
+    P.contrib_ptr.upload(contrib_ptr, s); P.contrib_src.upload(contrib_src, s);
+    P.mem_ptr.upload(mem_ptr, s); P.mem_code.upload(mem_code, s);
+    P.items.upload(items, s);
+    P.G.alloc(size_t(g_size)); P.G.zero(s);
+    P.contrib.alloc(size_t(n_slots)); P.contrib.zero(s);
+    P.e_r.alloc(size_t(n_agg)); P.e_r.zero(s); P.e_v.alloc(size_t(n_agg)); P.e_v.zero(s); P.e_t.alloc(size_t(n_agg)); P.e_t.zero(s);
+    P.coarse_ok.alloc(size_t(n_comp)); P.coarse_ok.zero(s);
+    P.coarse_age = -1;
+    CUDA_TRY(cudaFuncSetAttribute(coarse_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(2 * 1024 * sizeof(double))));
+}
+
 void phased_plan_build(tm_mesh* m, RankMesh& r) {
     if (r.pplan) return;
     r.pplan.reset(new PhasedPlan());
@@ -521,6 +677,7 @@ void phased_plan_build(tm_mesh* m, RankMesh& r) {
     P.state.alloc((size_t)n_comp); P.state.zero(s);
     P.partials.alloc(size_t(P.n_wtiles + P.n_chunks) * K_NACC); P.partials.zero(s);
     P.count.alloc(2); P.count.zero(s);
+    phased_coarse_build(m, r, P, comps, wtiles, tile_rows);
     CUDA_TRY(cudaMallocHost(&P.h_count, 2 * sizeof(int)));
     CUDA_TRY(cudaStreamSynchronize(s));
 }
@@ -529,14 +686,42 @@ template <int PHASE>
 void phased_launch(tm_mesh* m, RankMesh& r, const KPArgs& a) {
     const PhasedPlan& P = *r.pplan;
     const unsigned g_tiles = unsigned((P.n_wtiles + KP_WARPS - 1) / KP_WARPS), g_chunks = unsigned(P.n_chunks);
+    const bool co = a.coarse != nullptr && PHASE != KP_ADD;
+    // the boundary chunks neither read what the tiles of the same phase write nor write the same nodes: they run beside them
+    // (the mesh's second, high-priority stream; inside the captured graph this is a fork and a join)
+    cudaStream_t st = m->stream, sc = m->stream;
+    if (g_tiles && g_chunks && !std::getenv("TM_KRYLOV_SERIAL_CHUNKS")) {
+        sc = m->comm_stream;
+        CUDA_TRY(cudaEventRecord(m->ev_rim, st));
+        CUDA_TRY(cudaStreamWaitEvent(sc, m->ev_rim, 0));
+    }
     if (r.has_pq) {
-        if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, true, true>), g_tiles, KP_THREADS, m->stream, a);
-        if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, true, false>), g_chunks, KP_THREADS, m->stream, a);
+        if (co) {
+            if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, true, true, true>), g_tiles, KP_THREADS, st, a);
+            if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, true, false, true>), g_chunks, KP_THREADS, sc, a);
+        } else {
+            if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, true, true, false>), g_tiles, KP_THREADS, st, a);
+            if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, true, false, false>), g_chunks, KP_THREADS, sc, a);
+        }
     } else {
-        if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, false, true>), g_tiles, KP_THREADS, m->stream, a);
-        if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, false, false>), g_chunks, KP_THREADS, m->stream, a);
+        if (co) {
+            if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, false, true, true>), g_tiles, KP_THREADS, st, a);
+            if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, false, false, true>), g_chunks, KP_THREADS, sc, a);
+        } else {
+            if (g_tiles) LAUNCH((krylov_phase_kernel<PHASE, false, true, false>), g_tiles, KP_THREADS, st, a);
+            if (g_chunks) LAUNCH((krylov_phase_kernel<PHASE, false, false, false>), g_chunks, KP_THREADS, sc, a);
+        }
+    }
+    if (sc != st) {
+        CUDA_TRY(cudaEventRecord(m->ev_x, sc));
+        CUDA_TRY(cudaStreamWaitEvent(st, m->ev_x, 0));
     }
     if (PHASE != KP_ADD) LAUNCH((krylov_finalize_kernel<PHASE>), unsigned((P.n_comp + 3) / 4), 128, m->stream, a);
+    if (co) {
+        krylov_coarse_kernel<PHASE><<<unsigned(P.n_comp), KC_THREADS, size_t(P.nc_max) * (1 + KC_SPLIT) * sizeof(double2), m->stream>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+    }
 }
 
 void krylov_solve_phased(tm_mesh* m, RankMesh& r, const tm_smooth_options* o, tm_smooth_stats* st) {
@@ -554,6 +739,12 @@ void krylov_solve_phased(tm_mesh* m, RankMesh& r, const tm_smooth_options* o, tm
     a.max_iters = o->max_inner_iterations > 0x7fffffffull ? 0x7fffffff : int32_t(o->max_inner_iterations);
     a.max_restarts = 60;
     a.polish = std::max(0, int(o->inner_refinement_cycles));
+    if (P.n_items > 0) {
+        if (P.coarse_age < 0 || P.coarse_age >= P.coarse_every) { coarse_refresh(m, r, P); P.coarse_age = 0; }
+        P.coarse_age += 1;
+        a.coarse = P.coarse.p; a.coarse_ok = P.coarse_ok.p; a.agg = P.agg.p; a.contrib_ptr = P.contrib_ptr.p; a.contrib_src = P.contrib_src.p;
+        a.G = P.G.p; a.contrib = P.contrib.p; a.e_r = P.e_r.p; a.e_v = P.e_v.p; a.e_t = P.e_t.p; a.sslot0 = P.sslot0; a.jslot0 = P.jslot0; a.nc_max = P.nc_max;
+    }
     double2* const Pb[2] = {r.kp.p, r.kp2.p};
     double2* const Vb[2] = {r.kv.p, r.kv2.p};
     LAUNCH(krylov_reset_kernel, unsigned((P.n_comp + 127) / 128), 128, s, P.state.p, P.n_comp);

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(const CoarseItem* 
                                                               const int32_t* __restrict__ mem_ptr, const int32_t* __restrict__ mem_code,
                                                               const int32_t* __restrict__ agg_block, const int32_t* __restrict__ agg, const DevBlock* __restrict__ blocks,
                                                               const SmoothedRow* __restrict__ srows, const JunctionRow* __restrict__ jrows,
-                                                              const double2* __restrict__ xc, const double2* __restrict__ pq, double* __restrict__ G) {
+                                                              const double2* __restrict__ xc, const double2* __restrict__ pq, double* __restrict__ G, int transposed) {
     const int lane = threadIdx.x & 31;
     const int w = int((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (w >= n_items) return;
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) coarse_assemble_kernel(const CoarseItem* 
         else sum += k_junction<MODE_APPLY>(jrows[idx], u).res.x;
     }
     sum = warp_sum(sum);
-    if (lane == 0) G[C.g_off + (int64_t)it.I * C.nc + J] = sum;
+    // transposed: the inverse of A_c^T is G^T, which the phased path reads column-wise (coalesced over the output index)
+    if (lane == 0) G[C.g_off + (transposed ? (int64_t)J * C.nc + it.I : (int64_t)it.I * C.nc + J)] = sum;
 }
 
 __global__ void __launch_bounds__(COARSE_INV_THREADS) coarse_invert_kernel(const KCoarse* __restrict__ coarse, double* G, int32_t* __restrict__ ok) {

@@ -48,13 +48,22 @@ struct KPArgs {
     int32_t n_wtiles, n_chunks, n_comp, cycle;
     double rtol, atol;
     int32_t max_iters, max_restarts, polish, _pad;
+    // COARSE (krylov_coarse.cuh): the two-level preconditioner, where an iteration is bandwidth-bound and halving their number pays
+    const KCoarse* coarse;       // per component; need_base unused, slot numbering below
+    const int32_t* coarse_ok;
+    const int32_t* agg;          // per node: aggregate within its component, -1 outside the coarse space
+    const int32_t *contrib_ptr, *contrib_src;
+    const double* G;
+    double2* contrib;            // slots: 4 per warp tile (8-lane segments) | one per smoothed row | one per junction row
+    double2 *e_r, *e_v, *e_t;    // G P^T x per aggregate (mesh-wide numbering)
+    int32_t sslot0, jslot0, nc_max, _pad2;
 };
 
 enum KPhase : int { KP_R0 = 0, KP_A = 1, KP_B = 2, KP_C = 3, KP_ADD = 4 };
 
 // TILES = true: the interior warp tiles (grid = ceil(n_wtiles / 4)); false: the boundary chunks (grid = n_chunks).  Two kernels
 // rather than one so that the register count of the tile path (the bandwidth path) is not set by the gather-heavy row path.
-template <int PHASE, bool HAS_PQ, bool TILES>
+template <int PHASE, bool HAS_PQ, bool TILES, bool COARSE>
 __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_tile_ctas = TILES ? 0x7fffffff : 0;
@@ -77,16 +86,37 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
     if (S.final_) return;
     const int d0 = S.done[0], d1 = S.done[1];
     if (PHASE != KP_R0 && PHASE != KP_ADD && d0 && d1) return;
-    double acc[K_NACC] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double acc[K_NACC] = {};
     auto mirror = [&](double2* f, int sb, int se, double2 val) {
         for (int k = sb; k < se; ++k) f[a.slaves[k].self] = val;
+    };
+    // COARSE: the hatted directions of krylov_kernels.cuh; e_x live in global memory (written by krylov_coarse_kernel)
+    const double2 z2 = make_double2(0.0, 0.0);
+    bool co = false;
+    const double2 *er = nullptr, *ev = nullptr;
+    if (COARSE) {
+        const KCoarse C = a.coarse[comp];
+        co = C.nc > 0 && a.coarse_ok[comp] != 0;
+        er = a.e_r + C.agg_base; ev = a.e_v + C.agg_base;
+    }
+    auto e_at = [&](const double2* e, int64_t k) {
+        const int J = __ldg(a.agg + k);
+        return J >= 0 ? ldg2(e + J) : z2;                          // written by an earlier launch: read-only here
+    };
+    double2 tsum = z2;                                             // restriction of what the phase produces: per lane, then per 8-lane segment
+    auto tile_contrib = [&]() {
+        if (COARSE && co) {
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) { tsum.x += __shfl_xor_sync(0xffffffffu, tsum.x, o); tsum.y += __shfl_xor_sync(0xffffffffu, tsum.y, o); }
+            if ((lane & 7) == 0) a.contrib[(size_t)slot * 4 + (lane >> 3)] = tsum;
+        }
     };
     // boundary rows of a chunk: thread q of the CTA takes row q of the concatenation smoothed | junction | sliding
     auto for_bnd = [&](auto&& fs, auto&& fj, auto&& fl) {
         const int n_s = ch.s_end - ch.s_begin, n_j = ch.j_end - ch.j_begin, n_l = ch.l_end - ch.l_begin;
         const int q = tid;
-        if (q < n_s) fs(a.srows[ch.s_begin + q]);
-        else if (q < n_s + n_j) fj(a.jrows[ch.j_begin + q - n_s]);
+        if (q < n_s) fs(a.sslot0 + ch.s_begin + q, a.srows[ch.s_begin + q]);
+        else if (q < n_s + n_j) fj(a.jslot0 + ch.j_begin + q - n_s, a.jrows[ch.j_begin + q - n_s]);
         else if (q < n_s + n_j + n_l) fl(a.lrows[ch.l_begin + q - n_s - n_j]);
     };
     if (PHASE == KP_R0) {
@@ -101,15 +131,21 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
             acc[0] += res.x * res.x; acc[1] += res.y * res.y;
         };
         if (is_tile) {
-            k_interior_march<MODE_RESID, HAS_PQ>(t, a.blocks[t.block], xval, a.xc, a.pq, [&](int64_t k, double2 res, double2) { init(k, res, 0, 0); });
+            k_interior_march<MODE_RESID, HAS_PQ>(t, a.blocks[t.block], xval, a.xc, a.pq, [&](int64_t k, double2 res, double2) { init(k, res, 0, 0); tsum = tsum + res; });
+            tile_contrib();
         } else {
-            for_bnd([&](const SmoothedRow& row) {
+            for_bnd([&](int sl, const SmoothedRow& row) {
                         double b2x = 0.0, b2y = 0.0;
                         const KRow o = k_smoothed<MODE_RESID, HAS_PQ>(row, xval, a.xc, a.pq, b2x, b2y);
                         init(row.g0, o.res, row.slave_begin, row.slave_end);
+                        if (COARSE && co) a.contrib[sl] = o.res;
                         if (a.cycle == 0) { acc[2] += b2x; acc[3] += b2y; }
                     },
-                    [&](const JunctionRow& row) { init(row.self, k_junction<MODE_RESID>(row, xval).res, row.slave_begin, row.slave_end); },
+                    [&](int sl, const JunctionRow& row) {
+                        const double2 res = k_junction<MODE_RESID>(row, xval).res;
+                        init(row.self, res, row.slave_begin, row.slave_end);
+                        if (COARSE && co) a.contrib[sl] = res;
+                    },
                     [&](const SlidingRow& row) { init(row.self, k_sliding<MODE_RESID>(row, xval).res, row.slave_begin, row.slave_end); });
             if (a.cycle == 0 && (int)blockIdx.x == a.comps[comp].ch_begin) {  // the component's first chunk also sums the constant part of ||b||^2
                 const KPComp K = a.comps[comp];
@@ -125,7 +161,9 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
         const bool dx = d0 != 0, dy = d1 != 0;
         const double bx = S.beta[0], by = S.beta[1], ox = S.omega[0], oy = S.omega[1];
         auto pval = [&](int64_t k) {
-            const double2 rr = a.r[k], vv = a.v_old[k], pp = a.p_old[k];
+            double2 rr = a.r[k], vv = a.v_old[k];
+            const double2 pp = a.p_old[k];
+            if (COARSE && co) { rr = rr + e_at(er, k); vv = vv + e_at(ev, k); }
             return make_double2(dx ? 0.0 : rr.x + bx * (pp.x - ox * vv.x), dy ? 0.0 : rr.y + by * (pp.y - oy * vv.y));
         };
         auto put = [&](int64_t k, const KRow& o, int sb, int se) {
@@ -135,11 +173,20 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
             acc[0] += h.x * o.res.x; acc[1] += h.y * o.res.y;
         };
         if (is_tile) {
-            k_interior_march<MODE_APPLY, HAS_PQ>(t, a.blocks[t.block], pval, a.xc, a.pq, [&](int64_t k, double2 res, double2 c) { put(k, KRow{res, c}, 0, 0); });
+            k_interior_march<MODE_APPLY, HAS_PQ>(t, a.blocks[t.block], pval, a.xc, a.pq, [&](int64_t k, double2 res, double2 c) { put(k, KRow{res, c}, 0, 0); tsum = tsum + res; });
+            tile_contrib();
         } else {
             double u0, u1;
-            for_bnd([&](const SmoothedRow& row) { put(row.g0, k_smoothed<MODE_APPLY, HAS_PQ>(row, pval, a.xc, a.pq, u0, u1), row.slave_begin, row.slave_end); },
-                    [&](const JunctionRow& row) { put(row.self, k_junction<MODE_APPLY>(row, pval), row.slave_begin, row.slave_end); },
+            for_bnd([&](int sl, const SmoothedRow& row) {
+                        const KRow o = k_smoothed<MODE_APPLY, HAS_PQ>(row, pval, a.xc, a.pq, u0, u1);
+                        put(row.g0, o, row.slave_begin, row.slave_end);
+                        if (COARSE && co) a.contrib[sl] = o.res;
+                    },
+                    [&](int sl, const JunctionRow& row) {
+                        const KRow o = k_junction<MODE_APPLY>(row, pval);
+                        put(row.self, o, row.slave_begin, row.slave_end);
+                        if (COARSE && co) a.contrib[sl] = o.res;
+                    },
                     [&](const SlidingRow& row) { put(row.self, k_sliding<MODE_APPLY>(row, pval), row.slave_begin, row.slave_end); });
         }
     } else if (PHASE == KP_B) {
@@ -147,7 +194,8 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
         const bool mx = d0 != 0, my = d1 != 0;
         const double ax = S.alpha[0], ay = S.alpha[1];
         auto sval = [&](int64_t k) {
-            const double2 rr = a.r[k], vv = a.v_old[k];
+            double2 rr = a.r[k], vv = a.v_old[k];
+            if (COARSE && co) { rr = rr + e_at(er, k); vv = vv + e_at(ev, k); }
             return make_double2(mx ? 0.0 : rr.x - ax * vv.x, my ? 0.0 : rr.y - ay * vv.y);
         };
         auto put = [&](int64_t k, const KRow& o) {
@@ -155,28 +203,48 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
             double2 dd = a.d[k];
             if (!mx) dd.x += ax * pp.x;
             if (!my) dd.y += ay * pp.y;
-            a.s[k] = o.centre; a.t[k] = o.res; a.d[k] = dd;
-            acc[0] += o.centre.x * o.centre.x; acc[1] += o.centre.y * o.centre.y;
-            acc[2] += o.centre.x * o.res.x; acc[3] += o.centre.y * o.res.y;
+            double2 ss = o.centre;                                  // COARSE: the centre is s^; the residual s is kept
+            if (COARSE && co) {
+                const double2 rr = a.r[k], vv = a.v_old[k];
+                ss = make_double2(mx ? 0.0 : rr.x - ax * vv.x, my ? 0.0 : rr.y - ay * vv.y);
+            }
+            a.s[k] = ss; a.t[k] = o.res; a.d[k] = dd;
+            acc[0] += ss.x * ss.x; acc[1] += ss.y * ss.y;
+            acc[2] += ss.x * o.res.x; acc[3] += ss.y * o.res.y;
             acc[4] += o.res.x * o.res.x; acc[5] += o.res.y * o.res.y;
         };
         if (is_tile) {
-            k_interior_march<MODE_APPLY, HAS_PQ>(t, a.blocks[t.block], sval, a.xc, a.pq, [&](int64_t k, double2 res, double2 c) { put(k, KRow{res, c}); });
+            k_interior_march<MODE_APPLY, HAS_PQ>(t, a.blocks[t.block], sval, a.xc, a.pq, [&](int64_t k, double2 res, double2 c) { put(k, KRow{res, c}); tsum = tsum + res; });
+            tile_contrib();
         } else {
             double u0, u1;
-            for_bnd([&](const SmoothedRow& row) { put(row.g0, k_smoothed<MODE_APPLY, HAS_PQ>(row, sval, a.xc, a.pq, u0, u1)); },
-                    [&](const JunctionRow& row) { put(row.self, k_junction<MODE_APPLY>(row, sval)); },
+            for_bnd([&](int sl, const SmoothedRow& row) {
+                        const KRow o = k_smoothed<MODE_APPLY, HAS_PQ>(row, sval, a.xc, a.pq, u0, u1);
+                        put(row.g0, o);
+                        if (COARSE && co) a.contrib[sl] = o.res;
+                    },
+                    [&](int sl, const JunctionRow& row) {
+                        const KRow o = k_junction<MODE_APPLY>(row, sval);
+                        put(row.self, o);
+                        if (COARSE && co) a.contrib[sl] = o.res;
+                    },
                     [&](const SlidingRow& row) { put(row.self, k_sliding<MODE_APPLY>(row, sval)); });
         }
     } else if (PHASE == KP_C) {
         const bool ex = d0 != 0, ey = d1 != 0;
         const double ox = S.omega[0], oy = S.omega[1];
+        const double ax = S.alpha[0], ay = S.alpha[1];
         struct RD { double2 r, d, h; };
         auto load = [&](int64_t k) {
             const double2 ss = a.s[k], tt = a.t[k];
             RD o{a.r[k], a.d[k], a.rhat[k]};
-            if (!ex) { o.d.x += ox * ss.x; o.r.x = ss.x - ox * tt.x; }
-            if (!ey) { o.d.y += oy * ss.y; o.r.y = ss.y - oy * tt.y; }
+            double2 sh = ss;                                        // COARSE: d takes s^ = s + P e_s, e_s = e_r - alpha e_v
+            if (COARSE && co) {
+                const int J = __ldg(a.agg + k);
+                if (J >= 0) { const double2 e1 = ldg2(er + J), e2 = ldg2(ev + J); sh.x += e1.x - ax * e2.x; sh.y += e1.y - ay * e2.y; }
+            }
+            if (!ex) { o.d.x += ox * sh.x; o.r.x = ss.x - ox * tt.x; }
+            if (!ey) { o.d.y += oy * sh.y; o.r.y = ss.y - oy * tt.y; }
             return o;
         };
         auto store = [&](int64_t k, const RD& o) {
@@ -188,8 +256,8 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
         if (is_tile) {
             k_interior_nodes_march(t, a.blocks[t.block], load, store);
         } else {
-            for_bnd([&](const SmoothedRow& row) { upd(row.g0, row.slave_begin, row.slave_end); },
-                    [&](const JunctionRow& row) { upd(row.self, row.slave_begin, row.slave_end); },
+            for_bnd([&](int, const SmoothedRow& row) { upd(row.g0, row.slave_begin, row.slave_end); },
+                    [&](int, const JunctionRow& row) { upd(row.self, row.slave_begin, row.slave_end); },
                     [&](const SlidingRow& row) { upd(row.self, row.slave_begin, row.slave_end); });
         }
     } else {  // KP_ADD: x += d on the rows of the component; copies follow their root (x_copy = x_root + shift)
@@ -202,8 +270,8 @@ __global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a
         if (is_tile) {
             k_interior_nodes_march(t, a.blocks[t.block], load, [&](int64_t k, double2 xx) { a.xnew[k] = xx; });
         } else {
-            for_bnd([&](const SmoothedRow& row) { upd(row.g0, row.slave_begin, row.slave_end); },
-                    [&](const JunctionRow& row) { upd(row.self, row.slave_begin, row.slave_end); },
+            for_bnd([&](int, const SmoothedRow& row) { upd(row.g0, row.slave_begin, row.slave_end); },
+                    [&](int, const JunctionRow& row) { upd(row.self, row.slave_begin, row.slave_end); },
                     [&](const SlidingRow& row) { upd(row.self, row.slave_begin, row.slave_end); });
         }
         return;
@@ -307,6 +375,68 @@ __global__ void __launch_bounds__(128) krylov_finalize_kernel(const KPArgs a) {
             if (fabs(S.rho_new[c]) < eps) { S.done[c] = 2; continue; }
             S.beta[c] = (S.rho_new[c] / S.rho_old[c]) * (S.alpha[c] / S.omega[c]);
         }
+    }
+}
+
+// COARSE, after the finalisation of a phase: a CTA per component adds the contribution slots of every aggregate in the fixed order
+// of the host's lists (c = P^T x) and forms e = G c -- R0: e_r (and e_v = 0), A: e_v, B: e_t; after C: e_r -= alpha e_v + omega e_t.
+constexpr int KC_THREADS = 1024, KC_SPLIT = 4;   // the sum over the aggregates is split in KC_SPLIT parts of KC_THREADS / KC_SPLIT output rows each
+template <int PHASE>
+__global__ void __launch_bounds__(KC_THREADS) krylov_coarse_kernel(const KPArgs a) {
+    extern __shared__ double2 sh_c[];                               // c (nc_max), then the partial products (KC_SPLIT x nc_max)
+    const int comp = (int)blockIdx.x, tid = threadIdx.x;
+    const KState& S = a.state[comp];
+    if (S.final_) return;
+    const KCoarse C = a.coarse[comp];
+    const int nc = C.nc;
+    if (nc == 0 || !a.coarse_ok[comp]) return;
+    double2* const er = a.e_r + C.agg_base;
+    double2* const ev = a.e_v + C.agg_base;
+    double2* const et = a.e_t + C.agg_base;
+    if (PHASE == KP_C) {
+        const double ax = S.alpha[0], ay = S.alpha[1], ox = S.omega[0], oy = S.omega[1];
+        for (int J = tid; J < nc; J += KC_THREADS) {
+            const double2 r0 = er[J], v0 = ev[J], t0 = et[J];
+            er[J] = make_double2((r0.x - ax * v0.x) - ox * t0.x, (r0.y - ay * v0.y) - oy * t0.y);
+        }
+        return;
+    }
+    if (PHASE != KP_R0 && S.done[0] && S.done[1]) return;
+    for (int J = tid; J < nc; J += KC_THREADS) {
+        double2 sum = make_double2(0.0, 0.0);
+        const int qe = a.contrib_ptr[C.agg_base + J + 1];
+#pragma unroll 4
+        for (int q = a.contrib_ptr[C.agg_base + J]; q < qe; ++q) sum = sum + __ldcg(a.contrib + a.contrib_src[q]);
+        sh_c[J] = sum;
+    }
+    __syncthreads();
+    // e = G c with G stored transposed (coarse_assemble_kernel): thread (part, J') adds its quarter of the aggregates, coalesced over J'
+    double2* const part = sh_c + a.nc_max;
+    const double* GT = a.G + C.g_off;
+    constexpr int ROWS = KC_THREADS / KC_SPLIT;
+    const int g = tid / ROWS, l = tid - g * ROWS;
+    const int per = (nc + KC_SPLIT - 1) / KC_SPLIT, j0 = g * per, j1 = min(nc, j0 + per);
+    for (int base = 0; base < nc; base += ROWS) {
+        const int Jp = base + l;
+        if (Jp < nc) {
+            double sx = 0.0, sy = 0.0;
+#pragma unroll 8
+            for (int J = j0; J < j1; ++J) {
+                const double gv = __ldg(GT + (size_t)J * nc + Jp);
+                const double2 c = sh_c[J];
+                sx += gv * c.x; sy += gv * c.y;
+            }
+            part[(size_t)g * a.nc_max + Jp] = make_double2(sx, sy);
+        }
+    }
+    __syncthreads();
+    double2* const dst = PHASE == KP_R0 ? er : (PHASE == KP_A ? ev : et);
+    for (int Jp = tid; Jp < nc; Jp += KC_THREADS) {
+        double2 sum = part[Jp];
+#pragma unroll
+        for (int q = 1; q < KC_SPLIT; ++q) sum = sum + part[(size_t)q * a.nc_max + Jp];
+        dst[Jp] = sum;
+        if (PHASE == KP_R0) ev[Jp] = make_double2(0.0, 0.0);
     }
 }
 

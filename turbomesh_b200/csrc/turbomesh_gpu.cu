@@ -274,6 +274,14 @@ struct PhasedPlan {
     std::vector<KPComp> h_comps;
     std::vector<KState> h_state;
     int n_comp = 0, n_wtiles = 0, n_chunks = 0;
+    // two-level preconditioner (krylov_coarse.cuh); n_items == 0: not in use
+    DevBuf<KCoarse> coarse;
+    DevBuf<int32_t> coarse_ok, agg, contrib_ptr, contrib_src, mem_ptr, mem_code, agg_block;
+    DevBuf<CoarseItem> items;
+    DevBuf<double> G;
+    DevBuf<double2> contrib, e_r, e_v, e_t;
+    int64_t g_size = 0;
+    int n_items = 0, nc_max = 0, coarse_age = -1, coarse_every = 1, sslot0 = 0, jslot0 = 0;
     ~PhasedPlan() { if (h_count) cudaFreeHost(h_count); }
 };
 
@@ -1396,7 +1404,7 @@ int tm_mesh_begin_smoothing(tm_mesh* m, const tm_smooth_options* o) {
                 rp->mg_E.zero(s);
                 rp->aa_head = -1; rp->aa_count = 0; rp->aa_have_x = false;
             }
-        for (auto& rp : m->ranks) if (rp->kplan) rp->kplan->coarse_age = -1;   // the coarse operator is rebuilt from the new mesh
+        for (auto& rp : m->ranks) { if (rp->kplan) rp->kplan->coarse_age = -1; if (rp->pplan) rp->pplan->coarse_age = -1; }   // the coarse operator is rebuilt from the new mesh
         m->outer_done = 0;
         m->begun = true;
         CUDA_TRY(cudaStreamSynchronize(s));
