@@ -764,6 +764,10 @@ void krylov_solve_phased(tm_mesh* m, RankMesh& r, const tm_smooth_options* o, tm
             phased_launch<KP_C>(m, r, x);
         }
     };
+    // graphs (of two iterations) between two looks at the systems' states: a look costs a stream synchronisation, not looking
+    // costs iterations nobody needs; with the coarse space a solve is ~60 iterations, without ~150
+    int polls_every = P.n_items > 0 ? 2 : 4;
+    if (const char* e = std::getenv("TM_KRYLOV_POLL")) polls_every = std::max(1, std::atoi(e));
     cudaGraphExec_t exec = nullptr;
     uint64_t launches_per_graph = 0;
     if (m->use_graph) {
@@ -792,7 +796,7 @@ void krylov_solve_phased(tm_mesh* m, RankMesh& r, const tm_smooth_options* o, tm
             poll();
             if (P.h_count[1] == 0) break;                         // every component is final
             while (P.h_count[0] > 0) {
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < polls_every; ++k) {
                     if (exec) { CUDA_TRY(cudaGraphLaunch(exec, s)); g_launches.fetch_add(launches_per_graph, std::memory_order_relaxed); }
                     else two_iterations();
                 }
