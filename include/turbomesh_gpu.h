@@ -176,6 +176,11 @@ void tm_mesh_destroy(tm_mesh *mesh);
 
 int tm_mesh_upload_block(tm_mesh *mesh, size_t block, const double *xy);     /* host -> device  */
 int tm_mesh_download_block(tm_mesh *mesh, size_t block, double *xy);         /* device -> host  */
+/* The same copy-back (smooth.zig:139-153) without holding the mesh: the block is snapshot on the device and the snapshot goes
+ * to `xy` (pinned host memory, for the copy to overlap) on a stream of its own, so the next tm_mesh_tfi_block /
+ * tm_mesh_smooth may start while the result of this one is still on its way.  `xy` is valid after tm_mesh_download_wait. */
+int tm_mesh_download_block_async(tm_mesh *mesh, size_t block, double *xy);
+int tm_mesh_download_wait(tm_mesh *mesh);
 /* TFI of one block directly into the device mesh; edge arrays are HOST pointers (O(ni+nj) data) and stay
  * cached on the device, so tm_mesh_tfi_block_resident can re-run the TFI without any host traffic. */
 int tm_mesh_tfi_block(tm_mesh *mesh, size_t block,

@@ -230,3 +230,32 @@ def test_two_level_preconditioner_is_a_drop_in(gpu_lib, monkeypatch):
         assert err <= 1e-9 * chord_of(mesh), (coarse, err / chord_of(mesh))
         its[coarse] = st["inner_iterations"]
     assert its["1"] < 0.7 * its["0"], its
+
+
+def test_asynchronous_copy_back_survives_the_reuse_of_the_mesh(gpu_lib):
+    """tm_mesh_download_block_async snapshots the block on the device: what arrives after tm_mesh_download_wait is the mesh of
+    the moment of the call, although the handle has been overwritten (TFI again) and smoothed again in between."""
+    from turbomesh_b200 import smoothing, synthetic
+
+    spec = synthetic.cascade(2, 2, 65, 33)
+    sol = smoothing.CudaSolver(method="relax", sweeps_per_iteration=20, omega=0.9)
+    with smoothing.DeviceMesh(spec, upload=False) as dm:
+        def step(n):
+            for k, b in enumerate(spec.blocks):
+                dm.tfi_block(k, *b.edge_args())
+            dm.begin_smoothing(sol)
+            dm.smooth(n, sol)
+        step(1)
+        want = [dm.download_block(k) for k in range(len(spec.blocks))]
+        step(1)
+        got = [np.empty_like(w) for w in want]
+        for k in range(len(spec.blocks)):
+            dm.download_block_async(k, got[k])
+        step(3)                                    # the mesh moves on while the copies are in flight
+        for k in range(len(spec.blocks)):          # and a second round of copies into other buffers queues behind the first
+            dm.download_block_async(k, np.empty_like(want[k]))
+        dm.download_wait()
+        later = [dm.download_block(k) for k in range(len(spec.blocks))]
+    for g, w, l in zip(got, want, later):
+        assert np.array_equal(g, w)
+        assert not np.array_equal(l, w)

@@ -156,6 +156,8 @@ def load():
     L.tm_mesh_destroy.restype = None
     L.tm_mesh_upload_block.argtypes = [vp, C.c_size_t, dp]
     L.tm_mesh_download_block.argtypes = [vp, C.c_size_t, dp]
+    L.tm_mesh_download_block_async.argtypes = [vp, C.c_size_t, dp]
+    L.tm_mesh_download_wait.argtypes = [vp]
     L.tm_mesh_tfi_block.argtypes = [vp, C.c_size_t] + [dp] * 8
     L.tm_mesh_tfi_block_resident.argtypes = [vp, C.c_size_t]
     L.tm_mesh_set_white_groups.argtypes = [vp, C.POINTER(C.c_uint64), C.c_size_t]

@@ -298,4 +298,10 @@ __global__ void __launch_bounds__(256) viewer_wireframe_kernel(const ViewerBlock
     }
 }
 
+// tm_mesh_download_block_async: device memory -> page-locked host memory mapped into the device's address space (16-byte stores
+// over the host link; a grid-stride loop of a few CTAs is enough to fill it)
+__global__ void __launch_bounds__(256) host_store_kernel(double2* __restrict__ dst, const double2* __restrict__ src, int64_t n) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) dst[k] = __ldcs(src + k);
+}
+
 }  // namespace tmesh

@@ -309,6 +309,8 @@ struct RankMesh {
     DevBuf<SolveCtl> d_ctl;
     DevBuf<double2> kr, krhat, kp, kv, ks, kt, kd, kp2, kv2;
     bool krylov_ready = false;
+    DevBuf<double2> snapshot;                // tm_mesh_download_block_async
+    std::vector<cudaEvent_t> snap_copied;    // per block (global index): its snapshot has reached the host
     std::unique_ptr<KrylovPlan> kplan;       // single-rank meshes: built on the first Picard solve
     std::unique_ptr<PhasedPlan> pplan;
     std::vector<EdgeCache> edges;        // indexed by position in L.own_blocks
@@ -353,6 +355,7 @@ struct RankMesh {
     } p2p;
     ~RankMesh() {
         for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
+        for (cudaEvent_t e : snap_copied) if (e) cudaEventDestroy(e);
     }
     RankMesh() = default;
     DevBuf<RestrictRow> d_rrows;             // boundary rows of the next coarser level <- residuals of this level
@@ -406,6 +409,9 @@ struct tm_mesh {
     uint64_t outer_done = 0;  // outer iterations since begin_smoothing (the `n` of system.fill(n), smooth.zig:1107-1110)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t comm_stream = nullptr;          // the halo exchange of a sweep runs here, next to the bulk of the interior
+    cudaStream_t copy_stream = nullptr;          // tm_mesh_download_block_async: snapshots go to the host here while the mesh is used again
+    cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    bool copies_pending = false;
     cudaEvent_t ev_rim = nullptr, ev_x = nullptr;
     bool use_graph = true;                       // TM_GRAPH=0: launch the BiCGStab iteration kernel by kernel
     bool overlap = true;                         // TM_OVERLAP=0: exchange on the main stream after the whole sweep
@@ -430,6 +436,9 @@ struct tm_mesh {
         if (ev_rim) cudaEventDestroy(ev_rim);
         if (ev_x) cudaEventDestroy(ev_x);
         if (comm_stream) cudaStreamDestroy(comm_stream);
+        if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+        if (ev_snap) cudaEventDestroy(ev_snap);
+        if (ev_copied) cudaEventDestroy(ev_copied);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (own_stream && stream) cudaStreamDestroy(stream);
@@ -1055,6 +1064,13 @@ void create_common(tm_mesh* m, const tm_block* blocks, size_t n_blocks, const tm
         CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUDA_TRY(cudaStreamCreateWithPriority(&m->comm_stream, cudaStreamNonBlocking, hi));
     }
+    {
+        int lo = 0, hi = 0;  // highest priority: its few CTAs must not queue behind the waves of a sweep
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&m->copy_stream, cudaStreamNonBlocking, hi));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_snap, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&m->ev_copied, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_rim, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming));
     if (const char* e = std::getenv("TM_OVERLAP")) m->overlap = std::atoi(e) != 0;
@@ -1258,6 +1274,51 @@ int tm_mesh_download_block(tm_mesh* m, size_t block, double* xy) {
         const auto& B = m->topo.blocks[block];
         CUDA_TRY(cudaMemcpyAsync(xy, r.X[r.cur].p + r.L.loff[block], size_t(B.ni * B.nj) * sizeof(double2), cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
+    });
+}
+
+// Asynchronous read-back: the block is snapshot on the device (a device-to-device copy on the mesh's stream, ~0.1 ms per
+// GB) and the snapshot goes to the host on a stream of its own, so the mesh can be overwritten -- the next TFI, the next
+// smoothing call -- while the previous result is still on its way.  The blocks of one step are snapshot into one buffer.
+int tm_mesh_download_block_async(tm_mesh* m, size_t block, double* xy) {
+    return guarded([&] {
+        RankMesh& r = owner_of_block(m, block);
+        if (!xy) TM_THROW(TM_ERR_INVALID_ARGUMENT, "xy is NULL");
+        CUDA_TRY(cudaSetDevice(m->device));
+        const auto& B = m->topo.blocks[block];
+        if (r.snapshot.n != size_t(r.N)) r.snapshot.alloc(size_t(r.N));
+        const size_t off = size_t(r.L.loff[block]), bytes = size_t(B.ni * B.nj) * sizeof(double2);
+        if (r.snap_copied.size() != m->topo.blocks.size()) r.snap_copied.assign(m->topo.blocks.size(), nullptr);
+        cudaEvent_t& done = r.snap_copied[block];
+        // this block's part of the snapshot may still be read by the copy an earlier call started (other blocks' copies do not matter)
+        if (done) CUDA_TRY(cudaStreamWaitEvent(m->stream, done, 0));
+        else CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        CUDA_TRY(cudaMemcpyAsync(r.snapshot.p + off, r.X[r.cur].p + off, bytes, cudaMemcpyDeviceToDevice, m->stream));
+        CUDA_TRY(cudaEventRecord(m->ev_snap, m->stream));
+        CUDA_TRY(cudaStreamWaitEvent(m->copy_stream, m->ev_snap, 0));
+        // Page-locked destination: a few CTAs store the snapshot straight into the host memory (it is mapped into the device's
+        // address space), not the copy engine -- the mesh's own small read-backs (statistics, checks) use the device-to-host
+        // engine in submission order and would wait for the whole block behind a DMA copy of it.
+        cudaPointerAttributes attr{};
+        void* mapped = nullptr;
+        if (cudaPointerGetAttributes(&attr, xy) == cudaSuccess && attr.type == cudaMemoryTypeHost && cudaHostGetDevicePointer(&mapped, xy, 0) == cudaSuccess && mapped &&
+            (reinterpret_cast<uintptr_t>(mapped) & 15) == 0) {
+            static const int store_ctas = [] { const char* e = std::getenv("TM_HOST_STORE_CTAS"); return e ? std::max(1, std::atoi(e)) : 16; }();
+            LAUNCH(host_store_kernel, unsigned(store_ctas), 256, m->copy_stream, reinterpret_cast<double2*>(mapped), (const double2*)(r.snapshot.p + off), int64_t(B.ni * B.nj));
+        } else {
+            (void)cudaGetLastError();
+            CUDA_TRY(cudaMemcpyAsync(xy, r.snapshot.p + off, bytes, cudaMemcpyDeviceToHost, m->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(done, m->copy_stream));
+        m->copies_pending = true;
+    });
+}
+int tm_mesh_download_wait(tm_mesh* m) {
+    return guarded([&] {
+        if (!m) TM_THROW(TM_ERR_INVALID_ARGUMENT, "mesh is NULL");
+        CUDA_TRY(cudaSetDevice(m->device));
+        CUDA_TRY(cudaStreamSynchronize(m->copy_stream));
+        m->copies_pending = false;
     });
 }
 

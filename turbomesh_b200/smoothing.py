@@ -249,6 +249,14 @@ class DeviceMesh:
         check(self._L.tm_mesh_download_block(self._h, block, _dp(out)))
         return out
 
+    def download_block_async(self, block: int, out: np.ndarray) -> None:
+        """Starts the copy-back of a block into ``out`` (pinned host memory) and returns; the mesh may be reused at once
+        (``tm_mesh_download_block_async``).  ``out`` is valid after :meth:`download_wait`."""
+        check(self._L.tm_mesh_download_block_async(self._h, block, _dp(out)))
+
+    def download_wait(self) -> None:
+        check(self._L.tm_mesh_download_wait(self._h))
+
     def download(self):
         """Copies all blocks held by this process back into ``self.mesh`` (in place, like smooth.zig:139-153)."""
         for k, b in enumerate(self.mesh.blocks):

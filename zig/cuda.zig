@@ -61,6 +61,8 @@ pub extern fn tm_mesh_destroy(mesh: ?*tm_mesh) callconv(.c) void;
 pub extern fn tm_mesh_begin_smoothing(mesh: *tm_mesh, opts: *const tm_smooth_options) callconv(.c) c_int;
 pub extern fn tm_mesh_smooth(mesh: *tm_mesh, opts: *const tm_smooth_options, stats: ?*tm_smooth_stats) callconv(.c) c_int;
 pub extern fn tm_mesh_download_block(mesh: *tm_mesh, block: usize, xy: [*]f64) callconv(.c) c_int;
+pub extern fn tm_mesh_download_block_async(mesh: *tm_mesh, block: usize, xy: [*]f64) callconv(.c) c_int;
+pub extern fn tm_mesh_download_wait(mesh: *tm_mesh) callconv(.c) c_int;
 /// cgns.zig:69-101 / 110-161 on the device: x[j*ni + i], y[j*ni + i] (field 0 = coordinates, 1 = control function P,Q)
 pub extern fn tm_mesh_download_block_soa(mesh: *tm_mesh, block: usize, field: c_int, x: [*]f64, y: [*]f64) callconv(.c) c_int;
 pub extern fn tm_release_cached_memory() callconv(.c) void;
