@@ -248,7 +248,10 @@ def test_asynchronous_copy_back_survives_the_reuse_of_the_mesh(gpu_lib):
         step(1)
         want = [dm.download_block(k) for k in range(len(spec.blocks))]
         step(1)
-        got = [np.empty_like(w) for w in want]
+        import torch
+        pinned = [torch.empty(w.shape, dtype=torch.float64, pin_memory=True) for w in want]
+        # page-locked buffers take the store-by-CTAs path, the last block a pageable buffer (copy engine)
+        got = [t.numpy() for t in pinned[:-1]] + [np.empty_like(want[-1])]
         for k in range(len(spec.blocks)):
             dm.download_block_async(k, got[k])
         step(3)                                    # the mesh moves on while the copies are in flight
