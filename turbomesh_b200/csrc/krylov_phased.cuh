@@ -15,6 +15,9 @@ namespace tmesh {
 
 constexpr int KP_THREADS = 128;              // 4 warp tiles per CTA
 constexpr int KP_WARPS = KP_THREADS / 32;
+#ifndef KP_MIN_CTAS
+#define KP_MIN_CTAS 4
+#endif
 
 struct BChunk { int32_t comp, s_begin, s_end, j_begin, j_end, l_begin, l_end, _pad; };   // <= KP_THREADS boundary rows of ONE component
 
@@ -64,7 +67,7 @@ enum KPhase : int { KP_R0 = 0, KP_A = 1, KP_B = 2, KP_C = 3, KP_ADD = 4 };
 // TILES = true: the interior warp tiles (grid = ceil(n_wtiles / 4)); false: the boundary chunks (grid = n_chunks).  Two kernels
 // rather than one so that the register count of the tile path (the bandwidth path) is not set by the gather-heavy row path.
 template <int PHASE, bool HAS_PQ, bool TILES, bool COARSE>
-__global__ void __launch_bounds__(KP_THREADS) krylov_phase_kernel(const KPArgs a) {
+__global__ void __launch_bounds__(KP_THREADS, KP_MIN_CTAS) krylov_phase_kernel(const KPArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_tile_ctas = TILES ? 0x7fffffff : 0;
     const bool is_tile = TILES;
