@@ -580,11 +580,22 @@ def gpu_cuts(args, torch, local, n_cuts, repeats=2):
         if best is None or sec < best[0]:
             best = (sec, st)
     sec, st = best
+    # the caller in front of the path on the device as well: O4H blocking of the same number of cuts (T106 cell counts) from the
+    # blade points -- spline fit, edge discretisation, normal offset, combination in six launches (turbomesh_b200/blocking.py)
+    from turbomesh_b200.blocking import Cells, Cut, O4HBatch
+    from turbomesh_b200.clustering import Roberts
+    cells = Cells(o_grid=40, middle_i=100, in_up_j=30, in_down_j=10, in_i=10, out_up_j=40, out_down_j=10, out_i=10, down_j=40, bulge=40, upstream_i=20, downstream_i=10)
+    cuts = [Cut(z["b0_x_i_min"] * sc, z["b1_x_i_min"] * sc, float(meta["pitch"]) * sc) for sc in scales]
+    O4HBatch(cells, Roberts(0.5, 1.03), device=local).run(cuts[:2])
+    t0 = time.perf_counter()
+    blocked, _ = O4HBatch(cells, Roberts(0.5, 1.03), device=local).run(cuts)
+    t_blocking = time.perf_counter() - t0
+    assert len(blocked.blocks) == len(batch.blocks)
     worst = max(max(dm.component_stats(c)["norm_r"][xy] / dm.component_stats(c)["tolerance"][xy] for xy in range(2)) for c in range(0, n_cuts, max(1, n_cuts // 16)))
     dm.close()
     peak = measured_peak()[0]
     rate = st["nodes"] * st["operator_applications"] / st["gpu_seconds"]
-    return {"cuts": n_cuts, "nodes": st["nodes"], "seconds": sec, "solver_seconds": st["gpu_seconds"], "create_seconds": t_create, "cuts_per_second": n_cuts / sec,
+    return {"cuts": n_cuts, "nodes": st["nodes"], "seconds": sec, "solver_seconds": st["gpu_seconds"], "create_seconds": t_create, "blocking_seconds": t_blocking, "cuts_per_second": n_cuts / sec,
             "krylov_iterations": st["inner_iterations"], "operator_applications": st["operator_applications"], "converged": st["converged"],
             "worst_sampled_residual_over_own_tolerance": worst, "node_updates_per_s": rate, "roofline_frac_48B": rate * BYTES_PER_NODE_UPDATE_PQ / 1e9 / peak,
             "solver": "matrix-free BiCGStab on the row-scaled systems, one launch per phase over all cuts, two-level preconditioner (aggregates of 16 x 8 nodes, "

@@ -258,3 +258,70 @@ def test_spline_fit_on_the_device(gpu_lib):
     assert np.array_equal(e_dev.points, e_host.points)
     with pytest.raises(Exception):
         FittedSpline.fit_batch([np.array([(0.0, 0.0), (1.0, 1.0), (1.0, 1.0), (2.0, 0.0)])])     # CoincidentParameters
+
+
+def _host_blocking(counts, blade_clustering, up, down, pitch):
+    """the sequential host restatement of O4H.run (the checker): the eight blocks' edge arrays + the topology"""
+    from inputgen.geometry import Geometry, Profile
+    from inputgen.templates import O4H, NumCells
+
+    calls = []
+
+    def record(*args):
+        calls.append([np.array(a, dtype=np.float64, copy=True) for a in args])
+        return np.zeros((len(args[4]), 1, 2))
+
+    one = O4H(blade_clustering=blade_clustering, num_cells=NumCells(**counts)).run(Geometry(pitch, Profile(down, up)), tfi=record)
+    return calls, one
+
+
+@pytest.mark.parametrize("blade", ["uniform", "roberts"])
+def test_o4h_blocking_of_a_batch_of_cuts_on_the_device(gpu_lib, blade):
+    """blocking.O4HBatch (spline fit, edge discretisation, normal offset, combination -- six launches for any number of cuts)
+    against the sequential host restatement of O4H.run, cut by cut: every edge of every block bit for bit where the
+    clusterings are uniform, to a few ulp where CUDA's pow / tanh enter (Roberts blade clustering, the O-grid's j edges);
+    identical connections and conditions; and the batch runs through TFI + smoothing (connectionDataCheck accepts it)."""
+    from turbomesh_b200 import smoothing
+    from turbomesh_b200.blocking import Cells, Cut, O4HBatch
+    from turbomesh_b200.clustering import Roberts, Uniform
+
+    spec, z, meta = load_fixture("t106_white")
+    up0, down0, pitch0 = z["b0_x_i_min"], z["b1_x_i_min"], float(meta["pitch"])
+    counts = dict(o_grid=8, middle_i=20, in_up_j=6, in_down_j=7, in_i=5, out_up_j=8, out_down_j=6, out_i=5, down_j=6, bulge=6, upstream_i=5, downstream_i=6)   # >= 6 nodes per connection (smooth.zig:631)
+    cl = Uniform() if blade == "uniform" else Roberts(0.5, 1.03)
+    scales = [1.0, 1.2, 0.6]
+    cuts = [Cut(up0 * s, down0 * s, pitch0 * s) for s in scales]
+    mesh, groups = O4HBatch(Cells(**counts), cl).run(cuts)
+    assert len(mesh.blocks) == 8 * len(scales) and groups == [(0, 1), (8, 9), (16, 17)]
+    n_conn = 0
+    for k, s in enumerate(scales):
+        calls, one = _host_blocking(counts, cl, up0 * s, down0 * s, pitch0 * s)
+        for b in range(8):
+            got = mesh.blocks[8 * k + b].edge_args()
+            for q, (g, w) in enumerate(zip(got, calls[b])):
+                assert g.shape == w.shape
+                exact = blade == "uniform" and not (b < 2 and q in (2, 3, 6, 7))       # the O-grid's j edges carry the tanh clustering
+                if exact:
+                    assert np.array_equal(g, w), (k, b, q)
+                else:
+                    assert np.abs(g - w).max() <= 1e-13 * max(1.0, np.abs(w).max()), (k, b, q, np.abs(g - w).max())
+        for c_dev, c_host in zip(mesh.connections[n_conn:n_conn + len(one.connections)], one.connections):
+            for r_dev, r_host in zip(c_dev.ranges, c_host.ranges):
+                assert (r_dev.block - 8 * k, r_dev.side, r_dev.start, r_dev.end) == (r_host.block, r_host.side, r_host.start, r_host.end)
+            assert c_dev.periodicity == c_host.periodicity
+        n_conn += len(one.connections)
+        for bc_dev, bc_host in zip(mesh.boundary_conditions[2 * k:2 * k + 2], one.boundary_conditions):
+            assert (bc_dev.range.block - 8 * k, bc_dev.range.side, bc_dev.range.start, bc_dev.range.end, bc_dev.kind) == \
+                   (bc_host.range.block, bc_host.range.side, bc_host.range.start, bc_host.range.end, bc_host.kind)
+    assert n_conn == len(mesh.connections)
+    with smoothing.DeviceMesh(mesh, upload=False) as dm:
+        for k, b in enumerate(mesh.blocks):
+            dm.tfi_block(k, *b.edge_args())
+        dm.set_white_groups(groups)
+        assert dm.component_count == len(scales)
+        sol = smoothing.CudaSolver()
+        cf = smoothing.White(meta["ds_target"], meta["theta_target"])
+        dm.begin_smoothing(sol, cf)
+        st = dm.smooth(2, sol, cf)
+        assert st["converged"] == 1
+        assert all(np.isfinite(dm.download_block(k)).all() for k in range(len(mesh.blocks)))

@@ -354,3 +354,32 @@ def test_spline_t106a_surface_length_known_answer():
     pts = z["points_over_chord"] * float(z["chord"])
     polyline = float(np.sqrt((np.diff(pts, axis=0) ** 2).sum(axis=1)).sum())
     assert 0.99 * polyline < spline.integrate() < polyline
+
+
+def test_o4h_template_tables_match_the_sequential_restatement():
+    """blocking.py keeps the O4H template as data (edge lengths, views of the combined edges, connections, conditions in terms
+    of the cell counts); the sequential host restatement of O4H.run (tests/inputgen/templates.py) builds the same topology
+    edge by edge -- both must agree for any cell counts."""
+    from inputgen.geometry import Geometry, Profile
+    from inputgen.templates import O4H, NumCells
+    from turbomesh_b200.blocking import BLOCKS, Cells, _BLOCK_EDGES, _lengths, connections
+    from turbomesh_b200.clustering import Uniform
+    from util import load_fixture
+
+    spec, z, meta = load_fixture("t106_white")
+    up, down, pitch = z["b0_x_i_min"], z["b1_x_i_min"], float(meta["pitch"])
+    for counts in (dict(o_grid=8, middle_i=20, in_up_j=6, in_down_j=4, in_i=5, out_up_j=8, out_down_j=4, out_i=5, down_j=6, bulge=6, upstream_i=4, downstream_i=3),
+                   dict(o_grid=5, middle_i=9, in_up_j=3, in_down_j=7, in_i=4, out_up_j=5, out_down_j=6, out_i=3, down_j=8, bulge=4, upstream_i=6, downstream_i=7)):
+        sizes = []
+        one = O4H(blade_clustering=Uniform(), num_cells=NumCells(**counts)).run(
+            Geometry(pitch, Profile(down, up)), tfi=lambda *a: sizes.append((len(a[4]), len(a[6]))) or np.zeros((len(a[4]), len(a[6]), 2)))
+        n = _lengths(Cells(**counts))
+        assert list(one.names) == list(BLOCKS)
+        assert sizes == [(n[_BLOCK_EDGES[b][0]], n[_BLOCK_EDGES[b][2]]) for b in BLOCKS]
+        conns, conds = connections(Cells(**counts), pitch)
+        assert len(conns) == len(one.connections) == 21
+        for a, b in zip(conns, one.connections):
+            assert [(r.block, r.side, r.start, r.end) for r in a.ranges] == [(r.block, r.side, r.start, r.end) for r in b.ranges]
+            assert a.periodicity == b.periodicity
+        assert [(c.range.block, c.range.side, c.range.start, c.range.end, c.kind) for c in conds] == \
+               [(c.range.block, c.range.side, c.range.start, c.range.end, c.kind) for c in one.boundary_conditions]
