@@ -14,7 +14,7 @@ in six device launches whatever its size:
 
 The result is a mesh of ``EdgeBlock``s (8 per cut, the cuts concatenated, no connection between cuts) for
 ``tm_mesh_tfi_block`` + ``tm_mesh_smooth``, and the White groups.  Every edge is bit-identical to what the sequential host
-restatement (``tests/inputgen/templates.py``, the checker) produces: the kernels reproduce the reference's operation
+restatement of ``O4H.run`` kept with the tests (the checker) produces: the kernels reproduce the reference's operation
 order and the few host operations here (corner points from the leading / trailing edge, pitch and distances) are written
 exactly as ``O4H.zig`` writes them.
 """
