@@ -71,7 +71,7 @@ class TmEdgeJob(C.Structure):
     _fields_ = [("n", C.c_uint64), ("curve_kind", C.c_uint32), ("clustering_kind", C.c_uint32),
                 ("line_start", C.c_double * 2), ("line_end", C.c_double * 2), ("spline", C.POINTER(TmSpline)),
                 ("alpha", C.c_double), ("beta", C.c_double), ("delta_s", C.c_double),
-                ("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double))]
+                ("points", C.c_void_p), ("clustering", C.c_void_p)]   # double*: plain addresses, set from numpy without a cast per job
 
 
 class TmComponentStats(C.Structure):
@@ -91,15 +91,15 @@ class TmSplineFitJob(C.Structure):
 
 
 class TmEdgeView(C.Structure):
-    _fields_ = [("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double)), ("n", C.c_uint64), ("start", C.c_uint64), ("end", C.c_uint64)]
+    _fields_ = [("points", C.c_void_p), ("clustering", C.c_void_p), ("n", C.c_uint64), ("start", C.c_uint64), ("end", C.c_uint64)]
 
 
 class TmCombineJob(C.Structure):
-    _fields_ = [("views", C.POINTER(TmEdgeView)), ("n_views", C.c_uint64), ("points", C.POINTER(C.c_double)), ("clustering", C.POINTER(C.c_double))]
+    _fields_ = [("views", C.c_void_p), ("n_views", C.c_uint64), ("points", C.c_void_p), ("clustering", C.c_void_p)]
 
 
 class TmProjectJob(C.Structure):
-    _fields_ = [("points", C.POINTER(C.c_double)), ("n", C.c_uint64), ("distance", C.c_double), ("out", C.POINTER(C.c_double))]
+    _fields_ = [("points", C.c_void_p), ("n", C.c_uint64), ("distance", C.c_double), ("out", C.c_void_p)]
 
 
 class TurbomeshGpuError(RuntimeError):

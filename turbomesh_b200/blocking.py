@@ -21,6 +21,7 @@ exactly as ``O4H.zig`` writes them.
 from __future__ import annotations
 
 from dataclasses import dataclass
+from functools import lru_cache
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -33,7 +34,7 @@ from .synthetic import EdgeBlock
 BLOCKS = ("blade_up", "blade_down", "in", "out", "down", "up", "upstream", "downstream")   # block order of O4H.zig:115-420
 
 
-@dataclass
+@dataclass(frozen=True)
 class Cells:
     """Cell counts of the template, ``O4H.zig:46-65``."""
 
@@ -64,6 +65,7 @@ class _Line:
         self.start, self.end = (float(start[0]), float(start[1])), (float(end[0]), float(end[1]))
 
 
+@lru_cache(maxsize=None)
 def _views(c: Cells) -> Dict[str, List[Tuple[str, int, int]]]:
     """The combined edges as lists of (edge, first index, last index) -- ``EdgeView``s, O4H.zig:168-420."""
     nu, nd = c.up, c.down
@@ -81,6 +83,7 @@ def _views(c: Cells) -> Dict[str, List[Tuple[str, int, int]]]:
     }
 
 
+@lru_cache(maxsize=None)
 def _lengths(c: Cells) -> Dict[str, int]:
     """Number of points of every edge, from the cell counts alone."""
     v = _views(c)

@@ -60,6 +60,21 @@ int set_error(int code, const std::string& msg) {
         CUDA_TRY(cudaGetLastError());                                \
     } while (0)
 
+// Device -> host of per-job slices: consecutive jobs whose host slices are adjacent (a caller that keeps the edges of a batch in
+// one buffer) travel in ONE copy instead of one each -- thousands of small copies into pageable memory cost ~15 us apiece.
+template <class T, class Host, class Off, class Cnt>
+void copy_out_runs(size_t n_jobs, const T* dev, Host host, Off off, Cnt cnt, cudaStream_t s) {
+    size_t k = 0;
+    while (k < n_jobs) {
+        T* const h0 = host(k);
+        const int64_t o0 = off(k);
+        size_t n = cnt(k), e = k + 1;
+        while (e < n_jobs && host(e) == h0 + n && off(e) == o0 + int64_t(n)) { n += cnt(e); ++e; }
+        CUDA_TRY(cudaMemcpyAsync(h0, dev + o0, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+        k = e;
+    }
+}
+
 void require_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -1812,10 +1827,10 @@ int tm_edges_discretize(const tm_edge_job* jobs, size_t n_jobs, int device) {
             d_pts.alloc(size_t(total));
             d_cl.alloc(size_t(total));
             LAUNCH(edge_discretize_kernel, unsigned(n_jobs), 128, s, (const EdgeJob*)d_jobs.p, (const double*)d_tables.p, d_pts.p, d_cl.p);
-            for (size_t k = 0; k < n_jobs; ++k) {
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].points, d_pts.p + dev_jobs[k].out_off, size_t(jobs[k].n) * sizeof(double2), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].clustering, d_cl.p + dev_jobs[k].out_off, size_t(jobs[k].n) * sizeof(double), cudaMemcpyDeviceToHost, s));
-            }
+            copy_out_runs(n_jobs, (const double2*)d_pts.p, [&](size_t k) { return reinterpret_cast<double2*>(jobs[k].points); },
+                          [&](size_t k) { return dev_jobs[k].out_off; }, [&](size_t k) { return size_t(jobs[k].n); }, s);
+            copy_out_runs(n_jobs, (const double*)d_cl.p, [&](size_t k) { return jobs[k].clustering; }, [&](size_t k) { return dev_jobs[k].out_off; },
+                          [&](size_t k) { return size_t(jobs[k].n); }, s);
             CUDA_TRY(cudaStreamSynchronize(s));
         } catch (...) {
             cudaStreamDestroy(s);
@@ -1858,14 +1873,14 @@ int tm_splines_fit(const tm_spline_fit_job* jobs, size_t n_jobs, int device) {
                    d_samples.p, d_len.p, d_err.p);
             int err = 0;
             CUDA_TRY(cudaMemcpyAsync(&err, d_err.p, sizeof err, cudaMemcpyDeviceToHost, s));
-            for (size_t k = 0; k < n_jobs; ++k) {
-                const size_t n = size_t(dj[k].n);
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].params, d_params.p + dj[k].pt_off, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].second_derivs_x, d_zx.p + dj[k].pt_off, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].second_derivs_y, d_zy.p + dj[k].pt_off, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].sample_arc, d_arc.p + dj[k].arc_off, size_t(dj[k].n_samples) * sizeof(double), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].total_length, d_len.p + k, sizeof(double), cudaMemcpyDeviceToHost, s));
-            }
+            auto n_of = [&](size_t k) { return size_t(dj[k].n); };
+            auto pt_off = [&](size_t k) { return dj[k].pt_off; };
+            copy_out_runs(n_jobs, (const double*)d_params.p, [&](size_t k) { return jobs[k].params; }, pt_off, n_of, s);
+            copy_out_runs(n_jobs, (const double*)d_zx.p, [&](size_t k) { return jobs[k].second_derivs_x; }, pt_off, n_of, s);
+            copy_out_runs(n_jobs, (const double*)d_zy.p, [&](size_t k) { return jobs[k].second_derivs_y; }, pt_off, n_of, s);
+            copy_out_runs(n_jobs, (const double*)d_arc.p, [&](size_t k) { return jobs[k].sample_arc; }, [&](size_t k) { return dj[k].arc_off; },
+                          [&](size_t k) { return size_t(dj[k].n_samples); }, s);
+            copy_out_runs(n_jobs, (const double*)d_len.p, [&](size_t k) { return jobs[k].total_length; }, [&](size_t k) { return int64_t(k); }, [&](size_t) { return size_t(1); }, s);
             CUDA_TRY(cudaStreamSynchronize(s));
             if (err) TM_THROW(TM_ERR_INVALID_ARGUMENT, "spline fit: coincident consecutive points (CoincidentParameters, spline.zig:176-178)");
         } catch (...) {
@@ -1927,10 +1942,10 @@ int tm_edges_combine(const tm_combine_job* jobs, size_t n_jobs, int device) {
             d_pts.alloc(size_t(total)); d_cl.alloc(size_t(total));
             LAUNCH(edge_combine_kernel, unsigned(n_jobs), 128, s, (const CombineJob*)d_jobs.p, (const CombineView*)d_views.p, (const double2*)d_src_pts.p,
                    (const double*)d_src_cl.p, d_pts.p, d_cl.p);
-            for (size_t k = 0; k < n_jobs; ++k) {
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].points, d_pts.p + dj[k].out_off, size_t(dj[k].n) * sizeof(double2), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].clustering, d_cl.p + dj[k].out_off, size_t(dj[k].n) * sizeof(double), cudaMemcpyDeviceToHost, s));
-            }
+            copy_out_runs(n_jobs, (const double2*)d_pts.p, [&](size_t k) { return reinterpret_cast<double2*>(jobs[k].points); }, [&](size_t k) { return dj[k].out_off; },
+                          [&](size_t k) { return size_t(dj[k].n); }, s);
+            copy_out_runs(n_jobs, (const double*)d_cl.p, [&](size_t k) { return jobs[k].clustering; }, [&](size_t k) { return dj[k].out_off; },
+                          [&](size_t k) { return size_t(dj[k].n); }, s);
             CUDA_TRY(cudaStreamSynchronize(s));
         } catch (...) {
             cudaStreamDestroy(s);
@@ -1964,8 +1979,8 @@ int tm_edges_project_normal(const tm_project_job* jobs, size_t n_jobs, int devic
             d_jobs.upload(dj, s); d_in.upload(in, s);
             d_out.alloc(size_t(total));
             LAUNCH(project_normal_kernel, unsigned(n_jobs), 128, s, (const ProjectJob*)d_jobs.p, (const double2*)d_in.p, d_out.p);
-            for (size_t k = 0; k < n_jobs; ++k)
-                CUDA_TRY(cudaMemcpyAsync(jobs[k].out, d_out.p + dj[k].off, size_t(dj[k].n) * sizeof(double2), cudaMemcpyDeviceToHost, s));
+            copy_out_runs(n_jobs, (const double2*)d_out.p, [&](size_t k) { return reinterpret_cast<double2*>(jobs[k].out); }, [&](size_t k) { return dj[k].off; },
+                          [&](size_t k) { return size_t(dj[k].n); }, s);
             CUDA_TRY(cudaStreamSynchronize(s));
         } catch (...) {
             cudaStreamDestroy(s);

@@ -16,6 +16,11 @@ from . import clustering as cluster
 from .boundary import Condition, Connection
 
 
+def _addr(a: np.ndarray) -> int:
+    """address of the first element of a contiguous array (cheaper than ``a.ctypes`` when there are thousands of them)"""
+    return a.__array_interface__["data"][0]
+
+
 class Edge:
     """``discrete.zig:12-91``: points (n,2) + clustering (n,) of one block edge."""
 
@@ -44,13 +49,18 @@ class Edge:
         from . import _lib
 
         jobs = (_lib.TmEdgeJob * max(len(specs), 1))()
-        keep, splines, out = [], {}, []
+        total = sum(int(n) for n, _, _ in specs)
+        pts_all, cl_all = np.empty((total, 2), dtype=np.float64), np.empty(total, dtype=np.float64)   # one buffer for the batch, an edge = a slice
+        p0, c0 = _addr(pts_all), _addr(cl_all)
+        keep, splines, off = [], {}, 0
+        bounds = []
         for k, (n, curve, clustering) in enumerate(specs):
             j = jobs[k]
-            j.n = int(n)
-            pts, cl = np.empty((n, 2), dtype=np.float64), np.empty(n, dtype=np.float64)
-            out.append((pts, cl))
-            j.points, j.clustering = pts.ctypes.data_as(C.POINTER(C.c_double)), cl.ctypes.data_as(C.POINTER(C.c_double))
+            n = int(n)
+            j.n = n
+            j.points, j.clustering = p0 + 16 * off, c0 + 8 * off
+            bounds.append((off, off + n))
+            off += n
             if isinstance(clustering, cluster.Uniform):
                 j.clustering_kind = 0
             elif isinstance(clustering, cluster.Roberts):
@@ -75,7 +85,7 @@ class Edge:
             else:
                 raise TypeError("curve must be a line (start, end) or a fitted spline (params, points, second_derivs, sample_arc, total_length)")
         _lib.check(_lib.load().tm_edges_discretize(jobs, len(specs), device))
-        return [Edge(p, c) for p, c in out]
+        return [Edge(pts_all[a:b], cl_all[a:b]) for a, b in bounds]
 
     def copy(self) -> "Edge":
         return Edge(self.points.copy(), self.clustering.copy())
@@ -88,42 +98,42 @@ class Edge:
 
         from . import _lib
 
-        dp = C.POINTER(C.c_double)
         cj = (_lib.TmCombineJob * max(len(jobs), 1))()
-        keep, out = [], []
+        n_views = sum(len(views) for views in jobs)
+        cv = (_lib.TmEdgeView * max(n_views, 1))()            # the views of all jobs in one array
+        v0, vsize = C.addressof(cv), C.sizeof(_lib.TmEdgeView)
+        sizes = [sum(abs(int(a) - int(b)) + 1 for _, a, b in views) - (len(views) - 1) for views in jobs]
+        total = sum(sizes)
+        pts_all, cl_all = np.empty((total, 2), dtype=np.float64), np.empty(total, dtype=np.float64)
+        p0, c0 = _addr(pts_all), _addr(cl_all)
+        off = q = 0
+        bounds = []
         for k, views in enumerate(jobs):
-            cv = (_lib.TmEdgeView * len(views))()
-            n = 0
-            for v, (edge, start, end) in enumerate(views):
-                cv[v].points, cv[v].clustering = edge.points.ctypes.data_as(dp), edge.clustering.ctypes.data_as(dp)
-                cv[v].n, cv[v].start, cv[v].end = len(edge.clustering), int(start), int(end)
-                n += abs(int(start) - int(end)) + 1
-            n -= len(views) - 1
-            pts, cl = np.empty((n, 2), dtype=np.float64), np.empty(n, dtype=np.float64)
-            cj[k].views, cj[k].n_views, cj[k].points, cj[k].clustering = cv, len(views), pts.ctypes.data_as(dp), cl.ctypes.data_as(dp)
-            keep.append(cv)
-            out.append((pts, cl))
+            cj[k].views, cj[k].n_views, cj[k].points, cj[k].clustering = v0 + q * vsize, len(views), p0 + 16 * off, c0 + 8 * off
+            for edge, start, end in views:
+                v = cv[q]
+                v.points, v.clustering, v.n, v.start, v.end = _addr(edge.points), _addr(edge.clustering), len(edge.clustering), int(start), int(end)
+                q += 1
+            bounds.append((off, off + sizes[k]))
+            off += sizes[k]
         _lib.check(_lib.load().tm_edges_combine(cj, len(jobs), device))
-        return [Edge(p, c) for p, c in out]
+        return [Edge(pts_all[a:b], cl_all[a:b]) for a, b in bounds]
 
     @staticmethod
     def project_normal_batch(jobs, device: int = -1) -> List[np.ndarray]:
         """``projectNormal`` (``templates/O4H.zig:531-574``) for many edges at once on the GPU: ``jobs`` = [(points (n, 2), distance)]."""
-        import ctypes as C
-
         from . import _lib
 
-        dp = C.POINTER(C.c_double)
         cj = (_lib.TmProjectJob * max(len(jobs), 1))()
-        keep, out = [], []
-        for k, (points, distance) in enumerate(jobs):
-            src = np.ascontiguousarray(points, dtype=np.float64)
-            dst = np.empty_like(src)
-            cj[k].points, cj[k].n, cj[k].distance, cj[k].out = src.ctypes.data_as(dp), len(src), float(distance), dst.ctypes.data_as(dp)
-            keep.append(src)
-            out.append(dst)
+        srcs = [np.ascontiguousarray(points, dtype=np.float64) for points, _ in jobs]
+        out_all = np.empty((sum(len(a) for a in srcs), 2), dtype=np.float64)
+        o0, off, bounds = _addr(out_all), 0, []
+        for k, (src, (_, distance)) in enumerate(zip(srcs, jobs)):
+            cj[k].points, cj[k].n, cj[k].distance, cj[k].out = _addr(src), len(src), float(distance), o0 + 16 * off
+            bounds.append((off, off + len(src)))
+            off += len(src)
         _lib.check(_lib.load().tm_edges_project_normal(cj, len(jobs), device))
-        return out
+        return [out_all[a:b] for a, b in bounds]
 
 
 class FittedSpline:
@@ -141,18 +151,22 @@ class FittedSpline:
 
         dp = C.POINTER(C.c_double)
         jobs = (_lib.TmSplineFitJob * max(len(point_sets), 1))()
-        keep, out = [], []
-        for k, pts in enumerate(point_sets):
-            src = np.ascontiguousarray(pts, dtype=np.float64)
+        srcs = [np.ascontiguousarray(pts, dtype=np.float64) for pts in point_sets]
+        total = sum(len(a) for a in srcs)
+        # one buffer per table for the whole batch (the library then brings each back in one copy); a spline = slices of them
+        params, zx, zy = np.empty(total), np.empty(total), np.empty(total)
+        arcs, lengths = np.empty(len(srcs) * n_samples), np.empty(max(len(srcs), 1))
+        off, bounds = 0, []
+        for k, src in enumerate(srcs):
             n = len(src)
-            arrs = [np.empty(n), np.empty(n), np.empty(n), np.empty(n_samples), np.empty(1)]
             j = jobs[k]
             j.n_points, j.points, j.n_samples = n, src.ctypes.data_as(dp), n_samples
-            j.params, j.second_derivs_x, j.second_derivs_y, j.sample_arc, j.total_length = [a.ctypes.data_as(dp) for a in arrs]
-            keep.append(src)
-            out.append((src, arrs))
-        _lib.check(_lib.load().tm_splines_fit(jobs, len(point_sets), device))
-        return [FittedSpline(src, a[0], a[1], a[2], a[3], float(a[4][0])) for src, a in out]
+            j.params, j.second_derivs_x, j.second_derivs_y = [C.cast(_addr(a) + 8 * off, dp) for a in (params, zx, zy)]
+            j.sample_arc, j.total_length = C.cast(_addr(arcs) + 8 * k * n_samples, dp), C.cast(_addr(lengths) + 8 * k, dp)
+            bounds.append((off, off + n))
+            off += n
+        _lib.check(_lib.load().tm_splines_fit(jobs, len(srcs), device))
+        return [FittedSpline(src, params[a:b], zx[a:b], zy[a:b], arcs[k * n_samples:(k + 1) * n_samples], float(lengths[k])) for k, (src, (a, b)) in enumerate(zip(srcs, bounds))]
 
 
 TfiFn = Callable[..., np.ndarray]
