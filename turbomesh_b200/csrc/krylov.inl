@@ -739,7 +739,11 @@ void krylov_solve_phased(tm_mesh* m, RankMesh& r, const tm_smooth_options* o, tm
     a.max_iters = o->max_inner_iterations > 0x7fffffffull ? 0x7fffffff : int32_t(o->max_inner_iterations);
     a.max_restarts = 60;
     a.polish = std::max(0, int(o->inner_refinement_cycles));
-    if (P.n_items > 0) {
+    // Without TM_KRYLOV_COARSE in the environment the coarse space is used with the reference's kind of settings only: "exact
+    // Picard step" runs (inner_refinement_cycles > 0, parity against the oracle) stay with point-Jacobi, whose iterates never
+    // move along the nearly singular direction of a mesh with a collapsed cell.
+    const bool use_coarse = P.n_items > 0 && (std::getenv("TM_KRYLOV_COARSE") != nullptr || o->inner_refinement_cycles == 0);
+    if (use_coarse) {
         if (P.coarse_age < 0 || P.coarse_age >= P.coarse_every) { coarse_refresh(m, r, P); P.coarse_age = 0; }
         P.coarse_age += 1;
         a.coarse = P.coarse.p; a.coarse_ok = P.coarse_ok.p; a.agg = P.agg.p; a.contrib_ptr = P.contrib_ptr.p; a.contrib_src = P.contrib_src.p;
@@ -766,7 +770,7 @@ void krylov_solve_phased(tm_mesh* m, RankMesh& r, const tm_smooth_options* o, tm
     };
     // graphs (of two iterations) between two looks at the systems' states: a look costs a stream synchronisation, not looking
     // costs iterations nobody needs; with the coarse space a solve is ~60 iterations, without ~150
-    int polls_every = P.n_items > 0 ? 2 : 4;
+    int polls_every = use_coarse ? 2 : 4;
     if (const char* e = std::getenv("TM_KRYLOV_POLL")) polls_every = std::max(1, std::atoi(e));
     cudaGraphExec_t exec = nullptr;
     uint64_t launches_per_graph = 0;
