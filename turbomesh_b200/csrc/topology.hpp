@@ -12,6 +12,9 @@
 //   sliding    inlet/outlet node: x Dirichlet, y Neumann                                 (smooth.zig:837-859, 1115-1165)
 //   slave      "connected" copy: x = x_root + shift, master chains resolved here         (smooth.zig:804-812, 904-915)
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -177,12 +180,20 @@ struct Topology {
         for (size_t c = 0; c < nbc; ++c) {
             if (!range_ok(bcs[c].range) || bcs[c].kind > TM_BC_OUTLET) TM_THROW(TM_ERR_TOPOLOGY, "condition %zu: invalid range or kind", c);
         }
-        find_components(conns, nc);
-        find_junctions(conns, nc);
-        classify(conns, nc, bcs, nbc);
-        build_rows(conns, nc, bcs, nbc);
-        build_pairs(conns, nc);
-        check_white(conns, nc);
+        const bool timing = std::getenv("TM_TOPO_TIMING") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!timing) return;
+            const auto t1 = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "topology %-16s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            t0 = t1;
+        };
+        find_components(conns, nc); lap("components");
+        find_junctions(conns, nc); lap("junctions");
+        classify(conns, nc, bcs, nbc); lap("classify");
+        build_rows(conns, nc, bcs, nbc); lap("rows");
+        build_pairs(conns, nc); lap("pairs");
+        check_white(conns, nc); lap("white");
     }
 
   private:
