@@ -533,18 +533,22 @@ void phased_coarse_build(tm_mesh* m, RankMesh& r, PhasedPlan& P, const std::vect
         if (!patch[size_t(t.block)].ai) continue;
         const auto& B = T.blocks[size_t(t.block)];
         const int32_t ab = coarse[size_t(T.comp_of_block[size_t(t.block)])].agg_base;
+        // the four 8-lane segments of the warp: columns j0 + 8 s of one row group (plain tile) or row group s of a strip tile
+        const int groups = wtile_groups(t), rr = wtile_rows(t), segs_per_group = groups ? wtile_width(t) / 8 : 4;
         for (int seg = 0; seg < 4; ++seg) {
-            const int64_t j = t.j0 + 8 * seg;
-            if (j > B.nj - 2) break;
-            slots[size_t(ab + patch_of(size_t(t.block), t.i0, j))].push_back(int32_t(4 * w + size_t(seg)));
+            const int g = groups ? seg / segs_per_group : 0;
+            const int64_t i_first = t.i0 + int64_t(g) * rr, j_first = t.j0 + 8 * (seg - g * segs_per_group);
+            if (j_first > B.nj - 2 || i_first > B.ni - 2 || (groups && g >= groups)) continue;
+            slots[size_t(ab + patch_of(size_t(t.block), i_first, j_first))].push_back(int32_t(4 * w + size_t(seg)));
+            const int64_t i_last = std::min<int64_t>(i_first + rr, B.ni - 1), j_last = std::min<int64_t>(j_first + 8, B.nj - 1);
+            for (int64_t i = i_first; i < i_last; ++i)
+                for (int64_t j = j_first; j < j_last; ++j) {
+                    const int32_t I = agg[size_t(B.off + i * B.nj + j)];
+                    members[size_t(ab + I)].push_back(int32_t(B.off + i * B.nj + j));
+                    for (int di = -1; di <= 1; ++di)
+                        for (int dj = -1; dj <= 1; ++dj) add_unique(nbrs[size_t(ab + I)], agg[size_t(B.off + (i + di) * B.nj + j + dj)]);
+                }
         }
-        for (int64_t i = t.i0; i < t.i0 + t.rows; ++i)
-            for (int64_t j = t.j0; j < t.j0 + 32 && j <= B.nj - 2; ++j) {
-                const int32_t I = agg[size_t(B.off + i * B.nj + j)];
-                members[size_t(ab + I)].push_back(int32_t(B.off + i * B.nj + j));
-                for (int di = -1; di <= 1; ++di)
-                    for (int dj = -1; dj <= 1; ++dj) add_unique(nbrs[size_t(ab + I)], agg[size_t(B.off + (i + di) * B.nj + j + dj)]);
-            }
     }
     for (size_t q = 0; q < r.L.smoothed.size(); ++q) {
         const SmoothedRow& row = r.L.smoothed[q];
@@ -639,9 +643,19 @@ void phased_plan_build(tm_mesh* m, RankMesh& r) {
             const int64_t interior_i = B.ni - 2;
             const int64_t n_i = std::max<int64_t>(1, (interior_i + tile_rows - 1) / tile_rows);
             const int64_t rr = (interior_i + n_i - 1) / n_i;
+            // the last <= 16 columns of a block would fill at most half of a warp: four or two row groups of them share one (strip tiles)
+            const int64_t rem = (B.nj - 2) % 32, n_full = (B.nj - 2) / 32;
+            const bool strips = rem > 0 && rem <= 16 && n_i >= 2 && !std::getenv("TM_KRYLOV_NO_STRIPS");
+            const int64_t strip_w = rem <= 8 ? 8 : 16, per_warp = 32 / strip_w;
             for (int64_t i0 = 1; i0 <= B.ni - 2; i0 += rr)
                 for (int64_t j0 = 1; j0 <= B.nj - 2; j0 += 32) {
+                    if (strips && j0 == 1 + 32 * n_full) continue;
                     wtiles.push_back(WTile{int32_t(b), int32_t(i0), int32_t(j0), int32_t(std::min<int64_t>(rr, B.ni - 1 - i0))});
+                    wt_comp.push_back(c);
+                }
+            if (strips)
+                for (int64_t g0 = 0; g0 < n_i; g0 += per_warp) {
+                    wtiles.push_back(WTile{int32_t(b), int32_t(1 + g0 * rr), int32_t(1 + 32 * n_full), int32_t(rr | (std::min<int64_t>(per_warp, n_i - g0) << 16) | (strip_w << 24))});
                     wt_comp.push_back(c);
                 }
         }

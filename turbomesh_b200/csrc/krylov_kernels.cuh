@@ -51,6 +51,26 @@ constexpr int K_MAX_GROUP = 160; // CTAs of a group (one per SM)
 constexpr int K_REC = 16;        // doubles of a CTA's record in the exchange (128 bytes): K_NACC sums, the stamp in the last one
 
 struct WTile { int32_t block, i0, j0, rows; };   // 32 columns starting at interior column j0, `rows` rows starting at interior row i0
+// STRIP tiles (phased path only): the last <= 16 columns of a block, whose own tile would fill at most half of the warp, packed
+// four (<= 8 columns) or two (<= 16) row groups to a warp -- with W = 8 or 16 lanes per group, lanes W g .. W g + W - 1 march rows
+// i0 + g * rows .. of columns j0 .. j0 + W - 1.  `rows` then carries the number of row groups in bits 16 .. 23 and W in bits 24 .. 31.
+__host__ __device__ inline int wtile_rows(const WTile& t) { return t.rows & 0xffff; }
+__host__ __device__ inline int wtile_groups(const WTile& t) { return (t.rows >> 16) & 0xff; }   // 0: a plain tile
+__host__ __device__ inline int wtile_width(const WTile& t) { return (t.rows >> 24) & 0xff; }
+struct WLane { int i0, j; bool active; };
+__device__ __forceinline__ WLane wtile_lane(const WTile& t, const DevBlock& b) {
+    const int lane = threadIdx.x & 31, groups = wtile_groups(t);
+    WLane l;
+    if (groups == 0) {
+        l.i0 = t.i0; l.j = t.j0 + lane; l.active = l.j <= b.nj - 2;
+    } else {
+        const int W = wtile_width(t), g = lane / W;
+        l.i0 = t.i0 + g * wtile_rows(t); l.j = t.j0 + (lane - g * W);
+        l.active = g < groups && l.j <= b.nj - 2 && l.i0 <= b.ni - 2;
+        if (!l.active) l.i0 = t.i0;
+    }
+    return l;
+}
 
 struct KComp {   // one independent system: ranges into the component-sorted tables
     int32_t wt_begin, wt_end;
@@ -231,14 +251,13 @@ __device__ __forceinline__ void k_interior(const WTile& t, const DevBlock& b, U&
 // wavefronts, but the kernel is latency-bound at 4 CTAs/SM and forcing 6 CTAs/SM only added spills: 740 -> 820 ms on 128 cuts.)
 template <int MODE, bool HAS_PQ, class U, class Epi>
 __device__ __forceinline__ void k_interior_march(const WTile& t, const DevBlock& b, U&& u, const double2* __restrict__ xc, const double2* __restrict__ pq, Epi&& epi) {
-    const int lane = threadIdx.x & 31;
     const int nj = b.nj;
-    const int j = t.j0 + lane;
-    const bool active = j <= nj - 2;
-    const int jc = active ? j : nj - 2;
-    const int i_end = min(t.i0 + t.rows, b.ni - 1);
+    const WLane wl = wtile_lane(t, b);
+    const bool active = wl.active;
+    const int jc = active ? wl.j : nj - 2;
+    const int i_end = min(wl.i0 + wtile_rows(t), b.ni - 1);
     const double2* cb = xc + b.off;
-    int64_t l = (int64_t)(t.i0 - 1) * nj + jc;
+    int64_t l = (int64_t)(wl.i0 - 1) * nj + jc;
     double2 Cm = u(b.off + l), Dm = u(b.off + l + 1) - u(b.off + l - 1);
     double2 cCm = ldg2(cb + l);
     l += nj;
@@ -246,7 +265,7 @@ __device__ __forceinline__ void k_interior_march(const WTile& t, const DevBlock&
     double2 C0 = u(b.off + l), D0 = rt - lf, R0 = (rt - C0) + (lf - C0);
     double2 cC0 = ldg2(cb + l), cD0 = ldg2(cb + l + 1) - ldg2(cb + l - 1);
 #pragma unroll 1
-    for (int i = t.i0; i < i_end; ++i) {
+    for (int i = wl.i0; i < i_end; ++i) {
         const int64_t lp = l + nj;
         const double2 lfp = u(b.off + lp - 1), rtp = u(b.off + lp + 1);
         const double2 Cp = u(b.off + lp), Dp = rtp - lfp, Rp = (rtp - Cp) + (lfp - Cp);
@@ -268,11 +287,12 @@ __device__ __forceinline__ void k_interior_march(const WTile& t, const DevBlock&
 // vector updates over a tall tile
 template <class Load, class Store>
 __device__ __forceinline__ void k_interior_nodes_march(const WTile& t, const DevBlock& b, Load&& load, Store&& store) {
-    const int j = t.j0 + (threadIdx.x & 31);
-    if (j > b.nj - 2) return;
-    const int i_end = min(t.i0 + t.rows, b.ni - 1);
+    const WLane wl = wtile_lane(t, b);
+    if (!wl.active) return;
+    const int j = wl.j;
+    const int i_end = min(wl.i0 + wtile_rows(t), b.ni - 1);
 #pragma unroll 4
-    for (int i = t.i0; i < i_end; ++i) {
+    for (int i = wl.i0; i < i_end; ++i) {
         const int64_t k = b.off + (int64_t)i * b.nj + j;
         store(k, load(k));
     }
