@@ -586,10 +586,12 @@ def gpu_cuts(args, torch, local, n_cuts, repeats=2):
     from turbomesh_b200.clustering import Roberts
     cells = Cells(o_grid=40, middle_i=100, in_up_j=30, in_down_j=10, in_i=10, out_up_j=40, out_down_j=10, out_i=10, down_j=40, bulge=40, upstream_i=20, downstream_i=10)
     cuts = [Cut(z["b0_x_i_min"] * sc, z["b1_x_i_min"] * sc, float(meta["pitch"]) * sc) for sc in scales]
-    O4HBatch(cells, Roberts(0.5, 1.03), device=local).run(cuts[:2])
-    t0 = time.perf_counter()
-    blocked, _ = O4HBatch(cells, Roberts(0.5, 1.03), device=local).run(cuts)
-    t_blocking = time.perf_counter() - t0
+    t_blocking = None
+    for _ in range(3):   # the first batch of a process also pays the first touch of its host buffers (0.2 s); a stream of batches does not
+        t0 = time.perf_counter()
+        blocked, _ = O4HBatch(cells, Roberts(0.5, 1.03), device=local).run(cuts)
+        dt = time.perf_counter() - t0
+        t_blocking = dt if t_blocking is None else min(t_blocking, dt)
     assert len(blocked.blocks) == len(batch.blocks)
     worst = max(max(dm.component_stats(c)["norm_r"][xy] / dm.component_stats(c)["tolerance"][xy] for xy in range(2)) for c in range(0, n_cuts, max(1, n_cuts // 16)))
     dm.close()
