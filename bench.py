@@ -604,7 +604,7 @@ def gpu_cuts(args, torch, local, n_cuts, repeats=2):
                       "direct coarse solve); rtol 1e-6 atol 1e-8 max 1000",
             "note": "every cut is its own linear system (own ||b||, tolerance, iteration count).  node_updates_per_s counts the operator applications actually "
                     "done: the coarse space cuts them by 2.7x (3131 -> ~1170 per node), so the rate and its roofline fraction fall while the time to "
-                    "solution improves (0.73 -> 0.45 s); an application still moves ~200 B per node through HBM at ~3 TB/s (latency-limited launches)"}
+                    "solution improves (0.73 -> 0.40 s); an application still moves ~200 B per node through HBM at ~3 TB/s (latency-limited launches)"}
 
 
 def configs_block(args, torch, local):
