@@ -1,4 +1,5 @@
-// krylov_coarse.cuh -- coarse space of the two-level preconditioner of the persistent BiCGStab kernel (krylov_kernels.cuh).
+// krylov_coarse.cuh -- coarse space of the two-level preconditioner of the BiCGStab kernels: on by default in the phased launches
+// of a batch (krylov_phased.cuh), opt-in in the persistent kernel (krylov_kernels.cuh); DESIGN.md 4 has the measurements.
 //
 // What it replaces: the reference's strong preconditioner (ILU(0), src/core/smoothing/GMRES.zig:199-298).  The inner systems
 // are elliptic: with point-Jacobi (BiCGStab.zig's `diagonal`) the iteration count grows with the node count along the
@@ -22,7 +23,8 @@
 //                            elliptic operator: weakly diagonally dominant); a CTA per component.  A vanishing or non-finite
 //                            pivot switches the coarse space of that component off (the solve is then plain Jacobi-BiCGStab).
 //
-// The application (restriction inside the phases, the product with G after the phase's barrier) is in krylov_kernels.cuh.
+// The application (restriction inside the phases, the product with G after the phase's exchange / finalisation) is in
+// krylov_kernels.cuh and krylov_phased.cuh (krylov_coarse_kernel).
 #pragma once
 #include "krylov_kernels.cuh"
 

@@ -12,7 +12,7 @@
 //     working set of a solve (10 fields x 16 B x 25 k nodes = 4 MB for a T106 cut) stays in the 126 MB L2 while ~30 cuts
 //     are in flight: the iteration is bound by L2 latency / bandwidth, not by HBM and not by launch cadence.
 //   * An iteration is TWO phases inside the kernel, each ended by one exchange between the CTAs of the group that is barrier
-//     and reduction at once (stamped values, see reduce(); co-residency comes from the cooperative launch):
+//     and reduction at once (a stamped record per CTA, see reduce(); co-residency comes from the cooperative launch):
 //         A  v = A p  with  p = r + beta (p - omega v),  r = s - omega t  formed on the fly at every stencil node (p and v
 //            ping-pong); the owner also stores r and takes d += omega s of the previous iteration;  rhat.v
 //         B  t = A s  with  s = r - alpha v  formed on the fly likewise; d += alpha p;  s.s, t.s, t.t, rhat.s, rhat.t
