@@ -808,7 +808,14 @@ def run_e2e_cascade(args, spec, dm, my_blocks, solver, torch, dist, world, nodes
     blocks back into pinned host memory (``tm_mesh_download_block``, D2H inside).  Wall clock, max over ranks."""
     outs = {b: torch.empty((spec.blocks[b].size[0], spec.blocks[b].size[1], 2), dtype=torch.float64, pin_memory=True) for b in my_blocks}
     host = {b: outs[b].numpy() for b in my_blocks}
-    edges = {b: spec.blocks[b].edge_args() for b in my_blocks}
+    def pinned(a):   # the step's inputs live in page-locked host memory, like its outputs
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        t.numpy()[...] = a
+        keep.append(t)
+        return t.numpy()
+
+    keep = []
+    edges = {b: tuple(pinned(np.ascontiguousarray(a, dtype=np.float64)) for a in spec.blocks[b].edge_args()) for b in my_blocks}
     h2d = sum(a.nbytes for b in my_blocks for a in edges[b])
     d2h = sum(host[b].nbytes for b in my_blocks)
 
