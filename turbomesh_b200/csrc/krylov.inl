@@ -149,7 +149,14 @@ void coarse_plan_build(tm_mesh* m, RankMesh& r, KrylovPlan& P, const std::vector
                     }
                 }
         }
-        auto bnd_crank = [&](int q) { return (gwarps - 1 - (q % std::max(K.bnd_warps, 1))) / K_WARPS; };   // the kernel's for_bnd
+        auto bnd_crank = [&](int q) {   // the kernel's for_bnd: which CTA of the group evaluates boundary row q of the component
+            int back = 0;
+            if (K.bw_s == 0 && K.bw_j == 0) back = q % std::max(K.bnd_warps, 1);
+            else if (q < n_s) back = q % K.bw_s;
+            else if (q < n_s + n_j) back = K.bw_s + (q - n_s) % K.bw_j;
+            else back = K.bw_s + K.bw_j + (q - n_s - n_j) % (K.bnd_warps - K.bw_s - K.bw_j);
+            return (gwarps - 1 - back) / K_WARPS;
+        };
         for (int q = 0; q < n_s; ++q) {
             const SmoothedRow& row = r.L.smoothed[size_t(K.s_begin + q)];
             const int32_t I = agg[size_t(row.g0)];
@@ -347,6 +354,22 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
         else if (nt + bnd_chunks <= group_warps) K.bnd_warps = int32_t(group_warps - nt);
         else K.bnd_warps = int32_t(std::max<int64_t>(1, std::min<int64_t>(group_warps / 2, (2 * bnd_chunks * group_warps + (nt + 2 * bnd_chunks) / 2) / (nt + 2 * bnd_chunks))));
         if (const char* e = std::getenv("TM_KRYLOV_BND_WARPS")) K.bnd_warps = std::max(bnd_chunks ? 1 : 0, std::min(group_warps - 1, std::atoi(e)));
+        // the boundary warps by kind of row, shared out by work (an interface row 1, a junction row 1.5, a sliding row 0.2); every kind
+        // present needs a warp, else all kinds share all warps
+        K.bw_s = K.bw_j = 0;
+        {
+            const int n_s = K.s_end - K.s_begin, n_j = K.j_end - K.j_begin, n_l = K.l_end - K.l_begin;
+            const int kinds = (n_s > 0) + (n_j > 0) + (n_l > 0);
+            if (kinds >= 2 && K.bnd_warps >= 2 * kinds && !std::getenv("TM_KRYLOV_BND_MIXED")) {
+                const double ws = n_s, wj = 1.5 * n_j, wl = 0.2 * n_l, total = ws + wj + wl;
+                int bj = n_j ? std::max(1, int(K.bnd_warps * wj / total + 0.5)) : 0;
+                int bl = n_l ? std::max(1, int(K.bnd_warps * wl / total + 0.5)) : 0;
+                int bs = K.bnd_warps - bj - bl;
+                if (n_s == 0) { bl += bs; bs = 0; }
+                if (bs >= (n_s ? 1 : 0) && (bs > 0 || bj > 0)) { K.bw_s = bs; K.bw_j = bj; }
+                if (K.bw_s == 0 && K.bw_j == 0) { K.bw_s = 0; K.bw_j = 0; }
+            }
+        }
         K.wt_begin = int32_t(wtiles.size());
         for (size_t b = 0; b < T.blocks.size(); ++b) {
             if (T.comp_of_block[b] != c) continue;

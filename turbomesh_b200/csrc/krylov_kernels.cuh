@@ -78,7 +78,18 @@ struct KComp {   // one independent system: ranges into the component-sorted tab
     int32_t rt_begin, rt_end;
     int32_t nodes;
     int32_t bnd_warps;   // warps of the group (from its end) that take the boundary rows and no tiles
+    int32_t bw_s, bw_j;  // of these, the first bw_s take the interface rows, the next bw_j the junction rows, the rest the sliding rows
+                         // (a warp with rows of one kind does not serialise three row evaluators); 0, 0: all kinds on all of them
 };
+// which warp (counted from the END of the group) and which rows of its kind a boundary-row warp takes; shared with the host (krylov.inl)
+struct KBndPart { int kind, first, stride, count, base; };   // rows first + lane * stride, + 32 * stride, ... < count of `kind`; q = base + row
+__host__ __device__ inline KBndPart k_bnd_part(const KComp& K, int back) {
+    const int n_s = K.s_end - K.s_begin, n_j = K.j_end - K.j_begin, n_l = K.l_end - K.l_begin;
+    if (K.bw_s == 0 && K.bw_j == 0) return KBndPart{-1, back, K.bnd_warps, n_s + n_j + n_l, 0};
+    if (back < K.bw_s) return KBndPart{0, back, K.bw_s, n_s, 0};
+    if (back < K.bw_s + K.bw_j) return KBndPart{1, back - K.bw_s, K.bw_j, n_j, n_s};
+    return KBndPart{2, back - K.bw_s - K.bw_j, K.bnd_warps - K.bw_s - K.bw_j, n_l, n_s + n_j};
+}
 struct KCtl {    // per component; index 0 = x solve, 1 = y solve
     double tol[2], norm_b[2], norm_r[2];
     int32_t done[2];     // 1 converged, 2 breakdown, 3 iteration cap
@@ -571,10 +582,11 @@ auto mirror = [&](int sb, int se, auto&& put_copy) {   // put_copy(node of the c
         auto for_bnd = [&](auto&& fs, auto&& fj, auto&& fl) {
             const int back = gwarps - 1 - gwarp;
             if (back >= w_bnd) return;
-            const int q0 = back + lane * w_bnd, dq = 32 * w_bnd;
-            for (int q = q0; q < n_bnd; q += dq) {
-                if (q < n_s) fs(q, a.srows[K.s_begin + q]);
-                else if (q < n_s + n_j) fj(q, a.jrows[K.j_begin + q - n_s]);
+            const KBndPart part = k_bnd_part(K, back);
+            for (int row = part.first + lane * part.stride; row < part.count; row += 32 * part.stride) {
+                const int q = part.base + row;
+                if (part.kind == 0 || (part.kind < 0 && q < n_s)) fs(q, a.srows[K.s_begin + q]);
+                else if (part.kind == 1 || (part.kind < 0 && q < n_s + n_j)) fj(q, a.jrows[K.j_begin + q - n_s]);
                 else fl(q, a.lrows[K.l_begin + q - n_s - n_j]);
             }
         };
