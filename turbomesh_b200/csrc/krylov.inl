@@ -344,8 +344,8 @@ void krylov_plan_build(tm_mesh* m, RankMesh& r) {
             return n;
         };
         const int64_t bnd_chunks = (int64_t(K.s_end - K.s_begin) + (K.j_end - K.j_begin) + (K.l_end - K.l_begin) + 31) / 32;
-        int rows = 1;
-        if (tiles_with(1) + bnd_chunks > group_warps) rows = K_TILE_ROWS;
+        int rows = 1;   // the fewest rows per tile with which the phase is a single round, else the most
+        while (rows < K_TILE_ROWS && tiles_with(rows) + bnd_chunks > group_warps) rows *= 2;
         if (const char* e = std::getenv("TM_KRYLOV_TILE_ROWS")) rows = std::max(1, std::min(K_TILE_ROWS, std::atoi(e)));
         // warps set aside for the boundary rows: all that are left in a single round, else a share by work (32 boundary rows
         // cost about two tiles: three kinds of rows, gathers across blocks)

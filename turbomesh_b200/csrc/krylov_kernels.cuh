@@ -46,7 +46,7 @@ namespace tmesh {
 constexpr int K_THREADS = 256;
 constexpr int K_WARPS = K_THREADS / 32;
 constexpr int K_NACC = 10;       // sums a phase reduces
-constexpr int K_TILE_ROWS = 2;   // rows of a warp tile
+constexpr int K_TILE_ROWS = 2;   // rows of a warp tile (at most; 4 was tried: spills and 1.5 x slower on LS89 x4)
 constexpr int K_MAX_GROUP = 160; // CTAs of a group (one per SM)
 constexpr int K_REC = 16;        // doubles of a CTA's record in the exchange (128 bytes): K_NACC sums, the stamp in the last one
 
