@@ -112,7 +112,8 @@ def test_every_cut_of_a_batch_is_solved_as_its_own_system(gpu_lib, orc, monkeypa
     O.close()
 
 
-def test_two_level_preconditioner_in_the_batch_path(gpu_lib, monkeypatch):
+@pytest.mark.parametrize("tile_rows", [8, 16])
+def test_two_level_preconditioner_in_the_batch_path(gpu_lib, monkeypatch, tile_rows):
     """The coarse space of the phased launches (krylov_phased.cuh, on by default for batches with tall tiles): the cuts of a
     batch reach the same exact Picard sequence -- cut 0 (the unscaled T106) against the extended-precision truth, the others
     against the point-Jacobi run -- with well under 60 % of the Krylov iterations."""
@@ -126,7 +127,7 @@ def test_two_level_preconditioner_in_the_batch_path(gpu_lib, monkeypatch):
     cf = smoothing.White(meta["ds_target"], meta["theta_target"])
     sol = smoothing.CudaSolver.tight()
     monkeypatch.setenv("TM_KRYLOV", "phased")
-    monkeypatch.setenv("TM_KRYLOV_TILE_ROWS", "8")     # tall tiles: what a large batch gets (a small one has 2-row tiles and no coarse space)
+    monkeypatch.setenv("TM_KRYLOV_TILE_ROWS", str(tile_rows))     # tall tiles: what a large batch gets (16 rows from 2 M nodes on; a small batch has 2-row tiles and no coarse space)
     res, its = {}, {}
     for coarse in ("0", "1"):
         monkeypatch.setenv("TM_KRYLOV_COARSE", coarse)
